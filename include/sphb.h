@@ -1,0 +1,202 @@
+/* sphb.h — C ABI of libsphb.so, the B200 (sm_100a) SPH step for bbeni/sphugo.
+ *
+ * This is the drop-in boundary for ONE hot path of the reference: everything
+ * (*Simulation).Step() does (reference sim/sph.go:64-198), i.e. spatial index,
+ * periodic kNN (k = 32), density, pressure + artificial-viscosity force and the
+ * leapfrog drift/kick with periodic wrap and reflections.  The reference has no
+ * FFI of its own (it is pure Go); these entry points are what a cgo shim in
+ * package `sim` binds (see INTEGRATION.md and go/sim/backend_cuda.go).
+ *
+ * Conventions
+ *   - every function returns 0 (SPHB_OK) or a negative sphb_status; the text
+ *     of the last failure is sphb_last_error(sim) (library-owned string).
+ *   - plain pointers and sizes only; host pointers are borrowed for the
+ *     duration of the call (cgo rule: no Go pointer is retained).
+ *   - there is NO CPU fallback in this library: without a CUDA device
+ *     sphb_create fails with SPHB_E_CUDA.
+ *   - one call at a time per handle (the Go shim holds sim.IsBusy, sph.go:20,66).
+ *   - every entry point calls cudaSetDevice (goroutines hop OS threads).
+ *   - particle order on the device is cell order and changes every step, like
+ *     the reference's in-place tree partition (core.go:126-164); join on `id`
+ *     (the reference's Particle.Z, core.go:41).
+ */
+#ifndef SPHB_H
+#define SPHB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPHB_NN 32 /* NN_SIZE, reference sim/core.go:14 */
+
+/* open axis marker: == Go math.MaxFloat64 (config-parser.go:139-145) */
+#define SPHB_OPEN_HI 1.7976931348623157e308
+#define SPHB_OPEN_LO (-1.7976931348623157e308)
+
+typedef enum {
+  SPHB_OK = 0,
+  SPHB_E_INVALID = -1,       /* bad argument / bad handle / half-open axis (nearest-neighbour.go:44,53 panics) */
+  SPHB_E_CUDA = -2,          /* CUDA runtime error or no device */
+  SPHB_E_NOMEM = -3,         /* capacity exceeded / allocation failed */
+  SPHB_E_KNN_UNDERFULL = -4, /* fewer than 32 (particle,image) candidates exist: the reference would
+                                keep sentinel slots (nearest-neighbour.go:155-165); we refuse instead */
+  SPHB_E_KERNEL = -5,        /* TopHat2D has no derivative (sph.go:251-253 panics) */
+  SPHB_E_STATE = -6          /* call order: e.g. density before knn */
+} sphb_status;
+
+typedef enum {
+  SPHB_KERNEL_TOPHAT = 0,   /* sim.TopHat2D   sph.go:244-257 (density only) */
+  SPHB_KERNEL_MONAGHAN = 1, /* sim.Monahan2D  sph.go:259-276 */
+  SPHB_KERNEL_WENDLAND = 2  /* sim.Wendtland2D sph.go:284-304 */
+} sphb_kernel;
+
+/* Numeric part of sim.SphConfig (config-parser.go:111-128). */
+typedef struct {
+  double dt_half;        /* DeltaTHalf */
+  double gamma;          /* Gamma */
+  double particle_mass;  /* ParticleMass */
+  double accel[2];       /* Acceleration */
+  double hor[2];         /* HorPeriodicity;  {SPHB_OPEN_LO, SPHB_OPEN_HI} = open */
+  double ver[2];         /* VertPeriodicity */
+  double refl_L, refl_R; /* Reflections.L/.R on x; disabled = SPHB_OPEN_LO / SPHB_OPEN_HI */
+  double refl_U, refl_D; /* Reflections.U (low y) / .D (high y) */
+  int32_t kernel;        /* sphb_kernel */
+  int32_t precision;     /* 64: everything fp64 (reference precision). 32: pair arithmetic in fp32 on
+                            cell-relative coordinates, state kept in fp64 */
+  int32_t device;        /* CUDA device ordinal of this handle (one process / handle per GPU) */
+  int32_t flags;         /* SPHB_FLAG_* */
+} sphb_params;
+
+#define SPHB_FLAG_KEEP_NN_LIST 1u /* always materialise the neighbour list (needed by download of NN_*) */
+
+typedef struct sphb_sim sphb_sim; /* opaque, owned by the library */
+
+/* Fields for sphb_download / sphb_upload: bit i of the mask <-> host_ptrs[i]. */
+enum {
+  SPHB_F_POS = 0,    /* double[2n]  Particle.Pos            */
+  SPHB_F_VEL = 1,    /* double[2n]  Particle.Vel            */
+  SPHB_F_RHO = 2,    /* double[n]   Particle.Rho            */
+  SPHB_F_C = 3,      /* double[n]   Particle.C              */
+  SPHB_F_E = 4,      /* double[n]   Particle.E              */
+  SPHB_F_EDOT = 5,   /* double[n]   Particle.EDot           */
+  SPHB_F_VDOT = 6,   /* double[2n]  Particle.VDot           */
+  SPHB_F_EPRED = 7,  /* double[n]   Particle.EPred          */
+  SPHB_F_VPRED = 8,  /* double[2n]  Particle.VPred          */
+  SPHB_F_H = 9,      /* double[n]   Particle.NNDists[0]     */
+  SPHB_F_ID = 10,    /* int64[n]    Particle.Z              */
+  SPHB_F_NN_IDX = 11,/* int32[32n]  index (current device order) of Particle.NearestNeighbours[k];
+                                     slot order is ascending index, NOT the reference's descending distance */
+  SPHB_F_NN_DIST = 12,/* double[32n] Particle.NNDists[k] for the same slots */
+  SPHB_F_NN_POS = 13, /* double[64n] Particle.NNPos[k] (neighbour image position in the query frame) */
+  SPHB_F_COUNT = 14
+};
+#define SPHB_MASK(f) (1u << (f))
+
+/* reductions, sph.go:441-463 */
+enum { SPHB_SUM_E = 0, SPHB_SUM_RHO = 1, SPHB_LAST_VEL_NORM = 2 /* TotalMomentum's `=` bug, sph.go:460 */ };
+
+/* phases reported by sphb_phase_times (milliseconds, CUDA events, last step) */
+enum {
+  SPHB_PH_KEYS = 0,   /* drift-1 + cell keys                       (replaces Partition, core.go:126) */
+  SPHB_PH_SORT = 1,   /* radix sort of (key, index)                 (replaces Treebuild, core.go:172) */
+  SPHB_PH_REORDER = 2,/* SoA gather + predict + cell table                                         */
+  SPHB_PH_KNN = 3,    /* kNN + density + sound speed (+ fallback)   (nearest-neighbour.go:28, sph.go:306,423) */
+  SPHB_PH_FORCE = 4,  /* force + kick + drift-2 + boundaries        (sph.go:327, 122-193) */
+  SPHB_PH_TOTAL = 5,
+  SPHB_PH_COUNT = 6
+};
+
+/* counters reported by sphb_counters (cumulative since create) */
+enum {
+  SPHB_CNT_STEPS = 0,
+  SPHB_CNT_KERNEL_LAUNCHES = 1,
+  SPHB_CNT_KNN_FALLBACK = 2, /* particles that needed the ring-expansion search */
+  SPHB_CNT_REGRIDS = 3,
+  SPHB_CNT_COUNT = 4
+};
+
+/* == sim.MakeSimulationFromConf + MakeCells (sph.go:40-54, core.go:93-105).
+ * pos_xy, vel_xy: interleaved x,y. vel/e/rho/id may be NULL (zeros; id = index).
+ * capacity >= n reserves room for sphb_append (Sources, sph.go:72-86). */
+int sphb_create(const sphb_params* p, int64_t n, int64_t capacity, const double* pos_xy,
+                const double* vel_xy, const double* e, const double* rho, const int64_t* id,
+                sphb_sim** out);
+void sphb_destroy(sphb_sim* s);
+const char* sphb_last_error(const sphb_sim* s); /* s may be NULL: error of the last failed create */
+
+/* sim.Config is a public mutable field (sph.go:15); precision/device cannot change. */
+int sphb_set_params(sphb_sim* s, const sphb_params* p);
+int sphb_get_params(const sphb_sim* s, sphb_params* p);
+int64_t sphb_count(const sphb_sim* s);        /* len(sim.Root.Particles) */
+int64_t sphb_current_step(const sphb_sim* s); /* sim.CurrentStep */
+
+/* == append(sim.Root.Particles, spawned...) + MakeCells (sph.go:75-86) */
+int sphb_append(sphb_sim* s, int64_t n, const double* pos_xy, const double* vel_xy, const double* e,
+                const double* rho, const int64_t* id);
+
+/* == (*Simulation).Step() x nsteps, including the step-0 special case (sph.go:64-198). Asynchronous:
+ * returns after enqueueing; sphb_sync / download / reduce wait for it. */
+int sphb_step(sphb_sim* s, int32_t nsteps);
+/* == (*Simulation).CalculateForces() (sph.go:403-435) */
+int sphb_calc_forces(sphb_sim* s);
+/* batch == for all i: Particles[i].FindNearestNeighboursPeriodic(root, hor, ver) (nearest-neighbour.go:28-67);
+ * both {SPHB_OPEN_LO,SPHB_OPEN_HI} == FindNearestNeighbours (:15-23). Materialises the neighbour list. */
+int sphb_knn(sphb_sim* s, const double hor[2], const double ver[2]);
+/* batch == for all i: Particles[i].Rho = Density2D(p, sim, kernel) (sph.go:306-323); needs a prior knn */
+int sphb_density(sphb_sim* s, int32_t kernel);
+
+int sphb_sync(sphb_sim* s); /* wait for the device; surfaces asynchronous errors (kNN underfull, ...) */
+
+/* copy the selected fields into caller-owned host buffers (each sized for `capacity` particles);
+ * *n_out = number of particles. Order = current device order; join on SPHB_F_ID. */
+int sphb_download(sphb_sim* s, uint32_t field_mask, void* const* host_ptrs, int64_t capacity,
+                  int64_t* n_out);
+/* overwrite device state (same order as the last download) for POS, VEL, E, RHO, VDOT, EDOT:
+ * Root.Particles is public and examples poke it directly (density.go:12-15). */
+int sphb_upload(sphb_sim* s, uint32_t field_mask, const void* const* host_ptrs, int64_t n);
+
+int sphb_reduce(sphb_sim* s, int32_t which, double* out); /* TotalEnergy / TotalDensity / TotalMomentum */
+int sphb_phase_times(sphb_sim* s, double* ms, int32_t n); /* n <= SPHB_PH_COUNT */
+int sphb_counters(const sphb_sim* s, int64_t* out, int32_t n); /* n <= SPHB_CNT_COUNT */
+
+/* device-resident variants for callers that already hold device memory (bench.py `value`, the
+ * multi-GPU slab driver): pointers are CUDA device pointers on the handle's device. */
+int sphb_create_device(const sphb_params* p, int64_t n, int64_t capacity, const double* d_pos_xy,
+                       const double* d_vel_xy, const double* d_e, const int64_t* d_id, sphb_sim** out);
+
+/* ---- slab decomposition: one handle per GPU owns particles with x in [x_lo, x_hi).
+ * The exchange itself (NCCL send/recv) is done by the caller on the device buffers below. ---- */
+typedef struct {
+  double x_lo, x_hi;   /* owned interval; ghosts live outside it */
+  int32_t has_left;    /* a neighbour slab exists on the low-x side (periodic ring or interior) */
+  int32_t has_right;
+} sphb_slab;
+
+int sphb_slab_set(sphb_sim* s, const sphb_slab* slab);
+/* max smoothing length of the last force evaluation (device reduction; the caller all-reduces it) */
+int sphb_max_h(sphb_sim* s, double* out);
+/* StepBegin: sources/step-0 handling + drift-1 + predict on owned particles (sph.go:108-117). */
+int sphb_slab_step_begin(sphb_sim* s);
+/* pack owned particles within `width` of the low (side 0) / high (side 1) edge as ghost records
+ * {x, y, vpx, vpy, epred, id} = 6 x 8 bytes into d_buf (device); *count_out = records written. */
+int sphb_slab_pack_halo(sphb_sim* s, int32_t side, double width, void* d_buf, int64_t cap_records,
+                        int64_t* count_out);
+/* append received ghost records; x_shift is added to x (periodic ring wrap). */
+int sphb_slab_add_ghosts(sphb_sim* s, const void* d_buf, int64_t count, double x_shift);
+/* forces on owned particles using owned+ghost candidates, then kick/drift-2/boundaries, ghosts dropped */
+int sphb_slab_step_end(sphb_sim* s);
+/* pack (and remove) owned particles that left [x_lo, x_hi) to side 0/1 as migration records
+ * {x, y, vx, vy, e, vdotx, vdoty, edot, h, id} = 10 x 8 bytes */
+int sphb_slab_pack_migrants(sphb_sim* s, int32_t side, void* d_buf, int64_t cap_records,
+                            int64_t* count_out);
+int sphb_slab_add_migrants(sphb_sim* s, const void* d_buf, int64_t count, double x_shift);
+
+#define SPHB_HALO_RECORD_DOUBLES 6
+#define SPHB_MIGRANT_RECORD_DOUBLES 10
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPHB_H */

@@ -1,0 +1,297 @@
+"""ctypes binding of libsphb.so — exactly the C ABI of include/sphb.h (what the Go cgo shim binds).
+
+No numeric work happens in Python; without the built CUDA library every call fails loudly
+(there is no CPU fallback anywhere in this package).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsphb.so")
+
+NN = 32
+OPEN_LO, OPEN_HI = -1.7976931348623157e308, 1.7976931348623157e308
+OPEN = (OPEN_LO, OPEN_HI)
+
+OK, E_INVALID, E_CUDA, E_NOMEM, E_KNN_UNDERFULL, E_KERNEL, E_STATE = 0, -1, -2, -3, -4, -5, -6
+KERNEL_TOPHAT, KERNEL_MONAGHAN, KERNEL_WENDLAND = 0, 1, 2
+
+FIELDS = ["pos", "vel", "rho", "c", "e", "edot", "vdot", "epred", "vpred", "h", "id", "nn_idx", "nn_dist", "nn_pos"]
+FIELD_BIT = {name: i for i, name in enumerate(FIELDS)}
+FIELD_SHAPE = {  # trailing shape, dtype
+    "pos": ((2,), np.float64), "vel": ((2,), np.float64), "rho": ((), np.float64), "c": ((), np.float64),
+    "e": ((), np.float64), "edot": ((), np.float64), "vdot": ((2,), np.float64), "epred": ((), np.float64),
+    "vpred": ((2,), np.float64), "h": ((), np.float64), "id": ((), np.int64), "nn_idx": ((NN,), np.int32),
+    "nn_dist": ((NN,), np.float64), "nn_pos": ((NN, 2), np.float64),
+}
+SUM_E, SUM_RHO, LAST_VEL_NORM = 0, 1, 2
+PHASES = ["keys", "sort", "reorder", "knn", "force", "total"]
+COUNTERS = ["steps", "kernel_launches", "knn_fallback", "regrids"]
+HALO_RECORD_DOUBLES, MIGRANT_RECORD_DOUBLES = 6, 10
+
+EXPORTS = [
+    "sphb_create", "sphb_destroy", "sphb_last_error", "sphb_set_params", "sphb_get_params", "sphb_count",
+    "sphb_current_step", "sphb_append", "sphb_step", "sphb_calc_forces", "sphb_knn", "sphb_density", "sphb_sync",
+    "sphb_download", "sphb_upload", "sphb_reduce", "sphb_phase_times", "sphb_counters", "sphb_create_device",
+    "sphb_slab_set", "sphb_max_h", "sphb_slab_step_begin", "sphb_slab_pack_halo", "sphb_slab_add_ghosts",
+    "sphb_slab_step_end", "sphb_slab_pack_migrants", "sphb_slab_add_migrants",
+]
+
+
+class Params(C.Structure):
+    """sphb_params == numeric part of sim.SphConfig (config-parser.go:111-128)."""
+
+    _fields_ = [
+        ("dt_half", C.c_double), ("gamma", C.c_double), ("particle_mass", C.c_double),
+        ("accel", C.c_double * 2), ("hor", C.c_double * 2), ("ver", C.c_double * 2),
+        ("refl_L", C.c_double), ("refl_R", C.c_double), ("refl_U", C.c_double), ("refl_D", C.c_double),
+        ("kernel", C.c_int32), ("precision", C.c_int32), ("device", C.c_int32), ("flags", C.c_int32),
+    ]
+
+
+class Slab(C.Structure):
+    _fields_ = [("x_lo", C.c_double), ("x_hi", C.c_double), ("has_left", C.c_int32), ("has_right", C.c_int32)]
+
+
+class SphbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libsphb error {code}: {msg}")
+        self.code = code
+
+
+_LIB = None
+
+
+def lib():
+    """Load libsphb.so; raises if it has not been built (python -m sphugo_b200.build)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python -m sphugo_b200.build` "
+                          "(the CUDA library is the only implementation; there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, dp, ip = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)
+    pp = C.POINTER(Params)
+    L.sphb_create.restype = C.c_int
+    L.sphb_create.argtypes = [pp, C.c_int64, C.c_int64, vp, vp, vp, vp, vp, C.POINTER(vp)]
+    L.sphb_create_device.restype = C.c_int
+    L.sphb_create_device.argtypes = [pp, C.c_int64, C.c_int64, vp, vp, vp, vp, C.POINTER(vp)]
+    L.sphb_destroy.restype = None
+    L.sphb_destroy.argtypes = [vp]
+    L.sphb_last_error.restype = C.c_char_p
+    L.sphb_last_error.argtypes = [vp]
+    L.sphb_set_params.restype = C.c_int
+    L.sphb_set_params.argtypes = [vp, pp]
+    L.sphb_get_params.restype = C.c_int
+    L.sphb_get_params.argtypes = [vp, pp]
+    L.sphb_count.restype = C.c_int64
+    L.sphb_count.argtypes = [vp]
+    L.sphb_current_step.restype = C.c_int64
+    L.sphb_current_step.argtypes = [vp]
+    L.sphb_append.restype = C.c_int
+    L.sphb_append.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp]
+    L.sphb_step.restype = C.c_int
+    L.sphb_step.argtypes = [vp, C.c_int32]
+    L.sphb_calc_forces.restype = C.c_int
+    L.sphb_calc_forces.argtypes = [vp]
+    L.sphb_knn.restype = C.c_int
+    L.sphb_knn.argtypes = [vp, dp, dp]
+    L.sphb_density.restype = C.c_int
+    L.sphb_density.argtypes = [vp, C.c_int32]
+    L.sphb_sync.restype = C.c_int
+    L.sphb_sync.argtypes = [vp]
+    L.sphb_download.restype = C.c_int
+    L.sphb_download.argtypes = [vp, C.c_uint32, C.POINTER(vp), C.c_int64, ip]
+    L.sphb_upload.restype = C.c_int
+    L.sphb_upload.argtypes = [vp, C.c_uint32, C.POINTER(vp), C.c_int64]
+    L.sphb_reduce.restype = C.c_int
+    L.sphb_reduce.argtypes = [vp, C.c_int32, dp]
+    L.sphb_phase_times.restype = C.c_int
+    L.sphb_phase_times.argtypes = [vp, dp, C.c_int32]
+    L.sphb_counters.restype = C.c_int
+    L.sphb_counters.argtypes = [vp, ip, C.c_int32]
+    L.sphb_slab_set.restype = C.c_int
+    L.sphb_slab_set.argtypes = [vp, C.POINTER(Slab)]
+    L.sphb_max_h.restype = C.c_int
+    L.sphb_max_h.argtypes = [vp, dp]
+    L.sphb_slab_step_begin.restype = C.c_int
+    L.sphb_slab_step_begin.argtypes = [vp]
+    L.sphb_slab_pack_halo.restype = C.c_int
+    L.sphb_slab_pack_halo.argtypes = [vp, C.c_int32, C.c_double, vp, C.c_int64, ip]
+    L.sphb_slab_add_ghosts.restype = C.c_int
+    L.sphb_slab_add_ghosts.argtypes = [vp, vp, C.c_int64, C.c_double]
+    L.sphb_slab_step_end.restype = C.c_int
+    L.sphb_slab_step_end.argtypes = [vp]
+    L.sphb_slab_pack_migrants.restype = C.c_int
+    L.sphb_slab_pack_migrants.argtypes = [vp, C.c_int32, vp, C.c_int64, ip]
+    L.sphb_slab_add_migrants.restype = C.c_int
+    L.sphb_slab_add_migrants.argtypes = [vp, vp, C.c_int64, C.c_double]
+    _LIB = L
+    return L
+
+
+def make_params(dt_half=0.001, gamma=1.66666, particle_mass=1.0, accel=(0.0, 0.0), hor=OPEN, ver=OPEN,
+                refl=(OPEN_LO, OPEN_HI, OPEN_LO, OPEN_HI), kernel=KERNEL_MONAGHAN, precision=64, device=0, flags=0):
+    """Defaults == sim.MakeConfig() (config-parser.go:131-149)."""
+    p = Params()
+    p.dt_half, p.gamma, p.particle_mass = dt_half, gamma, particle_mass
+    p.accel[0], p.accel[1] = accel
+    p.hor[0], p.hor[1] = hor
+    p.ver[0], p.ver[1] = ver
+    p.refl_L, p.refl_R, p.refl_U, p.refl_D = refl
+    p.kernel, p.precision, p.device, p.flags = kernel, precision, device, flags
+    return p
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+class Handle:
+    """Thin RAII wrapper of an sphb_sim*; every method is one C-ABI call."""
+
+    def __init__(self, params: Params, pos, vel=None, e=None, rho=None, ids=None, capacity=None):
+        L = lib()
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 2)
+        n = pos.shape[0]
+        vel = None if vel is None else np.ascontiguousarray(vel, dtype=np.float64).reshape(n, 2)
+        e = None if e is None else np.ascontiguousarray(e, dtype=np.float64).reshape(n)
+        rho = None if rho is None else np.ascontiguousarray(rho, dtype=np.float64).reshape(n)
+        ids = None if ids is None else np.ascontiguousarray(ids, dtype=np.int64).reshape(n)
+        self._h = C.c_void_p()
+        rc = L.sphb_create(C.byref(params), n, capacity or n, _ptr(pos), _ptr(vel), _ptr(e), _ptr(rho), _ptr(ids),
+                           C.byref(self._h))
+        if rc:
+            raise SphbError(rc, L.sphb_last_error(None).decode())
+
+    @classmethod
+    def from_device(cls, params: Params, n, d_pos, d_vel=None, d_e=None, d_id=None, capacity=None):
+        """d_* are CUDA device pointers (ints) on params.device."""
+        L = lib()
+        self = cls.__new__(cls)
+        self._h = C.c_void_p()
+        rc = L.sphb_create_device(C.byref(params), n, capacity or n, C.c_void_p(d_pos),
+                                  C.c_void_p(d_vel) if d_vel else None, C.c_void_p(d_e) if d_e else None,
+                                  C.c_void_p(d_id) if d_id else None, C.byref(self._h))
+        if rc:
+            raise SphbError(rc, L.sphb_last_error(None).decode())
+        return self
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().sphb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc:
+            raise SphbError(rc, lib().sphb_last_error(self._h).decode())
+
+    # -- one method per ABI entry point
+    @property
+    def n(self):
+        return int(lib().sphb_count(self._h))
+
+    @property
+    def current_step(self):
+        return int(lib().sphb_current_step(self._h))
+
+    def set_params(self, p: Params):
+        self._chk(lib().sphb_set_params(self._h, C.byref(p)))
+
+    def get_params(self) -> Params:
+        p = Params()
+        self._chk(lib().sphb_get_params(self._h, C.byref(p)))
+        return p
+
+    def append(self, pos, vel=None, e=None, rho=None, ids=None):
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 2)
+        n = pos.shape[0]
+        vel = None if vel is None else np.ascontiguousarray(vel, dtype=np.float64).reshape(n, 2)
+        e = None if e is None else np.ascontiguousarray(e, dtype=np.float64).reshape(n)
+        rho = None if rho is None else np.ascontiguousarray(rho, dtype=np.float64).reshape(n)
+        ids = None if ids is None else np.ascontiguousarray(ids, dtype=np.int64).reshape(n)
+        self._chk(lib().sphb_append(self._h, n, _ptr(pos), _ptr(vel), _ptr(e), _ptr(rho), _ptr(ids)))
+
+    def step(self, nsteps=1):
+        self._chk(lib().sphb_step(self._h, nsteps))
+
+    def calc_forces(self):
+        self._chk(lib().sphb_calc_forces(self._h))
+
+    def knn(self, hor=OPEN, ver=OPEN):
+        h = (C.c_double * 2)(*hor)
+        v = (C.c_double * 2)(*ver)
+        self._chk(lib().sphb_knn(self._h, h, v))
+
+    def density(self, kernel):
+        self._chk(lib().sphb_density(self._h, kernel))
+
+    def sync(self):
+        self._chk(lib().sphb_sync(self._h))
+
+    def download(self, fields, out=None):
+        """dict name -> array in current device order. `out` may hold preallocated (e.g. pinned) arrays."""
+        n = self.n
+        arrs, ptrs, mask = {}, (C.c_void_p * len(FIELDS))(), 0
+        for name in fields:
+            shp, dt = FIELD_SHAPE[name]
+            a = out[name] if out is not None and name in out else np.empty((n,) + shp, dtype=dt)
+            arrs[name] = a
+            ptrs[FIELD_BIT[name]] = a.ctypes.data
+            mask |= 1 << FIELD_BIT[name]
+        nout = C.c_int64()
+        self._chk(lib().sphb_download(self._h, mask, ptrs, n, C.byref(nout)))
+        return arrs
+
+    def upload(self, **fields):
+        n = self.n
+        ptrs, mask, keep = (C.c_void_p * len(FIELDS))(), 0, []
+        for name, a in fields.items():
+            shp, dt = FIELD_SHAPE[name]
+            a = np.ascontiguousarray(a, dtype=dt).reshape((n,) + shp)
+            keep.append(a)
+            ptrs[FIELD_BIT[name]] = a.ctypes.data
+            mask |= 1 << FIELD_BIT[name]
+        self._chk(lib().sphb_upload(self._h, mask, ptrs, n))
+
+    def reduce(self, which):
+        out = C.c_double()
+        self._chk(lib().sphb_reduce(self._h, which, C.byref(out)))
+        return out.value
+
+    def max_h(self):
+        out = C.c_double()
+        self._chk(lib().sphb_max_h(self._h, C.byref(out)))
+        return out.value
+
+    def phase_times(self):
+        ms = (C.c_double * len(PHASES))()
+        self._chk(lib().sphb_phase_times(self._h, ms, len(PHASES)))
+        return dict(zip(PHASES, list(ms)))
+
+    def counters(self):
+        out = (C.c_int64 * len(COUNTERS))()
+        self._chk(lib().sphb_counters(self._h, out, len(COUNTERS)))
+        return dict(zip(COUNTERS, [int(x) for x in out]))
+
+    def state(self, fields=("pos", "vel", "rho", "c", "e", "edot", "vdot", "epred", "vpred", "h", "id"),
+              sort_by_id=True):
+        d = self.download(list(dict.fromkeys(list(fields) + ["id"])))
+        if "nn_idx" in d:  # neighbour indices -> neighbour ids (order independent)
+            idx = d["nn_idx"].astype(np.int64)
+            d["nn_id"] = np.where(idx >= 0, d["id"][np.clip(idx, 0, None)], -1)
+        if sort_by_id:
+            o = np.argsort(d["id"], kind="stable")
+            d = {k: v[o] for k, v in d.items()}
+        return d

@@ -1,0 +1,681 @@
+// sphb.cu — host side of libsphb.so: the C ABI declared in include/sphb.h.
+//
+// One sphb_sim = one GPU = one CUDA stream.  All particle state is device resident SoA; the
+// entry points only enqueue kernels (sphb_step is asynchronous) and nothing on the step path
+// needs a host round trip: the cell grid lives in device memory and is rebuilt by a kernel.
+// There is no CPU fallback: every numeric result comes out of the kernels in sphb_kernels.cuh.
+//
+// Reference being replaced: (*Simulation).Step / CalculateForces, sim/sph.go:64-198,403-435.
+#include "sphb_kernels.cuh"
+#include "../../include/sphb.h"
+
+#include <cfloat>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Soa {  // one copy of the per-particle state (two copies: the reorder gathers from one into the other)
+  double2 *pos = nullptr, *vel = nullptr, *vdot = nullptr, *vpred = nullptr;
+  double *e = nullptr, *edot = nullptr, *epred = nullptr;
+  int64_t* id = nullptr;
+  double4* pc = nullptr;  // {rho, c, h, P/rho^2}
+  uint8_t* ghost = nullptr;
+};
+
+}  // namespace
+
+struct sphb_sim {
+  sphb_params prm{};
+  int device = 0;
+  int64_t n = 0;        // owned particles
+  int64_t nghost = 0;   // slab mode: ghosts appended behind the owned ones until step_end
+  int64_t cap = 0;      // capacity (owned + ghosts)
+  int64_t cur_step = 0;
+  cudaStream_t st = nullptr;
+  Soa a, b;             // a = current
+  double2* spos = nullptr;
+  double* hguess = nullptr;
+  uint32_t *keys[2] = {nullptr, nullptr}, *vals[2] = {nullptr, nullptr};
+  uint32_t* hist = nullptr;
+  uint32_t* cellStart = nullptr;
+  uint32_t* nn = nullptr;
+  int* failList = nullptr;
+  int* failCount = nullptr;   // [0] = count; [1] = cumulative fallback particles
+  uint32_t* dflags = nullptr;
+  double* statPart = nullptr;
+  double* stats = nullptr;    // STAT_N doubles
+  GridP* grid = nullptr;
+  void* scratch = nullptr;    // download / upload staging
+  size_t scratchBytes = 0;
+  int ncell_max = 0;
+  int sort_passes = 0;
+  int nblk_sort_cap = 0;
+  bool stats_dirty = true;
+  bool have_list = false;     // nn/spos/grid describe the current particle order
+  double knn_hor[2] = {0, 0}, knn_ver[2] = {0, 0};
+  // slab mode
+  bool slab_on = false;
+  sphb_slab slab{};
+  double slab_w = 0.0;        // ghost width used for the pending evaluation
+  cudaEvent_t ev[SPHB_PH_COUNT + 1] = {};
+  bool ev_valid = false;
+  int64_t counters[SPHB_CNT_COUNT] = {0, 0, 0, 0};
+  GridTune gtune{};
+  KnnTune ktune{};
+  std::string err;
+};
+
+namespace {
+
+int fail(sphb_sim* s, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (s) s->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CK(s, call)                                                                              \
+  do {                                                                                           \
+    cudaError_t e__ = (call);                                                                    \
+    if (e__ != cudaSuccess)                                                                      \
+      return fail((s), SPHB_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+#define CKL(s) CK(s, cudaGetLastError())
+
+inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+bool axis_open(const double a[2]) { return a[0] == SPHB_OPEN_LO; }
+
+int check_params(sphb_sim* s, const sphb_params* p) {
+  if (!p) return fail(s, SPHB_E_INVALID, "params is NULL");
+  if (p->kernel < 0 || p->kernel > 2) return fail(s, SPHB_E_INVALID, "unknown kernel %d", p->kernel);
+  if (p->precision != 64) return fail(s, SPHB_E_INVALID, "precision %d not available in this build (64 only)", p->precision);
+  // nearest-neighbour.go:44,53: an axis is either open on both ends or periodic
+  if ((p->hor[0] == SPHB_OPEN_LO) != (p->hor[1] == SPHB_OPEN_HI) && p->hor[0] == SPHB_OPEN_LO)
+    return fail(s, SPHB_E_INVALID, "cannot have open and periodic boundary in horizontal at same time");
+  if ((p->ver[0] == SPHB_OPEN_LO) != (p->ver[1] == SPHB_OPEN_HI) && p->ver[0] == SPHB_OPEN_LO)
+    return fail(s, SPHB_E_INVALID, "cannot have open and periodic boundary in vertical at same time");
+  if (!axis_open(p->hor) && !(p->hor[1] > p->hor[0])) return fail(s, SPHB_E_INVALID, "empty horizontal period");
+  if (!axis_open(p->ver) && !(p->ver[1] > p->ver[0])) return fail(s, SPHB_E_INVALID, "empty vertical period");
+  return SPHB_OK;
+}
+
+PhysP make_phys(const sphb_params& p, int kernel) {
+  PhysP ph;
+  ph.dtH = p.dt_half; ph.gamma = p.gamma; ph.mass = p.particle_mass; ph.gx = p.accel[0]; ph.gy = p.accel[1];
+  ph.hor0 = p.hor[0]; ph.hor1 = p.hor[1]; ph.ver0 = p.ver[0]; ph.ver1 = p.ver[1];
+  ph.rL = p.refl_L; ph.rR = p.refl_R; ph.rU = p.refl_U; ph.rD = p.refl_D;
+  // Go untyped-constant expressions rounded once (sph.go:249,261,275,293,303)
+  const double MONAGHAN = 0x1.5d3b3e3583243p+3;  // 6*40/(pi*7)
+  const double WEND_F = 0x1.1d34a60108f72p+1;    // 4*7/(pi*4)
+  const double WEND_DF = 0x1.1d34a60108f72p+2;   // 8*7/(pi*4)
+  const double TOPHAT = 0x1.45f306dc9c883p-2;    // 1/pi
+  ph.Fpref = kernel == 0 ? TOPHAT : (kernel == 1 ? MONAGHAN : WEND_F);
+  ph.DFpref = kernel == 0 ? 1.0 : (kernel == 1 ? MONAGHAN : WEND_DF);
+  ph.cfac = p.gamma * (p.gamma - 1.0);
+  ph.kernel = kernel;
+  return ph;
+}
+
+template <typename T>
+cudaError_t dalloc(T*& p, size_t count) {
+  return cudaMalloc((void**)&p, (count ? count : 1) * sizeof(T));
+}
+
+cudaError_t alloc_soa(Soa& x, size_t cap) {
+  cudaError_t e;
+  if ((e = dalloc(x.pos, cap)) != cudaSuccess) return e;
+  if ((e = dalloc(x.vel, cap)) != cudaSuccess) return e;
+  if ((e = dalloc(x.vdot, cap)) != cudaSuccess) return e;
+  if ((e = dalloc(x.vpred, cap)) != cudaSuccess) return e;
+  if ((e = dalloc(x.e, cap)) != cudaSuccess) return e;
+  if ((e = dalloc(x.edot, cap)) != cudaSuccess) return e;
+  if ((e = dalloc(x.epred, cap)) != cudaSuccess) return e;
+  if ((e = dalloc(x.id, cap)) != cudaSuccess) return e;
+  if ((e = dalloc(x.pc, cap)) != cudaSuccess) return e;
+  if ((e = dalloc(x.ghost, cap)) != cudaSuccess) return e;
+  return cudaSuccess;
+}
+void free_soa(Soa& x) {
+  cudaFree(x.pos); cudaFree(x.vel); cudaFree(x.vdot); cudaFree(x.vpred);
+  cudaFree(x.e); cudaFree(x.edot); cudaFree(x.epred); cudaFree(x.id); cudaFree(x.pc); cudaFree(x.ghost);
+  x = Soa{};
+}
+
+void zero_soa_range(sphb_sim* s, Soa& x, int64_t off, int64_t cnt) {
+  cudaMemsetAsync(x.pos + off, 0, cnt * sizeof(double2), s->st);
+  cudaMemsetAsync(x.vel + off, 0, cnt * sizeof(double2), s->st);
+  cudaMemsetAsync(x.vdot + off, 0, cnt * sizeof(double2), s->st);
+  cudaMemsetAsync(x.vpred + off, 0, cnt * sizeof(double2), s->st);
+  cudaMemsetAsync(x.e + off, 0, cnt * sizeof(double), s->st);
+  cudaMemsetAsync(x.edot + off, 0, cnt * sizeof(double), s->st);
+  cudaMemsetAsync(x.epred + off, 0, cnt * sizeof(double), s->st);
+  cudaMemsetAsync(x.pc + off, 0, cnt * sizeof(double4), s->st);
+  cudaMemsetAsync(x.ghost + off, 0, cnt * sizeof(uint8_t), s->st);
+}
+
+int ensure_scratch(sphb_sim* s, size_t bytes) {
+  if (bytes <= s->scratchBytes) return SPHB_OK;
+  CK(s, cudaStreamSynchronize(s->st));
+  cudaFree(s->scratch);
+  s->scratch = nullptr; s->scratchBytes = 0;
+  CK(s, cudaMalloc(&s->scratch, bytes));
+  s->scratchBytes = bytes;
+  return SPHB_OK;
+}
+
+int enter(sphb_sim* s) {
+  if (!s) return SPHB_E_INVALID;
+  CK(s, cudaSetDevice(s->device));
+  return SPHB_OK;
+}
+
+// ---- one force evaluation -----------------------------------------------------------------------
+enum { MODE_ASIS = 0, MODE_INIT = 1, MODE_DRIFT = 2 };
+
+int refresh_stats(sphb_sim* s) {
+  const int ntot = (int)(s->n + s->nghost);
+  const int nb = ntot > 0 ? std::min(STAT_BLOCKS, cdiv(ntot, 256)) : 1;
+  k_stats_partial<<<nb, 256, 0, s->st>>>(s->a.pos, s->a.pc, s->a.e, (int)s->n, s->statPart);
+  k_stats_final<<<1, 32, 0, s->st>>>(s->statPart, nb, s->stats);
+  s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 2;
+  CKL(s);
+  s->stats_dirty = false;
+  return SPHB_OK;
+}
+
+template <int KERNEL>
+void launch_knn(sphb_sim* s, int ntot, const PhysP& ph) {
+  KnnOut out{s->a.pc, s->nn, s->failList, s->failCount};
+  const int tiles = cdiv(ntot, 32);
+  const size_t smem = (size_t)KNN_WARPS * s->ktune.cap * 32 * (sizeof(double) + sizeof(uint32_t));
+  static bool attr_done[3] = {false, false, false};
+  if (!attr_done[KERNEL]) {
+    cudaFuncSetAttribute(k_knn_fast<KERNEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_done[KERNEL] = true;
+  }
+  k_knn_fast<KERNEL><<<cdiv(tiles, KNN_WARPS), KNN_THREADS, smem, s->st>>>(s->spos, s->keys[s->sort_passes & 1],
+                                                                         s->cellStart, s->hguess, s->a.epred, ntot,
+                                                                         s->grid, ph, s->ktune, out);
+  k_knn_fallback<KERNEL><<<148 * 4, 128, 0, s->st>>>(s->spos, s->keys[s->sort_passes & 1], s->cellStart, s->hguess,
+                                                   s->a.epred, ntot, s->grid, ph, out, s->dflags);
+}
+
+template <int KERNEL>
+void launch_force(sphb_sim* s, int ntot, const PhysP& ph, bool integrate) {
+  ForceIO io{s->spos, s->a.vpred, s->a.pc, s->nn, s->a.pos, s->a.vel, s->a.e, s->a.vdot, s->a.edot};
+  if (integrate) k_force<KERNEL, true><<<cdiv(ntot, 128), 128, 0, s->st>>>(io, ntot, s->grid, ph);
+  else k_force<KERNEL, false><<<cdiv(ntot, 128), 128, 0, s->st>>>(io, ntot, s->grid, ph);
+}
+
+// sort + reorder + kNN (+ density with `kernel`); the neighbour list, spos and grid then describe s->a
+int build_neighbours(sphb_sim* s, int mode, const double hor[2], const double ver[2], int kernel, bool timed) {
+  const int ntot = (int)(s->n + s->nghost);
+  if (ntot <= 0) return fail(s, SPHB_E_STATE, "Simulation not initialized: no particles (sph.go:92-94)");
+  if (s->stats_dirty) { int rc = refresh_stats(s); if (rc) return rc; }
+  const PhysP ph = make_phys(s->prm, kernel);
+  const double dtH = s->prm.dt_half;
+  if (timed) cudaEventRecord(s->ev[SPHB_PH_KEYS], s->st);
+  k_make_grid<<<1, 32, 0, s->st>>>(s->stats, ntot, hor[0], hor[1], ver[0], ver[1], s->slab.x_lo - s->slab_w,
+                                   s->slab.x_hi + s->slab_w, s->slab_on ? 1 : 0, s->gtune, s->grid);
+  if (mode == MODE_DRIFT) k_keys<true><<<cdiv(ntot, 256), 256, 0, s->st>>>(s->a.pos, s->a.vel, ntot, s->grid, dtH, s->keys[0]);
+  else k_keys<false><<<cdiv(ntot, 256), 256, 0, s->st>>>(s->a.pos, s->a.vel, ntot, s->grid, dtH, s->keys[0]);
+  s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 2;
+  if (timed) cudaEventRecord(s->ev[SPHB_PH_SORT], s->st);
+  const int nblk = cdiv(ntot, RS_TILE);
+  for (int p = 0; p < s->sort_passes; ++p) {
+    const int in = p & 1, out = in ^ 1, shift = 8 * p;
+    k_rs_hist<<<nblk, RS_THREADS, 0, s->st>>>(s->keys[in], ntot, shift, s->hist, nblk);
+    k_excl_scan<<<1, 1024, 0, s->st>>>(s->hist, RS_BINS * nblk);
+    if (p == 0)
+      k_rs_scatter<true><<<nblk, RS_THREADS, 0, s->st>>>(s->keys[in], s->vals[in], s->keys[out], s->vals[out], ntot, shift, s->hist, nblk);
+    else
+      k_rs_scatter<false><<<nblk, RS_THREADS, 0, s->st>>>(s->keys[in], s->vals[in], s->keys[out], s->vals[out], ntot, shift, s->hist, nblk);
+    s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 3;
+  }
+  const int fin = s->sort_passes & 1;
+  if (timed) cudaEventRecord(s->ev[SPHB_PH_REORDER], s->st);
+  StateIn in{s->a.pos, s->a.vel, s->a.vdot, s->a.vpred, s->a.e, s->a.edot, s->a.epred, s->a.id, s->a.pc, s->a.ghost};
+  StateOut out{s->b.pos, s->b.vel, s->b.vdot, s->b.vpred, s->b.e, s->b.edot, s->b.epred, s->b.id, s->b.pc, s->b.ghost, s->spos, s->hguess};
+  const int rb = cdiv(ntot, 256);
+  if (mode == MODE_DRIFT) k_reorder<2><<<rb, 256, 0, s->st>>>(in, out, s->keys[fin], s->vals[fin], ntot, s->grid, dtH, s->cellStart);
+  else if (mode == MODE_INIT) k_reorder<1><<<rb, 256, 0, s->st>>>(in, out, s->keys[fin], s->vals[fin], ntot, s->grid, dtH, s->cellStart);
+  else k_reorder<0><<<rb, 256, 0, s->st>>>(in, out, s->keys[fin], s->vals[fin], ntot, s->grid, dtH, s->cellStart);
+  std::swap(s->a, s->b);
+  cudaMemsetAsync(s->failCount, 0, sizeof(int), s->st);
+  if (timed) cudaEventRecord(s->ev[SPHB_PH_KNN], s->st);
+  switch (kernel) {
+    case 0: launch_knn<0>(s, ntot, ph); break;
+    case 1: launch_knn<1>(s, ntot, ph); break;
+    default: launch_knn<2>(s, ntot, ph); break;
+  }
+  s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 3;
+  CKL(s);
+  s->have_list = true;
+  s->knn_hor[0] = hor[0]; s->knn_hor[1] = hor[1]; s->knn_ver[0] = ver[0]; s->knn_ver[1] = ver[1];
+  return SPHB_OK;
+}
+
+// CalculateForces (sph.go:403-435) [+ kick, drift-2, wrap, reflections when integrate (sph.go:122-193)]
+int forces(sphb_sim* s, int mode, bool integrate) {
+  if (s->prm.kernel == SPHB_KERNEL_TOPHAT)
+    return fail(s, SPHB_E_KERNEL, "TopHat2D.DF: not defined. derivative is delta distribution! (sph.go:251-253)");
+  int rc = build_neighbours(s, mode, s->prm.hor, s->prm.ver, s->prm.kernel, true);
+  if (rc) return rc;
+  const int ntot = (int)(s->n + s->nghost);
+  const PhysP ph = make_phys(s->prm, s->prm.kernel);
+  cudaEventRecord(s->ev[SPHB_PH_FORCE], s->st);
+  if (s->prm.kernel == 1) launch_force<1>(s, ntot, ph, integrate);
+  else launch_force<2>(s, ntot, ph, integrate);
+  s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 1;
+  cudaEventRecord(s->ev[SPHB_PH_TOTAL], s->st);
+  s->ev_valid = true;
+  if (!s->slab_on) { rc = refresh_stats(s); if (rc) return rc; }
+  else s->stats_dirty = true;
+  CKL(s);
+  return SPHB_OK;
+}
+
+int check_async(sphb_sim* s) {
+  uint32_t fl = 0;
+  int fc[2] = {0, 0};
+  CK(s, cudaMemcpyAsync(&fl, s->dflags, sizeof fl, cudaMemcpyDeviceToHost, s->st));
+  CK(s, cudaMemcpyAsync(fc, s->failCount, sizeof fc, cudaMemcpyDeviceToHost, s->st));
+  CK(s, cudaStreamSynchronize(s->st));
+  s->counters[SPHB_CNT_KNN_FALLBACK] = fc[1];
+  if (fl & DFLAG_UNDERFULL) {
+    cudaMemsetAsync(s->dflags, 0, sizeof(uint32_t), s->st);
+    return fail(s, SPHB_E_KNN_UNDERFULL,
+                "kNN: fewer than 32 (particle, image) candidates exist for some particle; the reference would keep "
+                "sentinel slots (nearest-neighbour.go:155-165)");
+  }
+  return SPHB_OK;
+}
+
+int upload_common(sphb_sim* s, int64_t off, int64_t n, const double* pos_xy, const double* vel_xy, const double* e,
+                  const double* rho, const int64_t* id, cudaMemcpyKind kind, int64_t id_base) {
+  zero_soa_range(s, s->a, off, n);
+  CK(s, cudaMemcpyAsync(s->a.pos + off, pos_xy, n * sizeof(double2), kind, s->st));
+  if (vel_xy) CK(s, cudaMemcpyAsync(s->a.vel + off, vel_xy, n * sizeof(double2), kind, s->st));
+  if (e) CK(s, cudaMemcpyAsync(s->a.e + off, e, n * sizeof(double), kind, s->st));
+  if (id) CK(s, cudaMemcpyAsync(s->a.id + off, id, n * sizeof(int64_t), kind, s->st));
+  else k_iota64<<<cdiv(n, 256), 256, 0, s->st>>>(s->a.id + off, (int)n, id_base);
+  if (rho) {
+    if (kind == cudaMemcpyHostToDevice) {
+      int rc = ensure_scratch(s, n * sizeof(double)); if (rc) return rc;
+      CK(s, cudaMemcpyAsync(s->scratch, rho, n * sizeof(double), kind, s->st));
+      k_set_pc<<<cdiv(n, 256), 256, 0, s->st>>>(s->a.pc + off, (int)n, (const double*)s->scratch, 0);
+    } else {
+      k_set_pc<<<cdiv(n, 256), 256, 0, s->st>>>(s->a.pc + off, (int)n, rho, 0);
+    }
+  }
+  CKL(s);
+  CK(s, cudaStreamSynchronize(s->st));  // host buffers are borrowed for the duration of the call only
+  s->stats_dirty = true;
+  s->have_list = false;
+  return SPHB_OK;
+}
+
+int create_common(const sphb_params* p, int64_t n, int64_t capacity, const double* pos_xy, const double* vel_xy,
+                  const double* e, const double* rho, const int64_t* id, cudaMemcpyKind kind, sphb_sim** out) {
+  if (!out) return fail(nullptr, SPHB_E_INVALID, "out is NULL");
+  *out = nullptr;
+  int rc = check_params(nullptr, p);
+  if (rc) return rc;
+  if (n < 0 || (n > 0 && !pos_xy)) return fail(nullptr, SPHB_E_INVALID, "bad particle arrays");
+  if (capacity < n) capacity = n;
+  if (capacity < 1) capacity = 1;
+  if (capacity >= (int64_t)IDX_MASK) return fail(nullptr, SPHB_E_NOMEM, "capacity %lld exceeds 2^28-1 particles per device", (long long)capacity);
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    return fail(nullptr, SPHB_E_CUDA, "no CUDA device (%s): libsphb has no CPU fallback", ce == cudaSuccess ? "device count 0" : cudaGetErrorString(ce));
+  if (p->device < 0 || p->device >= ndev) return fail(nullptr, SPHB_E_INVALID, "device %d out of range (%d devices)", p->device, ndev);
+  sphb_sim* s = new (std::nothrow) sphb_sim();
+  if (!s) return fail(nullptr, SPHB_E_NOMEM, "out of host memory");
+  s->prm = *p; s->device = p->device; s->n = n; s->cap = capacity;
+#define CKC(call)                                                                                   \
+  do {                                                                                              \
+    cudaError_t e__ = (call);                                                                       \
+    if (e__ != cudaSuccess) {                                                                       \
+      int code = (e__ == cudaErrorMemoryAllocation) ? SPHB_E_NOMEM : SPHB_E_CUDA;                    \
+      fail(nullptr, code, "%s failed: %s", #call, cudaGetErrorString(e__));                         \
+      sphb_destroy(s);                                                                              \
+      return code;                                                                                  \
+    }                                                                                               \
+  } while (0)
+  CKC(cudaSetDevice(s->device));
+  CKC(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
+  const size_t cap = (size_t)capacity, cap32 = (cap + 31) / 32 * 32;
+  CKC(alloc_soa(s->a, cap));
+  CKC(alloc_soa(s->b, cap));
+  CKC(dalloc(s->spos, cap));
+  CKC(dalloc(s->hguess, cap));
+  for (int k = 0; k < 2; ++k) { CKC(dalloc(s->keys[k], cap)); CKC(dalloc(s->vals[k], cap)); }
+  s->nblk_sort_cap = cdiv(capacity, RS_TILE);
+  CKC(dalloc(s->hist, (size_t)RS_BINS * s->nblk_sort_cap));
+  // cell table: about 2 particles per cell at most; the radix sort covers ceil(log2(ncell)/8) digits
+  int64_t ncm = std::max<int64_t>(64, std::min<int64_t>(capacity / 2 + 1, (int64_t)1 << 30));
+  s->ncell_max = (int)ncm;
+  int bits = 1;
+  while (((int64_t)1 << bits) < ncm) ++bits;
+  s->sort_passes = (bits + 7) / 8;
+  CKC(dalloc(s->cellStart, (size_t)ncm + 2));
+  CKC(dalloc(s->nn, cap32 * SPHB_K));
+  CKC(dalloc(s->failList, cap));
+  CKC(dalloc(s->failCount, 2));
+  CKC(dalloc(s->dflags, 1));
+  CKC(dalloc(s->statPart, (size_t)STAT_BLOCKS * STAT_N));
+  CKC(dalloc(s->stats, STAT_N));
+  CKC(dalloc(s->grid, 1));
+  for (auto& ev : s->ev) CKC(cudaEventCreate(&ev));
+  CKC(cudaMemsetAsync(s->failCount, 0, 2 * sizeof(int), s->st));
+  CKC(cudaMemsetAsync(s->dflags, 0, sizeof(uint32_t), s->st));
+  CKC(cudaMemsetAsync(s->nn, 0xff, cap32 * SPHB_K * sizeof(uint32_t), s->st));
+#undef CKC
+  s->gtune.cell_per_h = 0.62;
+  s->gtune.ppc0 = 4.0;
+  s->gtune.ncell_max = s->ncell_max;
+  s->gtune.force_nc = 0;
+  s->ktune.guess_margin = 0.08;
+  s->ktune.k_target = 46.0;
+  s->ktune.cap = 64;
+  if (const char* ev = getenv("SPHB_CELL_PER_H")) s->gtune.cell_per_h = atof(ev);
+  if (const char* ev = getenv("SPHB_PPC0")) s->gtune.ppc0 = atof(ev);
+  if (const char* ev = getenv("SPHB_FORCE_NC")) s->gtune.force_nc = atoi(ev);
+  if (const char* ev = getenv("SPHB_GUESS_MARGIN")) s->ktune.guess_margin = atof(ev);
+  if (const char* ev = getenv("SPHB_K_TARGET")) s->ktune.k_target = atof(ev);
+  if (const char* ev = getenv("SPHB_KNN_CAP")) s->ktune.cap = std::max(32, std::min(96, atoi(ev)));
+  if (n > 0) {
+    rc = upload_common(s, 0, n, pos_xy, vel_xy, e, rho, id, kind, 0);
+    if (rc) { g_create_error = s->err; sphb_destroy(s); return rc; }
+  }
+  *out = s;
+  return SPHB_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int sphb_create(const sphb_params* p, int64_t n, int64_t capacity, const double* pos_xy, const double* vel_xy,
+                const double* e, const double* rho, const int64_t* id, sphb_sim** out) {
+  return create_common(p, n, capacity, pos_xy, vel_xy, e, rho, id, cudaMemcpyHostToDevice, out);
+}
+
+int sphb_create_device(const sphb_params* p, int64_t n, int64_t capacity, const double* d_pos_xy,
+                       const double* d_vel_xy, const double* d_e, const int64_t* d_id, sphb_sim** out) {
+  return create_common(p, n, capacity, d_pos_xy, d_vel_xy, d_e, nullptr, d_id, cudaMemcpyDeviceToDevice, out);
+}
+
+void sphb_destroy(sphb_sim* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  if (s->st) cudaStreamSynchronize(s->st);
+  free_soa(s->a); free_soa(s->b);
+  cudaFree(s->spos); cudaFree(s->hguess);
+  for (int k = 0; k < 2; ++k) { cudaFree(s->keys[k]); cudaFree(s->vals[k]); }
+  cudaFree(s->hist); cudaFree(s->cellStart); cudaFree(s->nn); cudaFree(s->failList); cudaFree(s->failCount);
+  cudaFree(s->dflags); cudaFree(s->statPart); cudaFree(s->stats); cudaFree(s->grid); cudaFree(s->scratch);
+  for (auto& ev : s->ev) if (ev) cudaEventDestroy(ev);
+  if (s->st) cudaStreamDestroy(s->st);
+  delete s;
+}
+
+const char* sphb_last_error(const sphb_sim* s) { return s ? s->err.c_str() : g_create_error.c_str(); }
+
+int sphb_set_params(sphb_sim* s, const sphb_params* p) {
+  int rc = enter(s); if (rc) return rc;
+  rc = check_params(s, p); if (rc) return rc;
+  if (p->device != s->device) return fail(s, SPHB_E_INVALID, "device cannot change after create");
+  s->prm = *p;
+  return SPHB_OK;
+}
+int sphb_get_params(const sphb_sim* s, sphb_params* p) {
+  if (!s || !p) return SPHB_E_INVALID;
+  *p = s->prm;
+  return SPHB_OK;
+}
+int64_t sphb_count(const sphb_sim* s) { return s ? s->n : -1; }
+int64_t sphb_current_step(const sphb_sim* s) { return s ? s->cur_step : -1; }
+
+int sphb_append(sphb_sim* s, int64_t n, const double* pos_xy, const double* vel_xy, const double* e, const double* rho,
+                const int64_t* id) {
+  int rc = enter(s); if (rc) return rc;
+  if (n < 0 || (n > 0 && !pos_xy)) return fail(s, SPHB_E_INVALID, "bad particle arrays");
+  if (s->nghost) return fail(s, SPHB_E_STATE, "append while ghosts are attached");
+  if (s->n + n > s->cap) return fail(s, SPHB_E_NOMEM, "append: %lld + %lld exceeds capacity %lld", (long long)s->n, (long long)n, (long long)s->cap);
+  if (n == 0) return SPHB_OK;
+  rc = upload_common(s, s->n, n, pos_xy, vel_xy, e, rho, id, cudaMemcpyHostToDevice, s->n);
+  if (rc) return rc;
+  s->n += n;
+  return SPHB_OK;
+}
+
+int sphb_step(sphb_sim* s, int32_t nsteps) {
+  int rc = enter(s); if (rc) return rc;
+  if (s->slab_on) return fail(s, SPHB_E_STATE, "slab mode: use sphb_slab_step_begin / _end");
+  for (int32_t k = 0; k < nsteps; ++k) {
+    if (s->cur_step == 0) {  // sph.go:89-103: VPred = Vel, EPred = E, forces once
+      rc = forces(s, MODE_INIT, false); if (rc) return rc;
+    }
+    rc = forces(s, MODE_DRIFT, true); if (rc) return rc;
+    s->cur_step += 1;
+    s->counters[SPHB_CNT_STEPS] += 1;
+  }
+  return SPHB_OK;
+}
+
+int sphb_calc_forces(sphb_sim* s) {
+  int rc = enter(s); if (rc) return rc;
+  if (s->slab_on) return fail(s, SPHB_E_STATE, "slab mode: use sphb_slab_step_begin / _end");
+  return forces(s, MODE_ASIS, false);
+}
+
+int sphb_knn(sphb_sim* s, const double hor[2], const double ver[2]) {
+  int rc = enter(s); if (rc) return rc;
+  if (!hor || !ver) return fail(s, SPHB_E_INVALID, "hor/ver is NULL");
+  if (hor[0] == SPHB_OPEN_LO && hor[1] != SPHB_OPEN_HI)
+    return fail(s, SPHB_E_INVALID, "cannot have open and periodic boundary in horizontal at same time!");
+  if (ver[0] == SPHB_OPEN_LO && ver[1] != SPHB_OPEN_HI)
+    return fail(s, SPHB_E_INVALID, "cannot have open and periodic boundary in vertical at same time!");
+  if ((hor[0] != SPHB_OPEN_LO && !(hor[1] > hor[0])) || (ver[0] != SPHB_OPEN_LO && !(ver[1] > ver[0])))
+    return fail(s, SPHB_E_INVALID, "empty period");
+  rc = build_neighbours(s, MODE_ASIS, hor, ver, s->prm.kernel, false);
+  if (rc) return rc;
+  s->stats_dirty = true;
+  return check_async(s);
+}
+
+int sphb_density(sphb_sim* s, int32_t kernel) {
+  int rc = enter(s); if (rc) return rc;
+  if (kernel < 0 || kernel > 2) return fail(s, SPHB_E_INVALID, "unknown kernel %d", kernel);
+  if (!s->have_list) return fail(s, SPHB_E_STATE, "density before knn: NNDists[0] is 0 (sph.go:307)");
+  const int ntot = (int)(s->n + s->nghost);
+  const PhysP ph = make_phys(s->prm, kernel);
+  switch (kernel) {
+    case 0: k_density_from_list<0><<<cdiv(ntot, 128), 128, 0, s->st>>>(s->spos, s->nn, ntot, s->grid, ph, s->a.pc); break;
+    case 1: k_density_from_list<1><<<cdiv(ntot, 128), 128, 0, s->st>>>(s->spos, s->nn, ntot, s->grid, ph, s->a.pc); break;
+    default: k_density_from_list<2><<<cdiv(ntot, 128), 128, 0, s->st>>>(s->spos, s->nn, ntot, s->grid, ph, s->a.pc); break;
+  }
+  s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 1;
+  CKL(s);
+  s->stats_dirty = true;
+  return SPHB_OK;
+}
+
+int sphb_sync(sphb_sim* s) {
+  int rc = enter(s); if (rc) return rc;
+  return check_async(s);
+}
+
+int sphb_download(sphb_sim* s, uint32_t mask, void* const* hp, int64_t capacity, int64_t* n_out) {
+  int rc = enter(s); if (rc) return rc;
+  rc = check_async(s); if (rc) return rc;
+  const int64_t n = s->n;
+  if (n_out) *n_out = n;
+  if (mask == 0) return SPHB_OK;
+  if (!hp) return fail(s, SPHB_E_INVALID, "host_ptrs is NULL");
+  if (capacity < n) return fail(s, SPHB_E_NOMEM, "download: capacity %lld < %lld particles", (long long)capacity, (long long)n);
+  if (mask >> SPHB_F_COUNT) return fail(s, SPHB_E_INVALID, "unknown field bits in mask 0x%x", mask);
+  for (int f = 0; f < SPHB_F_COUNT; ++f)
+    if ((mask & SPHB_MASK(f)) && !hp[f]) return fail(s, SPHB_E_INVALID, "host_ptrs[%d] is NULL", f);
+  if (n == 0) return SPHB_OK;
+#define D2H(field, src, bytes) \
+  if (mask & SPHB_MASK(field)) CK(s, cudaMemcpyAsync(hp[field], (src), (size_t)(bytes), cudaMemcpyDeviceToHost, s->st))
+  D2H(SPHB_F_POS, s->a.pos, n * 16);
+  D2H(SPHB_F_VEL, s->a.vel, n * 16);
+  D2H(SPHB_F_E, s->a.e, n * 8);
+  D2H(SPHB_F_EDOT, s->a.edot, n * 8);
+  D2H(SPHB_F_VDOT, s->a.vdot, n * 16);
+  D2H(SPHB_F_EPRED, s->a.epred, n * 8);
+  D2H(SPHB_F_VPRED, s->a.vpred, n * 16);
+  D2H(SPHB_F_ID, s->a.id, n * 8);
+  if (mask & (SPHB_MASK(SPHB_F_RHO) | SPHB_MASK(SPHB_F_C) | SPHB_MASK(SPHB_F_H))) {
+    rc = ensure_scratch(s, (size_t)n * 3 * sizeof(double)); if (rc) return rc;
+    double* sc = (double*)s->scratch;
+    k_split_pc<<<cdiv(n, 256), 256, 0, s->st>>>(s->a.pc, (int)n, sc, sc + n, sc + 2 * n);
+    CKL(s);
+    D2H(SPHB_F_RHO, sc, n * 8);
+    D2H(SPHB_F_C, sc + n, n * 8);
+    D2H(SPHB_F_H, sc + 2 * n, n * 8);
+    CK(s, cudaStreamSynchronize(s->st));
+  }
+  if (mask & (SPHB_MASK(SPHB_F_NN_IDX) | SPHB_MASK(SPHB_F_NN_DIST) | SPHB_MASK(SPHB_F_NN_POS))) {
+    if (!s->have_list) return fail(s, SPHB_E_STATE, "no neighbour list for the current particle order: call knn / calc_forces first");
+    // chunked so that the staging buffer stays small next to the state
+    const int64_t chunk = std::min<int64_t>(n, (int64_t)1 << 20);
+    const size_t per = SPHB_K * (sizeof(int32_t) + sizeof(double) + sizeof(double2));
+    rc = ensure_scratch(s, (size_t)chunk * per); if (rc) return rc;
+    for (int64_t off = 0; off < n; off += chunk) {
+      const int64_t m = std::min(chunk, n - off);
+      // kernel indexes particles globally; run it on [off, off+m) by offsetting outputs
+      double* dist = (double*)s->scratch;
+      double2* npos = (double2*)(dist + (size_t)chunk * SPHB_K);
+      int32_t* idx = (int32_t*)(npos + (size_t)chunk * SPHB_K);
+      k_expand_list<<<cdiv(m, 128), 128, 0, s->st>>>(s->spos, s->a.pos, s->nn, (int)off, (int)m, s->grid,
+                                                    (mask & SPHB_MASK(SPHB_F_NN_IDX)) ? idx : nullptr,
+                                                    (mask & SPHB_MASK(SPHB_F_NN_DIST)) ? dist : nullptr,
+                                                    (mask & SPHB_MASK(SPHB_F_NN_POS)) ? npos : nullptr);
+      CKL(s);
+      if (mask & SPHB_MASK(SPHB_F_NN_IDX))
+        CK(s, cudaMemcpyAsync((int32_t*)hp[SPHB_F_NN_IDX] + off * SPHB_K, idx, (size_t)m * SPHB_K * 4, cudaMemcpyDeviceToHost, s->st));
+      if (mask & SPHB_MASK(SPHB_F_NN_DIST))
+        CK(s, cudaMemcpyAsync((double*)hp[SPHB_F_NN_DIST] + off * SPHB_K, dist, (size_t)m * SPHB_K * 8, cudaMemcpyDeviceToHost, s->st));
+      if (mask & SPHB_MASK(SPHB_F_NN_POS))
+        CK(s, cudaMemcpyAsync((double*)hp[SPHB_F_NN_POS] + off * SPHB_K * 2, npos, (size_t)m * SPHB_K * 16, cudaMemcpyDeviceToHost, s->st));
+      CK(s, cudaStreamSynchronize(s->st));
+    }
+  }
+#undef D2H
+  CK(s, cudaStreamSynchronize(s->st));
+  return SPHB_OK;
+}
+
+int sphb_upload(sphb_sim* s, uint32_t mask, const void* const* hp, int64_t n) {
+  int rc = enter(s); if (rc) return rc;
+  if (n != s->n) return fail(s, SPHB_E_INVALID, "upload: n = %lld but the simulation holds %lld particles", (long long)n, (long long)s->n);
+  const uint32_t allowed = SPHB_MASK(SPHB_F_POS) | SPHB_MASK(SPHB_F_VEL) | SPHB_MASK(SPHB_F_E) | SPHB_MASK(SPHB_F_RHO) |
+                           SPHB_MASK(SPHB_F_VDOT) | SPHB_MASK(SPHB_F_EDOT) | SPHB_MASK(SPHB_F_EPRED) | SPHB_MASK(SPHB_F_VPRED);
+  if (mask & ~allowed) return fail(s, SPHB_E_INVALID, "upload: field mask 0x%x has non-writable fields", mask);
+  if (mask && !hp) return fail(s, SPHB_E_INVALID, "host_ptrs is NULL");
+  for (int f = 0; f < SPHB_F_COUNT; ++f)
+    if ((mask & SPHB_MASK(f)) && !hp[f]) return fail(s, SPHB_E_INVALID, "host_ptrs[%d] is NULL", f);
+  if (n == 0) return SPHB_OK;
+#define H2D(field, dst, bytes) \
+  if (mask & SPHB_MASK(field)) CK(s, cudaMemcpyAsync((dst), hp[field], (size_t)(bytes), cudaMemcpyHostToDevice, s->st))
+  H2D(SPHB_F_POS, s->a.pos, n * 16);
+  H2D(SPHB_F_VEL, s->a.vel, n * 16);
+  H2D(SPHB_F_E, s->a.e, n * 8);
+  H2D(SPHB_F_EDOT, s->a.edot, n * 8);
+  H2D(SPHB_F_VDOT, s->a.vdot, n * 16);
+  H2D(SPHB_F_EPRED, s->a.epred, n * 8);
+  H2D(SPHB_F_VPRED, s->a.vpred, n * 16);
+#undef H2D
+  if (mask & SPHB_MASK(SPHB_F_RHO)) {
+    rc = ensure_scratch(s, (size_t)n * sizeof(double)); if (rc) return rc;
+    CK(s, cudaMemcpyAsync(s->scratch, hp[SPHB_F_RHO], (size_t)n * 8, cudaMemcpyHostToDevice, s->st));
+    k_set_pc<<<cdiv(n, 256), 256, 0, s->st>>>(s->a.pc, (int)n, (const double*)s->scratch, 0);
+    CKL(s);
+  }
+  if (mask & SPHB_MASK(SPHB_F_POS)) s->have_list = false;  // the list describes the old positions; h stays a valid first guess
+  s->stats_dirty = true;
+  CK(s, cudaStreamSynchronize(s->st));
+  return SPHB_OK;
+}
+
+int sphb_reduce(sphb_sim* s, int32_t which, double* out) {
+  int rc = enter(s); if (rc) return rc;
+  if (!out) return fail(s, SPHB_E_INVALID, "out is NULL");
+  rc = check_async(s); if (rc) return rc;
+  if (which == SPHB_LAST_VEL_NORM) {  // TotalMomentum assigns instead of accumulating (sph.go:457-463)
+    if (s->n == 0) { *out = 0.0; return SPHB_OK; }
+    double v[2];
+    CK(s, cudaMemcpyAsync(v, s->a.vel + (s->n - 1), sizeof v, cudaMemcpyDeviceToHost, s->st));
+    CK(s, cudaStreamSynchronize(s->st));
+    *out = std::sqrt(v[0] * v[0] + v[1] * v[1]);
+    return SPHB_OK;
+  }
+  if (which != SPHB_SUM_E && which != SPHB_SUM_RHO) return fail(s, SPHB_E_INVALID, "unknown reduction %d", which);
+  if (s->n == 0) { *out = 0.0; return SPHB_OK; }
+  if (s->stats_dirty) { rc = refresh_stats(s); if (rc) return rc; }
+  double st[STAT_N];
+  CK(s, cudaMemcpyAsync(st, s->stats, sizeof st, cudaMemcpyDeviceToHost, s->st));
+  CK(s, cudaStreamSynchronize(s->st));
+  *out = which == SPHB_SUM_E ? st[6] : st[7];
+  return SPHB_OK;
+}
+
+int sphb_max_h(sphb_sim* s, double* out) {
+  int rc = enter(s); if (rc) return rc;
+  if (!out) return fail(s, SPHB_E_INVALID, "out is NULL");
+  if (s->stats_dirty) { rc = refresh_stats(s); if (rc) return rc; }
+  double st[STAT_N];
+  CK(s, cudaMemcpyAsync(st, s->stats, sizeof st, cudaMemcpyDeviceToHost, s->st));
+  CK(s, cudaStreamSynchronize(s->st));
+  *out = st[8] > 0.0 ? st[5] : 0.0;
+  return SPHB_OK;
+}
+
+int sphb_phase_times(sphb_sim* s, double* ms, int32_t n) {
+  int rc = enter(s); if (rc) return rc;
+  if (!ms || n < 0 || n > SPHB_PH_COUNT) return fail(s, SPHB_E_INVALID, "bad arguments");
+  if (!s->ev_valid) return fail(s, SPHB_E_STATE, "no step has run yet");
+  CK(s, cudaStreamSynchronize(s->st));
+  double t[SPHB_PH_COUNT];
+  for (int k = 0; k < SPHB_PH_TOTAL; ++k) {
+    float f = 0;
+    CK(s, cudaEventElapsedTime(&f, s->ev[k], s->ev[k + 1]));
+    t[k] = f;
+  }
+  float f = 0;
+  CK(s, cudaEventElapsedTime(&f, s->ev[0], s->ev[SPHB_PH_TOTAL]));
+  t[SPHB_PH_TOTAL] = f;
+  for (int k = 0; k < n; ++k) ms[k] = t[k];
+  return SPHB_OK;
+}
+
+int sphb_counters(const sphb_sim* s, int64_t* out, int32_t n) {
+  if (!s || !out || n < 0 || n > SPHB_CNT_COUNT) return SPHB_E_INVALID;
+  for (int k = 0; k < n; ++k) out[k] = s->counters[k];
+  return SPHB_OK;
+}
+
+// ---- slab decomposition: implemented in sphb_slab.inc (same translation unit) ----
+#include "sphb_slab.inc"
+
+}  // extern "C"

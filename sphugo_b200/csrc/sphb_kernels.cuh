@@ -1,0 +1,877 @@
+// sphb_kernels.cuh — device code of libsphb.so (sm_100a).
+//
+// The hot path of bbeni/sphugo's (*Simulation).Step() (reference sim/sph.go:64-198), re-designed for a
+// B200: no tree, no per-particle priority queue in memory.  Pipeline per force evaluation
+//   K1 keys      drift-1 + uniform-cell key                 (replaces Partition      core.go:126-164)
+//   SORT         stable LSD radix sort of (key, index)      (replaces Treebuild      core.go:172-224)
+//   K2 reorder   SoA gather + predict + cell table          (replaces BoundingSpheres core.go:229-312)
+//   K3 knn       exact kNN(32) + density + sound speed      (nearest-neighbour.go:28-165, sph.go:306-323,423-429)
+//   K4 force     pressure + viscosity, kick, drift-2, walls (sph.go:327-401, 122-193)
+// Nothing here is a dense contraction, so there are no tensor-core instructions: the kernels are
+// latency/issue and bandwidth bound and are laid out for coalesced SoA access, warp-uniform
+// (broadcast) candidate loads and shared-memory staging of the per-particle candidate columns.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define SPHB_K 32
+#define IMG_SHIFT 28
+#define IDX_MASK 0x0FFFFFFFu
+
+struct GridP {
+  double ox, oy;        // origin of cell (0,0)
+  double dx, dy;        // cell edge
+  double inv_dx, inv_dy;
+  double Lx, Ly;        // period of a wrapping axis (hor[1]-hor[0]), 0 if the axis is open
+  double lox, loy;      // low end of the periodic interval
+  int ncx, ncy;
+  int wrapx, wrapy;
+};
+
+struct PhysP {
+  double dtH, gamma, mass, gx, gy;
+  double hor0, hor1, ver0, ver1;      // Step()'s wrap interval (sph.go:147-167); +-DBL_MAX when open
+  double rL, rR, rU, rD;              // reflections (sph.go:170-193)
+  double Fpref, DFpref, cfac;         // kernel prefactors; cfac = gamma*(gamma-1) (sph.go:426)
+  int kernel;
+};
+
+struct KnnTune {
+  double guess_margin;   // search radius = h_prev * (1 + margin)
+  double k_target;       // expected candidates inside the first-guess radius when no h_prev exists
+  int cap;               // candidate column capacity per particle (shared memory)
+};
+
+// device-side status word
+#define DFLAG_UNDERFULL 1u
+
+// -------------------------------------------------------------------------------------------------
+// small helpers
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double wrap_coord(double x, double lo, double L) {
+  // canonical image in [lo, lo+L); exact identity for lo <= x < lo+L
+  double w = floor((x - lo) / L);
+  double xs = (w == 0.0) ? x : __dsub_rn(x, __dmul_rn(w, L));
+  if (xs < lo) xs = __dadd_rn(xs, L);
+  else if (xs >= lo + L) xs = __dsub_rn(xs, L);
+  return xs;
+}
+
+__device__ __forceinline__ int cell_of(double xs, double o, double inv, int nc) {
+  int c = (int)floor((xs - o) * inv);
+  return c < 0 ? 0 : (c >= nc ? nc - 1 : c);
+}
+
+__device__ __forceinline__ int floor_div(int a, int b) {  // b > 0
+  int q = a / b;
+  return (a % b < 0) ? q - 1 : q;
+}
+
+// d^2 exactly as linear-algebra.go:61-64 evaluates it on amd64: two products, one sum, no FMA
+__device__ __forceinline__ double dist_sq(double dx, double dy) {
+  return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+}
+
+// SPH kernels, sph.go:244-304.  q = r / h with h the distance to the 32nd neighbour.
+template <int KERNEL>
+__device__ __forceinline__ double kern_F(double q) {
+  if (KERNEL == 0) return 1.0;
+  if (KERNEL == 1) {
+    if (q < 0.5) return q * q * q - q * q + (1.0 / 6.0);
+    double t = 1.0 - q;
+    return t * t * t / 3.0;
+  }
+  double t = 1.0 - q;
+  double t2 = t * t;
+  return t2 * t2 * (1.0 + 4.0 * q);
+}
+template <int KERNEL>
+__device__ __forceinline__ double kern_DF(double q) {
+  if (KERNEL == 1) {
+    if (q < 0.5) return 3.0 * q * q - 2.0 * q;
+    double t = 1.0 - q;
+    return -t * t;
+  }
+  double t = 1.0 - q;
+  return -10.0 * q * t * t * t;
+}
+
+// -------------------------------------------------------------------------------------------------
+// K1: (optional drift-1) + cell key.  Reads pos, vel; writes key, val=index.
+// -------------------------------------------------------------------------------------------------
+template <bool DRIFT>
+__global__ void __launch_bounds__(256) k_keys(const double2* __restrict__ pos, const double2* __restrict__ vel, int n,
+                                             const GridP* __restrict__ gp, double dtH, uint32_t* __restrict__ keys) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const GridP g = *gp;
+  double2 p = pos[i];
+  if (DRIFT) {  // Pos += Vel*dtHalf (sph.go:112-113): product then sum, unfused
+    double2 v = vel[i];
+    p.x = __dadd_rn(p.x, __dmul_rn(v.x, dtH));
+    p.y = __dadd_rn(p.y, __dmul_rn(v.y, dtH));
+  }
+  double xs = g.wrapx ? wrap_coord(p.x, g.lox, g.Lx) : p.x;
+  double ys = g.wrapy ? wrap_coord(p.y, g.loy, g.Ly) : p.y;
+  int cx = cell_of(xs, g.ox, g.inv_dx, g.ncx);
+  int cy = cell_of(ys, g.oy, g.inv_dy, g.ncy);
+  keys[i] = (uint32_t)cy * (uint32_t)g.ncx + (uint32_t)cx;
+}
+
+// -------------------------------------------------------------------------------------------------
+// SORT: stable LSD radix sort, 8-bit digits, three kernels per pass (histogram / scan / scatter).
+// No look-back spinning: a hung sort would hang the step.
+// -------------------------------------------------------------------------------------------------
+#define RS_THREADS 256
+#define RS_WARPS 8
+#define RS_ITEMS 16
+#define RS_TILE (RS_THREADS * RS_ITEMS)  // 4096 keys per block
+#define RS_BINS 256
+
+__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint32_t* __restrict__ keys, int n, int shift,
+                                                        uint32_t* __restrict__ hist, int nblk) {
+  __shared__ uint32_t h[RS_BINS];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  int base = blockIdx.x * RS_TILE;
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; ++k) {
+    int idx = base + k * RS_THREADS + threadIdx.x;
+    bool valid = idx < n;
+    uint32_t d = valid ? ((keys[idx] >> shift) & 255u) : (256u + (threadIdx.x & 31));
+    uint32_t peers = __match_any_sync(0xffffffffu, d);
+    if (valid && (__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&h[d], __popc(peers));
+  }
+  __syncthreads();
+  hist[threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];
+}
+
+// exclusive scan of m uint32 in place, one block of 1024 threads (m <= a few million)
+__global__ void __launch_bounds__(1024) k_excl_scan(uint32_t* __restrict__ a, int m) {
+  __shared__ uint32_t wsum[32];
+  __shared__ uint32_t carry_s;
+  int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int per = (m + 1023) / 1024;
+  int b = tid * per, e = min(b + per, m);
+  uint32_t sum = 0;
+  for (int i = b; i < e; ++i) sum += a[i];
+  uint32_t x = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) wsum[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = wsum[lane];
+    uint32_t xs = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, xs, o);
+      if (lane >= o) xs += y;
+    }
+    wsum[lane] = xs - w;  // exclusive
+    if (lane == 31) carry_s = xs;
+  }
+  __syncthreads();
+  uint32_t run = wsum[warp] + (x - sum);
+  for (int i = b; i < e; ++i) {
+    uint32_t v = a[i];
+    a[i] = run;
+    run += v;
+  }
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint32_t* __restrict__ keys_in,
+                                                           const uint32_t* __restrict__ vals_in,
+                                                           uint32_t* __restrict__ keys_out,
+                                                           uint32_t* __restrict__ vals_out, int n, int shift,
+                                                           const uint32_t* __restrict__ offs, int nblk) {
+  __shared__ uint32_t wcount[RS_WARPS][RS_BINS];
+  int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int k = tid; k < RS_WARPS * RS_BINS; k += RS_THREADS) (&wcount[0][0])[k] = 0;
+  __syncthreads();
+
+  // each warp owns a contiguous run of RS_ITEMS*32 keys, walked in order: stable ranking
+  int wbase = blockIdx.x * RS_TILE + warp * (RS_ITEMS * 32);
+  uint32_t key[RS_ITEMS], rank[RS_ITEMS];
+  const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    int idx = wbase + r * 32 + lane;
+    bool valid = idx < n;
+    key[r] = valid ? keys_in[idx] : 0xffffffffu;
+    uint32_t d = valid ? ((key[r] >> shift) & 255u) : (256u + lane);
+    uint32_t peers = __match_any_sync(0xffffffffu, d);
+    uint32_t pre = valid ? wcount[warp][d] : 0u;
+    rank[r] = pre + __popc(peers & lt);
+    __syncwarp();
+    if (valid && (__ffs(peers) - 1) == lane) wcount[warp][d] = pre + __popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+  {  // digit `tid`: exclusive prefix over the warps of this block on top of the global offset
+    uint32_t run = offs[tid * nblk + blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) {
+      uint32_t t = wcount[w][tid];
+      wcount[w][tid] = run;
+      run += t;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    int idx = wbase + r * 32 + lane;
+    if (idx < n) {
+      uint32_t d = (key[r] >> shift) & 255u;
+      uint32_t dst = wcount[warp][d] + rank[r];
+      keys_out[dst] = key[r];
+      vals_out[dst] = FIRST ? (uint32_t)idx : vals_in[idx];
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// K2: gather the SoA into cell order, predict, write the search positions and the cell table.
+// MODE 0: CalculateForces() on the state as it is (VPred/EPred gathered)           sph.go:403
+// MODE 1: step-0 initialisation: VPred = Vel, EPred = E                            sph.go:97-100
+// MODE 2: drift-1 + predict                                                        sph.go:108-117
+// -------------------------------------------------------------------------------------------------
+struct StateIn {
+  const double2 *pos, *vel, *vdot, *vpred;
+  const double *e, *edot, *epred;
+  const int64_t* id;
+  const double4* pc;  // {rho, c, h, P}
+  const uint8_t* ghost;
+};
+struct StateOut {
+  double2 *pos, *vel, *vdot, *vpred;
+  double *e, *edot, *epred;
+  int64_t* id;
+  double4* pc;
+  uint8_t* ghost;
+  double2* spos;   // wrapped search positions
+  double* hguess;  // h of the previous evaluation in the new order (0 = unknown)
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_reorder(StateIn in, StateOut out, const uint32_t* __restrict__ keys,
+                                                const uint32_t* __restrict__ perm, int n, const GridP* __restrict__ gp, double dtH,
+                                                uint32_t* __restrict__ cellStart) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const GridP g = *gp;
+  const int ncell = g.ncx * g.ncy;
+  uint32_t i = perm[j];
+  double2 p = in.pos[i], v = in.vel[i], a = in.vdot[i];
+  double e = in.e[i], ed = in.edot[i];
+  double4 pc = in.pc[i];
+  double2 vp;
+  double ep;
+  if (MODE == 2) {
+    p.x = __dadd_rn(p.x, __dmul_rn(v.x, dtH));
+    p.y = __dadd_rn(p.y, __dmul_rn(v.y, dtH));
+    vp.x = __dadd_rn(v.x, __dmul_rn(a.x, dtH));
+    vp.y = __dadd_rn(v.y, __dmul_rn(a.y, dtH));
+    ep = __dadd_rn(e, __dmul_rn(ed, dtH));
+  } else if (MODE == 1) {
+    vp = v;
+    ep = e;
+  } else {
+    vp = in.vpred[i];
+    ep = in.epred[i];
+  }
+  out.pos[j] = p;
+  out.vel[j] = v;
+  out.vdot[j] = a;
+  out.e[j] = e;
+  out.edot[j] = ed;
+  out.vpred[j] = vp;
+  out.epred[j] = ep;
+  out.id[j] = in.id[i];
+  out.pc[j] = pc;
+  out.ghost[j] = in.ghost[i];
+  out.hguess[j] = pc.z;
+  double2 sp;
+  sp.x = g.wrapx ? wrap_coord(p.x, g.lox, g.Lx) : p.x;
+  sp.y = g.wrapy ? wrap_coord(p.y, g.loy, g.Ly) : p.y;
+  out.spos[j] = sp;
+
+  // cell table from the sorted keys: cellStart[c] = first j with key >= c
+  uint32_t k = keys[j];
+  uint32_t kprev = (j == 0) ? 0u : keys[j - 1];
+  if (j == 0) {
+    for (uint32_t c = 0; c <= k; ++c) cellStart[c] = 0;
+  } else if (k != kprev) {
+    for (uint32_t c = kprev + 1; c <= k; ++c) cellStart[c] = (uint32_t)j;
+  }
+  if (j == n - 1) {
+    for (uint32_t c = k + 1; c <= (uint32_t)ncell; ++c) cellStart[c] = (uint32_t)n;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// K3: exact kNN (k = 32) + density + sound speed.
+//
+// One warp = 32 consecutive particles of the cell-sorted order (about 3 cells of one grid row).  Every
+// lane has a search radius rg (previous h plus a margin, or a density estimate).  The warp walks the
+// UNION of its lanes' stencils row by row; rows of cells are contiguous in memory, so a row of the union
+// is one contiguous particle range and all 32 lanes load the same candidate (one broadcast transaction).
+// A lane keeps every candidate with d^2 < rg^2 in its shared-memory column.  If it collected between 32
+// and CAP, the 32 nearest of them are the exact answer (everything within rg was seen); otherwise the
+// particle goes to the ring-expansion fallback kernel.  The bounded top-k is then a trim of the few
+// surplus entries instead of a per-candidate priority-queue update (nearest-neighbour.go:139-153).
+// -------------------------------------------------------------------------------------------------
+#define KNN_WARPS 4
+#define KNN_THREADS (KNN_WARPS * 32)
+
+struct KnnOut {
+  double4* pc;      // {rho, c, h, P = c^2/(gamma rho)}
+  uint32_t* nn;     // [tile][slot][lane], entry = index | image code << 28
+  int* failList;
+  int* failCount;
+};
+
+__device__ __forceinline__ int warp_min_i(int v, uint32_t mask) {
+  // min over lanes in mask (others pass INT_MAX)
+  return __reduce_min_sync(0xffffffffu, (mask >> (threadIdx.x & 31)) & 1u ? v : 0x7fffffff);
+}
+__device__ __forceinline__ int warp_max_i(int v, uint32_t mask) {
+  return __reduce_max_sync(0xffffffffu, (mask >> (threadIdx.x & 31)) & 1u ? v : (int)0x80000000);
+}
+
+// finish one particle whose candidate column holds cnt >= 32 entries (d2 >= 0), from any column layout:
+// trims to the 32 smallest, returns h^2, leaves removed entries marked with d2 = -1
+template <typename D2Ref>
+__device__ __forceinline__ double trim_to_k(D2Ref d2at, int cnt) {
+  for (int r = cnt - SPHB_K; r > 0; --r) {
+    double m = -1.0;
+    int ms = 0;
+    for (int s = 0; s < cnt; ++s) {
+      double v = d2at(s);
+      if (v > m) { m = v; ms = s; }
+    }
+    d2at(ms) = -1.0;
+  }
+  double m = -1.0;
+  for (int s = 0; s < cnt; ++s) {
+    double v = d2at(s);
+    if (v > m) m = v;
+  }
+  return m;
+}
+
+template <int KERNEL>
+__global__ void __launch_bounds__(KNN_THREADS) k_knn_fast(const double2* __restrict__ spos,
+                                                         const uint32_t* __restrict__ keys,
+                                                         const uint32_t* __restrict__ cellStart,
+                                                         const double* __restrict__ hguess,
+                                                         const double* __restrict__ epred, int n, const GridP* __restrict__ gp, PhysP ph,
+                                                         KnnTune tune, KnnOut out) {
+  const GridP g = *gp;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int CAP = tune.cap;
+  double* d2col = reinterpret_cast<double*>(smem_raw) + (size_t)warp * CAP * 32 + lane;
+  uint32_t* idcol = reinterpret_cast<uint32_t*>(reinterpret_cast<double*>(smem_raw) + (size_t)KNN_WARPS * CAP * 32) +
+                    (size_t)warp * CAP * 32 + lane;
+
+  const int tile = blockIdx.x * KNN_WARPS + warp;
+  const int i = tile * 32 + lane;
+  const bool valid = i < n;
+  if (tile * 32 >= n) return;  // whole warp out of range (warp-uniform)
+
+  double xa = 0, ya = 0, rg = 0;
+  int cxa = 0, cya = 0;
+  if (valid) {
+    double2 p = spos[i];
+    xa = p.x; ya = p.y;
+    uint32_t k = keys[i];
+    cya = (int)(k / (uint32_t)g.ncx);
+    cxa = (int)(k - (uint32_t)cya * (uint32_t)g.ncx);
+    double hp = hguess[i];
+    if (hp > 0.0) {
+      rg = hp * (1.0 + tune.guess_margin);
+    } else {
+      // density estimate from the 3x3 block of cells around the particle
+      int x0 = max(cxa - 1, 0), x1 = min(cxa + 1, g.ncx - 1);
+      int y0 = max(cya - 1, 0), y1 = min(cya + 1, g.ncy - 1);
+      uint32_t c = 0;
+      for (int r = y0; r <= y1; ++r) c += cellStart[r * g.ncx + x1 + 1] - cellStart[r * g.ncx + x0];
+      double area = (double)(x1 - x0 + 1) * g.dx * (double)(y1 - y0 + 1) * g.dy;
+      rg = sqrt(tune.k_target * area / (3.141592653589793 * (double)(c > 0 ? c : 1)));
+    }
+  }
+  const double rg2 = rg * rg;
+  // unwrapped cell range that contains every point within rg (slightly widened: see DESIGN.md, exactness)
+  const double rw = rg * (1.0 + 1e-6);
+  int clo = (int)floor((xa - rw - g.ox) * g.inv_dx), chi = (int)floor((xa + rw - g.ox) * g.inv_dx);
+  int rlo = (int)floor((ya - rw - g.oy) * g.inv_dy), rhi = (int)floor((ya + rw - g.oy) * g.inv_dy);
+  clo = min(clo, cxa); chi = max(chi, cxa);
+  rlo = min(rlo, cya); rhi = max(rhi, cya);
+
+  int cnt = 0;
+  bool bad = false;  // stencil wider than the period: needs the multi-image fallback
+  uint32_t todo = __ballot_sync(0xffffffffu, valid);
+  while (todo) {
+    // next group: all remaining lanes that sit in the same grid row as the first remaining lane
+    const int lead = __ffs(todo) - 1;
+    const int grow = __shfl_sync(0xffffffffu, cya, lead);
+    const uint32_t grp = __ballot_sync(0xffffffffu, valid && cya == grow) & todo;
+    todo &= ~grp;
+    const bool mine = (grp >> lane) & 1u;
+    int c0 = warp_min_i(clo, grp), c1 = warp_max_i(chi, grp);
+    int r0 = warp_min_i(rlo, grp), r1 = warp_max_i(rhi, grp);
+    bool gbad = false;
+    if (g.wrapx) { if (c1 - c0 + 1 > g.ncx) gbad = true; }
+    else { c0 = max(c0, 0); c1 = min(c1, g.ncx - 1); c0 = min(c0, g.ncx - 1); c1 = max(c1, 0); }
+    if (g.wrapy) { if (r1 - r0 + 1 > g.ncy) gbad = true; }
+    else { r0 = max(r0, 0); r1 = min(r1, g.ncy - 1); r0 = min(r0, g.ncy - 1); r1 = max(r1, 0); }
+    if (gbad) { if (mine) bad = true; continue; }
+
+    for (int ru = r0; ru <= r1; ++ru) {
+      int iy = g.wrapy ? floor_div(ru, g.ncy) : 0;
+      const int row = ru - iy * g.ncy;
+      const double qy = (iy == 0) ? ya : __dadd_rn(ya, -(double)iy * g.Ly);  // query shifted like nearest-neighbour.go:59,72
+      // up to three x pieces (images -1, 0, +1)
+      int ix0 = g.wrapx ? floor_div(c0, g.ncx) : 0, ix1 = g.wrapx ? floor_div(c1, g.ncx) : 0;
+      for (int ix = ix0; ix <= ix1; ++ix) {
+        const int a = max(c0, ix * g.ncx) - ix * g.ncx, b = min(c1, ix * g.ncx + g.ncx - 1) - ix * g.ncx;
+        const double qx = (ix == 0) ? xa : __dadd_rn(xa, -(double)ix * g.Lx);
+        const uint32_t code = (uint32_t)((ix + 1) * 3 + (iy + 1)) << IMG_SHIFT;
+        const int s = (int)cellStart[row * g.ncx + a], e = (int)cellStart[row * g.ncx + b + 1];
+        for (int j = s; j < e; j += 4) {
+          double2 pb[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) pb[u] = spos[min(j + u, e - 1)];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const double d2 = dist_sq(qx - pb[u].x, qy - pb[u].y);
+            const bool acc = mine && (j + u < e) && (d2 < rg2) && (j + u != i);
+            if (acc) {
+              if (cnt < CAP) { d2col[cnt * 32] = d2; idcol[cnt * 32] = (uint32_t)(j + u) | code; }
+              ++cnt;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  const bool ok = valid && !bad && cnt >= SPHB_K && cnt <= CAP;
+  if (valid && !ok) {
+    int slot = atomicAdd(out.failCount, 1);
+    out.failList[slot] = i;
+  }
+  if (!ok) cnt = 0;
+  // trim the surplus (cnt - 32 largest) and get h^2
+  double h2 = trim_to_k([&](int s) -> double& { return d2col[s * 32]; }, cnt);
+  if (ok) {
+    const double h = sqrt(h2);
+    const double inv_h = 1.0 / h;
+    double acc = 0.0;
+    int kslot = 0;
+    uint32_t* nncol = out.nn + (size_t)tile * 32 * 32 + lane;
+    for (int s = 0; s < cnt; ++s) {
+      const double v = d2col[s * 32];
+      if (v >= 0.0) {
+        acc += kern_F<KERNEL>(sqrt(v) * inv_h);
+        nncol[kslot * 32] = idcol[s * 32];
+        ++kslot;
+      }
+    }
+    // Density2D (sph.go:322), sound speed (sph.go:426-428), pressure term c^2/(gamma rho) (sph.go:332,360)
+    const double rho = ph.Fpref * ph.mass * acc / (h * h);
+    const double c = sqrt(ph.cfac * epred[i]);
+    out.pc[i] = make_double4(rho, c, h, c * c / (ph.gamma * rho));
+  }
+}
+
+// Fallback: one thread per failed particle, ring expansion until the result is certified exact.
+// Handles everything the fast path refuses: too few / too many candidates inside the guess, stencils
+// wider than the period (several images of the same particle, like the reference's 3x3 image loop).
+template <int KERNEL>
+__global__ void __launch_bounds__(128) k_knn_fallback(const double2* __restrict__ spos,
+                                                     const uint32_t* __restrict__ keys,
+                                                     const uint32_t* __restrict__ cellStart,
+                                                     const double* __restrict__ hguess,
+                                                     const double* __restrict__ epred, int n, const GridP* __restrict__ gp, PhysP ph,
+                                                     KnnOut out, uint32_t* __restrict__ dflags) {
+  const GridP g = *gp;
+  const int nfail = *out.failCount;
+  if (blockIdx.x == 0 && threadIdx.x == 0) out.failCount[1] += nfail;  // cumulative, read by sphb_counters
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nfail; f += gridDim.x * blockDim.x) {
+    const int i = out.failList[f];
+    const double2 pa = spos[i];
+    const uint32_t k = keys[i];
+    const int cya = (int)(k / (uint32_t)g.ncx), cxa = (int)(k - (uint32_t)cya * (uint32_t)g.ncx);
+    double R = hguess[i] > 0.0 ? 1.5 * hguess[i] : 1.5 * fmax(g.dx, g.dy);
+    double td[SPHB_K];  // sorted descending like the reference queue: td[0] = current 32nd-best
+    uint32_t ti[SPHB_K];
+    int found = 0;
+    for (int iter = 0; iter < 64; ++iter) {
+#pragma unroll
+      for (int s = 0; s < SPHB_K; ++s) { td[s] = 1.7976931348623157e308; ti[s] = 0xffffffffu; }
+      found = 0;
+      // unwrapped cell block covering [pa - R, pa + R]; sides that cannot hide anything are "complete"
+      int c0 = (int)floor((pa.x - R - g.ox) * g.inv_dx), c1 = (int)floor((pa.x + R - g.ox) * g.inv_dx);
+      int r0 = (int)floor((pa.y - R - g.oy) * g.inv_dy), r1 = (int)floor((pa.y + R - g.oy) * g.inv_dy);
+      c0 = min(c0, cxa); c1 = max(c1, cxa); r0 = min(r0, cya); r1 = max(r1, cya);
+      bool doneL, doneR, doneD, doneU;
+      if (g.wrapx) { doneL = c0 <= -g.ncx; doneR = c1 >= 2 * g.ncx - 1; c0 = max(c0, -g.ncx); c1 = min(c1, 2 * g.ncx - 1); }
+      else { doneL = c0 <= 0; doneR = c1 >= g.ncx - 1; c0 = min(max(c0, 0), g.ncx - 1); c1 = max(min(c1, g.ncx - 1), 0); }
+      if (g.wrapy) { doneD = r0 <= -g.ncy; doneU = r1 >= 2 * g.ncy - 1; r0 = max(r0, -g.ncy); r1 = min(r1, 2 * g.ncy - 1); }
+      else { doneD = r0 <= 0; doneU = r1 >= g.ncy - 1; r0 = min(max(r0, 0), g.ncy - 1); r1 = max(min(r1, g.ncy - 1), 0); }
+      for (int ru = r0; ru <= r1; ++ru) {
+        const int iy = g.wrapy ? floor_div(ru, g.ncy) : 0;
+        const int row = ru - iy * g.ncy;
+        const double qy = (iy == 0) ? pa.y : __dadd_rn(pa.y, -(double)iy * g.Ly);
+        for (int cu = c0; cu <= c1; ++cu) {
+          const int ix = g.wrapx ? floor_div(cu, g.ncx) : 0;
+          const int col = cu - ix * g.ncx;
+          const double qx = (ix == 0) ? pa.x : __dadd_rn(pa.x, -(double)ix * g.Lx);
+          const uint32_t code = (uint32_t)((ix + 1) * 3 + (iy + 1)) << IMG_SHIFT;
+          const int s = (int)cellStart[row * g.ncx + col], e = (int)cellStart[row * g.ncx + col + 1];
+          for (int j = s; j < e; ++j) {
+            const double2 pb = spos[j];
+            const double d2 = dist_sq(qx - pb.x, qy - pb.y);
+            if (d2 < td[0] && j != i) {  // strict, self excluded in every image (nearest-neighbour.go:79)
+              int t = 1;
+              for (; t < SPHB_K && td[t] > d2; ++t) { td[t - 1] = td[t]; ti[t - 1] = ti[t]; }
+              td[t - 1] = d2; ti[t - 1] = (uint32_t)j | code;
+              ++found;
+            }
+          }
+        }
+      }
+      const bool all = doneL && doneR && doneD && doneU;
+      if (found >= SPHB_K) {
+        // certified if the 32nd distance does not reach past the scanned block on any open side
+        const double d = sqrt(td[0]);
+        const double reachL = doneL ? 1e300 : pa.x - (g.ox + (double)c0 * g.dx);
+        const double reachR = doneR ? 1e300 : (g.ox + (double)(c1 + 1) * g.dx) - pa.x;
+        const double reachD = doneD ? 1e300 : pa.y - (g.oy + (double)r0 * g.dy);
+        const double reachU = doneU ? 1e300 : (g.oy + (double)(r1 + 1) * g.dy) - pa.y;
+        const double reach = fmin(fmin(reachL, reachR), fmin(reachD, reachU));
+        if (d * (1.0 + 1e-9) <= reach) break;
+        R = d * (1.0 + 1e-6);  // guaranteed to suffice next time
+      } else {
+        if (all) break;  // fewer than 32 (particle, image) candidates exist at all
+        R *= 2.0;
+      }
+    }
+    const int tile = i >> 5, lane = i & 31;
+    uint32_t* nncol = out.nn + (size_t)tile * 32 * 32 + lane;
+    if (found < SPHB_K) {
+      atomicOr(dflags, DFLAG_UNDERFULL);
+      for (int s = 0; s < SPHB_K; ++s) nncol[s * 32] = 0xffffffffu;
+      out.pc[i] = make_double4(0.0, 0.0, 0.0, 0.0);
+      continue;
+    }
+    const double h = sqrt(td[0]);
+    const double inv_h = 1.0 / h;
+    double acc = 0.0;
+    for (int s = 0; s < SPHB_K; ++s) {
+      acc += kern_F<KERNEL>(sqrt(td[s]) * inv_h);
+      nncol[s * 32] = ti[s];
+    }
+    const double rho = ph.Fpref * ph.mass * acc / (h * h);
+    const double c = sqrt(ph.cfac * epred[i]);
+    out.pc[i] = make_double4(rho, c, h, c * c / (ph.gamma * rho));
+  }
+}
+
+// image offset of a list entry: the query is shifted by -(img)*L exactly as in K3
+__device__ __forceinline__ void decode_entry(uint32_t ent, const GridP& g, int& j, double& offx, double& offy) {
+  j = (int)(ent & IDX_MASK);
+  const int code = (int)(ent >> IMG_SHIFT);
+  const int ix = code / 3 - 1, iy = code % 3 - 1;
+  offx = -(double)ix * g.Lx;
+  offy = -(double)iy * g.Ly;
+}
+
+// Density2D for an arbitrary kernel from the stored list (examples/density, sph.go:306-323)
+template <int KERNEL>
+__global__ void __launch_bounds__(128) k_density_from_list(const double2* __restrict__ spos,
+                                                          const uint32_t* __restrict__ nn, int n, const GridP* __restrict__ gp, PhysP ph,
+                                                          double4* __restrict__ pc) {
+  const GridP g = *gp;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double2 pa = spos[i];
+  double4 q = pc[i];
+  const double h = q.z;
+  if (!(h > 0.0)) return;
+  const double inv_h = 1.0 / h;
+  const uint32_t* col = nn + (size_t)(i >> 5) * 1024 + (i & 31);
+  double acc = 0.0;
+  for (int s = 0; s < SPHB_K; ++s) {
+    int j; double ox, oy;
+    decode_entry(col[s * 32], g, j, ox, oy);
+    const double2 pb = spos[j];
+    const double d = sqrt(dist_sq((pa.x + ox) - pb.x, (pa.y + oy) - pb.y));
+    acc += kern_F<KERNEL>(fmin(d * inv_h, 1.0));
+  }
+  q.x = ph.Fpref * ph.mass * acc / (h * h);
+  q.w = q.y * q.y / (ph.gamma * q.x);
+  pc[i] = q;
+}
+
+// -------------------------------------------------------------------------------------------------
+// K4: AccelerationAndEDot2D (sph.go:327-401) over the neighbour list, fused with kick, drift-2,
+// periodic wrap and reflections (sph.go:122-193) when INTEGRATE.
+// -------------------------------------------------------------------------------------------------
+struct ForceIO {
+  const double2* spos;
+  const double2* vpred;
+  const double4* pc;
+  const uint32_t* nn;
+  double2* pos;
+  double2* vel;
+  double* e;
+  double2* vdot;
+  double* edot;
+};
+
+template <int KERNEL, bool INTEGRATE>
+__global__ void __launch_bounds__(128) k_force(ForceIO io, int n, const GridP* __restrict__ gp, PhysP ph) {
+  const GridP g = *gp;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double2 pa = io.spos[i];
+  const double2 va = io.vpred[i];
+  const double4 qa = io.pc[i];  // rho, c, h, P
+  const double h = qa.z, inv_h = 1.0 / h;
+  const uint32_t* col = io.nn + (size_t)(i >> 5) * 1024 + (i & 31);
+  double ax = 0.0, ay = 0.0, aed = 0.0;
+#pragma unroll 4
+  for (int s = 0; s < SPHB_K; ++s) {
+    int j; double ox, oy;
+    decode_entry(col[s * 32], g, j, ox, oy);
+    const double2 pb = io.spos[j];
+    const double2 vb = io.vpred[j];
+    const double4 qb = io.pc[j];
+    // rAB = NNPos - Pos with NNPos = neighbour - offset (nearest-neighbour.go:80, sph.go:372)
+    const double rx = (pb.x - ox) - pa.x, ry = (pb.y - oy) - pa.y;
+    const double vx = vb.x - va.x, vy = vb.y - va.y;
+    const double r2 = dist_sq(rx, ry);
+    const double d = sqrt(r2);
+    const double dot = vx * rx + vy * ry;
+    double pi = 0.0;
+    if (dot < 0.0) {  // artificial viscosity, sph.go:375-388
+      const double cAB = 0.5 * (qa.y + qb.y);
+      const double rhoAB = 0.5 * (qa.x + qb.x);
+      const double hAB = 0.5 * (qa.z + qb.z);
+      const double mu = dot * hAB / (r2 + 0.01);
+      pi = (-0.75 * cAB * mu + 1.5 * mu * mu) / rhoAB;
+    }
+    const double dk = kern_DF<KERNEL>(fmin(d * inv_h, 1.0));
+    const double w = (pi + qa.w + qb.w) * dk / d;
+    ax += rx * w;
+    ay += ry * w;
+    aed += dot * dk;
+  }
+  const double f = ph.mass * ph.DFpref / (h * h * h);
+  double2 a = make_double2(ax * f + ph.gx, ay * f + ph.gy);
+  const double ed = qa.w * aed * ph.mass;  // Benz formulation, sph.go:400
+  io.vdot[i] = a;
+  io.edot[i] = ed;
+  if (INTEGRATE) {
+    double2 p = io.pos[i], v = io.vel[i];
+    double e = io.e[i];
+    const double dt = 2.0 * ph.dtH;
+    // kick (sph.go:122-127), drift 2 (sph.go:130-135): unfused like the reference
+    v.x = __dadd_rn(v.x, __dmul_rn(a.x, dt));
+    v.y = __dadd_rn(v.y, __dmul_rn(a.y, dt));
+    e = __dadd_rn(e, __dmul_rn(__dmul_rn(ed, 2.0), ph.dtH));
+    p.x = __dadd_rn(p.x, __dmul_rn(v.x, ph.dtH));
+    p.y = __dadd_rn(p.y, __dmul_rn(v.y, ph.dtH));
+    // periodic wrap, single shift, X shift skips the Y test (sph.go:147-167)
+    if (p.x < ph.hor0) p.x = __dadd_rn(p.x, ph.hor1 - ph.hor0);
+    else if (p.x > ph.hor1) p.x = __dsub_rn(p.x, ph.hor1 - ph.hor0);
+    else if (p.y < ph.ver0) p.y = __dadd_rn(p.y, ph.ver1 - ph.ver0);
+    else if (p.y > ph.ver1) p.y = __dsub_rn(p.y, ph.ver1 - ph.ver0);
+    // reflections L, R, U, D: pos -= pos - wall (sph.go:170-193)
+    if (p.x < ph.rL) { p.x = __dsub_rn(p.x, __dsub_rn(p.x, ph.rL)); v.x = -v.x; }
+    if (p.x > ph.rR) { p.x = __dsub_rn(p.x, __dsub_rn(p.x, ph.rR)); v.x = -v.x; }
+    if (p.y < ph.rU) { p.y = __dsub_rn(p.y, __dsub_rn(p.y, ph.rU)); v.y = -v.y; }
+    if (p.y > ph.rD) { p.y = __dsub_rn(p.y, __dsub_rn(p.y, ph.rD)); v.y = -v.y; }
+    io.pos[i] = p;
+    io.vel[i] = v;
+    io.e[i] = e;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// reductions and statistics
+// -------------------------------------------------------------------------------------------------
+// per-block partials of {min x, max x, min y, max y, sum h, max h, sum e, sum rho, #(h > 0)}; one block folds them
+#define STAT_N 9
+#define STAT_BLOCKS 592
+__device__ __forceinline__ double stat_comb(int k, double a, double b) {
+  return (k == 0 || k == 2) ? fmin(a, b) : ((k == 1 || k == 3 || k == 5) ? fmax(a, b) : a + b);
+}
+__device__ __forceinline__ double stat_init(int k) {
+  return (k == 0 || k == 2) ? 1.7976931348623157e308 : ((k == 1 || k == 3 || k == 5) ? -1.7976931348623157e308 : 0.0);
+}
+
+__global__ void __launch_bounds__(256) k_stats_partial(const double2* __restrict__ pos, const double4* __restrict__ pc,
+                                                      const double* __restrict__ e, int n, double* __restrict__ part) {
+  __shared__ double sh[8][STAT_N];
+  double v[STAT_N];
+#pragma unroll
+  for (int k = 0; k < STAT_N; ++k) v[k] = stat_init(k);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double2 p = pos[i];
+    double4 q = pc[i];
+    v[0] = fmin(v[0], p.x); v[1] = fmax(v[1], p.x);
+    v[2] = fmin(v[2], p.y); v[3] = fmax(v[3], p.y);
+    v[4] += q.z; v[5] = fmax(v[5], q.z);
+    v[6] += e[i]; v[7] += q.x;
+    v[8] += (q.z > 0.0) ? 1.0 : 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < STAT_N; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[k] = stat_comb(k, v[k], __shfl_xor_sync(0xffffffffu, v[k], o));
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0)
+    for (int k = 0; k < STAT_N; ++k) sh[warp][k] = v[k];
+  __syncthreads();
+  if (threadIdx.x < STAT_N) {
+    double r = sh[0][threadIdx.x];
+    for (int w = 1; w < 8; ++w) r = stat_comb(threadIdx.x, r, sh[w][threadIdx.x]);
+    part[blockIdx.x * STAT_N + threadIdx.x] = r;
+  }
+}
+__global__ void k_stats_final(const double* __restrict__ part, int nblk, double* __restrict__ outv) {
+  const int k = threadIdx.x;
+  if (k >= STAT_N) return;
+  double r = stat_init(k);
+  for (int b = 0; b < nblk; ++b) r = stat_comb(k, r, part[b * STAT_N + k]);
+  outv[k] = r;
+}
+
+// -------------------------------------------------------------------------------------------------
+// grid set-up on the device (one thread): the cell edge follows the mean smoothing length of the previous
+// evaluation, or a mean-density estimate when there is none.  Keeping GridP in device memory lets a
+// sequence of steps be enqueued without a host round trip (open axes: the box follows the particles).
+// hor/ver are the search periodicity (nearest-neighbour.go:28): {-DBL_MAX, DBL_MAX} = open.
+// -------------------------------------------------------------------------------------------------
+struct GridTune {
+  double cell_per_h;   // cell edge = cell_per_h * mean h
+  double ppc0;         // particles per cell for the first (h unknown) evaluation
+  int ncell_max;       // capacity of the cell table
+  int force_nc;        // > 0: fixed cells per axis (tests)
+};
+
+__global__ void k_make_grid(const double* __restrict__ stats, int n, double hor0, double hor1, double ver0, double ver1,
+                            double xlo_fixed, double xhi_fixed, int x_fixed, GridTune t, GridP* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  GridP g;
+  g.wrapx = !(hor0 == -1.7976931348623157e308);
+  g.wrapy = !(ver0 == -1.7976931348623157e308);
+  double ex, ey;
+  if (g.wrapx) { g.lox = hor0; g.Lx = hor1 - hor0; g.ox = hor0; ex = g.Lx; }
+  else if (x_fixed) { g.lox = 0; g.Lx = 0; g.ox = xlo_fixed; ex = xhi_fixed - xlo_fixed; }
+  else { g.lox = 0; g.Lx = 0; g.ox = stats[0]; ex = stats[1] - stats[0]; }
+  if (g.wrapy) { g.loy = ver0; g.Ly = ver1 - ver0; g.oy = ver0; ey = g.Ly; }
+  else { g.loy = 0; g.Ly = 0; g.oy = stats[2]; ey = stats[3] - stats[2]; }
+  const double scale = fmax(fmax(ex, ey), 1e-300);
+  if (!(ex > 1e-12 * scale)) ex = 1e-12 * scale;
+  if (!(ey > 1e-12 * scale)) ey = 1e-12 * scale;
+  double d;
+  const double nh = stats[8];
+  if (nh > 0.0) d = t.cell_per_h * stats[4] / nh;
+  else d = sqrt(t.ppc0 * ex * ey / (double)(n > 0 ? n : 1));
+  if (!(d > 0.0)) d = scale;
+  double fx = fmin(fmax(floor(ex / d), 1.0), 1.0e6), fy = fmin(fmax(floor(ey / d), 1.0), 1.0e6);
+  for (int it = 0; it < 8 && fx * fy > (double)t.ncell_max; ++it) {
+    d *= sqrt(fx * fy / (double)t.ncell_max) * 1.0001;
+    fx = fmax(floor(ex / d), 1.0);
+    fy = fmax(floor(ey / d), 1.0);
+  }
+  if (fx * fy > (double)t.ncell_max) { fx = 1.0; fy = 1.0; }
+  if (t.force_nc > 0) { fx = fy = (double)t.force_nc; }
+  g.ncx = (int)fx; g.ncy = (int)fy;
+  g.dx = ex / fx; g.dy = ey / fy;
+  g.inv_dx = 1.0 / g.dx; g.inv_dy = 1.0 / g.dy;
+  *out = g;
+}
+
+// expand the neighbour list for download in the reference's layout: [particle][slot], slots sorted by
+// DESCENDING distance so that slot 0 is the farthest neighbour = h (nearest-neighbour.go:139-153).
+// NN_IDX = index in current device order (-1 = none), NN_DIST = NNDists, NN_POS = NNPos (neighbour image
+// position in the frame of the query's raw position, nearest-neighbour.go:80).
+__global__ void __launch_bounds__(128) k_expand_list(const double2* __restrict__ spos, const double2* __restrict__ pos,
+                                                    const uint32_t* __restrict__ nn, int off, int m_count,
+                                                    const GridP* __restrict__ gp, int32_t* __restrict__ idx_out,
+                                                    double* __restrict__ dist_out, double2* __restrict__ pos_out) {
+  const int t_ = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t_ >= m_count) return;
+  const int i = off + t_;
+  const GridP g = *gp;
+  const double2 pa = spos[i];
+  const double2 praw = pos[i];
+  const uint32_t* col = nn + (size_t)(i >> 5) * 1024 + (i & 31);
+  double dd[SPHB_K];
+  uint32_t ee[SPHB_K];
+  int m = 0;
+  for (int s = 0; s < SPHB_K; ++s) {
+    const uint32_t ent = col[s * 32];
+    if (ent == 0xffffffffu) continue;
+    int j; double ox, oy;
+    decode_entry(ent, g, j, ox, oy);
+    const double2 pb = spos[j];
+    const double d2 = dist_sq((pa.x + ox) - pb.x, (pa.y + oy) - pb.y);
+    int t = m;  // insertion sort, descending; equal keys keep scan order
+    for (; t > 0 && dd[t - 1] < d2; --t) { dd[t] = dd[t - 1]; ee[t] = ee[t - 1]; }
+    dd[t] = d2; ee[t] = ent;
+    ++m;
+  }
+  for (int s = 0; s < SPHB_K; ++s) {
+    const size_t o = (size_t)t_ * SPHB_K + s;
+    if (s >= m) {
+      if (idx_out) idx_out[o] = -1;
+      if (dist_out) dist_out[o] = 0.0;
+      if (pos_out) pos_out[o] = make_double2(0.0, 0.0);
+      continue;
+    }
+    int j; double ox, oy;
+    decode_entry(ee[s], g, j, ox, oy);
+    const double2 pb = spos[j];
+    if (idx_out) idx_out[o] = j;
+    if (dist_out) dist_out[o] = sqrt(dd[s]);
+    if (pos_out) pos_out[o] = make_double2(praw.x + ((pb.x - ox) - pa.x), praw.y + ((pb.y - oy) - pa.y));
+  }
+}
+
+__global__ void __launch_bounds__(256) k_split_pc(const double4* __restrict__ pc, int n, double* __restrict__ rho,
+                                                 double* __restrict__ c, double* __restrict__ h) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double4 q = pc[i];
+  if (rho) rho[i] = q.x;
+  if (c) c[i] = q.y;
+  if (h) h[i] = q.z;
+}
+
+// upload helpers: scatter host-provided rho into pc.x, invalidate h when positions are overwritten
+__global__ void __launch_bounds__(256) k_set_pc(double4* __restrict__ pc, int n, const double* __restrict__ rho,
+                                               int zero_h) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double4 q = pc[i];
+  if (rho) q.x = rho[i];
+  if (zero_h) q.z = 0.0;
+  pc[i] = q;
+}
+
+__global__ void __launch_bounds__(256) k_iota64(int64_t* __restrict__ id, int n, int64_t base) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) id[i] = base + i;
+}

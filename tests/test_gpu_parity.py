@@ -1,0 +1,175 @@
+"""-m gpu parity tests: libsphb.so (CUDA, through the C ABI) against the CPU oracle on identical inputs.
+
+Bars (north_star): neighbour index sets bit-exact excluding exact distance ties; h, rho, accelerations and
+energies within 1e-12 (fp64 build), accelerations / EDot measured relative to sum|term| because the
+32-term sums nearly cancel on near-uniform data."""
+import numpy as np
+import pytest
+
+from tests import util as U
+from oracle import oracle as orc
+from sphugo_b200 import _lib as L
+from sphugo_b200 import gen
+
+pytestmark = pytest.mark.gpu
+TOL = U.TOL64
+
+
+def _knn_density_case(ic, hor, ver, kernels=(0, 1, 2), mass=1.0):
+    po, pg = U.params_pair(hor=hor, ver=ver, particle_mass=mass)
+    o = orc.Oracle(po, ic["pos"], ids=ic["id"])
+    o.knn(hor, ver, mode=0)
+    assert o.underfull == 0
+    g = L.Handle(pg, ic["pos"], ids=ic["id"])
+    g.knn(hor, ver)
+    ref = o.state(neighbours=True)
+    got = g.state(U.FIELDS_STATE + U.FIELDS_NN)
+    hard, excused = U.neighbour_sets_equal(got, ref)
+    assert hard == 0, f"{hard} particles with different neighbour sets ({excused} exact ties excused)"
+    assert U.rel_err(got["h"], ref["h"]) <= TOL
+    # lists are both sorted by descending distance: distances must agree slot by slot
+    assert U.rel_err(got["nn_dist"], ref["nn_dist"]) <= TOL
+    assert np.abs(got["nn_pos"] - ref["nn_pos"]).max() <= 1e-15 * max(1.0, np.abs(ref["nn_pos"]).max()) * 4
+    for k in kernels:
+        o.density(k)
+        g.density(k)
+        r = o.state()["rho"]
+        assert U.rel_err(g.state(["rho"])["rho"], r) <= TOL, f"density kernel {k}"
+    g.close(); o.close()
+
+
+def test_c1_density_example_periodic():
+    """examples/density main: N=1200, periodic [0,1]^2, TopHat/Monaghan/Wendland (density.go:41-97)."""
+    _knn_density_case(U.c1_density(), (0.0, 1.0), (0.0, 1.0))
+
+
+def test_c1_periodic_visual_open_and_periodic():
+    """periodicVisualTest: N=11200 on [0.1,0.9]^2, open vs periodic, TopHat (density.go:99-141)."""
+    ic = U.c1_periodic_visual()
+    _knn_density_case(ic, U.OPEN, U.OPEN, kernels=(0,))
+    _knn_density_case(ic, (0.1, 0.9), (0.1, 0.9), kernels=(0,))
+
+
+def test_mixed_open_periodic_axes():
+    ic = gen.spawn([(3000, (0.0, 0.0), (1.0, 1.0))], seed=7)
+    _knn_density_case(ic, (0.0, 1.0), U.OPEN, kernels=(1,))
+    _knn_density_case(ic, U.OPEN, (0.0, 1.0), kernels=(2,))
+
+
+def test_knn_matches_exact_bruteforce_clustered():
+    """non-uniform data (h varies x10): the stencil scan must stay exact (ring-expansion fallback)."""
+    rng = np.random.default_rng(3)
+    pos = np.concatenate([rng.random((1500, 2)), 0.5 + 0.01 * rng.standard_normal((1500, 2))])
+    ic = dict(pos=pos, id=np.arange(len(pos), dtype=np.int64))
+    po, pg = U.params_pair()
+    o = orc.Oracle(po, ic["pos"], ids=ic["id"])
+    o.knn(U.OPEN, U.OPEN, mode=1)
+    g = L.Handle(pg, ic["pos"], ids=ic["id"])
+    g.knn(U.OPEN, U.OPEN)
+    ref, got = o.state(neighbours=True), g.state(U.FIELDS_STATE + U.FIELDS_NN)
+    hard, _ = U.neighbour_sets_equal(got, ref)
+    assert hard == 0
+    assert U.rel_err(got["h"], ref["h"]) <= TOL
+
+
+def _step_case(ic, steps, check_every=1, tol_first=TOL, tol_traj=1e-9, **cfg):
+    po, pg = U.params_pair(**cfg)
+    o = orc.Oracle(po, ic["pos"], ic.get("vel"), ic.get("e"), None, ic["id"])
+    g = L.Handle(pg, ic["pos"], ic.get("vel"), ic.get("e"), None, ic["id"])
+    done = 0
+    while done < steps:
+        k = min(check_every, steps - done)
+        o.step(k)
+        g.step(k)
+        done += k
+        ref = o.state(neighbours=True)
+        got = g.state(U.FIELDS_STATE)
+        assert g.current_step == o.current_step == done
+        tol = tol_first if done == 1 else tol_traj
+        asc, esc = U.force_scales(ref, po)
+        L_ = max(1.0, float(np.abs(ref["pos"]).max()))
+        assert np.abs(got["pos"] - ref["pos"]).max() <= tol * L_, f"pos step {done}"
+        assert U.rel_err(got["h"], ref["h"]) <= tol, f"h step {done}"
+        assert U.rel_err(got["rho"], ref["rho"]) <= tol, f"rho step {done}"
+        assert U.rel_err(got["c"], ref["c"]) <= tol, f"c step {done}"
+        assert U.rel_err(got["vdot"], ref["vdot"], asc) <= tol, f"vdot step {done}"
+        assert U.rel_err(got["edot"], ref["edot"], esc) <= tol, f"edot step {done}"
+        vs = np.abs(ref["vel"]).max() + asc.max() * 2 * po.dt_half
+        assert np.abs(got["vel"] - ref["vel"]).max() <= tol * vs, f"vel step {done}"
+        assert U.rel_err(got["e"], ref["e"], esc * 2 * po.dt_half) <= tol, f"e step {done}"
+        assert abs(g.reduce(L.SUM_E) - o.total_energy()) <= 1e-12 * abs(o.total_energy())
+        assert abs(g.reduce(L.SUM_RHO) - o.total_density()) <= 1e-12 * abs(o.total_density())
+    g.close(); o.close()
+
+
+def test_c2_default_simulation_steps():
+    """sim.MakeSimulation(): 1000 U([0,1]^2), MakeConfig defaults, open boundaries (sph.go:23-30)."""
+    _step_case(gen.spawn([(1000, (0, 0), (1, 1))]), steps=10)
+
+
+def test_c2_example_config_steps():
+    """generated example.sph-config (config-parser.go:872-924): Wendland, periodic x, gravity, floor."""
+    ic = gen.spawn([(260, (0.2, 0.3), (0.8, 0.4)), (700, (0.2, 0.6), (0.8, 0.99))])
+    _step_case(ic, steps=8, gamma=4.666, particle_mass=1e6, accel=(0.0, 0.55), dt_half=0.00324, kernel=2,
+               hor=(0.2, 0.8), ver=(-100.0, 100.0), refl=(L.OPEN_LO, L.OPEN_HI, L.OPEN_LO, 0.99))
+
+
+def test_c2_tube_config_steps():
+    """generated tube.sph-config (config-parser.go:926-973): reflections L, U, D."""
+    ic = gen.spawn([(4000, (0.2, 0.25), (0.5, 0.5)), (700, (0.5, 0.25), (0.8, 0.5))])
+    _step_case(ic, steps=6, particle_mass=1e5, accel=(0.0, 0.05), dt_half=0.00424, kernel=2,
+               refl=(0.2, L.OPEN_HI, 0.25, 0.5))
+
+
+def test_speed_test_shape_small():
+    """examples/speed-test shape at reduced N: open box, g = (0, 0.2) (speed-test.go:22-30)."""
+    ic = gen.spawn([(20000, (0, 0), (1, 1))])
+    _step_case(ic, steps=3, accel=(0.0, 0.2), dt_half=0.002)
+
+
+def test_periodic_box_steps_with_wrap():
+    """C3 shape at reduced N: periodic [0,1]^2, jittered lattice, moving so that particles wrap."""
+    pos = gen.jittered_lattice(128, 128)
+    n = len(pos)
+    vel = np.tile(np.array([[3.0, -2.0]]), (n, 1))
+    ic = dict(pos=pos, vel=vel, e=np.full(n, 0.01), id=np.arange(n, dtype=np.int64))
+    _step_case(ic, steps=5, hor=(0.0, 1.0), ver=(0.0, 1.0), accel=(0.0, 0.2), dt_half=0.001)
+
+
+def test_errors_and_edge_cases():
+    po, pg = U.params_pair()
+    with pytest.raises(L.SphbError) as ei:  # half-open axis panics in the reference (nearest-neighbour.go:44)
+        L.Handle(L.make_params(hor=(L.OPEN_LO, 1.0)), np.random.rand(100, 2))
+    assert ei.value.code == L.E_INVALID
+    g = L.Handle(pg, np.random.default_rng(0).random((20, 2)))
+    with pytest.raises(L.SphbError) as ei:  # fewer than 32 candidates
+        g.knn(U.OPEN, U.OPEN)
+    assert ei.value.code == L.E_KNN_UNDERFULL
+    g.close()
+    g = L.Handle(L.make_params(kernel=0), np.random.default_rng(0).random((200, 2)))
+    with pytest.raises(L.SphbError) as ei:  # TopHat2D.DF panics (sph.go:251)
+        g.step(1)
+    assert ei.value.code == L.E_KERNEL
+    with pytest.raises(L.SphbError) as ei:
+        g.density(1)
+    assert ei.value.code == L.E_STATE
+    g.close()
+    # empty simulation: Step panics "Simulation not initialized" (sph.go:92-94)
+    g = L.Handle(pg, np.zeros((0, 2)), capacity=64)
+    with pytest.raises(L.SphbError):
+        g.step(1)
+    g.close()
+
+
+def test_tiny_periodic_box_multi_image():
+    """N = 40 in a periodic box: the 3x3 images supply neighbours, one particle can appear via two images."""
+    ic = gen.spawn([(40, (0, 0), (1, 1))], seed=5)
+    po, pg = U.params_pair(hor=(0.0, 1.0), ver=(0.0, 1.0))
+    o = orc.Oracle(po, ic["pos"], ids=ic["id"])
+    o.knn((0.0, 1.0), (0.0, 1.0), mode=1)
+    g = L.Handle(pg, ic["pos"], ids=ic["id"])
+    g.knn((0.0, 1.0), (0.0, 1.0))
+    ref, got = o.state(neighbours=True), g.state(U.FIELDS_STATE + U.FIELDS_NN)
+    assert U.rel_err(got["h"], ref["h"]) <= TOL
+    assert U.rel_err(got["nn_dist"], ref["nn_dist"]) <= TOL
+    assert (np.sort(got["nn_id"], 1) == np.sort(ref["nn_id"], 1)).all()
