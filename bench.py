@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py — particle-updates/s of the full SPH step (sort, kNN k=32, density, force, leapfrog) on B200.
+
+Contract (driver):  python bench.py --gpus N --steps K --warmup W [--impl reference]
+prints ONE JSON line on rank 0.  A "step" is one (*Simulation).Step() (reference sim/sph.go:64-198) over
+all particles.  Workload (see DESIGN.md "Measurement"): weak scaling, 2^25 jittered-lattice particles per
+GPU in a periodic box (BASELINE.json configs[4]: 256 M on 8 GPUs = 32 M per GPU), fp64.  --workload c3
+selects the 2^20-particle single-GPU box (configs[2]).
+
+value   : device-resident state, CUDA events around K asynchronous sphb_step calls (max over ranks)
+e2e     : the same K steps through the C ABI with HOST buffers: per step upload of the persistent state from
+          pinned memory, sphb_step, download of the results
+roofline: whole step as the dominant "kernel" chain, algorithmic bytes 652 B/particle, plus
+          per-phase fractions from the library's CUDA-event phase timers
+cpu_baseline / --impl reference: the CPU restatement of the reference Go path (oracle/, 1 core: package
+          sim is serial) on a bounded sample of the same lattice.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_ALG = {"keys": 40, "sort": 16, "reorder": 148, "knn": 176, "force": 272}  # fp64 bytes / particle, SURVEY §8d
+B_ALG_TOTAL = 652
+METRIC = "particle-updates/s per SPH step (k=32)"
+UNIT = "particle-updates/s"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def workload(name: str, n_gpus: int):
+    """(nx, ny, box, physics kwargs, description): an nx x ny jittered lattice filling the periodic box
+    [0, box[0]] x [0, box[1]].  Lattice spacing fixes h, so dt scales with it."""
+    phys = dict(accel=(0.0, 0.2), gamma=1.66666, particle_mass=1.0, kernel=1)
+    if name == "c3":
+        nx = ny = 1024
+        box = (1.0, 1.0)
+        phys["dt_half"] = 0.001
+        desc = "C3-P: 2^20 jittered-lattice particles, periodic [0,1]^2, Monaghan, g=(0,0.2), fp64"
+    elif name == "c5":
+        # weak scaling at C5's lattice spacing 2^-14: 2^25 sites per GPU; 8 GPUs = the 16384^2 box of configs[4]
+        nx, ny = {1: (8192, 4096), 2: (8192, 8192), 4: (16384, 8192), 8: (16384, 16384)}[n_gpus]
+        box = (nx / 16384.0, ny / 16384.0)
+        phys["dt_half"] = 6e-5
+        desc = (f"C5 share (BASELINE configs[4]): 2^25 jittered-lattice particles per GPU x {n_gpus} GPU(s) = {nx}x{ny} "
+                f"sites at spacing 2^-14, periodic box {box[0]}x{box[1]}, Monaghan, g=(0,0.2), fp64")
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    return nx, ny, box, phys, desc
+
+
+class ClockSampler:
+    """nvidia-smi clocks during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=3)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(steps=2, nx=512):
+    """Reference CPU path (oracle port of the Go code, faithful tree-walk mode) on a bounded sample: a
+    (nx x nx)-site periodic jittered lattice of the same kind, 1 thread (package sim is serial)."""
+    from oracle import oracle as orc
+    from sphugo_b200 import gen
+    pos = gen.jittered_lattice(nx, nx)
+    n = len(pos)
+    dt = 0.001 * (1024.0 / nx)
+    po = orc.make_params(hor=(0.0, 1.0), ver=(0.0, 1.0), accel=(0.0, 0.2), dt_half=dt)
+    o = orc.Oracle(po, pos, None, np.full(n, 0.01))
+    o.step(1)  # step 0 evaluates the forces twice (sph.go:89-103): excluded like in the GPU timing
+    t0 = time.perf_counter()
+    o.step(steps)
+    dt_s = time.perf_counter() - t0
+    o.close()
+    return n * steps / dt_s, n, dt_s / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nx, ny, box, phys, desc = workload(args.workload, args.gpus)
+    t_all = time.perf_counter()
+    sample_nx = 512 if args.steps * 4 <= 80 else 256
+    # K steps of the bounded sample after W warm-up steps (W capped: each costs seconds of CPU)
+    from oracle import oracle as orc
+    from sphugo_b200 import gen
+    pos = gen.jittered_lattice(sample_nx, sample_nx)
+    n_s = len(pos)
+    po = orc.make_params(hor=(0.0, 1.0), ver=(0.0, 1.0), accel=phys["accel"], dt_half=0.001 * 1024.0 / sample_nx)
+    o = orc.Oracle(po, pos, None, np.full(n_s, 0.01))
+    o.step(1 + min(args.warmup, 1))
+    K = max(1, min(args.steps, 8))
+    t0 = time.perf_counter()
+    o.step(K)
+    el = time.perf_counter() - t0
+    o.close()
+    v = n_s * K / el
+    line = {
+        "metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": K,
+        "warmup": 1 + min(args.warmup, 1), "ms_per_step": el / K * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "sample": f"{sample_nx}x{sample_nx} periodic jittered lattice ({n_s} particles) of the same kind"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": f"{K} Step() calls on {n_s} particles; C restatement of the serial Go path "
+                                   "(Go toolchain absent; package sim starts no goroutines so GOMAXPROCS is irrelevant)"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t_all,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def make_ic(nx, ny, box, rank, world):
+    """this rank's x-slab (equal site count) of the global nx x ny jittered lattice on [0,box]"""
+    from sphugo_b200 import gen
+    cols = nx // world
+    sx = box[0] / nx
+    x0 = rank * cols * sx
+    pos = gen.jittered_lattice(cols, ny, (x0, 0.0), (x0 + cols * sx, box[1]), 0.25, seed=gen.DEFAULT_SEED + rank)
+    return pos, (x0, x0 + cols * sx)
+
+
+def run_ours(args):
+    import torch
+    from sphugo_b200 import _lib as L
+    from sphugo_b200 import build as B
+    B.build()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libsphb has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    nx, ny, box, phys, desc = workload(args.workload, world)
+    if world > 1:
+        from sphugo_b200 import slab
+        return slab.bench(args, nx, ny, box, phys, desc, rank, world, local)
+
+    pos, _ = make_ic(nx, ny, box, 0, 1)
+    n = len(pos)
+    prm = L.make_params(hor=(0.0, box[0]), ver=(0.0, box[1]), device=local, **phys)
+    e0 = np.full(n, 0.01)
+    g = L.Handle(prm, pos, None, e0)
+    del pos
+    K, W = args.steps, max(args.warmup, 3)
+    g.step(1 + W)  # step 0 (double force evaluation) + W warm-up steps, untimed
+    g.sync()
+    c0 = g.counters()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ext = torch.cuda.ExternalStream(g.stream, device=torch.device("cuda", local))
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ev0.record(ext)          # CUDA events on the stream the kernels are launched on
+    g.step(K)                # asynchronous: enqueues K full steps
+    ev1.record(ext)
+    g.sync()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    dev_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    c1 = g.counters()
+    ms_per_step = dev_ms / K
+    # per-phase split from the library's CUDA-event phase timers (separate, untimed steps)
+    phase_acc = {k: 0.0 for k in L.PHASES}
+    KP = min(K, 5)
+    for _ in range(KP):
+        g.step(1)
+        pt = g.phase_times()
+        for k in L.PHASES:
+            phase_acc[k] += pt[k]
+    value = n * K / (dev_ms * 1e-3)
+    peak, peak_src = measured_peak()
+    achieved = n * B_ALG_TOTAL / (ms_per_step * 1e-3) / 1e9
+    phases = {}
+    for k in ("keys", "sort", "reorder", "knn", "force"):
+        ms = phase_acc[k] / KP
+        gbs = n * B_ALG[k] / (ms * 1e-3) / 1e9 if ms > 0 else None
+        phases[k] = {"ms": ms, "alg_GBps": gbs, "frac": gbs / peak if gbs else None}
+    dom = max(("keys", "sort", "reorder", "knn", "force"), key=lambda k: phase_acc[k])
+
+    # ---- e2e: host buffers through the C ABI, every step: upload state, step, download results
+    import ctypes as C
+    up_fields = ["pos", "vel", "e", "vdot", "edot"]
+    down_fields = ["pos", "vel", "e", "vdot", "edot", "rho", "h", "id"]
+    host = {}
+    for f in set(up_fields + down_fields):
+        shp, dt = L.FIELD_SHAPE[f]
+        t = torch.empty((n,) + shp, dtype=torch.float64 if dt == np.float64 else torch.int64).pin_memory()
+        host[f] = t.numpy()
+    g.download(down_fields, out=host)
+    h2d = sum(host[f].nbytes for f in up_fields)
+    d2h = sum(host[f].nbytes for f in down_fields)
+    Ke = max(3, min(K, 10))
+    for _ in range(2):
+        g.upload(**{f: host[f] for f in up_fields}); g.step(1); g.download(down_fields, out=host)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        g.upload(**{f: host[f] for f in up_fields})
+        g.step(1)
+        g.download(down_fields, out=host)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e_val = n * Ke / e2e_s
+    g.close()
+
+    cb_v, cb_n, cb_s = cpu_baseline(steps=2, nx=512) if not args.no_cpu else (None, 0, 0)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "particles": n, "l2": "state (>= 280 B/particle) exceeds the 126 MB L2; no flush needed",
+                   "timing": "CUDA events on the library stream around K asynchronous steps", "wall_ms_per_step": wall / K * 1e3},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "kernel": "whole step (5 phases); dominant phase: " + dom,
+                     "alg_bytes_per_particle": B_ALG_TOTAL, "phases": phases},
+        "cpu_baseline": None if cb_v is None else {
+            "value": cb_v, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"2 Step() calls on a {cb_n}-particle periodic jittered lattice ({cb_s:.2f} s/step); C restatement of the serial Go path"},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
+                "what": "sphb_upload(pos,vel,e,vdot,edot) + sphb_step(1) + sphb_download(pos,vel,e,vdot,edot,rho,h,id), pinned host buffers"},
+        "gpu_launches": c1["kernel_launches"] - c0["kernel_launches"],
+        "knn_fallback_particles": c1["knn_fallback"] - c0["knn_fallback"],
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c5", choices=["c3", "c5"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

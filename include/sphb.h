@@ -147,6 +147,9 @@ int sphb_knn(sphb_sim* s, const double hor[2], const double ver[2]);
 /* batch == for all i: Particles[i].Rho = Density2D(p, sim, kernel) (sph.go:306-323); needs a prior knn */
 int sphb_density(sphb_sim* s, int32_t kernel);
 
+/* the CUDA stream (cudaStream_t) every kernel of this handle is enqueued on: lets a caller record its own
+ * CUDA events around asynchronous sphb_step calls or order its own work (NCCL exchange) after them */
+void* sphb_stream(sphb_sim* s);
 int sphb_sync(sphb_sim* s); /* wait for the device; surfaces asynchronous errors (kNN underfull, ...) */
 
 /* copy the selected fields into caller-owned host buffers (each sized for `capacity` particles);

@@ -35,7 +35,7 @@ HALO_RECORD_DOUBLES, MIGRANT_RECORD_DOUBLES = 6, 10
 
 EXPORTS = [
     "sphb_create", "sphb_destroy", "sphb_last_error", "sphb_set_params", "sphb_get_params", "sphb_count",
-    "sphb_current_step", "sphb_append", "sphb_step", "sphb_calc_forces", "sphb_knn", "sphb_density", "sphb_sync",
+    "sphb_current_step", "sphb_append", "sphb_step", "sphb_calc_forces", "sphb_knn", "sphb_density", "sphb_stream", "sphb_sync",
     "sphb_download", "sphb_upload", "sphb_reduce", "sphb_phase_times", "sphb_counters", "sphb_create_device",
     "sphb_slab_set", "sphb_max_h", "sphb_slab_step_begin", "sphb_slab_pack_halo", "sphb_slab_add_ghosts",
     "sphb_slab_step_end", "sphb_slab_pack_migrants", "sphb_slab_add_migrants",
@@ -103,6 +103,8 @@ def lib():
     L.sphb_knn.argtypes = [vp, dp, dp]
     L.sphb_density.restype = C.c_int
     L.sphb_density.argtypes = [vp, C.c_int32]
+    L.sphb_stream.restype = C.c_void_p
+    L.sphb_stream.argtypes = [vp]
     L.sphb_sync.restype = C.c_int
     L.sphb_sync.argtypes = [vp]
     L.sphb_download.restype = C.c_int
@@ -236,6 +238,11 @@ class Handle:
 
     def density(self, kernel):
         self._chk(lib().sphb_density(self._h, kernel))
+
+    @property
+    def stream(self):
+        """cudaStream_t of the handle as an int (torch.cuda.ExternalStream(handle.stream))"""
+        return int(lib().sphb_stream(self._h) or 0)
 
     def sync(self):
         self._chk(lib().sphb_sync(self._h))

@@ -44,8 +44,9 @@ struct sphb_sim {
   Soa a, b;             // a = current
   double2* spos = nullptr;
   double* hguess = nullptr;
-  uint32_t *keys[2] = {nullptr, nullptr}, *vals[2] = {nullptr, nullptr};
-  uint32_t* hist = nullptr;
+  uint32_t *keys = nullptr, *keysSorted = nullptr, *rank = nullptr, *perm = nullptr;
+  uint32_t *cellCount = nullptr, *tileSum = nullptr;
+  int ntiles_cap = 0;
   uint32_t* cellStart = nullptr;
   uint32_t* nn = nullptr;
   int* failList = nullptr;
@@ -57,8 +58,6 @@ struct sphb_sim {
   void* scratch = nullptr;    // download / upload staging
   size_t scratchBytes = 0;
   int ncell_max = 0;
-  int sort_passes = 0;
-  int nblk_sort_cap = 0;
   bool stats_dirty = true;
   bool have_list = false;     // nn/spos/grid describe the current particle order
   double knn_hor[2] = {0, 0}, knn_ver[2] = {0, 0};
@@ -190,7 +189,7 @@ int refresh_stats(sphb_sim* s) {
   const int ntot = (int)(s->n + s->nghost);
   const int nb = ntot > 0 ? std::min(STAT_BLOCKS, cdiv(ntot, 256)) : 1;
   k_stats_partial<<<nb, 256, 0, s->st>>>(s->a.pos, s->a.pc, s->a.e, (int)s->n, s->statPart);
-  k_stats_final<<<1, 32, 0, s->st>>>(s->statPart, nb, s->stats);
+  k_stats_final<<<1, 32 * STAT_N, 0, s->st>>>(s->statPart, nb, s->stats);
   s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 2;
   CKL(s);
   s->stats_dirty = false;
@@ -207,10 +206,10 @@ void launch_knn(sphb_sim* s, int ntot, const PhysP& ph) {
     cudaFuncSetAttribute(k_knn_fast<KERNEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_done[KERNEL] = true;
   }
-  k_knn_fast<KERNEL><<<cdiv(tiles, KNN_WARPS), KNN_THREADS, smem, s->st>>>(s->spos, s->keys[s->sort_passes & 1],
+  k_knn_fast<KERNEL><<<cdiv(tiles, KNN_WARPS), KNN_THREADS, smem, s->st>>>(s->spos, s->keysSorted,
                                                                          s->cellStart, s->hguess, s->a.epred, ntot,
                                                                          s->grid, ph, s->ktune, out);
-  k_knn_fallback<KERNEL><<<148 * 4, 128, 0, s->st>>>(s->spos, s->keys[s->sort_passes & 1], s->cellStart, s->hguess,
+  k_knn_fallback<KERNEL><<<148 * 4, 128, 0, s->st>>>(s->spos, s->keysSorted, s->cellStart, s->hguess,
                                                    s->a.epred, ntot, s->grid, ph, out, s->dflags);
 }
 
@@ -231,29 +230,22 @@ int build_neighbours(sphb_sim* s, int mode, const double hor[2], const double ve
   if (timed) cudaEventRecord(s->ev[SPHB_PH_KEYS], s->st);
   k_make_grid<<<1, 32, 0, s->st>>>(s->stats, ntot, hor[0], hor[1], ver[0], ver[1], s->slab.x_lo - s->slab_w,
                                    s->slab.x_hi + s->slab_w, s->slab_on ? 1 : 0, s->gtune, s->grid);
-  if (mode == MODE_DRIFT) k_keys<true><<<cdiv(ntot, 256), 256, 0, s->st>>>(s->a.pos, s->a.vel, ntot, s->grid, dtH, s->keys[0]);
-  else k_keys<false><<<cdiv(ntot, 256), 256, 0, s->st>>>(s->a.pos, s->a.vel, ntot, s->grid, dtH, s->keys[0]);
-  s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 2;
+  if (mode == MODE_DRIFT) k_keys<true><<<cdiv(ntot, 256), 256, 0, s->st>>>(s->a.pos, s->a.vel, ntot, s->grid, dtH, s->keys, s->rank, s->cellCount);
+  else k_keys<false><<<cdiv(ntot, 256), 256, 0, s->st>>>(s->a.pos, s->a.vel, ntot, s->grid, dtH, s->keys, s->rank, s->cellCount);
   if (timed) cudaEventRecord(s->ev[SPHB_PH_SORT], s->st);
-  const int nblk = cdiv(ntot, RS_TILE);
-  for (int p = 0; p < s->sort_passes; ++p) {
-    const int in = p & 1, out = in ^ 1, shift = 8 * p;
-    k_rs_hist<<<nblk, RS_THREADS, 0, s->st>>>(s->keys[in], ntot, shift, s->hist, nblk);
-    k_excl_scan<<<1, 1024, 0, s->st>>>(s->hist, RS_BINS * nblk);
-    if (p == 0)
-      k_rs_scatter<true><<<nblk, RS_THREADS, 0, s->st>>>(s->keys[in], s->vals[in], s->keys[out], s->vals[out], ntot, shift, s->hist, nblk);
-    else
-      k_rs_scatter<false><<<nblk, RS_THREADS, 0, s->st>>>(s->keys[in], s->vals[in], s->keys[out], s->vals[out], ntot, shift, s->hist, nblk);
-    s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 3;
-  }
-  const int fin = s->sort_passes & 1;
+  // counting sort: scan of the cell counts, then the permutation
+  k_scan_tiles<<<s->ntiles_cap, SC_THREADS, 0, s->st>>>(s->cellCount, s->grid, s->tileSum);
+  k_excl_scan<<<1, 1024, 0, s->st>>>(s->tileSum, s->ntiles_cap, s->grid);
+  k_scan_apply<<<s->ntiles_cap, SC_THREADS, 0, s->st>>>(s->cellCount, s->grid, s->tileSum, s->cellStart);
+  k_scatter_perm<<<cdiv(ntot, 256), 256, 0, s->st>>>(s->keys, s->rank, s->cellStart, ntot, s->perm);
+  s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 6;
   if (timed) cudaEventRecord(s->ev[SPHB_PH_REORDER], s->st);
   StateIn in{s->a.pos, s->a.vel, s->a.vdot, s->a.vpred, s->a.e, s->a.edot, s->a.epred, s->a.id, s->a.pc, s->a.ghost};
   StateOut out{s->b.pos, s->b.vel, s->b.vdot, s->b.vpred, s->b.e, s->b.edot, s->b.epred, s->b.id, s->b.pc, s->b.ghost, s->spos, s->hguess};
   const int rb = cdiv(ntot, 256);
-  if (mode == MODE_DRIFT) k_reorder<2><<<rb, 256, 0, s->st>>>(in, out, s->keys[fin], s->vals[fin], ntot, s->grid, dtH, s->cellStart);
-  else if (mode == MODE_INIT) k_reorder<1><<<rb, 256, 0, s->st>>>(in, out, s->keys[fin], s->vals[fin], ntot, s->grid, dtH, s->cellStart);
-  else k_reorder<0><<<rb, 256, 0, s->st>>>(in, out, s->keys[fin], s->vals[fin], ntot, s->grid, dtH, s->cellStart);
+  if (mode == MODE_DRIFT) k_reorder<2><<<rb, 256, 0, s->st>>>(in, out, s->keys, s->perm, ntot, s->grid, dtH, s->cellStart, s->keysSorted);
+  else if (mode == MODE_INIT) k_reorder<1><<<rb, 256, 0, s->st>>>(in, out, s->keys, s->perm, ntot, s->grid, dtH, s->cellStart, s->keysSorted);
+  else k_reorder<0><<<rb, 256, 0, s->st>>>(in, out, s->keys, s->perm, ntot, s->grid, dtH, s->cellStart, s->keysSorted);
   std::swap(s->a, s->b);
   cudaMemsetAsync(s->failCount, 0, sizeof(int), s->st);
   if (timed) cudaEventRecord(s->ev[SPHB_PH_KNN], s->st);
@@ -364,16 +356,15 @@ int create_common(const sphb_params* p, int64_t n, int64_t capacity, const doubl
   CKC(alloc_soa(s->b, cap));
   CKC(dalloc(s->spos, cap));
   CKC(dalloc(s->hguess, cap));
-  for (int k = 0; k < 2; ++k) { CKC(dalloc(s->keys[k], cap)); CKC(dalloc(s->vals[k], cap)); }
-  s->nblk_sort_cap = cdiv(capacity, RS_TILE);
-  CKC(dalloc(s->hist, (size_t)RS_BINS * s->nblk_sort_cap));
+  CKC(dalloc(s->keys, cap)); CKC(dalloc(s->keysSorted, cap)); CKC(dalloc(s->rank, cap)); CKC(dalloc(s->perm, cap));
   // cell table: about 2 particles per cell at most; the radix sort covers ceil(log2(ncell)/8) digits
   int64_t ncm = std::max<int64_t>(64, std::min<int64_t>(capacity / 2 + 1, (int64_t)1 << 30));
   s->ncell_max = (int)ncm;
-  int bits = 1;
-  while (((int64_t)1 << bits) < ncm) ++bits;
-  s->sort_passes = (bits + 7) / 8;
-  CKC(dalloc(s->cellStart, (size_t)ncm + 2));
+  s->ntiles_cap = cdiv(ncm + 1, SC_TILE);
+  CKC(dalloc(s->cellStart, (size_t)s->ntiles_cap * SC_TILE + 8));
+  CKC(dalloc(s->cellCount, (size_t)s->ntiles_cap * SC_TILE + 8));
+  CKC(dalloc(s->tileSum, (size_t)s->ntiles_cap));
+  CKC(cudaMemsetAsync(s->cellCount, 0, ((size_t)s->ntiles_cap * SC_TILE + 8) * sizeof(uint32_t), s->st));
   CKC(dalloc(s->nn, cap32 * SPHB_K));
   CKC(dalloc(s->failList, cap));
   CKC(dalloc(s->failCount, 2));
@@ -428,8 +419,8 @@ void sphb_destroy(sphb_sim* s) {
   if (s->st) cudaStreamSynchronize(s->st);
   free_soa(s->a); free_soa(s->b);
   cudaFree(s->spos); cudaFree(s->hguess);
-  for (int k = 0; k < 2; ++k) { cudaFree(s->keys[k]); cudaFree(s->vals[k]); }
-  cudaFree(s->hist); cudaFree(s->cellStart); cudaFree(s->nn); cudaFree(s->failList); cudaFree(s->failCount);
+  cudaFree(s->keys); cudaFree(s->keysSorted); cudaFree(s->rank); cudaFree(s->perm);
+  cudaFree(s->cellCount); cudaFree(s->tileSum); cudaFree(s->cellStart); cudaFree(s->nn); cudaFree(s->failList); cudaFree(s->failCount);
   cudaFree(s->dflags); cudaFree(s->statPart); cudaFree(s->stats); cudaFree(s->grid); cudaFree(s->scratch);
   for (auto& ev : s->ev) if (ev) cudaEventDestroy(ev);
   if (s->st) cudaStreamDestroy(s->st);
@@ -517,6 +508,8 @@ int sphb_density(sphb_sim* s, int32_t kernel) {
   s->stats_dirty = true;
   return SPHB_OK;
 }
+
+void* sphb_stream(sphb_sim* s) { return s ? (void*)s->st : nullptr; }
 
 int sphb_sync(sphb_sim* s) {
   int rc = enter(s); if (rc) return rc;

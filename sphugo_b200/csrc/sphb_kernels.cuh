@@ -97,11 +97,14 @@ __device__ __forceinline__ double kern_DF(double q) {
 }
 
 // -------------------------------------------------------------------------------------------------
-// K1: (optional drift-1) + cell key.  Reads pos, vel; writes key, val=index.
+// K1: (optional drift-1) + cell key + per-cell count.  Reads pos, vel; writes key, rank-in-cell.
+// The rank returned by the atomic is arbitrary among the particles of one cell; K2 re-ranks each cell by
+// the previous index so that the final order (and every later summation order) is deterministic.
 // -------------------------------------------------------------------------------------------------
 template <bool DRIFT>
 __global__ void __launch_bounds__(256) k_keys(const double2* __restrict__ pos, const double2* __restrict__ vel, int n,
-                                             const GridP* __restrict__ gp, double dtH, uint32_t* __restrict__ keys) {
+                                             const GridP* __restrict__ gp, double dtH, uint32_t* __restrict__ keys,
+                                             uint32_t* __restrict__ rank, uint32_t* __restrict__ cellCount) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const GridP g = *gp;
@@ -115,44 +118,68 @@ __global__ void __launch_bounds__(256) k_keys(const double2* __restrict__ pos, c
   double ys = g.wrapy ? wrap_coord(p.y, g.loy, g.Ly) : p.y;
   int cx = cell_of(xs, g.ox, g.inv_dx, g.ncx);
   int cy = cell_of(ys, g.oy, g.inv_dy, g.ncy);
-  keys[i] = (uint32_t)cy * (uint32_t)g.ncx + (uint32_t)cx;
+  const uint32_t k = (uint32_t)cy * (uint32_t)g.ncx + (uint32_t)cx;
+  keys[i] = k;
+  rank[i] = atomicAdd(&cellCount[k], 1u);
 }
 
 // -------------------------------------------------------------------------------------------------
-// SORT: stable LSD radix sort, 8-bit digits, three kernels per pass (histogram / scan / scatter).
-// No look-back spinning: a hung sort would hang the step.
+// SORT: counting sort by cell (replaces Treebuild, core.go:172-224).  Exclusive scan of the cell counts in
+// three small kernels (tile sums, scan of the tile sums, tile scan + offset); no look-back spinning.
+// cellStart[c] = first sorted index of cell c, for c in [0, ncell]; the counts are zeroed for the next step.
 // -------------------------------------------------------------------------------------------------
-#define RS_THREADS 256
-#define RS_WARPS 8
-#define RS_ITEMS 16
-#define RS_TILE (RS_THREADS * RS_ITEMS)  // 4096 keys per block
-#define RS_BINS 256
+#define SC_THREADS 256
+#define SC_ITEMS 8
+#define SC_TILE (SC_THREADS * SC_ITEMS)  // 2048 cells per block
 
-__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint32_t* __restrict__ keys, int n, int shift,
-                                                        uint32_t* __restrict__ hist, int nblk) {
-  __shared__ uint32_t h[RS_BINS];
-  h[threadIdx.x] = 0;
-  __syncthreads();
-  int base = blockIdx.x * RS_TILE;
+__device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* wsum, uint32_t& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t x = v;
 #pragma unroll
-  for (int k = 0; k < RS_ITEMS; ++k) {
-    int idx = base + k * RS_THREADS + threadIdx.x;
-    bool valid = idx < n;
-    uint32_t d = valid ? ((keys[idx] >> shift) & 255u) : (256u + (threadIdx.x & 31));
-    uint32_t peers = __match_any_sync(0xffffffffu, d);
-    if (valid && (__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&h[d], __popc(peers));
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
   }
+  if (lane == 31) wsum[warp] = x;
   __syncthreads();
-  hist[threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];
+  uint32_t pre = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < SC_THREADS / 32; ++w) {
+    const uint32_t t = wsum[w];
+    if (w < warp) pre += t;
+    tot += t;
+  }
+  total = tot;
+  __syncthreads();
+  return pre + x - v;
 }
 
-// exclusive scan of m uint32 in place, one block of 1024 threads (m <= a few million)
-__global__ void __launch_bounds__(1024) k_excl_scan(uint32_t* __restrict__ a, int m) {
+__global__ void __launch_bounds__(SC_THREADS) k_scan_tiles(const uint32_t* __restrict__ cnt, const GridP* __restrict__ gp,
+                                                          uint32_t* __restrict__ tileSum) {
+  __shared__ uint32_t wsum[SC_THREADS / 32];
+  const int m = gp->ncx * gp->ncy + 1;
+  const int base = blockIdx.x * SC_TILE;
+  if (base >= m) { if (threadIdx.x == 0) tileSum[blockIdx.x] = 0; return; }
+  uint32_t sum = 0;
+  const uint4* c4 = reinterpret_cast<const uint4*>(cnt + base) + threadIdx.x * 2;
+  if (base + SC_TILE <= m) {
+    const uint4 a = c4[0], b = c4[1];
+    sum = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
+  } else {
+    for (int k = 0; k < SC_ITEMS; ++k) { const int c = base + threadIdx.x * SC_ITEMS + k; if (c < m) sum += cnt[c]; }
+  }
+  uint32_t tot;
+  block_excl_scan_256(sum, wsum, tot);
+  if (threadIdx.x == 0) tileSum[blockIdx.x] = tot;
+}
+
+// exclusive scan of m uint32 in place, one block of 1024 threads (m = number of tiles, <= a few hundred thousand)
+__global__ void __launch_bounds__(1024) k_excl_scan(uint32_t* __restrict__ a, int m_cap, const GridP* __restrict__ gp) {
   __shared__ uint32_t wsum[32];
-  __shared__ uint32_t carry_s;
+  const int m = min(m_cap, (gp->ncx * gp->ncy + 1 + SC_TILE - 1) / SC_TILE);
   int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int per = (m + 1023) / 1024;
-  int b = tid * per, e = min(b + per, m);
+  int b = min(tid * per, m), e = min(b + per, m);
   uint32_t sum = 0;
   for (int i = b; i < e; ++i) sum += a[i];
   uint32_t x = sum;
@@ -172,7 +199,6 @@ __global__ void __launch_bounds__(1024) k_excl_scan(uint32_t* __restrict__ a, in
       if (lane >= o) xs += y;
     }
     wsum[lane] = xs - w;  // exclusive
-    if (lane == 31) carry_s = xs;
   }
   __syncthreads();
   uint32_t run = wsum[warp] + (x - sum);
@@ -183,55 +209,36 @@ __global__ void __launch_bounds__(1024) k_excl_scan(uint32_t* __restrict__ a, in
   }
 }
 
-template <bool FIRST>
-__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint32_t* __restrict__ keys_in,
-                                                           const uint32_t* __restrict__ vals_in,
-                                                           uint32_t* __restrict__ keys_out,
-                                                           uint32_t* __restrict__ vals_out, int n, int shift,
-                                                           const uint32_t* __restrict__ offs, int nblk) {
-  __shared__ uint32_t wcount[RS_WARPS][RS_BINS];
-  int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int k = tid; k < RS_WARPS * RS_BINS; k += RS_THREADS) (&wcount[0][0])[k] = 0;
-  __syncthreads();
+__global__ void __launch_bounds__(SC_THREADS) k_scan_apply(uint32_t* __restrict__ cnt, const GridP* __restrict__ gp,
+                                                          const uint32_t* __restrict__ tileOff,
+                                                          uint32_t* __restrict__ cellStart) {
+  __shared__ uint32_t wsum[SC_THREADS / 32];
+  const int m = gp->ncx * gp->ncy + 1;
+  const int base = blockIdx.x * SC_TILE;
+  if (base >= m) return;
+  uint32_t v[SC_ITEMS];
+  uint32_t sum = 0;
+  const int c0 = base + threadIdx.x * SC_ITEMS;
+#pragma unroll
+  for (int k = 0; k < SC_ITEMS; ++k) {
+    v[k] = (c0 + k < m) ? cnt[c0 + k] : 0u;
+    sum += v[k];
+  }
+  uint32_t tot;
+  uint32_t run = block_excl_scan_256(sum, wsum, tot) + tileOff[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < SC_ITEMS; ++k) {
+    if (c0 + k < m) { cellStart[c0 + k] = run; cnt[c0 + k] = 0u; }
+    run += v[k];
+  }
+}
 
-  // each warp owns a contiguous run of RS_ITEMS*32 keys, walked in order: stable ranking
-  int wbase = blockIdx.x * RS_TILE + warp * (RS_ITEMS * 32);
-  uint32_t key[RS_ITEMS], rank[RS_ITEMS];
-  const uint32_t lt = (1u << lane) - 1u;
-#pragma unroll
-  for (int r = 0; r < RS_ITEMS; ++r) {
-    int idx = wbase + r * 32 + lane;
-    bool valid = idx < n;
-    key[r] = valid ? keys_in[idx] : 0xffffffffu;
-    uint32_t d = valid ? ((key[r] >> shift) & 255u) : (256u + lane);
-    uint32_t peers = __match_any_sync(0xffffffffu, d);
-    uint32_t pre = valid ? wcount[warp][d] : 0u;
-    rank[r] = pre + __popc(peers & lt);
-    __syncwarp();
-    if (valid && (__ffs(peers) - 1) == lane) wcount[warp][d] = pre + __popc(peers);
-    __syncwarp();
-  }
-  __syncthreads();
-  {  // digit `tid`: exclusive prefix over the warps of this block on top of the global offset
-    uint32_t run = offs[tid * nblk + blockIdx.x];
-#pragma unroll
-    for (int w = 0; w < RS_WARPS; ++w) {
-      uint32_t t = wcount[w][tid];
-      wcount[w][tid] = run;
-      run += t;
-    }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int r = 0; r < RS_ITEMS; ++r) {
-    int idx = wbase + r * 32 + lane;
-    if (idx < n) {
-      uint32_t d = (key[r] >> shift) & 255u;
-      uint32_t dst = wcount[warp][d] + rank[r];
-      keys_out[dst] = key[r];
-      vals_out[dst] = FIRST ? (uint32_t)idx : vals_in[idx];
-    }
-  }
+__global__ void __launch_bounds__(256) k_scatter_perm(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ rank,
+                                                     const uint32_t* __restrict__ cellStart, int n,
+                                                     uint32_t* __restrict__ perm) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  perm[cellStart[keys[i]] + rank[i]] = (uint32_t)i;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -260,14 +267,22 @@ struct StateOut {
 template <int MODE>
 __global__ void __launch_bounds__(256) k_reorder(StateIn in, StateOut out, const uint32_t* __restrict__ keys,
                                                 const uint32_t* __restrict__ perm, int n, const GridP* __restrict__ gp, double dtH,
-                                                uint32_t* __restrict__ cellStart) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
+                                                const uint32_t* __restrict__ cellStart, uint32_t* __restrict__ keysSorted) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
   const GridP g = *gp;
-  const int ncell = g.ncx * g.ncy;
-  uint32_t i = perm[j];
+  const uint32_t i = perm[t];
+  const uint32_t c = keys[i];
+  // position inside the cell = number of members with a smaller previous index (deterministic order);
+  // cells crowded beyond 64 (clamped border cells of an open box) keep the arbitrary atomic order
+  const uint32_t s = cellStart[c], e = cellStart[c + 1];
+  uint32_t j = (uint32_t)t;
+  if (e - s <= 64u) {
+    j = s;
+    for (uint32_t u = s; u < e; ++u) j += (perm[u] < i) ? 1u : 0u;
+  }
   double2 p = in.pos[i], v = in.vel[i], a = in.vdot[i];
-  double e = in.e[i], ed = in.edot[i];
+  double e_ = in.e[i], ed = in.edot[i];
   double4 pc = in.pc[i];
   double2 vp;
   double ep;
@@ -276,10 +291,10 @@ __global__ void __launch_bounds__(256) k_reorder(StateIn in, StateOut out, const
     p.y = __dadd_rn(p.y, __dmul_rn(v.y, dtH));
     vp.x = __dadd_rn(v.x, __dmul_rn(a.x, dtH));
     vp.y = __dadd_rn(v.y, __dmul_rn(a.y, dtH));
-    ep = __dadd_rn(e, __dmul_rn(ed, dtH));
+    ep = __dadd_rn(e_, __dmul_rn(ed, dtH));
   } else if (MODE == 1) {
     vp = v;
-    ep = e;
+    ep = e_;
   } else {
     vp = in.vpred[i];
     ep = in.epred[i];
@@ -287,7 +302,7 @@ __global__ void __launch_bounds__(256) k_reorder(StateIn in, StateOut out, const
   out.pos[j] = p;
   out.vel[j] = v;
   out.vdot[j] = a;
-  out.e[j] = e;
+  out.e[j] = e_;
   out.edot[j] = ed;
   out.vpred[j] = vp;
   out.epred[j] = ep;
@@ -299,18 +314,7 @@ __global__ void __launch_bounds__(256) k_reorder(StateIn in, StateOut out, const
   sp.x = g.wrapx ? wrap_coord(p.x, g.lox, g.Lx) : p.x;
   sp.y = g.wrapy ? wrap_coord(p.y, g.loy, g.Ly) : p.y;
   out.spos[j] = sp;
-
-  // cell table from the sorted keys: cellStart[c] = first j with key >= c
-  uint32_t k = keys[j];
-  uint32_t kprev = (j == 0) ? 0u : keys[j - 1];
-  if (j == 0) {
-    for (uint32_t c = 0; c <= k; ++c) cellStart[c] = 0;
-  } else if (k != kprev) {
-    for (uint32_t c = kprev + 1; c <= k; ++c) cellStart[c] = (uint32_t)j;
-  }
-  if (j == n - 1) {
-    for (uint32_t c = k + 1; c <= (uint32_t)ncell; ++c) cellStart[c] = (uint32_t)n;
-  }
+  keysSorted[j] = c;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -748,12 +752,14 @@ __global__ void __launch_bounds__(256) k_stats_partial(const double2* __restrict
     part[blockIdx.x * STAT_N + threadIdx.x] = r;
   }
 }
-__global__ void k_stats_final(const double* __restrict__ part, int nblk, double* __restrict__ outv) {
-  const int k = threadIdx.x;
-  if (k >= STAT_N) return;
+__global__ void __launch_bounds__(32 * STAT_N) k_stats_final(const double* __restrict__ part, int nblk,
+                                                            double* __restrict__ outv) {
+  const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;  // one warp per statistic
   double r = stat_init(k);
-  for (int b = 0; b < nblk; ++b) r = stat_comb(k, r, part[b * STAT_N + k]);
-  outv[k] = r;
+  for (int b = lane; b < nblk; b += 32) r = stat_comb(k, r, part[b * STAT_N + k]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) r = stat_comb(k, r, __shfl_xor_sync(0xffffffffu, r, o));
+  if (lane == 0) outv[k] = r;
 }
 
 // -------------------------------------------------------------------------------------------------
