@@ -241,30 +241,34 @@ def run_ours(args):
         phases[k] = {"ms": ms, "alg_GBps": gbs, "frac": gbs / peak if gbs else None}
     dom = max(("keys", "sort", "reorder", "knn", "force"), key=lambda k: phase_acc[k])
 
-    # ---- e2e: host buffers through the C ABI, every step: upload state, step, download results
-    import ctypes as C
-    up_fields = ["pos", "vel", "e", "vdot", "edot"]
-    down_fields = ["pos", "vel", "e", "vdot", "edot", "rho", "h", "id"]
-    host = {}
-    for f in set(up_fields + down_fields):
-        shp, dt = L.FIELD_SHAPE[f]
-        t = torch.empty((n,) + shp, dtype=torch.float64 if dt == np.float64 else torch.int64).pin_memory()
-        host[f] = t.numpy()
-    g.download(down_fields, out=host)
-    h2d = sum(host[f].nbytes for f in up_fields)
-    d2h = sum(host[f].nbytes for f in down_fields)
-    Ke = max(3, min(K, 10))
-    for _ in range(2):
-        g.upload(**{f: host[f] for f in up_fields}); g.step(1); g.download(down_fields, out=host)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(Ke):
-        g.upload(**{f: host[f] for f in up_fields})
-        g.step(1)
+    h2d = d2h = 0
+    e2e_val, Ke = 0.0, 0
+    if not args.no_e2e:
+        # ---- e2e: host buffers through the C ABI, every step: upload state, step, download results
+        import ctypes as C
+        up_fields = ["pos", "vel", "e", "vdot", "edot"]
+        down_fields = ["pos", "vel", "e", "vdot", "edot", "rho", "h", "id"]
+        host = {}
+        for f in set(up_fields + down_fields):
+            shp, dt = L.FIELD_SHAPE[f]
+            t = torch.empty((n,) + shp, dtype=torch.float64 if dt == np.float64 else torch.int64).pin_memory()
+            host[f] = t.numpy()
         g.download(down_fields, out=host)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    e2e_val = n * Ke / e2e_s
+        h2d = sum(host[f].nbytes for f in up_fields)
+        d2h = sum(host[f].nbytes for f in down_fields)
+        Ke = max(3, min(K, 10))
+        for _ in range(2):
+            g.upload(**{f: host[f] for f in up_fields}); g.step(1); g.download(down_fields, out=host)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(Ke):
+            g.upload(**{f: host[f] for f in up_fields})
+            g.step(1)
+            g.download(down_fields, out=host)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        e2e_val = n * Ke / e2e_s
+
     g.close()
 
     cb_v, cb_n, cb_s = cpu_baseline(steps=2, nx=512) if not args.no_cpu else (None, 0, 0)
@@ -297,6 +301,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c5", choices=["c3", "c5"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (tuning sweeps only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

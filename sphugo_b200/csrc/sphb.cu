@@ -60,6 +60,7 @@ struct sphb_sim {
   int ncell_max = 0;
   bool stats_dirty = true;
   bool have_list = false;     // nn/spos/grid describe the current particle order
+  bool have_h = false;        // pc.z holds smoothing lengths of a previous evaluation (search radius guess)
   double knn_hor[2] = {0, 0}, knn_ver[2] = {0, 0};
   // slab mode
   bool slab_on = false;
@@ -200,17 +201,19 @@ template <int KERNEL>
 void launch_knn(sphb_sim* s, int ntot, const PhysP& ph) {
   KnnOut out{s->a.pc, s->nn, s->failList, s->failCount};
   const int tiles = cdiv(ntot, 32);
-  const size_t smem = (size_t)KNN_WARPS * s->ktune.cap * 32 * (sizeof(double) + sizeof(uint32_t));
+  KnnTune kt = s->ktune;
+  kt.cap = s->have_h ? s->ktune.cap : s->ktune.cap0;  // first evaluation: radius from a density estimate, wider spread
+  const size_t smem = (size_t)KNN_WARPS * knn_smem_words_per_warp(kt.cap) * sizeof(uint32_t);
   static bool attr_done[3] = {false, false, false};
   if (!attr_done[KERNEL]) {
-    cudaFuncSetAttribute(k_knn_fast<KERNEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_knn_tile<KERNEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_done[KERNEL] = true;
   }
-  k_knn_fast<KERNEL><<<cdiv(tiles, KNN_WARPS), KNN_THREADS, smem, s->st>>>(s->spos, s->keysSorted,
-                                                                         s->cellStart, s->hguess, s->a.epred, ntot,
-                                                                         s->grid, ph, s->ktune, out);
+  k_knn_tile<KERNEL><<<cdiv(tiles, KNN_WARPS), KNN_THREADS, smem, s->st>>>(s->spos, s->keysSorted, s->cellStart,
+                                                                         s->hguess, s->a.epred, ntot, s->grid, ph, kt, out);
   k_knn_fallback<KERNEL><<<148 * 4, 128, 0, s->st>>>(s->spos, s->keysSorted, s->cellStart, s->hguess,
                                                    s->a.epred, ntot, s->grid, ph, out, s->dflags);
+  s->have_h = true;
 }
 
 template <int KERNEL>
@@ -377,19 +380,22 @@ int create_common(const sphb_params* p, int64_t n, int64_t capacity, const doubl
   CKC(cudaMemsetAsync(s->dflags, 0, sizeof(uint32_t), s->st));
   CKC(cudaMemsetAsync(s->nn, 0xff, cap32 * SPHB_K * sizeof(uint32_t), s->st));
 #undef CKC
-  s->gtune.cell_per_h = 0.62;
+  s->gtune.cell_per_h = 1.15;  // row height in units of the mean h: three rows cover +-rg
+  s->gtune.aspect = 0.32;      // dx / dy: narrow cells keep the horizontal rounding waste small
   s->gtune.ppc0 = 4.0;
   s->gtune.ncell_max = s->ncell_max;
   s->gtune.force_nc = 0;
-  s->ktune.guess_margin = 0.08;
+  s->ktune.guess_margin = 0.02;
   s->ktune.k_target = 46.0;
-  s->ktune.cap = 64;
+  s->ktune.cap = 42;
+  s->ktune.cap0 = 72;
   if (const char* ev = getenv("SPHB_CELL_PER_H")) s->gtune.cell_per_h = atof(ev);
   if (const char* ev = getenv("SPHB_PPC0")) s->gtune.ppc0 = atof(ev);
   if (const char* ev = getenv("SPHB_FORCE_NC")) s->gtune.force_nc = atoi(ev);
   if (const char* ev = getenv("SPHB_GUESS_MARGIN")) s->ktune.guess_margin = atof(ev);
   if (const char* ev = getenv("SPHB_K_TARGET")) s->ktune.k_target = atof(ev);
   if (const char* ev = getenv("SPHB_KNN_CAP")) s->ktune.cap = std::max(32, std::min(96, atoi(ev)));
+  if (const char* ev = getenv("SPHB_CELL_ASPECT")) s->gtune.aspect = atof(ev);
   if (n > 0) {
     rc = upload_common(s, 0, n, pos_xy, vel_xy, e, rho, id, kind, 0);
     if (rc) { g_create_error = s->err; sphb_destroy(s); return rc; }

@@ -40,6 +40,7 @@ struct KnnTune {
   double guess_margin;   // search radius = h_prev * (1 + margin)
   double k_target;       // expected candidates inside the first-guess radius when no h_prev exists
   int cap;               // candidate column capacity per particle (shared memory)
+  int cap0;              // same for the first evaluation (no previous h)
 };
 
 // device-side status word
@@ -318,19 +319,27 @@ __global__ void __launch_bounds__(256) k_reorder(StateIn in, StateOut out, const
 }
 
 // -------------------------------------------------------------------------------------------------
-// K3: exact kNN (k = 32) + density + sound speed.
+// K3: exact kNN (k = 32) + density + sound speed     (nearest-neighbour.go:28-165, sph.go:306-323,423-429)
 //
-// One warp = 32 consecutive particles of the cell-sorted order (about 3 cells of one grid row).  Every
-// lane has a search radius rg (previous h plus a margin, or a density estimate).  The warp walks the
-// UNION of its lanes' stencils row by row; rows of cells are contiguous in memory, so a row of the union
-// is one contiguous particle range and all 32 lanes load the same candidate (one broadcast transaction).
-// A lane keeps every candidate with d^2 < rg^2 in its shared-memory column.  If it collected between 32
-// and CAP, the 32 nearest of them are the exact answer (everything within rg was seen); otherwise the
-// particle goes to the ring-expansion fallback kernel.  The bounded top-k is then a trim of the few
-// surplus entries instead of a per-candidate priority-queue update (nearest-neighbour.go:139-153).
+// One warp = one tile = 32 consecutive particles of the cell-sorted order (a strip of one grid row), one
+// query per lane.  Every lane has a search radius rg (previous h plus a margin, or a density estimate).
+// The warp walks the UNION of its lanes' stencils row by row; a row of the union is a contiguous particle
+// range, which the warp stages into shared memory (coalesced) as fp32 coordinates relative to the tile.
+//   phase 1 (filter, fp32): every lane tests every staged candidate (shared-memory broadcast) and appends
+//           the ones with d2f < rg^2 (1 + delta) to its private shared-memory column {fp32 key, entry}.
+//   select  (fp32 keys)   : the cnt - 32 largest keys are removed (cnt is 33..40 with a tight rg).
+//   phase 2 (exact, fp64) : the 32 survivors get d^2 exactly as the reference computes it (unfused
+//           (p + off) - b, linear-algebra.go:61-64); h^2 = max; density and sound speed follow.
+// Exactness certificate per lane (else the particle goes to the ring-expansion fallback):
+//   32 <= cnt <= CAP, the fp32 gap between the 32nd and 33rd key exceeds the fp32 error bound delta
+//   (no rank ambiguity, exact ties included), and exact h^2 <= rg^2 (everything within h was staged).
+// fp32 error bound: coordinates relative to the tile, |v| <= V: each carries <= 2^-24 V rounding, so
+//   |d2f - d2| / d2 <= ~4 * 2^-24 * V / d + 3 * 2^-24; delta = 3 * (2^-22 * V / rg + 2^-21) covers it
+//   with a factor > 2 to spare near d ~ rg.
 // -------------------------------------------------------------------------------------------------
 #define KNN_WARPS 4
 #define KNN_THREADS (KNN_WARPS * 32)
+#define KNN_CMAX 128  // staged candidates per round
 
 struct KnnOut {
   double4* pc;      // {rho, c, h, P = c^2/(gamma rho)}
@@ -339,86 +348,97 @@ struct KnnOut {
   int* failCount;
 };
 
+// shared memory per warp: column of (CAP + 1) slots x 32 lanes x {fp32 key, entry} + staged candidates (float2)
+__host__ __device__ inline size_t knn_smem_words_per_warp(int cap) { return (size_t)(cap + 1) * 64 + KNN_CMAX * 2; }
+
 __device__ __forceinline__ int warp_min_i(int v, uint32_t mask) {
-  // min over lanes in mask (others pass INT_MAX)
   return __reduce_min_sync(0xffffffffu, (mask >> (threadIdx.x & 31)) & 1u ? v : 0x7fffffff);
 }
 __device__ __forceinline__ int warp_max_i(int v, uint32_t mask) {
   return __reduce_max_sync(0xffffffffu, (mask >> (threadIdx.x & 31)) & 1u ? v : (int)0x80000000);
 }
+__device__ __forceinline__ double warp_max_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
 
-// finish one particle whose candidate column holds cnt >= 32 entries (d2 >= 0), from any column layout:
-// trims to the 32 smallest, returns h^2, leaves removed entries marked with d2 = -1
-template <typename D2Ref>
-__device__ __forceinline__ double trim_to_k(D2Ref d2at, int cnt) {
-  for (int r = cnt - SPHB_K; r > 0; --r) {
-    double m = -1.0;
-    int ms = 0;
-    for (int s = 0; s < cnt; ++s) {
-      double v = d2at(s);
-      if (v > m) { m = v; ms = s; }
-    }
-    d2at(ms) = -1.0;
-  }
-  double m = -1.0;
-  for (int s = 0; s < cnt; ++s) {
-    double v = d2at(s);
-    if (v > m) m = v;
-  }
-  return m;
+// image code of a list entry: bits 2-3 = ix + 1, bits 0-1 = iy + 1 (ix, iy in {-1, 0, 1})
+__device__ __forceinline__ uint32_t img_code(int ix, int iy) { return (uint32_t)(((ix + 1) << 2) | (iy + 1)); }
+
+// branch-free append of one candidate to the lane's column: kp is the shared-space byte address of the next
+// free slot (stride 256 B), clamped to kend (the dump slot) so that an overflowing lane cannot leave its column
+__device__ __forceinline__ void knn_append(uint32_t& kp, float d2f, uint32_t en, float thr, uint32_t kend) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b32 kb;\n\t"
+      "setp.lt.f32 p, %1, %3;\n\t"
+      "mov.b32 kb, %1;\n\t"
+      "@p st.shared.v2.b32 [%0], {kb, %2};\n\t"
+      "@p add.u32 %0, %0, 256;\n\t"
+      "@p min.u32 %0, %0, %4;\n\t"
+      "}\n"
+      : "+r"(kp)
+      : "f"(d2f), "r"(en), "f"(thr), "r"(kend));
 }
 
 template <int KERNEL>
-__global__ void __launch_bounds__(KNN_THREADS) k_knn_fast(const double2* __restrict__ spos,
+__global__ void __launch_bounds__(KNN_THREADS, 4) k_knn_tile(const double2* __restrict__ spos,
                                                          const uint32_t* __restrict__ keys,
                                                          const uint32_t* __restrict__ cellStart,
                                                          const double* __restrict__ hguess,
-                                                         const double* __restrict__ epred, int n, const GridP* __restrict__ gp, PhysP ph,
-                                                         KnnTune tune, KnnOut out) {
+                                                         const double* __restrict__ epred, int n,
+                                                         const GridP* __restrict__ gp, PhysP ph, KnnTune tune,
+                                                         KnnOut out) {
   const GridP g = *gp;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(16) uint32_t smem_u[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int CAP = tune.cap;
-  double* d2col = reinterpret_cast<double*>(smem_raw) + (size_t)warp * CAP * 32 + lane;
-  uint32_t* idcol = reinterpret_cast<uint32_t*>(reinterpret_cast<double*>(smem_raw) + (size_t)KNN_WARPS * CAP * 32) +
-                    (size_t)warp * CAP * 32 + lane;
+  uint32_t* wbase = smem_u + (size_t)warp * knn_smem_words_per_warp(CAP);
+  uint2* col = reinterpret_cast<uint2*>(wbase) + lane;                       // [slot * 32] = {key, entry}
+  float4* candF4 = reinterpret_cast<float4*>(wbase + (size_t)(CAP + 1) * 64);  // two staged candidates each
+  float2* candF = reinterpret_cast<float2*>(candF4);
+  const uint32_t kbase = (uint32_t)__cvta_generic_to_shared(col);
+  const uint32_t kend = kbase + (uint32_t)CAP * 256u;
 
   const int tile = blockIdx.x * KNN_WARPS + warp;
+  if (tile * 32 >= n) return;  // whole warp out of range (warp-uniform)
   const int i = tile * 32 + lane;
   const bool valid = i < n;
-  if (tile * 32 >= n) return;  // whole warp out of range (warp-uniform)
 
   double xa = 0, ya = 0, rg = 0;
   int cxa = 0, cya = 0;
   if (valid) {
-    double2 p = spos[i];
+    const double2 p = spos[i];
     xa = p.x; ya = p.y;
-    uint32_t k = keys[i];
+    const uint32_t k = keys[i];
     cya = (int)(k / (uint32_t)g.ncx);
     cxa = (int)(k - (uint32_t)cya * (uint32_t)g.ncx);
-    double hp = hguess[i];
+    const double hp = hguess[i];
     if (hp > 0.0) {
       rg = hp * (1.0 + tune.guess_margin);
-    } else {
-      // density estimate from the 3x3 block of cells around the particle
-      int x0 = max(cxa - 1, 0), x1 = min(cxa + 1, g.ncx - 1);
-      int y0 = max(cya - 1, 0), y1 = min(cya + 1, g.ncy - 1);
+    } else {  // density estimate from the block of cells around the particle
+      const int wx = max(1, (int)(1.5 * g.dy * g.inv_dx));
+      const int x0 = max(cxa - wx, 0), x1 = min(cxa + wx, g.ncx - 1);
+      const int y0 = max(cya - 1, 0), y1 = min(cya + 1, g.ncy - 1);
       uint32_t c = 0;
       for (int r = y0; r <= y1; ++r) c += cellStart[r * g.ncx + x1 + 1] - cellStart[r * g.ncx + x0];
-      double area = (double)(x1 - x0 + 1) * g.dx * (double)(y1 - y0 + 1) * g.dy;
+      const double area = (double)(x1 - x0 + 1) * g.dx * (double)(y1 - y0 + 1) * g.dy;
       rg = sqrt(tune.k_target * area / (3.141592653589793 * (double)(c > 0 ? c : 1)));
     }
   }
   const double rg2 = rg * rg;
-  // unwrapped cell range that contains every point within rg (slightly widened: see DESIGN.md, exactness)
+  // unwrapped cell range that contains every point within rg (slightly widened)
   const double rw = rg * (1.0 + 1e-6);
   int clo = (int)floor((xa - rw - g.ox) * g.inv_dx), chi = (int)floor((xa + rw - g.ox) * g.inv_dx);
   int rlo = (int)floor((ya - rw - g.oy) * g.inv_dy), rhi = (int)floor((ya + rw - g.oy) * g.inv_dy);
   clo = min(clo, cxa); chi = max(chi, cxa);
   rlo = min(rlo, cya); rhi = max(rhi, cya);
 
-  int cnt = 0;
-  bool bad = false;  // stencil wider than the period: needs the multi-image fallback
+  uint32_t kp = kbase;
+  float deltaf = 0.0f;
+  bool bad = false;  // stencil wider than the period / fp32 bound not applicable: multi-image fallback
   uint32_t todo = __ballot_sync(0xffffffffu, valid);
   while (todo) {
     // next group: all remaining lanes that sit in the same grid row as the first remaining lane
@@ -436,56 +456,132 @@ __global__ void __launch_bounds__(KNN_THREADS) k_knn_fast(const double2* __restr
     else { r0 = max(r0, 0); r1 = min(r1, g.ncy - 1); r0 = min(r0, g.ncy - 1); r1 = max(r1, 0); }
     if (gbad) { if (mine) bad = true; continue; }
 
+    // fp32 frame of this group: origin at the centre of the union block; V bounds every |relative coordinate|
+    const double xref = g.ox + 0.5 * (double)(c0 + c1 + 1) * g.dx;
+    const double yref = g.oy + 0.5 * (double)(r0 + r1 + 1) * g.dy;
+    double V = fmax(0.5 * (double)(c1 - c0 + 1) * g.dx, 0.5 * (double)(r1 - r0 + 1) * g.dy);
+    // clamped border cells of an open axis may hold particles beyond the block: bound by the queries' reach
+    V = fmax(V, warp_max_d(mine ? fmax(fabs(xa - xref), fabs(ya - yref)) + rg : 0.0));
+    const float qfx = (float)(xa - xref), qfy = (float)(ya - yref);
+    const double delta = 3.0 * (2.384185791015625e-07 * V / fmax(rg, 1e-300) + 4.76837158203125e-07);
+    if (mine) deltaf = (float)delta;
+    if (mine && !(delta < 1e-3)) bad = true;  // tile far wider than this lane's radius: no useful fp32 bound
+    const float thrf = (mine && !bad) ? (float)(rg2 * (1.0 + delta)) * 1.0000002f : -1.0f;
+    const float Vf = (float)V * 1.000001f;
+
     for (int ru = r0; ru <= r1; ++ru) {
-      int iy = g.wrapy ? floor_div(ru, g.ncy) : 0;
+      const int iy = g.wrapy ? floor_div(ru, g.ncy) : 0;
       const int row = ru - iy * g.ncy;
-      const double qy = (iy == 0) ? ya : __dadd_rn(ya, -(double)iy * g.Ly);  // query shifted like nearest-neighbour.go:59,72
-      // up to three x pieces (images -1, 0, +1)
-      int ix0 = g.wrapx ? floor_div(c0, g.ncx) : 0, ix1 = g.wrapx ? floor_div(c1, g.ncx) : 0;
-      for (int ix = ix0; ix <= ix1; ++ix) {
+      const int ix0 = g.wrapx ? floor_div(c0, g.ncx) : 0, ix1 = g.wrapx ? floor_div(c1, g.ncx) : 0;
+      for (int ix = ix0; ix <= ix1; ++ix) {  // up to three x pieces (images -1, 0, +1)
         const int a = max(c0, ix * g.ncx) - ix * g.ncx, b = min(c1, ix * g.ncx + g.ncx - 1) - ix * g.ncx;
-        const double qx = (ix == 0) ? xa : __dadd_rn(xa, -(double)ix * g.Lx);
-        const uint32_t code = (uint32_t)((ix + 1) * 3 + (iy + 1)) << IMG_SHIFT;
+        const uint32_t code = img_code(ix, iy) << IMG_SHIFT;
+        // candidate position in the query frame: b + img * L  (the reference shifts the query by -img * L)
+        const double sx = (double)ix * g.Lx - xref, sy = (double)iy * g.Ly - yref;
         const int s = (int)cellStart[row * g.ncx + a], e = (int)cellStart[row * g.ncx + b + 1];
-        for (int j = s; j < e; j += 4) {
-          double2 pb[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) pb[u] = spos[min(j + u, e - 1)];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const double d2 = dist_sq(qx - pb[u].x, qy - pb[u].y);
-            const bool acc = mine && (j + u < e) && (d2 < rg2) && (j + u != i);
-            if (acc) {
-              if (cnt < CAP) { d2col[cnt * 32] = d2; idcol[cnt * 32] = (uint32_t)(j + u) | code; }
-              ++cnt;
+        for (int base = s; base < e; base += KNN_CMAX) {
+          const int len = min(KNN_CMAX, e - base);
+          const int len8 = (len + 7) & ~7;
+          __syncwarp();
+          for (int t = lane; t < len8; t += 32) {  // stage (coalesced); padded with unreachable dummies
+            float fx = 3.0e18f, fy = 3.0e18f;
+            if (t < len) {
+              const double2 pb = spos[base + t];
+              fx = (float)(pb.x + sx); fy = (float)(pb.y + sy);
+              // beyond the bounded block (clamped border cell): farther than every lane's reach, drop it
+              if (!(fabsf(fx) <= Vf && fabsf(fy) <= Vf)) { fx = 3.0e18f; fy = 3.0e18f; }
             }
+            candF[t] = make_float2(fx, fy);
+          }
+          __syncwarp();
+          const uint32_t en0 = (uint32_t)base | code;
+          for (int c = 0; c < len8; c += 8) {  // phase 1: fp32 filter, shared-memory broadcast, branch-free
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = candF4[(c >> 1) + u];
+            float d2f[8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float ax = v[u].x - qfx, ay = v[u].y - qfy, bx = v[u].z - qfx, by = v[u].w - qfy;
+              d2f[2 * u] = fmaf(ay, ay, ax * ax);
+              d2f[2 * u + 1] = fmaf(by, by, bx * bx);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) knn_append(kp, d2f[u], en0 + (uint32_t)(c + u), thrf, kend);
           }
         }
       }
     }
   }
+  __syncwarp();
 
-  const bool ok = valid && !bad && cnt >= SPHB_K && cnt <= CAP;
+  // the lane's own entry (d2f = 0, centre image) is in the column: remove it (nearest-neighbour.go:79)
+  int cnt = (int)((kp - kbase) >> 8);
+  bool ok = valid && !bad && kp != kend && cnt >= SPHB_K + 1;
+  if (ok) {
+    int fs = -1;
+    for (int s = 0; s < cnt; ++s)
+      if ((col[s * 32].y & IDX_MASK) == (uint32_t)i) fs = s;
+    if (fs >= 0) { --cnt; col[fs * 32] = col[cnt * 32]; }
+    else ok = false;
+  }
+  // select: remove the cnt - 32 largest fp32 keys (swap-remove); bkey = smallest removed = 33rd smallest
+  const int m = ok ? cnt - SPHB_K : 0;
+  int cur = ok ? cnt : 0;
+  uint32_t bkey = 0xffffffffu;
+  const int mmax = __reduce_max_sync(0xffffffffu, m);
+  for (int r = 0; r < mmax; ++r) {
+    if (r < m) {
+      uint32_t best = 0;
+      int bs = 0;
+      for (int s = 0; s < cur; ++s) {
+        const uint32_t k = col[s * 32].x;
+        if (k >= best) { best = k; bs = s; }
+      }
+      bkey = best;
+      --cur;
+      col[bs * 32] = col[cur * 32];
+    }
+  }
+  if (ok) {
+    uint32_t akey = 0;
+#pragma unroll 8
+    for (int s = 0; s < SPHB_K; ++s) akey = max(akey, col[s * 32].x);
+    // rank ambiguity (includes exact ties): the 33rd key must exceed the 32nd by more than the fp32 error
+    if (m > 0 && !(__uint_as_float(bkey) > __uint_as_float(akey) * (1.0f + deltaf) * 1.000001f)) ok = false;
+  }
+  // exact phase
+  double d2[SPHB_K];
+  double h2 = 0.0;
+  if (ok) {
+    const double qxm = __dadd_rn(xa, g.Lx), qxp = __dadd_rn(xa, -g.Lx);  // ix = -1 / +1: query + (-ix * L)
+    const double qym = __dadd_rn(ya, g.Ly), qyp = __dadd_rn(ya, -g.Ly);
+#pragma unroll
+    for (int s = 0; s < SPHB_K; ++s) {
+      const uint32_t en = col[s * 32].y;
+      const double2 pb = spos[en & IDX_MASK];
+      const uint32_t cx = (en >> (IMG_SHIFT + 2)) & 3u, cy = (en >> IMG_SHIFT) & 3u;
+      const double qx = cx == 1u ? xa : (cx == 0u ? qxm : qxp);
+      const double qy = cy == 1u ? ya : (cy == 0u ? qym : qyp);
+      d2[s] = dist_sq(qx - pb.x, qy - pb.y);
+      h2 = fmax(h2, d2[s]);
+    }
+    if (!(h2 <= rg2)) ok = false;  // something within h may not have been staged/accepted
+  }
   if (valid && !ok) {
-    int slot = atomicAdd(out.failCount, 1);
+    const int slot = atomicAdd(out.failCount, 1);
     out.failList[slot] = i;
   }
-  if (!ok) cnt = 0;
-  // trim the surplus (cnt - 32 largest) and get h^2
-  double h2 = trim_to_k([&](int s) -> double& { return d2col[s * 32]; }, cnt);
   if (ok) {
     const double h = sqrt(h2);
     const double inv_h = 1.0 / h;
     double acc = 0.0;
-    int kslot = 0;
     uint32_t* nncol = out.nn + (size_t)tile * 32 * 32 + lane;
-    for (int s = 0; s < cnt; ++s) {
-      const double v = d2col[s * 32];
-      if (v >= 0.0) {
-        acc += kern_F<KERNEL>(sqrt(v) * inv_h);
-        nncol[kslot * 32] = idcol[s * 32];
-        ++kslot;
-      }
+#pragma unroll
+    for (int s = 0; s < SPHB_K; ++s) {
+      const double d = d2[s] > 0.0 ? d2[s] * rsqrt(d2[s]) : 0.0;
+      acc += kern_F<KERNEL>(fmin(d * inv_h, 1.0));
+      nncol[s * 32] = col[s * 32].y;
     }
     // Density2D (sph.go:322), sound speed (sph.go:426-428), pressure term c^2/(gamma rho) (sph.go:332,360)
     const double rho = ph.Fpref * ph.mass * acc / (h * h);
@@ -494,32 +590,38 @@ __global__ void __launch_bounds__(KNN_THREADS) k_knn_fast(const double2* __restr
   }
 }
 
-// Fallback: one thread per failed particle, ring expansion until the result is certified exact.
-// Handles everything the fast path refuses: too few / too many candidates inside the guess, stencils
-// wider than the period (several images of the same particle, like the reference's 3x3 image loop).
+// Fallback: one WARP per failed particle, lanes = candidates, ring expansion until the result is certified
+// exact.  Handles everything the tile kernel refuses: too few / too many candidates inside the guess, fp32
+// rank ambiguity and exact ties, stencils wider than the period (several images of the same particle, like
+// the reference's 3x3 image loop).  The bounded top-32 is the reference's sorted queue
+// (nearest-neighbour.go:139-153) distributed over the warp: lane s holds slot s, descending, lane 0 = h^2;
+// an insertion is one ballot + one shuffle-down.  Candidates are inserted in scan order with the
+// reference's strict comparisons, so equal keys end up in the same relative order.
 template <int KERNEL>
 __global__ void __launch_bounds__(128) k_knn_fallback(const double2* __restrict__ spos,
                                                      const uint32_t* __restrict__ keys,
                                                      const uint32_t* __restrict__ cellStart,
                                                      const double* __restrict__ hguess,
-                                                     const double* __restrict__ epred, int n, const GridP* __restrict__ gp, PhysP ph,
-                                                     KnnOut out, uint32_t* __restrict__ dflags) {
+                                                     const double* __restrict__ epred, int n,
+                                                     const GridP* __restrict__ gp, PhysP ph, KnnOut out,
+                                                     uint32_t* __restrict__ dflags) {
   const GridP g = *gp;
   const int nfail = *out.failCount;
   if (blockIdx.x == 0 && threadIdx.x == 0) out.failCount[1] += nfail;  // cumulative, read by sphb_counters
-  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nfail; f += gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const double BIG = 1.7976931348623157e308;
+  for (int f = gwarp; f < nfail; f += nwarps) {
     const int i = out.failList[f];
     const double2 pa = spos[i];
     const uint32_t k = keys[i];
     const int cya = (int)(k / (uint32_t)g.ncx), cxa = (int)(k - (uint32_t)cya * (uint32_t)g.ncx);
     double R = hguess[i] > 0.0 ? 1.5 * hguess[i] : 1.5 * fmax(g.dx, g.dy);
-    double td[SPHB_K];  // sorted descending like the reference queue: td[0] = current 32nd-best
-    uint32_t ti[SPHB_K];
+    double td = BIG;
+    uint32_t ti = 0xffffffffu;
     int found = 0;
     for (int iter = 0; iter < 64; ++iter) {
-#pragma unroll
-      for (int s = 0; s < SPHB_K; ++s) { td[s] = 1.7976931348623157e308; ti[s] = 0xffffffffu; }
-      found = 0;
+      td = BIG; ti = 0xffffffffu; found = 0;
       // unwrapped cell block covering [pa - R, pa + R]; sides that cannot hide anything are "complete"
       int c0 = (int)floor((pa.x - R - g.ox) * g.inv_dx), c1 = (int)floor((pa.x + R - g.ox) * g.inv_dx);
       int r0 = (int)floor((pa.y - R - g.oy) * g.inv_dy), r1 = (int)floor((pa.y + R - g.oy) * g.inv_dy);
@@ -529,32 +631,51 @@ __global__ void __launch_bounds__(128) k_knn_fallback(const double2* __restrict_
       else { doneL = c0 <= 0; doneR = c1 >= g.ncx - 1; c0 = min(max(c0, 0), g.ncx - 1); c1 = max(min(c1, g.ncx - 1), 0); }
       if (g.wrapy) { doneD = r0 <= -g.ncy; doneU = r1 >= 2 * g.ncy - 1; r0 = max(r0, -g.ncy); r1 = min(r1, 2 * g.ncy - 1); }
       else { doneD = r0 <= 0; doneU = r1 >= g.ncy - 1; r0 = min(max(r0, 0), g.ncy - 1); r1 = max(min(r1, g.ncy - 1), 0); }
+      // image order: the reference loops the x image outermost (nearest-neighbour.go:57-61); only the
+      // relative order of exactly equal keys depends on it, which parity excludes
       for (int ru = r0; ru <= r1; ++ru) {
         const int iy = g.wrapy ? floor_div(ru, g.ncy) : 0;
         const int row = ru - iy * g.ncy;
         const double qy = (iy == 0) ? pa.y : __dadd_rn(pa.y, -(double)iy * g.Ly);
-        for (int cu = c0; cu <= c1; ++cu) {
-          const int ix = g.wrapx ? floor_div(cu, g.ncx) : 0;
-          const int col = cu - ix * g.ncx;
+        const int ix0 = g.wrapx ? floor_div(c0, g.ncx) : 0, ix1 = g.wrapx ? floor_div(c1, g.ncx) : 0;
+        for (int ix = ix0; ix <= ix1; ++ix) {
+          const int a = max(c0, ix * g.ncx) - ix * g.ncx, b = min(c1, ix * g.ncx + g.ncx - 1) - ix * g.ncx;
           const double qx = (ix == 0) ? pa.x : __dadd_rn(pa.x, -(double)ix * g.Lx);
-          const uint32_t code = (uint32_t)((ix + 1) * 3 + (iy + 1)) << IMG_SHIFT;
-          const int s = (int)cellStart[row * g.ncx + col], e = (int)cellStart[row * g.ncx + col + 1];
-          for (int j = s; j < e; ++j) {
-            const double2 pb = spos[j];
-            const double d2 = dist_sq(qx - pb.x, qy - pb.y);
-            if (d2 < td[0] && j != i) {  // strict, self excluded in every image (nearest-neighbour.go:79)
-              int t = 1;
-              for (; t < SPHB_K && td[t] > d2; ++t) { td[t - 1] = td[t]; ti[t - 1] = ti[t]; }
-              td[t - 1] = d2; ti[t - 1] = (uint32_t)j | code;
+          const uint32_t code = img_code(ix, iy) << IMG_SHIFT;
+          const int s = (int)cellStart[row * g.ncx + a], e = (int)cellStart[row * g.ncx + b + 1];
+          for (int j0 = s; j0 < e; j0 += 32) {
+            const int j = j0 + lane;
+            const bool have = j < e;
+            double d2 = BIG;
+            if (have) {
+              const double2 pb = spos[j];
+              d2 = dist_sq(qx - pb.x, qy - pb.y);
+            }
+            const double thr = __shfl_sync(0xffffffffu, td, 0);
+            // strict admission, self excluded in every image (nearest-neighbour.go:79)
+            uint32_t pend = __ballot_sync(0xffffffffu, have && d2 < thr && j != i);
+            while (pend) {
+              const int src = __ffs(pend) - 1;
+              pend &= pend - 1;
+              const double v = __shfl_sync(0xffffffffu, d2, src);
+              const uint32_t en = __shfl_sync(0xffffffffu, (uint32_t)j | code, src);
+              const double t0 = __shfl_sync(0xffffffffu, td, 0);
+              if (!(v < t0)) continue;  // the threshold tightened meanwhile (warp-uniform)
+              const int p = __popc(__ballot_sync(0xffffffffu, td > v));  // slots 0..p-1 shift towards 0
+              const double tdn = __shfl_down_sync(0xffffffffu, td, 1);
+              const uint32_t tin = __shfl_down_sync(0xffffffffu, ti, 1);
+              if (lane < p - 1) { td = tdn; ti = tin; }
+              else if (lane == p - 1) { td = v; ti = en; }
               ++found;
             }
           }
         }
       }
       const bool all = doneL && doneR && doneD && doneU;
+      const double t0 = __shfl_sync(0xffffffffu, td, 0);
       if (found >= SPHB_K) {
         // certified if the 32nd distance does not reach past the scanned block on any open side
-        const double d = sqrt(td[0]);
+        const double d = sqrt(t0);
         const double reachL = doneL ? 1e300 : pa.x - (g.ox + (double)c0 * g.dx);
         const double reachR = doneR ? 1e300 : (g.ox + (double)(c1 + 1) * g.dx) - pa.x;
         const double reachD = doneD ? 1e300 : pa.y - (g.oy + (double)r0 * g.dy);
@@ -567,24 +688,26 @@ __global__ void __launch_bounds__(128) k_knn_fallback(const double2* __restrict_
         R *= 2.0;
       }
     }
-    const int tile = i >> 5, lane = i & 31;
-    uint32_t* nncol = out.nn + (size_t)tile * 32 * 32 + lane;
+    const int tile = i >> 5, ql = i & 31;
+    uint32_t* nncol = out.nn + (size_t)tile * 32 * 32 + ql;
     if (found < SPHB_K) {
-      atomicOr(dflags, DFLAG_UNDERFULL);
-      for (int s = 0; s < SPHB_K; ++s) nncol[s * 32] = 0xffffffffu;
-      out.pc[i] = make_double4(0.0, 0.0, 0.0, 0.0);
+      if (lane == 0) atomicOr(dflags, DFLAG_UNDERFULL);
+      nncol[lane * 32] = 0xffffffffu;
+      if (lane == 0) out.pc[i] = make_double4(0.0, 0.0, 0.0, 0.0);
       continue;
     }
-    const double h = sqrt(td[0]);
+    const double h2 = __shfl_sync(0xffffffffu, td, 0);
+    const double h = sqrt(h2);
     const double inv_h = 1.0 / h;
-    double acc = 0.0;
-    for (int s = 0; s < SPHB_K; ++s) {
-      acc += kern_F<KERNEL>(sqrt(td[s]) * inv_h);
-      nncol[s * 32] = ti[s];
+    double acc = kern_F<KERNEL>(fmin(sqrt(td) * inv_h, 1.0));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    nncol[lane * 32] = ti;
+    if (lane == 0) {
+      const double rho = ph.Fpref * ph.mass * acc / (h * h);
+      const double c = sqrt(ph.cfac * epred[i]);
+      out.pc[i] = make_double4(rho, c, h, c * c / (ph.gamma * rho));
     }
-    const double rho = ph.Fpref * ph.mass * acc / (h * h);
-    const double c = sqrt(ph.cfac * epred[i]);
-    out.pc[i] = make_double4(rho, c, h, c * c / (ph.gamma * rho));
   }
 }
 
@@ -592,7 +715,7 @@ __global__ void __launch_bounds__(128) k_knn_fallback(const double2* __restrict_
 __device__ __forceinline__ void decode_entry(uint32_t ent, const GridP& g, int& j, double& offx, double& offy) {
   j = (int)(ent & IDX_MASK);
   const int code = (int)(ent >> IMG_SHIFT);
-  const int ix = code / 3 - 1, iy = code % 3 - 1;
+  const int ix = (code >> 2) - 1, iy = (code & 3) - 1;
   offx = -(double)ix * g.Lx;
   offy = -(double)iy * g.Ly;
 }
@@ -769,7 +892,8 @@ __global__ void __launch_bounds__(32 * STAT_N) k_stats_final(const double* __res
 // hor/ver are the search periodicity (nearest-neighbour.go:28): {-DBL_MAX, DBL_MAX} = open.
 // -------------------------------------------------------------------------------------------------
 struct GridTune {
-  double cell_per_h;   // cell edge = cell_per_h * mean h
+  double cell_per_h;   // cell height dy = cell_per_h * mean h
+  double aspect;       // dx = aspect * dy
   double ppc0;         // particles per cell for the first (h unknown) evaluation
   int ncell_max;       // capacity of the cell table
   int force_nc;        // > 0: fixed cells per axis (tests)
@@ -790,15 +914,16 @@ __global__ void k_make_grid(const double* __restrict__ stats, int n, double hor0
   const double scale = fmax(fmax(ex, ey), 1e-300);
   if (!(ex > 1e-12 * scale)) ex = 1e-12 * scale;
   if (!(ey > 1e-12 * scale)) ey = 1e-12 * scale;
-  double d;
+  double d;  // row height dy; dx = aspect * dy
+  const double asp = (t.aspect > 0.0) ? t.aspect : 1.0;
   const double nh = stats[8];
   if (nh > 0.0) d = t.cell_per_h * stats[4] / nh;
-  else d = sqrt(t.ppc0 * ex * ey / (double)(n > 0 ? n : 1));
+  else d = sqrt(t.ppc0 * ex * ey / ((double)(n > 0 ? n : 1) * asp));
   if (!(d > 0.0)) d = scale;
-  double fx = fmin(fmax(floor(ex / d), 1.0), 1.0e6), fy = fmin(fmax(floor(ey / d), 1.0), 1.0e6);
+  double fx = fmin(fmax(floor(ex / (d * asp)), 1.0), 1.0e6), fy = fmin(fmax(floor(ey / d), 1.0), 1.0e6);
   for (int it = 0; it < 8 && fx * fy > (double)t.ncell_max; ++it) {
     d *= sqrt(fx * fy / (double)t.ncell_max) * 1.0001;
-    fx = fmax(floor(ex / d), 1.0);
+    fx = fmax(floor(ex / (d * asp)), 1.0);
     fy = fmax(floor(ey / d), 1.0);
   }
   if (fx * fy > (double)t.ncell_max) { fx = 1.0; fy = 1.0; }
