@@ -1,8 +1,9 @@
 """Build libsphb.so (the CUDA product library) in-tree for sm_100a.
 
 `python -m sphugo_b200.build` or `sphugo_b200.build.build()`.  nvcc cross-compiles without a GPU.
---fmad=false: the reference is a GOAMD64=v1 build (no FMA contraction); the kNN distance
-arithmetic additionally uses explicit __dmul_rn/__dadd_rn so neighbour sets are bit-identical.
+The reference is a GOAMD64=v1 build (no FMA contraction): everything that decides a neighbour set
+or moves a particle (d^2, drift, kick, wrap, reflections) uses explicit __dmul_rn/__dadd_rn and is bit-identical;
+the 32-term density / force sums may contract to FMA (differences ~1e-16, tolerance 1e-12).
 """
 from __future__ import annotations
 
@@ -16,7 +17,7 @@ LIB = os.path.join(HERE, "libsphb.so")
 SOURCES = ["sphb.cu"]
 DEPS = ["sphb.cu", "sphb_kernels.cuh", "sphb_slab.inc", os.path.join("..", "..", "include", "sphb.h")]
 NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--fmad=false",
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-shared", "-Xcompiler", "-fPIC", "-diag-suppress", "550",
 ]
 

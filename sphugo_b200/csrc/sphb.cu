@@ -387,14 +387,14 @@ int create_common(const sphb_params* p, int64_t n, int64_t capacity, const doubl
   s->gtune.force_nc = 0;
   s->ktune.guess_margin = 0.02;
   s->ktune.k_target = 46.0;
-  s->ktune.cap = 42;
-  s->ktune.cap0 = 72;
+  s->ktune.cap = 50;   // room for 42 entries + 8 slack (overflow is checked once per 8 candidates)
+  s->ktune.cap0 = 80;
   if (const char* ev = getenv("SPHB_CELL_PER_H")) s->gtune.cell_per_h = atof(ev);
   if (const char* ev = getenv("SPHB_PPC0")) s->gtune.ppc0 = atof(ev);
   if (const char* ev = getenv("SPHB_FORCE_NC")) s->gtune.force_nc = atoi(ev);
   if (const char* ev = getenv("SPHB_GUESS_MARGIN")) s->ktune.guess_margin = atof(ev);
   if (const char* ev = getenv("SPHB_K_TARGET")) s->ktune.k_target = atof(ev);
-  if (const char* ev = getenv("SPHB_KNN_CAP")) s->ktune.cap = std::max(32, std::min(96, atoi(ev)));
+  if (const char* ev = getenv("SPHB_KNN_CAP")) s->ktune.cap = std::max(48, std::min(96, atoi(ev)));
   if (const char* ev = getenv("SPHB_CELL_ASPECT")) s->gtune.aspect = atof(ev);
   if (n > 0) {
     rc = upload_common(s, 0, n, pos_xy, vel_xy, e, rho, id, kind, 0);

@@ -73,14 +73,41 @@ __device__ __forceinline__ double dist_sq(double dx, double dy) {
   return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
 }
 
+// 1/sqrt(x) and 1/x for normal x > 0: hardware seed (MUFU.RSQ64H / RCP64H, ~2^-22) + two Newton steps, no special
+// cases and no branches; relative error ~2 ulp (every consumer carries a 1e-12 bar)
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double xy = x * y;
+  double e = fma(-xy, y, 1.0);
+  y = fma(0.5 * y, e, y);
+  xy = x * y;
+  e = fma(-xy, y, 1.0);
+  return fma(0.5 * y, e, y);
+}
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+// sqrt(x) from fast_rsqrt with one residual correction: faithfully rounded (almost always correctly rounded)
+__device__ __forceinline__ double fast_sqrt(double x, double y /* = fast_rsqrt(x) */) {
+  const double s = x * y;
+  return fma(0.5 * y, fma(-s, s, x), s);
+}
+
 // SPH kernels, sph.go:244-304.  q = r / h with h the distance to the 32nd neighbour.
 template <int KERNEL>
 __device__ __forceinline__ double kern_F(double q) {
   if (KERNEL == 0) return 1.0;
-  if (KERNEL == 1) {
-    if (q < 0.5) return q * q * q - q * q + (1.0 / 6.0);
-    double t = 1.0 - q;
-    return t * t * t / 3.0;
+  if (KERNEL == 1) {  // both pieces evaluated, selected without a branch
+    const double lo = q * q * q - q * q + (1.0 / 6.0);
+    const double t = 1.0 - q;
+    const double hi = t * t * t * (1.0 / 3.0);  // the reference divides by 3: <= 1 ulp apart
+    return q < 0.5 ? lo : hi;
   }
   double t = 1.0 - q;
   double t2 = t * t;
@@ -89,9 +116,9 @@ __device__ __forceinline__ double kern_F(double q) {
 template <int KERNEL>
 __device__ __forceinline__ double kern_DF(double q) {
   if (KERNEL == 1) {
-    if (q < 0.5) return 3.0 * q * q - 2.0 * q;
-    double t = 1.0 - q;
-    return -t * t;
+    const double lo = 3.0 * q * q - 2.0 * q;
+    const double t = 1.0 - q;
+    return q < 0.5 ? lo : -t * t;
   }
   double t = 1.0 - q;
   return -10.0 * q * t * t * t;
@@ -349,7 +376,7 @@ struct KnnOut {
 };
 
 // shared memory per warp: column of (CAP + 1) slots x 32 lanes x {fp32 key, entry} + staged candidates (float2)
-__host__ __device__ inline size_t knn_smem_words_per_warp(int cap) { return (size_t)(cap + 1) * 64 + KNN_CMAX * 2; }
+__host__ __device__ inline size_t knn_smem_words_per_warp(int cap) { return (size_t)cap * 64 + KNN_CMAX * 2; }
 
 __device__ __forceinline__ int warp_min_i(int v, uint32_t mask) {
   return __reduce_min_sync(0xffffffffu, (mask >> (threadIdx.x & 31)) & 1u ? v : 0x7fffffff);
@@ -367,8 +394,8 @@ __device__ __forceinline__ double warp_max_d(double v) {
 __device__ __forceinline__ uint32_t img_code(int ix, int iy) { return (uint32_t)(((ix + 1) << 2) | (iy + 1)); }
 
 // branch-free append of one candidate to the lane's column: kp is the shared-space byte address of the next
-// free slot (stride 256 B), clamped to kend (the dump slot) so that an overflowing lane cannot leave its column
-__device__ __forceinline__ void knn_append(uint32_t& kp, float d2f, uint32_t en, float thr, uint32_t kend) {
+// free slot (stride 256 B).  The caller checks the remaining room once per 8 candidates.
+__device__ __forceinline__ void knn_append(uint32_t& kp, float d2f, uint32_t en, float thr) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
@@ -377,10 +404,9 @@ __device__ __forceinline__ void knn_append(uint32_t& kp, float d2f, uint32_t en,
       "mov.b32 kb, %1;\n\t"
       "@p st.shared.v2.b32 [%0], {kb, %2};\n\t"
       "@p add.u32 %0, %0, 256;\n\t"
-      "@p min.u32 %0, %0, %4;\n\t"
       "}\n"
       : "+r"(kp)
-      : "f"(d2f), "r"(en), "f"(thr), "r"(kend));
+      : "f"(d2f), "r"(en), "f"(thr));
 }
 
 template <int KERNEL>
@@ -397,10 +423,10 @@ __global__ void __launch_bounds__(KNN_THREADS, 4) k_knn_tile(const double2* __re
   const int CAP = tune.cap;
   uint32_t* wbase = smem_u + (size_t)warp * knn_smem_words_per_warp(CAP);
   uint2* col = reinterpret_cast<uint2*>(wbase) + lane;                       // [slot * 32] = {key, entry}
-  float4* candF4 = reinterpret_cast<float4*>(wbase + (size_t)(CAP + 1) * 64);  // two staged candidates each
+  float4* candF4 = reinterpret_cast<float4*>(wbase + (size_t)CAP * 64);  // two staged candidates each
   float2* candF = reinterpret_cast<float2*>(candF4);
   const uint32_t kbase = (uint32_t)__cvta_generic_to_shared(col);
-  const uint32_t kend = kbase + (uint32_t)CAP * 256u;
+  const uint32_t klim = kbase + (uint32_t)(CAP - 8) * 256u;  // beyond this fewer than 8 free slots remain
 
   const int tile = blockIdx.x * KNN_WARPS + warp;
   if (tile * 32 >= n) return;  // whole warp out of range (warp-uniform)
@@ -438,6 +464,8 @@ __global__ void __launch_bounds__(KNN_THREADS, 4) k_knn_tile(const double2* __re
 
   uint32_t kp = kbase;
   float deltaf = 0.0f;
+  bool anyimg = false;  // some staged piece is a periodic image (warp-uniform)
+  bool ovf = false;  // column (nearly) full: stop appending, the lane goes to the fallback
   bool bad = false;  // stencil wider than the period / fp32 bound not applicable: multi-image fallback
   uint32_t todo = __ballot_sync(0xffffffffu, valid);
   while (todo) {
@@ -466,7 +494,7 @@ __global__ void __launch_bounds__(KNN_THREADS, 4) k_knn_tile(const double2* __re
     const double delta = 3.0 * (2.384185791015625e-07 * V / fmax(rg, 1e-300) + 4.76837158203125e-07);
     if (mine) deltaf = (float)delta;
     if (mine && !(delta < 1e-3)) bad = true;  // tile far wider than this lane's radius: no useful fp32 bound
-    const float thrf = (mine && !bad) ? (float)(rg2 * (1.0 + delta)) * 1.0000002f : -1.0f;
+    float thrf = (mine && !bad) ? (float)(rg2 * (1.0 + delta)) * 1.0000002f : -1.0f;
     const float Vf = (float)V * 1.000001f;
 
     for (int ru = r0; ru <= r1; ++ru) {
@@ -476,6 +504,7 @@ __global__ void __launch_bounds__(KNN_THREADS, 4) k_knn_tile(const double2* __re
       for (int ix = ix0; ix <= ix1; ++ix) {  // up to three x pieces (images -1, 0, +1)
         const int a = max(c0, ix * g.ncx) - ix * g.ncx, b = min(c1, ix * g.ncx + g.ncx - 1) - ix * g.ncx;
         const uint32_t code = img_code(ix, iy) << IMG_SHIFT;
+        anyimg |= (ix != 0) | (iy != 0);
         // candidate position in the query frame: b + img * L  (the reference shifts the query by -img * L)
         const double sx = (double)ix * g.Lx - xref, sy = (double)iy * g.Ly - yref;
         const int s = (int)cellStart[row * g.ncx + a], e = (int)cellStart[row * g.ncx + b + 1];
@@ -506,8 +535,10 @@ __global__ void __launch_bounds__(KNN_THREADS, 4) k_knn_tile(const double2* __re
               d2f[2 * u] = fmaf(ay, ay, ax * ax);
               d2f[2 * u + 1] = fmaf(by, by, bx * bx);
             }
+            if (kp > klim) { ovf = true; thrf = -1.0f; }
+            const uint32_t enb = en0 + (uint32_t)c;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) knn_append(kp, d2f[u], en0 + (uint32_t)(c + u), thrf, kend);
+            for (int u = 0; u < 8; ++u) knn_append(kp, d2f[u], enb + (uint32_t)u, thrf);
           }
         }
       }
@@ -515,78 +546,112 @@ __global__ void __launch_bounds__(KNN_THREADS, 4) k_knn_tile(const double2* __re
   }
   __syncwarp();
 
-  // the lane's own entry (d2f = 0, centre image) is in the column: remove it (nearest-neighbour.go:79)
-  int cnt = (int)((kp - kbase) >> 8);
-  bool ok = valid && !bad && kp != kend && cnt >= SPHB_K + 1;
-  if (ok) {
-    int fs = -1;
-    for (int s = 0; s < cnt; ++s)
-      if ((col[s * 32].y & IDX_MASK) == (uint32_t)i) fs = s;
-    if (fs >= 0) { --cnt; col[fs * 32] = col[cnt * 32]; }
-    else ok = false;
-  }
-  // select: remove the cnt - 32 largest fp32 keys (swap-remove); bkey = smallest removed = 33rd smallest
-  const int m = ok ? cnt - SPHB_K : 0;
-  int cur = ok ? cnt : 0;
-  uint32_t bkey = 0xffffffffu;
-  const int mmax = __reduce_max_sync(0xffffffffu, m);
-  for (int r = 0; r < mmax; ++r) {
-    if (r < m) {
-      uint32_t best = 0;
-      int bs = 0;
-      for (int s = 0; s < cur; ++s) {
-        const uint32_t k = col[s * 32].x;
-        if (k >= best) { best = k; bs = s; }
+  // The column holds cnt entries, one of them the lane itself (d2f = 0, centre image; self is excluded in
+  // every image, nearest-neighbour.go:79).  m = cnt - 33 entries with the largest keys must be dropped.
+  const int cnt = (int)((kp - kbase) >> 8);
+  bool ok = valid && !bad && !ovf && cnt >= SPHB_K + 1;
+  // select A: the 4 largest keys below `bound` per pass (a max/min insertion network on the fp32 bit patterns).
+  // T = smallest dropped key, akey = largest kept key.
+  int mrem = ok ? cnt - (SPHB_K + 1) : 0;
+  uint32_t bound = 0xffffffffu, T = 0xffffffffu, akey = 0u;
+  bool sel_done = !ok;
+  while (__any_sync(0xffffffffu, !sel_done)) {
+    uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+    const int lim = sel_done ? 0 : cnt;
+    for (int s = 0; s < lim; ++s) {
+      uint32_t k = col[s * 32].x;
+      k = k < bound ? k : 0u;
+      uint32_t a;
+      a = max(t0, k); k = min(t0, k); t0 = a;
+      a = max(t1, k); k = min(t1, k); t1 = a;
+      a = max(t2, k); k = min(t2, k); t2 = a;
+      t3 = max(t3, k);
+    }
+    if (!sel_done) {
+      if (mrem <= 3) {
+        T = mrem == 0 ? bound : (mrem == 1 ? t0 : (mrem == 2 ? t1 : t2));
+        akey = mrem == 0 ? t0 : (mrem == 1 ? t1 : (mrem == 2 ? t2 : t3));
+        sel_done = true;
+      } else {
+        mrem -= 4;
+        bound = t3;
       }
-      bkey = best;
-      --cur;
-      col[bs * 32] = col[cur * 32];
     }
   }
-  if (ok) {
-    uint32_t akey = 0;
-#pragma unroll 8
-    for (int s = 0; s < SPHB_K; ++s) akey = max(akey, col[s * 32].x);
-    // rank ambiguity (includes exact ties): the 33rd key must exceed the 32nd by more than the fp32 error
-    if (m > 0 && !(__uint_as_float(bkey) > __uint_as_float(akey) * (1.0f + deltaf) * 1.000001f)) ok = false;
-  }
-  // exact phase
-  double d2[SPHB_K];
+  // rank ambiguity (includes exact ties): the smallest dropped key must exceed the largest kept one by more
+  // than the fp32 error; with nothing dropped the bound is the acceptance threshold itself (checked as h^2 <= rg^2)
+  if (ok && T != 0xffffffffu && !(__uint_as_float(T) > __uint_as_float(akey) * (1.0f + deltaf) * 1.000001f)) ok = false;
+
+  // select B + exact phase: kept entries get d^2 exactly as the reference computes it; the list entry goes to
+  // global memory, the slot is reused for the exact d^2
   double h2 = 0.0;
-  if (ok) {
-    const double qxm = __dadd_rn(xa, g.Lx), qxp = __dadd_rn(xa, -g.Lx);  // ix = -1 / +1: query + (-ix * L)
-    const double qym = __dadd_rn(ya, g.Ly), qyp = __dadd_rn(ya, -g.Ly);
-#pragma unroll
-    for (int s = 0; s < SPHB_K; ++s) {
-      const uint32_t en = col[s * 32].y;
-      const double2 pb = spos[en & IDX_MASK];
-      const uint32_t cx = (en >> (IMG_SHIFT + 2)) & 3u, cy = (en >> IMG_SHIFT) & 3u;
-      const double qx = cx == 1u ? xa : (cx == 0u ? qxm : qxp);
-      const double qy = cy == 1u ? ya : (cy == 0u ? qym : qyp);
-      d2[s] = dist_sq(qx - pb.x, qy - pb.y);
-      h2 = fmax(h2, d2[s]);
+  uint32_t* np = out.nn + (size_t)tile * 32 * 32 + lane;  // next list slot of this lane (stride 32 words)
+  uint32_t wp = kbase;                                   // next d^2 slot (shared-space address, stride 256 B)
+  const uint32_t wend = kbase + 32u * 256u;
+  bool self_seen = false;
+  {
+    const int lim = ok ? cnt : 0;
+    if (!anyimg) {  // warp-uniform: no periodic image in this tile's block, the query is never shifted
+#pragma unroll 2
+      for (int s = 0; s < lim; ++s) {
+        const uint2 ke = col[s * 32];
+        const uint32_t j = ke.y & IDX_MASK;
+        self_seen |= (j == (uint32_t)i);
+        if (ke.x < T && j != (uint32_t)i && wp != wend) {
+          const double2 pb = spos[j];
+          const double d2 = dist_sq(xa - pb.x, ya - pb.y);
+          h2 = fmax(h2, d2);
+          *np = ke.y;
+          np += 32;
+          asm volatile("st.shared.f64 [%0], %1;" ::"r"(wp), "d"(d2));
+          wp += 256;
+        }
+      }
+    } else {
+      const double qxm = __dadd_rn(xa, g.Lx), qxp = __dadd_rn(xa, -g.Lx);  // ix = -1 / +1: query + (-ix * L)
+      const double qym = __dadd_rn(ya, g.Ly), qyp = __dadd_rn(ya, -g.Ly);
+      for (int s = 0; s < lim; ++s) {
+        const uint2 ke = col[s * 32];
+        const uint32_t j = ke.y & IDX_MASK;
+        self_seen |= (j == (uint32_t)i);
+        if (ke.x < T && j != (uint32_t)i && wp != wend) {
+          const double2 pb = spos[j];
+          const uint32_t cx = (ke.y >> (IMG_SHIFT + 2)) & 3u, cy = (ke.y >> IMG_SHIFT) & 3u;
+          const double qx = cx == 1u ? xa : (cx == 0u ? qxm : qxp);
+          const double qy = cy == 1u ? ya : (cy == 0u ? qym : qyp);
+          const double d2 = dist_sq(qx - pb.x, qy - pb.y);
+          h2 = fmax(h2, d2);
+          *np = ke.y;
+          np += 32;
+          asm volatile("st.shared.f64 [%0], %1;" ::"r"(wp), "d"(d2));
+          wp += 256;
+        }
+      }
     }
-    if (!(h2 <= rg2)) ok = false;  // something within h may not have been staged/accepted
   }
+  __syncwarp();
+  // exactly 32 kept (fails on key ties at a pass boundary; more than 32 cannot happen: at most cnt - 1 - m),
+  // and nothing within h can have been missed
+  if (ok && !(wp == wend && self_seen && h2 <= rg2)) ok = false;
   if (valid && !ok) {
     const int slot = atomicAdd(out.failCount, 1);
     out.failList[slot] = i;
   }
   if (ok) {
-    const double h = sqrt(h2);
-    const double inv_h = 1.0 / h;
+    const double inv_h = fast_rsqrt(h2);
+    const double h = fast_sqrt(h2, inv_h);
     double acc = 0.0;
-    uint32_t* nncol = out.nn + (size_t)tile * 32 * 32 + lane;
-#pragma unroll
+#pragma unroll 4
     for (int s = 0; s < SPHB_K; ++s) {
-      const double d = d2[s] > 0.0 ? d2[s] * rsqrt(d2[s]) : 0.0;
-      acc += kern_F<KERNEL>(fmin(d * inv_h, 1.0));
-      nncol[s * 32] = col[s * 32].y;
+      const double d2 = *reinterpret_cast<const double*>(&col[s * 32]);
+      const double d = d2 * fast_rsqrt(d2 + 1e-300);  // coincident particles: d = 0
+      acc += kern_F<KERNEL>(d * inv_h);                    // d <= h up to rounding
     }
     // Density2D (sph.go:322), sound speed (sph.go:426-428), pressure term c^2/(gamma rho) (sph.go:332,360)
-    const double rho = ph.Fpref * ph.mass * acc / (h * h);
-    const double c = sqrt(ph.cfac * epred[i]);
-    out.pc[i] = make_double4(rho, c, h, c * c / (ph.gamma * rho));
+    const double rho = ph.Fpref * ph.mass * acc * (inv_h * inv_h);
+    const double c2 = ph.cfac * epred[i];
+    const double c = c2 > 0.0 ? fast_sqrt(c2, fast_rsqrt(c2)) : sqrt(c2);
+    out.pc[i] = make_double4(rho, c, h, c * c * fast_rcp(ph.gamma * rho));
   }
 }
 
@@ -785,18 +850,21 @@ __global__ void __launch_bounds__(128) k_force(ForceIO io, int n, const GridP* _
     const double rx = (pb.x - ox) - pa.x, ry = (pb.y - oy) - pa.y;
     const double vx = vb.x - va.x, vy = vb.y - va.y;
     const double r2 = dist_sq(rx, ry);
-    const double d = sqrt(r2);
+    const double rinv = rsqrt(r2);  // coincident particles give Inf/NaN like the reference (sph.go:391)
+    const double d = r2 * rinv;
     const double dot = vx * rx + vy * ry;
     double pi = 0.0;
-    if (dot < 0.0) {  // artificial viscosity, sph.go:375-388
+    if (dot < 0.0) {  // artificial viscosity, sph.go:375-388; the two divisions share one reciprocal
       const double cAB = 0.5 * (qa.y + qb.y);
       const double rhoAB = 0.5 * (qa.x + qb.x);
       const double hAB = 0.5 * (qa.z + qb.z);
-      const double mu = dot * hAB / (r2 + 0.01);
-      pi = (-0.75 * cAB * mu + 1.5 * mu * mu) / rhoAB;
+      const double den = r2 + 0.01;
+      const double inv = 1.0 / (den * rhoAB);
+      const double mu = dot * hAB * (rhoAB * inv);
+      pi = (-0.75 * cAB * mu + 1.5 * mu * mu) * (den * inv);
     }
     const double dk = kern_DF<KERNEL>(fmin(d * inv_h, 1.0));
-    const double w = (pi + qa.w + qb.w) * dk / d;
+    const double w = (pi + qa.w + qb.w) * dk * rinv;
     ax += rx * w;
     ay += ry * w;
     aed += dot * dk;
