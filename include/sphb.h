@@ -169,35 +169,51 @@ int sphb_counters(const sphb_sim* s, int64_t* out, int32_t n); /* n <= SPHB_CNT_
 int sphb_create_device(const sphb_params* p, int64_t n, int64_t capacity, const double* d_pos_xy,
                        const double* d_vel_xy, const double* d_e, const int64_t* d_id, sphb_sim** out);
 
-/* ---- slab decomposition: one handle per GPU owns particles with x in [x_lo, x_hi).
- * The exchange itself (NCCL send/recv) is done by the caller on the device buffers below. ---- */
+/* ---- slab decomposition: one handle per GPU owns a set of particles, nominally those with x in
+ * [x_lo, x_hi).  The exchange itself (NCCL send/recv over NVLink) is done by the caller on device buffers; see
+ * sphugo_b200/slab.py.  One force evaluation:
+ *     sphb_slab_set            ghost widths for this evaluation (from the all-reduced max h)
+ *     sphb_slab_step_begin     drift-1 + predict on the owned particles               (sph.go:108-117)
+ *     sphb_slab_pack_halo x2   owned particles within ghost_w of an edge -> records   -> exchange
+ *     sphb_slab_add_ghosts x2  append the neighbour's records as ghosts
+ *     sphb_slab_step_end       sort, kNN, density on owned + inner ghosts, forces + kick + drift-2 + boundaries on
+ *                              owned, ghosts dropped                                   (sph.go:119-193)
+ * Ghost layer: ghosts within inner_w of the slab are full queries (their rho, c, h are recomputed redundantly, so
+ * no second exchange is needed), the rest up to ghost_w are candidates only; inner_w >= max h and
+ * ghost_w >= inner_w + max h are verified on the device (SPHB_E_GHOST_THIN otherwise).
+ * Ownership is a set, not a strict interval: a particle that drifts out of [x_lo, x_hi) stays owned (the ghost
+ * widths must cover the excursion) until the caller migrates it: pack_migrants x2 -> exchange -> add_migrants x2 ->
+ * finish_migration.  Positions are always the reference's global coordinates; with a periodic x axis each handle
+ * works in the image frame centred on its slab. */
 typedef struct {
-  double x_lo, x_hi;   /* owned interval; ghosts live outside it */
-  int32_t has_left;    /* a neighbour slab exists on the low-x side (periodic ring or interior) */
+  double x_lo, x_hi;        /* nominal owned interval */
+  double ghost_w, inner_w;  /* ghost layer width / width of the layer whose ghosts are evaluated */
+  int32_t has_left;         /* a neighbour slab exists on the low-x side (periodic ring or interior edge) */
   int32_t has_right;
 } sphb_slab;
 
-int sphb_slab_set(sphb_sim* s, const sphb_slab* slab);
-/* max smoothing length of the last force evaluation (device reduction; the caller all-reduces it) */
-int sphb_max_h(sphb_sim* s, double* out);
-/* StepBegin: sources/step-0 handling + drift-1 + predict on owned particles (sph.go:108-117). */
-int sphb_slab_step_begin(sphb_sim* s);
-/* pack owned particles within `width` of the low (side 0) / high (side 1) edge as ghost records
- * {x, y, vpx, vpy, epred, id} = 6 x 8 bytes into d_buf (device); *count_out = records written. */
-int sphb_slab_pack_halo(sphb_sim* s, int32_t side, double width, void* d_buf, int64_t cap_records,
-                        int64_t* count_out);
-/* append received ghost records; x_shift is added to x (periodic ring wrap). */
-int sphb_slab_add_ghosts(sphb_sim* s, const void* d_buf, int64_t count, double x_shift);
-/* forces on owned particles using owned+ghost candidates, then kick/drift-2/boundaries, ghosts dropped */
-int sphb_slab_step_end(sphb_sim* s);
-/* pack (and remove) owned particles that left [x_lo, x_hi) to side 0/1 as migration records
- * {x, y, vx, vy, e, vdotx, vdoty, edot, h, id} = 10 x 8 bytes */
-int sphb_slab_pack_migrants(sphb_sim* s, int32_t side, void* d_buf, int64_t cap_records,
-                            int64_t* count_out);
-int sphb_slab_add_migrants(sphb_sim* s, const void* d_buf, int64_t count, double x_shift);
+#define SPHB_E_GHOST_THIN (-7) /* a smoothing length reached past the ghost layer: widen and redo the evaluation */
 
-#define SPHB_HALO_RECORD_DOUBLES 6
-#define SPHB_MIGRANT_RECORD_DOUBLES 10
+int sphb_slab_set(sphb_sim* s, const sphb_slab* slab);
+/* max smoothing length of the owned particles after the last evaluation (device reduction; the caller all-reduces) */
+int sphb_max_h(sphb_sim* s, double* out);
+/* mode 0: CalculateForces on the state as is; 1: step-0 initialisation VPred = Vel, EPred = E (sph.go:97-100);
+ * 2: drift-1 + predict (sph.go:108-117).  Owned particles only, in place. */
+int sphb_slab_step_begin(sphb_sim* s, int32_t mode);
+/* pack owned particles within ghost_w of the low (side 0) / high (side 1) edge as ghost records
+ * {x, y, vpx, vpy, epred, id (int64 bits), h_prev} = 7 x 8 bytes into d_buf (device); *count_out = records written */
+int sphb_slab_pack_halo(sphb_sim* s, int32_t side, void* d_buf, int64_t cap_records, int64_t* count_out);
+int sphb_slab_add_ghosts(sphb_sim* s, const void* d_buf, int64_t count);
+/* integrate != 0: kick + drift-2 + wrap + reflections on the owned particles and CurrentStep += 1 */
+int sphb_slab_step_end(sphb_sim* s, int32_t integrate);
+/* pack owned particles whose x (slab frame) left [x_lo, x_hi) towards side 0/1 as migration records
+ * {x, y, vx, vy, e, vdotx, vdoty, edot, h, id, rho, c} = 12 x 8 bytes; they are removed by finish_migration */
+int sphb_slab_pack_migrants(sphb_sim* s, int32_t side, void* d_buf, int64_t cap_records, int64_t* count_out);
+int sphb_slab_add_migrants(sphb_sim* s, const void* d_buf, int64_t count);
+int sphb_slab_finish_migration(sphb_sim* s);
+
+#define SPHB_HALO_RECORD_DOUBLES 7
+#define SPHB_MIGRANT_RECORD_DOUBLES 12
 
 #ifdef __cplusplus
 }

@@ -17,7 +17,7 @@ NN = 32
 OPEN_LO, OPEN_HI = -1.7976931348623157e308, 1.7976931348623157e308
 OPEN = (OPEN_LO, OPEN_HI)
 
-OK, E_INVALID, E_CUDA, E_NOMEM, E_KNN_UNDERFULL, E_KERNEL, E_STATE = 0, -1, -2, -3, -4, -5, -6
+OK, E_INVALID, E_CUDA, E_NOMEM, E_KNN_UNDERFULL, E_KERNEL, E_STATE, E_GHOST_THIN = 0, -1, -2, -3, -4, -5, -6, -7
 KERNEL_TOPHAT, KERNEL_MONAGHAN, KERNEL_WENDLAND = 0, 1, 2
 
 FIELDS = ["pos", "vel", "rho", "c", "e", "edot", "vdot", "epred", "vpred", "h", "id", "nn_idx", "nn_dist", "nn_pos"]
@@ -31,14 +31,14 @@ FIELD_SHAPE = {  # trailing shape, dtype
 SUM_E, SUM_RHO, LAST_VEL_NORM = 0, 1, 2
 PHASES = ["keys", "sort", "reorder", "knn", "force", "total"]
 COUNTERS = ["steps", "kernel_launches", "knn_fallback", "regrids"]
-HALO_RECORD_DOUBLES, MIGRANT_RECORD_DOUBLES = 6, 10
+HALO_RECORD_DOUBLES, MIGRANT_RECORD_DOUBLES = 7, 12
 
 EXPORTS = [
     "sphb_create", "sphb_destroy", "sphb_last_error", "sphb_set_params", "sphb_get_params", "sphb_count",
     "sphb_current_step", "sphb_append", "sphb_step", "sphb_calc_forces", "sphb_knn", "sphb_density", "sphb_stream", "sphb_sync",
     "sphb_download", "sphb_upload", "sphb_reduce", "sphb_phase_times", "sphb_counters", "sphb_create_device",
     "sphb_slab_set", "sphb_max_h", "sphb_slab_step_begin", "sphb_slab_pack_halo", "sphb_slab_add_ghosts",
-    "sphb_slab_step_end", "sphb_slab_pack_migrants", "sphb_slab_add_migrants",
+    "sphb_slab_step_end", "sphb_slab_pack_migrants", "sphb_slab_add_migrants", "sphb_slab_finish_migration",
 ]
 
 
@@ -54,7 +54,10 @@ class Params(C.Structure):
 
 
 class Slab(C.Structure):
-    _fields_ = [("x_lo", C.c_double), ("x_hi", C.c_double), ("has_left", C.c_int32), ("has_right", C.c_int32)]
+    """sphb_slab"""
+
+    _fields_ = [("x_lo", C.c_double), ("x_hi", C.c_double), ("ghost_w", C.c_double), ("inner_w", C.c_double),
+                ("has_left", C.c_int32), ("has_right", C.c_int32)]
 
 
 class SphbError(RuntimeError):
@@ -122,17 +125,19 @@ def lib():
     L.sphb_max_h.restype = C.c_int
     L.sphb_max_h.argtypes = [vp, dp]
     L.sphb_slab_step_begin.restype = C.c_int
-    L.sphb_slab_step_begin.argtypes = [vp]
+    L.sphb_slab_step_begin.argtypes = [vp, C.c_int32]
     L.sphb_slab_pack_halo.restype = C.c_int
-    L.sphb_slab_pack_halo.argtypes = [vp, C.c_int32, C.c_double, vp, C.c_int64, ip]
+    L.sphb_slab_pack_halo.argtypes = [vp, C.c_int32, vp, C.c_int64, ip]
     L.sphb_slab_add_ghosts.restype = C.c_int
-    L.sphb_slab_add_ghosts.argtypes = [vp, vp, C.c_int64, C.c_double]
+    L.sphb_slab_add_ghosts.argtypes = [vp, vp, C.c_int64]
     L.sphb_slab_step_end.restype = C.c_int
-    L.sphb_slab_step_end.argtypes = [vp]
+    L.sphb_slab_step_end.argtypes = [vp, C.c_int32]
     L.sphb_slab_pack_migrants.restype = C.c_int
     L.sphb_slab_pack_migrants.argtypes = [vp, C.c_int32, vp, C.c_int64, ip]
     L.sphb_slab_add_migrants.restype = C.c_int
-    L.sphb_slab_add_migrants.argtypes = [vp, vp, C.c_int64, C.c_double]
+    L.sphb_slab_add_migrants.argtypes = [vp, vp, C.c_int64]
+    L.sphb_slab_finish_migration.restype = C.c_int
+    L.sphb_slab_finish_migration.argtypes = [vp]
     _LIB = L
     return L
 

@@ -65,7 +65,9 @@ struct sphb_sim {
   // slab mode
   bool slab_on = false;
   sphb_slab slab{};
-  double slab_w = 0.0;        // ghost width used for the pending evaluation
+  uint32_t* ownTile = nullptr; // tile sums of the owned-particle scan
+  int* packCount = nullptr;    // device counter of the pack kernels
+  int64_t nleaving = 0;        // particles packed for migration and not yet compacted away
   cudaEvent_t ev[SPHB_PH_COUNT + 1] = {};
   bool ev_valid = false;
   int64_t counters[SPHB_CNT_COUNT] = {0, 0, 0, 0};
@@ -210,17 +212,50 @@ void launch_knn(sphb_sim* s, int ntot, const PhysP& ph) {
     attr_done[KERNEL] = true;
   }
   k_knn_tile<KERNEL><<<cdiv(tiles, KNN_WARPS), KNN_THREADS, smem, s->st>>>(s->spos, s->keysSorted, s->cellStart,
-                                                                         s->hguess, s->a.epred, ntot, s->grid, ph, kt, out);
+                                                                         s->hguess, s->a.epred, ntot, s->grid, ph, kt, out,
+                                                                         s->slab_on ? s->a.ghost : nullptr, s->dflags);
   k_knn_fallback<KERNEL><<<148 * 4, 128, 0, s->st>>>(s->spos, s->keysSorted, s->cellStart, s->hguess,
                                                    s->a.epred, ntot, s->grid, ph, out, s->dflags);
   s->have_h = true;
 }
 
+SlabP make_slabp(const sphb_sim* s) {
+  SlabP sl{};
+  sl.x_lo = s->slab.x_lo; sl.x_hi = s->slab.x_hi; sl.ghost_w = s->slab.ghost_w; sl.inner_w = s->slab.inner_w;
+  sl.has_left = s->slab.has_left; sl.has_right = s->slab.has_right;
+  if (s->slab_on && !axis_open(s->prm.hor)) {  // image frame centred on the slab
+    sl.Lx = s->prm.hor[1] - s->prm.hor[0];
+    sl.frame_lo = 0.5 * (s->slab.x_lo + s->slab.x_hi) - 0.5 * sl.Lx;
+  }
+  return sl;
+}
+
 template <int KERNEL>
 void launch_force(sphb_sim* s, int ntot, const PhysP& ph, bool integrate) {
-  ForceIO io{s->spos, s->a.vpred, s->a.pc, s->nn, s->a.pos, s->a.vel, s->a.e, s->a.vdot, s->a.edot};
-  if (integrate) k_force<KERNEL, true><<<cdiv(ntot, 128), 128, 0, s->st>>>(io, ntot, s->grid, ph);
-  else k_force<KERNEL, false><<<cdiv(ntot, 128), 128, 0, s->st>>>(io, ntot, s->grid, ph);
+  ForceIO io{};
+  io.spos = s->spos; io.vpred = s->a.vpred; io.pc = s->a.pc; io.nn = s->nn;
+  io.pos = s->a.pos; io.vel = s->a.vel; io.e = s->a.e; io.vdot = s->a.vdot; io.edot = s->a.edot;
+  const int nb = cdiv(ntot, 128);
+  if (!s->slab_on) {
+    if (integrate) k_force<KERNEL, true, false><<<nb, 128, 0, s->st>>>(io, ntot, s->grid, ph, s->dflags);
+    else k_force<KERNEL, false, false><<<nb, 128, 0, s->st>>>(io, ntot, s->grid, ph, s->dflags);
+    return;
+  }
+  io.gflag = s->a.ghost; io.ownIdx = s->perm; io.epred = s->a.epred; io.id = s->a.id;
+  io.o_pos = s->b.pos; io.o_vel = s->b.vel; io.o_vdot = s->b.vdot; io.o_vpred = s->b.vpred;
+  io.o_e = s->b.e; io.o_edot = s->b.edot; io.o_epred = s->b.epred; io.o_id = s->b.id; io.o_pc = s->b.pc;
+  io.o_gflag = s->b.ghost;
+  if (integrate) k_force<KERNEL, true, true><<<nb, 128, 0, s->st>>>(io, ntot, s->grid, ph, s->dflags);
+  else k_force<KERNEL, false, true><<<nb, 128, 0, s->st>>>(io, ntot, s->grid, ph, s->dflags);
+}
+
+// exclusive prefix of (flag == owned) over [0, ntot) into s->perm (free once the reorder is done)
+void own_scan(sphb_sim* s, int ntot) {
+  const int nt = cdiv(ntot, SC_TILE);
+  k_flag_tiles<<<nt, SC_THREADS, 0, s->st>>>(s->a.ghost, ntot, s->ownTile);
+  k_excl_scan<<<1, 1024, 0, s->st>>>(s->ownTile, nt, nullptr);
+  k_flag_apply<<<nt, SC_THREADS, 0, s->st>>>(s->a.ghost, ntot, s->ownTile, s->perm);
+  s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 3;
 }
 
 // sort + reorder + kNN (+ density with `kernel`); the neighbour list, spos and grid then describe s->a
@@ -231,8 +266,8 @@ int build_neighbours(sphb_sim* s, int mode, const double hor[2], const double ve
   const PhysP ph = make_phys(s->prm, kernel);
   const double dtH = s->prm.dt_half;
   if (timed) cudaEventRecord(s->ev[SPHB_PH_KEYS], s->st);
-  k_make_grid<<<1, 32, 0, s->st>>>(s->stats, ntot, hor[0], hor[1], ver[0], ver[1], s->slab.x_lo - s->slab_w,
-                                   s->slab.x_hi + s->slab_w, s->slab_on ? 1 : 0, s->gtune, s->grid);
+  k_make_grid<<<1, 32, 0, s->st>>>(s->stats, ntot, hor[0], hor[1], ver[0], ver[1], make_slabp(s), s->slab_on ? 1 : 0,
+                                   s->gtune, s->grid);
   if (mode == MODE_DRIFT) k_keys<true><<<cdiv(ntot, 256), 256, 0, s->st>>>(s->a.pos, s->a.vel, ntot, s->grid, dtH, s->keys, s->rank, s->cellCount);
   else k_keys<false><<<cdiv(ntot, 256), 256, 0, s->st>>>(s->a.pos, s->a.vel, ntot, s->grid, dtH, s->keys, s->rank, s->cellCount);
   if (timed) cudaEventRecord(s->ev[SPHB_PH_SORT], s->st);
@@ -273,13 +308,18 @@ int forces(sphb_sim* s, int mode, bool integrate) {
   const int ntot = (int)(s->n + s->nghost);
   const PhysP ph = make_phys(s->prm, s->prm.kernel);
   cudaEventRecord(s->ev[SPHB_PH_FORCE], s->st);
+  if (s->slab_on) own_scan(s, ntot);
   if (s->prm.kernel == 1) launch_force<1>(s, ntot, ph, integrate);
   else launch_force<2>(s, ntot, ph, integrate);
   s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 1;
+  if (s->slab_on) {  // the force kernel wrote the owned particles compacted into the other copy: ghosts are gone
+    std::swap(s->a, s->b);
+    s->nghost = 0;
+    s->have_list = false;
+  }
   cudaEventRecord(s->ev[SPHB_PH_TOTAL], s->st);
   s->ev_valid = true;
-  if (!s->slab_on) { rc = refresh_stats(s); if (rc) return rc; }
-  else s->stats_dirty = true;
+  rc = refresh_stats(s); if (rc) return rc;
   CKL(s);
   return SPHB_OK;
 }
@@ -291,8 +331,11 @@ int check_async(sphb_sim* s) {
   CK(s, cudaMemcpyAsync(fc, s->failCount, sizeof fc, cudaMemcpyDeviceToHost, s->st));
   CK(s, cudaStreamSynchronize(s->st));
   s->counters[SPHB_CNT_KNN_FALLBACK] = fc[1];
+  if (fl) cudaMemsetAsync(s->dflags, 0, sizeof(uint32_t), s->st);
+  if (fl & DFLAG_BUF_FULL) return fail(s, SPHB_E_NOMEM, "slab: a halo/migration buffer or the particle capacity is too small");
+  if (fl & DFLAG_GHOST_THIN)
+    return fail(s, SPHB_E_GHOST_THIN, "slab: a smoothing length reached past the ghost layer (inner_w / ghost_w too small)");
   if (fl & DFLAG_UNDERFULL) {
-    cudaMemsetAsync(s->dflags, 0, sizeof(uint32_t), s->st);
     return fail(s, SPHB_E_KNN_UNDERFULL,
                 "kNN: fewer than 32 (particle, image) candidates exist for some particle; the reference would keep "
                 "sentinel slots (nearest-neighbour.go:155-165)");
@@ -371,6 +414,8 @@ int create_common(const sphb_params* p, int64_t n, int64_t capacity, const doubl
   CKC(dalloc(s->nn, cap32 * SPHB_K));
   CKC(dalloc(s->failList, cap));
   CKC(dalloc(s->failCount, 2));
+  CKC(dalloc(s->ownTile, (size_t)cdiv(capacity, SC_TILE) + 1));
+  CKC(dalloc(s->packCount, 1));
   CKC(dalloc(s->dflags, 1));
   CKC(dalloc(s->statPart, (size_t)STAT_BLOCKS * STAT_N));
   CKC(dalloc(s->stats, STAT_N));
@@ -427,6 +472,7 @@ void sphb_destroy(sphb_sim* s) {
   cudaFree(s->spos); cudaFree(s->hguess);
   cudaFree(s->keys); cudaFree(s->keysSorted); cudaFree(s->rank); cudaFree(s->perm);
   cudaFree(s->cellCount); cudaFree(s->tileSum); cudaFree(s->cellStart); cudaFree(s->nn); cudaFree(s->failList); cudaFree(s->failCount);
+  cudaFree(s->ownTile); cudaFree(s->packCount);
   cudaFree(s->dflags); cudaFree(s->statPart); cudaFree(s->stats); cudaFree(s->grid); cudaFree(s->scratch);
   for (auto& ev : s->ev) if (ev) cudaEventDestroy(ev);
   if (s->st) cudaStreamDestroy(s->st);
@@ -642,6 +688,7 @@ int sphb_reduce(sphb_sim* s, int32_t which, double* out) {
 int sphb_max_h(sphb_sim* s, double* out) {
   int rc = enter(s); if (rc) return rc;
   if (!out) return fail(s, SPHB_E_INVALID, "out is NULL");
+  rc = check_async(s); if (rc) return rc;  // the slab driver calls this once per evaluation: surfaces GHOST_THIN etc.
   if (s->stats_dirty) { rc = refresh_stats(s); if (rc) return rc; }
   double st[STAT_N];
   CK(s, cudaMemcpyAsync(st, s->stats, sizeof st, cudaMemcpyDeviceToHost, s->st));

@@ -26,6 +26,9 @@ struct GridP {
   double lox, loy;      // low end of the periodic interval
   int ncx, ncy;
   int wrapx, wrapy;
+  int framex;  // slab mode on a periodic x axis: positions are taken in the image frame [lox, lox + Lx) centred on
+               // the slab, but the grid itself does not wrap (the neighbour slabs supply ghosts instead)
+  int sides;   // slab mode: bit 0 / bit 1 = the low-x / high-x grid edge is a ghost-layer boundary, not an open end
 };
 
 struct PhysP {
@@ -45,6 +48,14 @@ struct KnnTune {
 
 // device-side status word
 #define DFLAG_UNDERFULL 1u
+#define DFLAG_GHOST_THIN 2u  // slab mode: some h reached past the ghost layer
+#define DFLAG_BUF_FULL 4u    // slab mode: a pack buffer or the particle capacity was exceeded
+
+// per-particle flag (Soa.ghost)
+#define GF_OWNED 0
+#define GF_INNER 1    // ghost, evaluated (kNN + density) so that owned particles can read its rho, c, h
+#define GF_OUTER 2    // ghost, candidate only
+#define GF_LEAVING 3  // owned, packed for migration, removed by the next compaction
 
 // -------------------------------------------------------------------------------------------------
 // small helpers
@@ -142,7 +153,7 @@ __global__ void __launch_bounds__(256) k_keys(const double2* __restrict__ pos, c
     p.x = __dadd_rn(p.x, __dmul_rn(v.x, dtH));
     p.y = __dadd_rn(p.y, __dmul_rn(v.y, dtH));
   }
-  double xs = g.wrapx ? wrap_coord(p.x, g.lox, g.Lx) : p.x;
+  double xs = (g.wrapx | g.framex) ? wrap_coord(p.x, g.lox, g.Lx) : p.x;
   double ys = g.wrapy ? wrap_coord(p.y, g.loy, g.Ly) : p.y;
   int cx = cell_of(xs, g.ox, g.inv_dx, g.ncx);
   int cy = cell_of(ys, g.oy, g.inv_dy, g.ncy);
@@ -204,7 +215,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_scan_tiles(const uint32_t* __res
 // exclusive scan of m uint32 in place, one block of 1024 threads (m = number of tiles, <= a few hundred thousand)
 __global__ void __launch_bounds__(1024) k_excl_scan(uint32_t* __restrict__ a, int m_cap, const GridP* __restrict__ gp) {
   __shared__ uint32_t wsum[32];
-  const int m = min(m_cap, (gp->ncx * gp->ncy + 1 + SC_TILE - 1) / SC_TILE);
+  const int m = gp ? min(m_cap, (gp->ncx * gp->ncy + 1 + SC_TILE - 1) / SC_TILE) : m_cap;
   int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int per = (m + 1023) / 1024;
   int b = min(tid * per, m), e = min(b + per, m);
@@ -339,7 +350,7 @@ __global__ void __launch_bounds__(256) k_reorder(StateIn in, StateOut out, const
   out.ghost[j] = in.ghost[i];
   out.hguess[j] = pc.z;
   double2 sp;
-  sp.x = g.wrapx ? wrap_coord(p.x, g.lox, g.Lx) : p.x;
+  sp.x = (g.wrapx | g.framex) ? wrap_coord(p.x, g.lox, g.Lx) : p.x;
   sp.y = g.wrapy ? wrap_coord(p.y, g.loy, g.Ly) : p.y;
   out.spos[j] = sp;
   keysSorted[j] = c;
@@ -416,7 +427,8 @@ __global__ void __launch_bounds__(KNN_THREADS, 4) k_knn_tile(const double2* __re
                                                          const double* __restrict__ hguess,
                                                          const double* __restrict__ epred, int n,
                                                          const GridP* __restrict__ gp, PhysP ph, KnnTune tune,
-                                                         KnnOut out) {
+                                                         KnnOut out, const uint8_t* __restrict__ gflag,
+                                                         uint32_t* __restrict__ dflags) {
   const GridP g = *gp;
   extern __shared__ __align__(16) uint32_t smem_u[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -431,7 +443,8 @@ __global__ void __launch_bounds__(KNN_THREADS, 4) k_knn_tile(const double2* __re
   const int tile = blockIdx.x * KNN_WARPS + warp;
   if (tile * 32 >= n) return;  // whole warp out of range (warp-uniform)
   const int i = tile * 32 + lane;
-  const bool valid = i < n;
+  // queries: owned particles and (slab mode) inner ghosts; outer ghosts are candidates only
+  const bool valid = i < n && (gflag == nullptr || gflag[i] != GF_OUTER);
 
   double xa = 0, ya = 0, rg = 0;
   int cxa = 0, cya = 0;
@@ -640,6 +653,8 @@ __global__ void __launch_bounds__(KNN_THREADS, 4) k_knn_tile(const double2* __re
   if (ok) {
     const double inv_h = fast_rsqrt(h2);
     const double h = fast_sqrt(h2, inv_h);
+    if (g.sides && (((g.sides & 1) && xa - g.ox < h) || ((g.sides & 2) && g.ox + (double)g.ncx * g.dx - xa < h)))
+      atomicOr(dflags, DFLAG_GHOST_THIN);
     double acc = 0.0;
 #pragma unroll 4
     for (int s = 0; s < SPHB_K; ++s) {
@@ -764,6 +779,8 @@ __global__ void __launch_bounds__(128) k_knn_fallback(const double2* __restrict_
     const double h2 = __shfl_sync(0xffffffffu, td, 0);
     const double h = sqrt(h2);
     const double inv_h = 1.0 / h;
+    if (lane == 0 && g.sides && (((g.sides & 1) && pa.x - g.ox < h) || ((g.sides & 2) && g.ox + (double)g.ncx * g.dx - pa.x < h)))
+      atomicOr(dflags, DFLAG_GHOST_THIN);
     double acc = kern_F<KERNEL>(fmin(sqrt(td) * inv_h, 1.0));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -826,13 +843,25 @@ struct ForceIO {
   double* e;
   double2* vdot;
   double* edot;
+  // slab mode: owned particles are written compacted (ghosts dropped) into the other state copy
+  const uint8_t* gflag;
+  const uint32_t* ownIdx;
+  const double* epred;
+  const int64_t* id;
+  double2 *o_pos, *o_vel, *o_vdot, *o_vpred;
+  double *o_e, *o_edot, *o_epred;
+  int64_t* o_id;
+  double4* o_pc;
+  uint8_t* o_gflag;
 };
 
-template <int KERNEL, bool INTEGRATE>
-__global__ void __launch_bounds__(128) k_force(ForceIO io, int n, const GridP* __restrict__ gp, PhysP ph) {
+template <int KERNEL, bool INTEGRATE, bool SLAB>
+__global__ void __launch_bounds__(128) k_force(ForceIO io, int n, const GridP* __restrict__ gp, PhysP ph,
+                                               uint32_t* __restrict__ dflags) {
   const GridP g = *gp;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (SLAB && io.gflag[i] != GF_OWNED) return;
   const double2 pa = io.spos[i];
   const double2 va = io.vpred[i];
   const double4 qa = io.pc[i];  // rho, c, h, P
@@ -846,6 +875,7 @@ __global__ void __launch_bounds__(128) k_force(ForceIO io, int n, const GridP* _
     const double2 pb = io.spos[j];
     const double2 vb = io.vpred[j];
     const double4 qb = io.pc[j];
+    if (SLAB && io.gflag[j] == GF_OUTER) atomicOr(dflags, DFLAG_GHOST_THIN);  // its rho, c, h were not evaluated
     // rAB = NNPos - Pos with NNPos = neighbour - offset (nearest-neighbour.go:80, sph.go:372)
     const double rx = (pb.x - ox) - pa.x, ry = (pb.y - oy) - pa.y;
     const double vx = vb.x - va.x, vy = vb.y - va.y;
@@ -872,11 +902,9 @@ __global__ void __launch_bounds__(128) k_force(ForceIO io, int n, const GridP* _
   const double f = ph.mass * ph.DFpref / (h * h * h);
   double2 a = make_double2(ax * f + ph.gx, ay * f + ph.gy);
   const double ed = qa.w * aed * ph.mass;  // Benz formulation, sph.go:400
-  io.vdot[i] = a;
-  io.edot[i] = ed;
+  double2 p = io.pos[i], v = io.vel[i];
+  double e = io.e[i];
   if (INTEGRATE) {
-    double2 p = io.pos[i], v = io.vel[i];
-    double e = io.e[i];
     const double dt = 2.0 * ph.dtH;
     // kick (sph.go:122-127), drift 2 (sph.go:130-135): unfused like the reference
     v.x = __dadd_rn(v.x, __dmul_rn(a.x, dt));
@@ -894,10 +922,214 @@ __global__ void __launch_bounds__(128) k_force(ForceIO io, int n, const GridP* _
     if (p.x > ph.rR) { p.x = __dsub_rn(p.x, __dsub_rn(p.x, ph.rR)); v.x = -v.x; }
     if (p.y < ph.rU) { p.y = __dsub_rn(p.y, __dsub_rn(p.y, ph.rU)); v.y = -v.y; }
     if (p.y > ph.rD) { p.y = __dsub_rn(p.y, __dsub_rn(p.y, ph.rD)); v.y = -v.y; }
-    io.pos[i] = p;
-    io.vel[i] = v;
-    io.e[i] = e;
   }
+  if (!SLAB) {
+    io.vdot[i] = a;
+    io.edot[i] = ed;
+    if (INTEGRATE) {
+      io.pos[i] = p;
+      io.vel[i] = v;
+      io.e[i] = e;
+    }
+  } else {
+    const uint32_t o = io.ownIdx[i];
+    io.o_pos[o] = p;
+    io.o_vel[o] = v;
+    io.o_e[o] = e;
+    io.o_vdot[o] = a;
+    io.o_edot[o] = ed;
+    io.o_vpred[o] = va;
+    io.o_epred[o] = io.epred[i];
+    io.o_id[o] = io.id[i];
+    io.o_pc[o] = qa;
+    io.o_gflag[o] = GF_OWNED;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// slab mode helpers
+// -------------------------------------------------------------------------------------------------
+struct SlabP {
+  double x_lo, x_hi, ghost_w, inner_w;
+  double Lx, frame_lo;  // periodic x: period and low end of the image frame centred on the slab; Lx = 0: none
+  int has_left, has_right;
+};
+
+__device__ __forceinline__ double slab_frame_x(double x, const SlabP& sl) {
+  return sl.Lx > 0.0 ? wrap_coord(x, sl.frame_lo, sl.Lx) : x;
+}
+
+// drift-1 + predict in place on the owned particles (sph.go:108-117) / step-0 initialisation (sph.go:97-100)
+template <int MODE>
+__global__ void __launch_bounds__(256) k_slab_predict(double2* __restrict__ pos, const double2* __restrict__ vel,
+                                                     const double2* __restrict__ vdot, double2* __restrict__ vpred,
+                                                     const double* __restrict__ e, const double* __restrict__ edot,
+                                                     double* __restrict__ epred, uint8_t* __restrict__ gflag, int n,
+                                                     double dtH) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  gflag[i] = GF_OWNED;
+  if (MODE == 0) return;
+  const double2 v = vel[i];
+  if (MODE == 2) {
+    double2 p = pos[i];
+    const double2 a = vdot[i];
+    p.x = __dadd_rn(p.x, __dmul_rn(v.x, dtH));
+    p.y = __dadd_rn(p.y, __dmul_rn(v.y, dtH));
+    pos[i] = p;
+    vpred[i] = make_double2(__dadd_rn(v.x, __dmul_rn(a.x, dtH)), __dadd_rn(v.y, __dmul_rn(a.y, dtH)));
+    epred[i] = __dadd_rn(e[i], __dmul_rn(edot[i], dtH));
+  } else {
+    vpred[i] = v;
+    epred[i] = e[i];
+  }
+}
+
+// append with one atomic per warp; returns the slot of this lane or -1
+__device__ __forceinline__ int warp_append_slot(bool want, int* counter) {
+  const uint32_t m = __ballot_sync(0xffffffffu, want);
+  if (m == 0) return -1;
+  const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(counter, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  return want ? base + __popc(m & ((1u << lane) - 1u)) : -1;
+}
+
+// ghost records {x, y, vpx, vpy, epred, id, h}
+__global__ void __launch_bounds__(256) k_pack_halo(const double2* __restrict__ pos, const double2* __restrict__ vpred,
+                                                  const double* __restrict__ epred, const int64_t* __restrict__ id,
+                                                  const double4* __restrict__ pc, int n, SlabP sl, int side,
+                                                  double* __restrict__ buf, int cap, int* __restrict__ counter,
+                                                  uint32_t* __restrict__ dflags) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool want = false;
+  double2 p = make_double2(0, 0);
+  if (i < n) {
+    p = pos[i];
+    const double xl = slab_frame_x(p.x, sl);
+    want = side == 0 ? (xl - sl.x_lo < sl.ghost_w) : (sl.x_hi - xl <= sl.ghost_w);
+  }
+  const int slot = warp_append_slot(want, counter);
+  if (slot < 0) return;
+  if (slot >= cap) { atomicOr(dflags, DFLAG_BUF_FULL); return; }
+  double* r = buf + (size_t)slot * 7;
+  const double2 vp = vpred[i];
+  r[0] = p.x; r[1] = p.y; r[2] = vp.x; r[3] = vp.y; r[4] = epred[i];
+  r[5] = __longlong_as_double(id[i]);
+  r[6] = pc[i].z;
+}
+
+__global__ void __launch_bounds__(256) k_add_ghosts(const double* __restrict__ buf, int count, SlabP sl,
+                                                   double2* __restrict__ pos, double2* __restrict__ vel,
+                                                   double2* __restrict__ vdot, double2* __restrict__ vpred,
+                                                   double* __restrict__ e, double* __restrict__ edot,
+                                                   double* __restrict__ epred, int64_t* __restrict__ id,
+                                                   double4* __restrict__ pc, uint8_t* __restrict__ gflag) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  const double* r = buf + (size_t)k * 7;
+  const double x = r[0];
+  pos[k] = make_double2(x, r[1]);
+  vel[k] = make_double2(0, 0);
+  vdot[k] = make_double2(0, 0);
+  vpred[k] = make_double2(r[2], r[3]);
+  e[k] = 0.0; edot[k] = 0.0;
+  epred[k] = r[4];
+  id[k] = __double_as_longlong(r[5]);
+  pc[k] = make_double4(0.0, 0.0, r[6], 0.0);
+  const double xl = slab_frame_x(x, sl);
+  gflag[k] = (xl >= sl.x_lo - sl.inner_w && xl < sl.x_hi + sl.inner_w) ? GF_INNER : GF_OUTER;
+}
+
+// migration records {x, y, vx, vy, e, vdotx, vdoty, edot, h, id, rho, c}
+__global__ void __launch_bounds__(256) k_pack_migrants(const double2* __restrict__ pos, const double2* __restrict__ vel,
+                                                      const double* __restrict__ e, const double2* __restrict__ vdot,
+                                                      const double* __restrict__ edot, const int64_t* __restrict__ id,
+                                                      const double4* __restrict__ pc, uint8_t* __restrict__ gflag,
+                                                      int n, SlabP sl, int side, double* __restrict__ buf, int cap,
+                                                      int* __restrict__ counter, uint32_t* __restrict__ dflags) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool want = false;
+  double2 p = make_double2(0, 0);
+  if (i < n && gflag[i] == GF_OWNED) {
+    p = pos[i];
+    const double xl = slab_frame_x(p.x, sl);
+    want = side == 0 ? (sl.has_left && xl < sl.x_lo) : (sl.has_right && xl >= sl.x_hi);
+  }
+  const int slot = warp_append_slot(want, counter);
+  if (slot < 0) return;
+  if (slot >= cap) { atomicOr(dflags, DFLAG_BUF_FULL); return; }
+  gflag[i] = GF_LEAVING;
+  double* r = buf + (size_t)slot * 12;
+  const double2 v = vel[i], a = vdot[i];
+  const double4 q = pc[i];
+  r[0] = p.x; r[1] = p.y; r[2] = v.x; r[3] = v.y; r[4] = e[i]; r[5] = a.x; r[6] = a.y; r[7] = edot[i];
+  r[8] = q.z; r[9] = __longlong_as_double(id[i]); r[10] = q.x; r[11] = q.y;
+}
+
+__global__ void __launch_bounds__(256) k_add_migrants(const double* __restrict__ buf, int count, double gamma,
+                                                     double2* __restrict__ pos, double2* __restrict__ vel,
+                                                     double2* __restrict__ vdot, double2* __restrict__ vpred,
+                                                     double* __restrict__ e, double* __restrict__ edot,
+                                                     double* __restrict__ epred, int64_t* __restrict__ id,
+                                                     double4* __restrict__ pc, uint8_t* __restrict__ gflag) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  const double* r = buf + (size_t)k * 12;
+  pos[k] = make_double2(r[0], r[1]);
+  vel[k] = make_double2(r[2], r[3]);
+  e[k] = r[4];
+  vdot[k] = make_double2(r[5], r[6]);
+  edot[k] = r[7];
+  vpred[k] = make_double2(r[2], r[3]);
+  epred[k] = r[4];
+  id[k] = __double_as_longlong(r[9]);
+  const double rho = r[10], c = r[11];
+  pc[k] = make_double4(rho, c, r[8], rho > 0.0 ? c * c / (gamma * rho) : 0.0);
+  gflag[k] = GF_OWNED;
+}
+
+// keep-scan over the flags: tile counts of flag == GF_OWNED, then per-element exclusive prefix
+__global__ void __launch_bounds__(SC_THREADS) k_flag_tiles(const uint8_t* __restrict__ gflag, int n,
+                                                          uint32_t* __restrict__ tileSum) {
+  __shared__ uint32_t wsum[SC_THREADS / 32];
+  const int base = blockIdx.x * SC_TILE + threadIdx.x * SC_ITEMS;
+  uint32_t sum = 0;
+#pragma unroll
+  for (int k = 0; k < SC_ITEMS; ++k) sum += (base + k < n && gflag[base + k] == GF_OWNED) ? 1u : 0u;
+  uint32_t tot;
+  block_excl_scan_256(sum, wsum, tot);
+  if (threadIdx.x == 0) tileSum[blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(SC_THREADS) k_flag_apply(const uint8_t* __restrict__ gflag, int n,
+                                                          const uint32_t* __restrict__ tileOff,
+                                                          uint32_t* __restrict__ ownIdx) {
+  __shared__ uint32_t wsum[SC_THREADS / 32];
+  const int base = blockIdx.x * SC_TILE + threadIdx.x * SC_ITEMS;
+  uint32_t v[SC_ITEMS], sum = 0;
+#pragma unroll
+  for (int k = 0; k < SC_ITEMS; ++k) {
+    v[k] = (base + k < n && gflag[base + k] == GF_OWNED) ? 1u : 0u;
+    sum += v[k];
+  }
+  uint32_t tot;
+  uint32_t run = block_excl_scan_256(sum, wsum, tot) + tileOff[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < SC_ITEMS; ++k) {
+    if (base + k < n) ownIdx[base + k] = run;
+    run += v[k];
+  }
+}
+
+// stable compaction of the owned particles (drops GF_LEAVING) into the other state copy
+__global__ void __launch_bounds__(256) k_compact(StateIn in, StateOut out, const uint32_t* __restrict__ ownIdx, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || in.ghost[i] != GF_OWNED) return;
+  const uint32_t o = ownIdx[i];
+  out.pos[o] = in.pos[i]; out.vel[o] = in.vel[i]; out.vdot[o] = in.vdot[i]; out.vpred[o] = in.vpred[i];
+  out.e[o] = in.e[i]; out.edot[o] = in.edot[i]; out.epred[o] = in.epred[i];
+  out.id[o] = in.id[i]; out.pc[o] = in.pc[i]; out.ghost[o] = GF_OWNED;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -968,14 +1200,25 @@ struct GridTune {
 };
 
 __global__ void k_make_grid(const double* __restrict__ stats, int n, double hor0, double hor1, double ver0, double ver1,
-                            double xlo_fixed, double xhi_fixed, int x_fixed, GridTune t, GridP* __restrict__ out) {
+                            SlabP sl, int slab_on, GridTune t, GridP* __restrict__ out) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   GridP g;
   g.wrapx = !(hor0 == -1.7976931348623157e308);
   g.wrapy = !(ver0 == -1.7976931348623157e308);
   double ex, ey;
-  if (g.wrapx) { g.lox = hor0; g.Lx = hor1 - hor0; g.ox = hor0; ex = g.Lx; }
-  else if (x_fixed) { g.lox = 0; g.Lx = 0; g.ox = xlo_fixed; ex = xhi_fixed - xlo_fixed; }
+  g.framex = 0; g.sides = 0;
+  if (slab_on) {  // the slab's own frame: ghosts extend the box on the sides that have a neighbour
+    const int periodic = g.wrapx;
+    g.wrapx = 0;
+    g.framex = periodic && sl.Lx > 0.0;
+    g.Lx = g.framex ? sl.Lx : 0.0;
+    g.lox = g.framex ? sl.frame_lo : 0.0;
+    const double lo = sl.has_left ? sl.x_lo - sl.ghost_w : stats[0];
+    const double hi = sl.has_right ? sl.x_hi + sl.ghost_w : stats[1];
+    g.ox = lo; ex = hi - lo;
+    g.sides = (sl.has_left ? 1 : 0) | (sl.has_right ? 2 : 0);
+  }
+  else if (g.wrapx) { g.lox = hor0; g.Lx = hor1 - hor0; g.ox = hor0; ex = g.Lx; }
   else { g.lox = 0; g.Lx = 0; g.ox = stats[0]; ex = stats[1] - stats[0]; }
   if (g.wrapy) { g.loy = ver0; g.Ly = ver1 - ver0; g.oy = ver0; ey = g.Ly; }
   else { g.loy = 0; g.Ly = 0; g.oy = stats[2]; ey = stats[3] - stats[2]; }
