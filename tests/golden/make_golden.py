@@ -1,0 +1,67 @@
+#!/usr/bin/env python
+"""Regenerates tests/golden/*.npz.
+
+The reference is pure Go and cannot run in this image (no Go toolchain), so the golden vectors are outputs of
+the CPU restatement in oracle/ (faithful mode: the reference's own tree walk and queue) on the reference's
+configurations.  They pin (a) the oracle against accidental change and (b) the CUDA path on the
+GPU box, where neither /root/reference nor a rebuilt oracle is needed to read them.
+    python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle import oracle as orc  # noqa: E402
+from sphugo_b200 import gen  # noqa: E402
+
+
+def save(name, **arrs):
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **arrs)
+    print(name, {k: getattr(v, "shape", None) for k, v in arrs.items()})
+
+
+def c1_density():
+    """examples/density main: 1000 + 200 particles, periodic [0,1]^2, three kernels (density.go:41-97)"""
+    ic = gen.spawn([(1000, (0.0, 0.0), (1.0, 1.0)), (200, (0.1, 0.0), (0.3, 0.4))])
+    o = orc.Oracle(orc.make_params(hor=(0, 1), ver=(0, 1)), ic["pos"], ids=ic["id"])
+    o.knn((0.0, 1.0), (0.0, 1.0), mode=0)
+    st = o.state(neighbours=True)
+    rho = []
+    for k in (0, 1, 2):
+        o.density(k)
+        rho.append(o.state()["rho"])
+    save("c1_density", pos=st["pos"], id=st["id"], h=st["h"], nn_id=np.sort(st["nn_id"], 1).astype(np.int32),
+         nn_dist=st["nn_dist"], rho_tophat=rho[0], rho_monaghan=rho[1], rho_wendland=rho[2])
+
+
+def c2_default():
+    """sim.MakeSimulation(): 1000 U([0,1]^2), MakeConfig defaults; states after 1 and 5 steps"""
+    ic = gen.spawn([(1000, (0, 0), (1, 1))])
+    o = orc.Oracle(orc.make_params(), ic["pos"], ic["vel"], ic["e"], None, ic["id"])
+    out = dict(pos0=ic["pos"], id=ic["id"])
+    for steps in (1, 5):
+        o.step(steps - o.current_step)
+        st = o.state()
+        for f in ("pos", "vel", "e", "rho", "h", "vdot", "edot"):
+            out[f"{f}_{steps}"] = st[f]
+    save("c2_default", **out)
+
+
+def c2_example_config():
+    """generated example.sph-config (config-parser.go:872-924), 4 steps"""
+    ic = gen.spawn([(260, (0.2, 0.3), (0.8, 0.4)), (700, (0.2, 0.6), (0.8, 0.99))])
+    kw = dict(gamma=4.666, particle_mass=1e6, accel=(0.0, 0.55), dt_half=0.00324, kernel=2, hor=(0.2, 0.8),
+              ver=(-100.0, 100.0), refl=(orc.OPEN[0], orc.OPEN[1], orc.OPEN[0], 0.99))
+    o = orc.Oracle(orc.make_params(**kw), ic["pos"], ic["vel"], ic["e"], None, ic["id"])
+    o.step(4)
+    st = o.state()
+    save("c2_example_config", pos0=ic["pos"], id=ic["id"], **{f: st[f] for f in ("pos", "vel", "e", "rho", "h", "vdot", "edot")})
+
+
+if __name__ == "__main__":
+    c1_density()
+    c2_default()
+    c2_example_config()

@@ -1,0 +1,69 @@
+"""CPU: the C-ABI shared library loads and exports every symbol include/sphb.h declares; without a GPU the
+product path fails loudly instead of computing anything on the CPU."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "sphb.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sphb_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from sphugo_b200 import build
+    so = build.build()
+    out = subprocess.run(["nm", "-D", "--defined-only", so], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (sphb_[a-z_0-9]+)", out))
+    declared = _declared()
+    assert len(declared) >= 28
+    missing = [f for f in declared if f not in exported]
+    assert not missing, missing
+    from sphugo_b200 import _lib
+    assert sorted(_lib.EXPORTS) == declared  # the ctypes binding covers the whole ABI
+    lib = _lib.lib()
+    for f in declared:
+        getattr(lib, f)
+
+
+def test_no_torch_or_cxx_types_in_the_abi():
+    src = open(os.path.join(ROOT, "include", "sphb.h")).read()
+    assert "torch" not in src and "std::" not in src and "#include <stdint.h>" in src
+    assert 'extern "C"' in src
+
+
+def test_no_cpu_fallback():
+    """without a CUDA device sphb_create must fail with SPHB_E_CUDA; the package never imports oracle/"""
+    import torch
+    from sphugo_b200 import _lib
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(_lib.SphbError) as ei:
+        _lib.Handle(_lib.make_params(), np.random.rand(100, 2))
+    assert ei.value.code == _lib.E_CUDA
+    assert "no CPU fallback" in str(ei.value)
+    for dp, _, files in os.walk(os.path.join(ROOT, "sphugo_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".inc")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "liborc" not in txt, f
+
+
+def test_params_struct_layout_matches_header():
+    from sphugo_b200 import _lib
+    from oracle import oracle as orc
+    assert C.sizeof(_lib.Params) == 13 * 8 + 4 * 4 == C.sizeof(orc.OrcParams)
+    assert C.sizeof(_lib.Slab) == 4 * 8 + 2 * 4
+
+
+def test_sm100a_sass_only():
+    from sphugo_b200 import build
+    out = subprocess.run(["cuobjdump", "-lelf", build.build()], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and "sm_90" not in out

@@ -173,3 +173,72 @@ def test_tiny_periodic_box_multi_image():
     assert U.rel_err(got["h"], ref["h"]) <= TOL
     assert U.rel_err(got["nn_dist"], ref["nn_dist"]) <= TOL
     assert (np.sort(got["nn_id"], 1) == np.sort(ref["nn_id"], 1)).all()
+
+
+def _golden(name):
+    import os
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+
+
+def test_golden_c1_density():
+    """committed golden vectors (tests/golden/make_golden.py): kNN sets, h and the three densities"""
+    g = _golden("c1_density")
+    h = L.Handle(L.make_params(hor=(0.0, 1.0), ver=(0.0, 1.0)), g["pos"], ids=g["id"])
+    h.knn((0.0, 1.0), (0.0, 1.0))
+    st = h.state(U.FIELDS_STATE + U.FIELDS_NN)
+    assert (np.sort(st["nn_id"], 1) == g["nn_id"]).all()
+    assert U.rel_err(st["h"], g["h"]) <= TOL
+    assert U.rel_err(st["nn_dist"], g["nn_dist"]) <= TOL
+    for k, name in ((0, "rho_tophat"), (1, "rho_monaghan"), (2, "rho_wendland")):
+        h.density(k)
+        assert U.rel_err(h.state(["rho"])["rho"], g[name]) <= TOL, name
+
+
+def test_golden_c2_default_and_example_config():
+    g = _golden("c2_default")
+    n = len(g["pos0"])
+    h = L.Handle(L.make_params(), g["pos0"], None, np.full(n, 0.01), None, g["id"])
+    h.step(1)
+    st = h.state()
+    for f in ("pos", "vel", "e", "rho", "h"):
+        assert U.rel_err(st[f], g[f + "_1"], np.abs(g[f + "_1"]).max() * 1e-3) <= TOL, f
+    h.step(4)
+    st = h.state()
+    for f in ("pos", "vel", "e", "rho", "h"):
+        assert U.rel_err(st[f], g[f + "_5"], np.abs(g[f + "_5"]).max() * 1e-3) <= 1e-9, f
+    g = _golden("c2_example_config")
+    n = len(g["pos0"])
+    kw = dict(gamma=4.666, particle_mass=1e6, accel=(0.0, 0.55), dt_half=0.00324, kernel=2, hor=(0.2, 0.8),
+              ver=(-100.0, 100.0), refl=(L.OPEN_LO, L.OPEN_HI, L.OPEN_LO, 0.99))
+    h = L.Handle(L.make_params(**kw), g["pos0"], None, np.full(n, 0.01), None, g["id"])
+    h.step(4)
+    st = h.state()
+    for f in ("pos", "vel", "e", "rho", "h"):
+        assert U.rel_err(st[f], g[f], np.abs(g[f]).max() * 1e-3) <= 1e-9, f
+
+
+def test_full_size_properties_c3():
+    """BASELINE size (2^20, periodic): properties that need no oracle: every list holds 32 distinct real
+    neighbours, h equals the largest listed distance, kNN is idempotent (recomputing from scratch with a cold
+    radius guess gives identical h), total energy and density are finite and positive."""
+    pos = gen.jittered_lattice(1024, 1024)
+    n = len(pos)
+    h = L.Handle(L.make_params(hor=(0.0, 1.0), ver=(0.0, 1.0), accel=(0.0, 0.2), dt_half=0.001), pos, None, np.full(n, 0.01))
+    h.step(2)
+    h1 = h.state(["h", "rho"])
+    assert np.isfinite(h1["h"]).all() and (h1["h"] > 0).all() and (h1["rho"] > 0).all()
+    h.knn((0.0, 1.0), (0.0, 1.0))
+    st = h.state(["h", "nn_idx", "nn_dist", "pos"])
+    assert (st["nn_idx"] >= 0).all()
+    srt = np.sort(st["nn_idx"], 1)
+    assert (np.diff(srt, axis=1) > 0).all()  # 32 distinct neighbours
+    assert np.array_equal(st["nn_dist"][:, 0], st["h"]) or U.rel_err(st["nn_dist"][:, 0], st["h"]) <= 1e-15
+    assert (np.diff(st["nn_dist"], axis=1) <= 0).all()
+    # cold start on the same positions: a fresh handle has no radius guess at all
+    g2 = L.Handle(L.make_params(hor=(0.0, 1.0), ver=(0.0, 1.0)), st["pos"], ids=st["id"])
+    g2.knn((0.0, 1.0), (0.0, 1.0))
+    s2 = g2.state(["h"])
+    assert U.rel_err(s2["h"], st["h"]) <= 1e-15
+    # mean neighbour count check: pi h^2 n ~ 33
+    assert abs(np.mean(np.pi * st["h"] ** 2 * n) - 33) < 1.5
+    assert np.isfinite(h.reduce(L.SUM_E)) and h.reduce(L.SUM_RHO) > 0

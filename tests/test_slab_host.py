@@ -1,0 +1,96 @@
+"""CPU: host-side logic of the slab decomposition incl. a world_size-2 gloo exchange."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+from sphugo_b200 import slab  # noqa: E402
+
+
+def test_topology_ring_and_open():
+    t = slab.Topology(4, [0, .25, .5, .75, 1.0], True)
+    assert [t.left(r) for r in range(4)] == [3, 0, 1, 2] and [t.right(r) for r in range(4)] == [1, 2, 3, 0]
+    t = slab.Topology(3, [0, 1, 2, 3], False)
+    assert t.left(0) is None and t.right(2) is None and t.left(1) == 0
+    assert slab.Topology(1, [0, 1], True).left(0) is None  # a single slab uses the wrapping-grid path
+    assert t.owner_of(np.array([0.5, 1.0, 2.999])).tolist() == [0, 1, 2]
+    with pytest.raises(ValueError):
+        slab.Topology(2, [0, 1], True)
+    with pytest.raises(ValueError):
+        slab.Topology(2, [0, 1, 1], True)
+
+
+def test_equal_count_bounds():
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.random(8000) * 0.5, 0.5 + rng.random(2000) * 0.5])  # 4:1 density like the shock tube
+    b = slab.equal_count_bounds(x, 4, 0.0, 1.0)
+    cnt = np.histogram(x, bins=b)[0]
+    assert cnt.sum() == 10000 and cnt.max() - cnt.min() <= 2
+    assert b[0] == 0.0 and b[-1] == 1.0 and all(b1 > b0 for b0, b1 in zip(b[:-1], b[1:]))
+
+
+def test_ghost_widths_cover_the_stencil():
+    gw, iw = slab.ghost_widths(0.01)
+    assert iw >= 0.01 and gw >= iw + 0.01
+
+
+def test_reference_halo_selection_periodic_frame():
+    pos = np.array([[0.01, 0.5], [0.26, 0.5], [0.49, 0.5], [0.74, 0.5], [0.99, 0.5]])
+    # slab [0, 0.25) of a ring: the particle at 0.99 is owned-looking from the frame (x - 1 = -0.01 < x_lo)
+    assert slab.reference_halo(pos[:1], 0.0, 0.25, 0.05, 0, 1.0).tolist() == [0]
+    assert slab.reference_halo(pos[4:], 0.75, 1.0, 0.05, 1, 1.0).tolist() == [0]
+    # the criterion is one-sided (strays below the edge are sent too); the frame puts 0.99 at -0.01
+    assert slab.reference_halo(pos, 0.25, 0.5, 0.05, 0, 1.0).tolist() == [0, 1, 4]
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        topo = slab.Topology(world, [k / world for k in range(world + 1)], True)
+        rng = np.random.default_rng(42)
+        pos = rng.random((4000, 2))
+        owner = topo.owner_of(pos[:, 0])
+        mine = pos[owner == rank]
+        x_lo, x_hi = topo.interval(rank)
+        gw = 0.03
+        ex = slab.DistExchange(topo, rank, torch.device("cpu"))
+        packs = []
+        for side in (0, 1):
+            idx = slab.reference_halo(mine, x_lo, x_hi, gw, side, 1.0)
+            buf = torch.zeros((len(idx) + 3, slab.HALO_DOUBLES), dtype=torch.float64)
+            buf[: len(idx), :2] = torch.from_numpy(mine[idx])
+            buf[: len(idx), 5] = float(rank)
+            packs += [buf, len(idx)]
+        rl, kl, rr, kr = ex.exchange(*packs, slab.HALO_DOUBLES)
+        # expected: what the neighbours select towards me
+        L, R = topo.left(rank), topo.right(rank)
+        exp_l = pos[owner == L][slab.reference_halo(pos[owner == L], *topo.interval(L), gw, 1, 1.0)]
+        exp_r = pos[owner == R][slab.reference_halo(pos[owner == R], *topo.interval(R), gw, 0, 1.0)]
+        ok = (kl == len(exp_l) and kr == len(exp_r) and np.array_equal(rl[:kl, :2].numpy(), exp_l)
+              and np.array_equal(rr[:kr, :2].numpy(), exp_r) and (rl[:kl, 5] == L).all() and (rr[:kr, 5] == R).all())
+        hm = ex.allreduce_max(float(rank + 1))
+        q.put((rank, bool(ok), kl, kr, hm))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_neighbour_exchange(world):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + world + (os.getpid() % 200)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] for r in res), res
+    assert all(r[2] > 0 and r[3] > 0 for r in res)
+    assert all(r[4] == float(world) for r in res)
