@@ -30,7 +30,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-B_ALG = {"keys": 40, "sort": 16, "reorder": 148, "knn": 176, "force": 272}  # fp64 bytes / particle, SURVEY §8d
+# algorithmic bytes / particle-update, SURVEY §8d: 300 + 44 s with s = sizeof(real)
+B_ALG_BY_PREC = {64: {"keys": 40, "sort": 16, "reorder": 148, "knn": 176, "force": 272},
+                 32: {"keys": 24, "sort": 16, "reorder": 84, "knn": 152, "force": 200}}
+B_ALG = B_ALG_BY_PREC[64]
 B_ALG_TOTAL = 652
 METRIC = "particle-updates/s per SPH step (k=32)"
 UNIT = "particle-updates/s"
@@ -193,6 +196,12 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     nx, ny, box, phys, desc = workload(args.workload, world)
+    global B_ALG, B_ALG_TOTAL
+    B_ALG = B_ALG_BY_PREC[args.precision]
+    B_ALG_TOTAL = sum(B_ALG.values())
+    phys["precision"] = args.precision
+    if args.precision == 32:
+        desc = desc.replace("fp64", "fp32 build (fp32 pair arithmetic, fp64 state)")
     if world > 1:
         from sphugo_b200 import slab
         return slab.bench(args, nx, ny, box, phys, desc, rank, world, local)
@@ -275,7 +284,7 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
+        "dtype": "f64" if args.precision == 64 else "f32", "data": "synthetic",
         "config": {"workload": desc, "particles": n, "l2": "state (>= 280 B/particle) exceeds the 126 MB L2; no flush needed",
                    "timing": "CUDA events on the library stream around K asynchronous steps", "wall_ms_per_step": wall / K * 1e3},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -300,6 +309,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c5", choices=["c3", "c5"])
+    ap.add_argument("--precision", type=int, default=64, choices=[64, 32], help="64: reference arithmetic; 32: the fp32 build")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (tuning sweeps only)")
     args = ap.parse_args()

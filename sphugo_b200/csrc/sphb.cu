@@ -73,6 +73,8 @@ struct sphb_sim {
   int64_t counters[SPHB_CNT_COUNT] = {0, 0, 0, 0};
   GridTune gtune{};
   KnnTune ktune{};
+  int force_nrec = 672;       // staged neighbour records per force block (shared memory)
+  bool force_gather = false;  // A/B switch: the unstaged gather kernel
   std::string err;
 };
 
@@ -104,7 +106,7 @@ bool axis_open(const double a[2]) { return a[0] == SPHB_OPEN_LO; }
 int check_params(sphb_sim* s, const sphb_params* p) {
   if (!p) return fail(s, SPHB_E_INVALID, "params is NULL");
   if (p->kernel < 0 || p->kernel > 2) return fail(s, SPHB_E_INVALID, "unknown kernel %d", p->kernel);
-  if (p->precision != 64) return fail(s, SPHB_E_INVALID, "precision %d not available in this build (64 only)", p->precision);
+  if (p->precision != 64 && p->precision != 32) return fail(s, SPHB_E_INVALID, "precision %d: 64 (reference arithmetic) or 32 (fp32 pair arithmetic)", p->precision);
   // nearest-neighbour.go:44,53: an axis is either open on both ends or periodic
   if ((p->hor[0] == SPHB_OPEN_LO) != (p->hor[1] == SPHB_OPEN_HI) && p->hor[0] == SPHB_OPEN_LO)
     return fail(s, SPHB_E_INVALID, "cannot have open and periodic boundary in horizontal at same time");
@@ -199,21 +201,29 @@ int refresh_stats(sphb_sim* s) {
   return SPHB_OK;
 }
 
-template <int KERNEL>
-void launch_knn(sphb_sim* s, int ntot, const PhysP& ph) {
+template <int KERNEL, bool F32>
+void launch_knn_p(sphb_sim* s, int ntot, const PhysP& ph) {
   KnnOut out{s->a.pc, s->nn, s->failList, s->failCount};
   const int tiles = cdiv(ntot, 32);
   KnnTune kt = s->ktune;
   kt.cap = s->have_h ? s->ktune.cap : s->ktune.cap0;  // first evaluation: radius from a density estimate, wider spread
-  const size_t smem = (size_t)KNN_WARPS * knn_smem_words_per_warp(kt.cap) * sizeof(uint32_t);
-  static bool attr_done[3] = {false, false, false};
-  if (!attr_done[KERNEL]) {
-    cudaFuncSetAttribute(k_knn_tile<KERNEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_done[KERNEL] = true;
+  kt.ncw = s->have_h ? s->ktune.ncw : s->ktune.ncw0;
+  const size_t smem = (size_t)KNN_WARPS * knn_smem_bytes_per_warp(kt.cap, kt.ncw, F32);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_knn_tile<KERNEL, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_done = true;
   }
-  k_knn_tile<KERNEL><<<cdiv(tiles, KNN_WARPS), KNN_THREADS, smem, s->st>>>(s->spos, s->keysSorted, s->cellStart,
-                                                                         s->hguess, s->a.epred, ntot, s->grid, ph, kt, out,
-                                                                         s->slab_on ? s->a.ghost : nullptr, s->dflags);
+  k_knn_tile<KERNEL, F32><<<cdiv(tiles, KNN_WARPS), KNN_THREADS, smem, s->st>>>(s->spos, s->keysSorted, s->cellStart,
+                                                                              s->hguess, s->a.epred, ntot, s->grid, ph, kt, out,
+                                                                              s->slab_on ? s->a.ghost : nullptr, s->dflags);
+}
+
+template <int KERNEL>
+void launch_knn(sphb_sim* s, int ntot, const PhysP& ph) {
+  if (s->prm.precision == 32) launch_knn_p<KERNEL, true>(s, ntot, ph);
+  else launch_knn_p<KERNEL, false>(s, ntot, ph);
+  KnnOut out{s->a.pc, s->nn, s->failList, s->failCount};
   k_knn_fallback<KERNEL><<<148 * 4, 128, 0, s->st>>>(s->spos, s->keysSorted, s->cellStart, s->hguess,
                                                    s->a.epred, ntot, s->grid, ph, out, s->dflags);
   s->have_h = true;
@@ -230,23 +240,42 @@ SlabP make_slabp(const sphb_sim* s) {
   return sl;
 }
 
+template <int KERNEL, bool INTEGRATE, bool SLAB, typename R>
+void launch_force_st(sphb_sim* s, const ForceIO& io, int ntot, const PhysP& ph) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_force_st<KERNEL, INTEGRATE, SLAB, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_done = true;
+  }
+  const int nrec = s->force_nrec;
+  const size_t smem = (size_t)nrec * 8 * sizeof(R);  // four arrays of two reals per staged record
+  k_force_st<KERNEL, INTEGRATE, SLAB, R><<<cdiv(ntot, FORCE_THREADS), FORCE_THREADS, smem, s->st>>>(io, ntot, s->grid, ph, nrec, s->dflags);
+}
+
+template <int KERNEL, bool INTEGRATE, bool SLAB>
+void launch_force_p(sphb_sim* s, const ForceIO& io, int ntot, const PhysP& ph) {
+  if (s->prm.precision == 32) launch_force_st<KERNEL, INTEGRATE, SLAB, float>(s, io, ntot, ph);
+  else if (s->force_gather) k_force<KERNEL, INTEGRATE, SLAB><<<cdiv(ntot, 128), 128, 0, s->st>>>(io, ntot, s->grid, ph, s->dflags);
+  else launch_force_st<KERNEL, INTEGRATE, SLAB, double>(s, io, ntot, ph);
+}
+
 template <int KERNEL>
 void launch_force(sphb_sim* s, int ntot, const PhysP& ph, bool integrate) {
   ForceIO io{};
   io.spos = s->spos; io.vpred = s->a.vpred; io.pc = s->a.pc; io.nn = s->nn;
+  io.keys = s->keysSorted; io.cellStart = s->cellStart;
   io.pos = s->a.pos; io.vel = s->a.vel; io.e = s->a.e; io.vdot = s->a.vdot; io.edot = s->a.edot;
-  const int nb = cdiv(ntot, 128);
   if (!s->slab_on) {
-    if (integrate) k_force<KERNEL, true, false><<<nb, 128, 0, s->st>>>(io, ntot, s->grid, ph, s->dflags);
-    else k_force<KERNEL, false, false><<<nb, 128, 0, s->st>>>(io, ntot, s->grid, ph, s->dflags);
+    if (integrate) launch_force_p<KERNEL, true, false>(s, io, ntot, ph);
+    else launch_force_p<KERNEL, false, false>(s, io, ntot, ph);
     return;
   }
   io.gflag = s->a.ghost; io.ownIdx = s->perm; io.epred = s->a.epred; io.id = s->a.id;
   io.o_pos = s->b.pos; io.o_vel = s->b.vel; io.o_vdot = s->b.vdot; io.o_vpred = s->b.vpred;
   io.o_e = s->b.e; io.o_edot = s->b.edot; io.o_epred = s->b.epred; io.o_id = s->b.id; io.o_pc = s->b.pc;
   io.o_gflag = s->b.ghost;
-  if (integrate) k_force<KERNEL, true, true><<<nb, 128, 0, s->st>>>(io, ntot, s->grid, ph, s->dflags);
-  else k_force<KERNEL, false, true><<<nb, 128, 0, s->st>>>(io, ntot, s->grid, ph, s->dflags);
+  if (integrate) launch_force_p<KERNEL, true, true>(s, io, ntot, ph);
+  else launch_force_p<KERNEL, false, true>(s, io, ntot, ph);
 }
 
 // exclusive prefix of (flag == owned) over [0, ntot) into s->perm (free once the reorder is done)
@@ -434,13 +463,18 @@ int create_common(const sphb_params* p, int64_t n, int64_t capacity, const doubl
   s->ktune.k_target = 46.0;
   s->ktune.cap = 50;   // room for 42 entries + 8 slack (overflow is checked once per 8 candidates)
   s->ktune.cap0 = 80;
+  s->ktune.ncw = 256;  // staged candidates per tile: a 32-particle strip of one row needs ~180 at 32 neighbours
+  s->ktune.ncw0 = 512;
   if (const char* ev = getenv("SPHB_CELL_PER_H")) s->gtune.cell_per_h = atof(ev);
   if (const char* ev = getenv("SPHB_PPC0")) s->gtune.ppc0 = atof(ev);
   if (const char* ev = getenv("SPHB_FORCE_NC")) s->gtune.force_nc = atoi(ev);
   if (const char* ev = getenv("SPHB_GUESS_MARGIN")) s->ktune.guess_margin = atof(ev);
   if (const char* ev = getenv("SPHB_K_TARGET")) s->ktune.k_target = atof(ev);
-  if (const char* ev = getenv("SPHB_KNN_CAP")) s->ktune.cap = std::max(48, std::min(96, atoi(ev)));
+  if (const char* ev = getenv("SPHB_KNN_CAP")) s->ktune.cap = std::max(44, std::min(96, atoi(ev)));
+  if (const char* ev = getenv("SPHB_KNN_NCW")) s->ktune.ncw = std::max(128, std::min(1024, atoi(ev) / 8 * 8));
   if (const char* ev = getenv("SPHB_CELL_ASPECT")) s->gtune.aspect = atof(ev);
+  if (const char* ev = getenv("SPHB_FORCE_NREC")) s->force_nrec = std::max(64, std::min(3072, atoi(ev)));
+  if (const char* ev = getenv("SPHB_FORCE_GATHER")) s->force_gather = atoi(ev) != 0;
   if (n > 0) {
     rc = upload_common(s, 0, n, pos_xy, vel_xy, e, rho, id, kind, 0);
     if (rc) { g_create_error = s->err; sphb_destroy(s); return rc; }

@@ -44,6 +44,8 @@ struct KnnTune {
   double k_target;       // expected candidates inside the first-guess radius when no h_prev exists
   int cap;               // candidate column capacity per particle (shared memory)
   int cap0;              // same for the first evaluation (no previous h)
+  int ncw;               // staged candidates per tile (shared memory), multiple of 8
+  int ncw0;              // same for the first evaluation
 };
 
 // device-side status word
@@ -74,35 +76,29 @@ __device__ __forceinline__ int cell_of(double xs, double o, double inv, int nc) 
   return c < 0 ? 0 : (c >= nc ? nc - 1 : c);
 }
 
-__device__ __forceinline__ int floor_div(int a, int b) {  // b > 0
-  int q = a / b;
-  return (a % b < 0) ? q - 1 : q;
-}
+// floor(u / nc) for u in [-nc, 2 nc): the periodic image (-1, 0, +1) an unwrapped cell index lies in.
+// Every caller bounds its stencil by one period (wider stencils are refused or clamped first).
+__device__ __forceinline__ int img_idx(int u, int nc) { return (u >= nc ? 1 : 0) - (u < 0 ? 1 : 0); }
 
 // d^2 exactly as linear-algebra.go:61-64 evaluates it on amd64: two products, one sum, no FMA
 __device__ __forceinline__ double dist_sq(double dx, double dy) {
   return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
 }
 
-// 1/sqrt(x) and 1/x for normal x > 0: hardware seed (MUFU.RSQ64H / RCP64H, ~2^-22) + two Newton steps, no special
-// cases and no branches; relative error ~2 ulp (every consumer carries a 1e-12 bar)
+// 1/sqrt(x) and 1/x for normal x > 0: hardware seed (MUFU.RSQ64H / RCP64H, ~2^-22) + one third-order step, no
+// special cases and no branches; relative error ~e^3 ~ 2^-64 before the final rounding (consumers carry a 1e-12 bar)
 __device__ __forceinline__ double fast_rsqrt(double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double xy = x * y;
-  double e = fma(-xy, y, 1.0);
-  y = fma(0.5 * y, e, y);
-  xy = x * y;
-  e = fma(-xy, y, 1.0);
-  return fma(0.5 * y, e, y);
+  const double e = fma(-(x * y), y, 1.0);  // 1 - x y^2
+  const double t = fma(0.375, e, 0.5);
+  return fma(y * e, t, y);                 // y (1 + e/2 + 3 e^2/8)
 }
 __device__ __forceinline__ double fast_rcp(double x) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  double e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-x, r, 1.0);
-  return fma(r, e, r);
+  const double e = fma(-x, r, 1.0);
+  return fma(r, fma(e, e, e), r);          // r (1 + e + e^2)
 }
 // sqrt(x) from fast_rsqrt with one residual correction: faithfully rounded (almost always correctly rounded)
 __device__ __forceinline__ double fast_sqrt(double x, double y /* = fast_rsqrt(x) */) {
@@ -375,9 +371,8 @@ __global__ void __launch_bounds__(256) k_reorder(StateIn in, StateOut out, const
 //   |d2f - d2| / d2 <= ~4 * 2^-24 * V / d + 3 * 2^-24; delta = 3 * (2^-22 * V / rg + 2^-21) covers it
 //   with a factor > 2 to spare near d ~ rg.
 // -------------------------------------------------------------------------------------------------
-#define KNN_WARPS 4
+#define KNN_WARPS 2
 #define KNN_THREADS (KNN_WARPS * 32)
-#define KNN_CMAX 128  // staged candidates per round
 
 struct KnnOut {
   double4* pc;      // {rho, c, h, P = c^2/(gamma rho)}
@@ -386,8 +381,11 @@ struct KnnOut {
   int* failCount;
 };
 
-// shared memory per warp: column of (CAP + 1) slots x 32 lanes x {fp32 key, entry} + staged candidates (float2)
-__host__ __device__ inline size_t knn_smem_words_per_warp(int cap) { return (size_t)cap * 64 + KNN_CMAX * 2; }
+// shared memory per warp: the staged candidates of the tile {fp64 position (exact phase), fp32 tile-relative
+// position (filter), list entry} = 28 B each, and a column of CAP slots x 32 lanes x {fp32 key, staged slot}
+__host__ __device__ inline size_t knn_smem_bytes_per_warp(int cap, int ncw, bool f32) {
+  return (size_t)cap * 256 + (size_t)ncw * (f32 ? 12 : 28);  // the fp32 build stages no fp64 positions
+}
 
 __device__ __forceinline__ int warp_min_i(int v, uint32_t mask) {
   return __reduce_min_sync(0xffffffffu, (mask >> (threadIdx.x & 31)) & 1u ? v : 0x7fffffff);
@@ -420,8 +418,8 @@ __device__ __forceinline__ void knn_append(uint32_t& kp, float d2f, uint32_t en,
       : "f"(d2f), "r"(en), "f"(thr));
 }
 
-template <int KERNEL>
-__global__ void __launch_bounds__(KNN_THREADS, 4) k_knn_tile(const double2* __restrict__ spos,
+template <int KERNEL, bool F32>
+__global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __restrict__ spos,
                                                          const uint32_t* __restrict__ keys,
                                                          const uint32_t* __restrict__ cellStart,
                                                          const double* __restrict__ hguess,
@@ -430,13 +428,15 @@ __global__ void __launch_bounds__(KNN_THREADS, 4) k_knn_tile(const double2* __re
                                                          KnnOut out, const uint8_t* __restrict__ gflag,
                                                          uint32_t* __restrict__ dflags) {
   const GridP g = *gp;
-  extern __shared__ __align__(16) uint32_t smem_u[];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int CAP = tune.cap;
-  uint32_t* wbase = smem_u + (size_t)warp * knn_smem_words_per_warp(CAP);
-  uint2* col = reinterpret_cast<uint2*>(wbase) + lane;                       // [slot * 32] = {key, entry}
-  float4* candF4 = reinterpret_cast<float4*>(wbase + (size_t)CAP * 64);  // two staged candidates each
-  float2* candF = reinterpret_cast<float2*>(candF4);
+  const int CAP = tune.cap, NCW = tune.ncw;
+  unsigned char* wb = smem_raw + (size_t)warp * knn_smem_bytes_per_warp(CAP, NCW, F32);
+  uint2* col = reinterpret_cast<uint2*>(wb) + lane;                                  // [slot * 32] = {key, staged slot}
+  float2* candF = reinterpret_cast<float2*>(wb + (size_t)CAP * 256);                 // fp32 tile-relative positions
+  const float4* candF4 = reinterpret_cast<const float4*>(candF);                     // two staged candidates each
+  uint32_t* candE = reinterpret_cast<uint32_t*>(wb + (size_t)CAP * 256 + (size_t)NCW * 8);   // index | image code << 28
+  double2* candD = reinterpret_cast<double2*>(wb + (size_t)CAP * 256 + (size_t)NCW * 12);    // exact positions (fp64 build)
   const uint32_t kbase = (uint32_t)__cvta_generic_to_shared(col);
   const uint32_t klim = kbase + (uint32_t)(CAP - 8) * 256u;  // beyond this fewer than 8 free slots remain
 
@@ -446,15 +446,16 @@ __global__ void __launch_bounds__(KNN_THREADS, 4) k_knn_tile(const double2* __re
   // queries: owned particles and (slab mode) inner ghosts; outer ghosts are candidates only
   const bool valid = i < n && (gflag == nullptr || gflag[i] != GF_OUTER);
 
-  double xa = 0, ya = 0, rg = 0;
+  double xa = 0, ya = 0, rg = 0, ep = 0;
   int cxa = 0, cya = 0;
   if (valid) {
     const double2 p = spos[i];
     xa = p.x; ya = p.y;
     const uint32_t k = keys[i];
+    const double hp = hguess[i];
+    ep = epred[i];
     cya = (int)(k / (uint32_t)g.ncx);
     cxa = (int)(k - (uint32_t)cya * (uint32_t)g.ncx);
-    const double hp = hguess[i];
     if (hp > 0.0) {
       rg = hp * (1.0 + tune.guess_margin);
     } else {  // density estimate from the block of cells around the particle
@@ -475,19 +476,16 @@ __global__ void __launch_bounds__(KNN_THREADS, 4) k_knn_tile(const double2* __re
   clo = min(clo, cxa); chi = max(chi, cxa);
   rlo = min(rlo, cya); rhi = max(rhi, cya);
 
-  uint32_t kp = kbase;
-  float deltaf = 0.0f;
-  bool anyimg = false;  // some staged piece is a periodic image (warp-uniform)
-  bool ovf = false;  // column (nearly) full: stop appending, the lane goes to the fallback
-  bool bad = false;  // stencil wider than the period / fp32 bound not applicable: multi-image fallback
+  // One pass of the whole pipeline per group of lanes that sit in the same grid row (a tile is a strip of one
+  // row, so there is one group unless the tile straddles the end of a row).
   uint32_t todo = __ballot_sync(0xffffffffu, valid);
   while (todo) {
-    // next group: all remaining lanes that sit in the same grid row as the first remaining lane
     const int lead = __ffs(todo) - 1;
     const int grow = __shfl_sync(0xffffffffu, cya, lead);
     const uint32_t grp = __ballot_sync(0xffffffffu, valid && cya == grow) & todo;
     todo &= ~grp;
     const bool mine = (grp >> lane) & 1u;
+    bool bad = false;  // stencil wider than the period / fp32 bound not applicable / staging area full: fallback
     int c0 = warp_min_i(clo, grp), c1 = warp_max_i(chi, grp);
     int r0 = warp_min_i(rlo, grp), r1 = warp_max_i(rhi, grp);
     bool gbad = false;
@@ -495,7 +493,37 @@ __global__ void __launch_bounds__(KNN_THREADS, 4) k_knn_tile(const double2* __re
     else { c0 = max(c0, 0); c1 = min(c1, g.ncx - 1); c0 = min(c0, g.ncx - 1); c1 = max(c1, 0); }
     if (g.wrapy) { if (r1 - r0 + 1 > g.ncy) gbad = true; }
     else { r0 = max(r0, 0); r1 = min(r1, g.ncy - 1); r0 = min(r0, g.ncy - 1); r1 = max(r1, 0); }
-    if (gbad) { if (mine) bad = true; continue; }
+
+    // the pieces of the union block: (row, x image) -> a contiguous range of the sorted order; lane p fetches piece p
+    const int ix0 = g.wrapx ? img_idx(c0, g.ncx) : 0, ix1 = g.wrapx ? img_idx(c1, g.ncx) : 0;
+    const int nix = ix1 - ix0 + 1, npc = (r1 - r0 + 1) * nix;
+    if (npc > 32) gbad = true;
+    int p_s = 0, p_len = 0, p_off = 0, nst = 0;
+    uint32_t p_code = 0;
+    if (!gbad) {
+      if (lane < npc) {
+        const int rr = lane / nix, ix = ix0 + (lane - rr * nix), ru = r0 + rr;
+        const int iy = g.wrapy ? img_idx(ru, g.ncy) : 0;
+        const int row = ru - iy * g.ncy;
+        const int a = max(c0, ix * g.ncx) - ix * g.ncx, b = min(c1, ix * g.ncx + g.ncx - 1) - ix * g.ncx;
+        p_s = (int)cellStart[row * g.ncx + a];
+        p_len = (int)cellStart[row * g.ncx + b + 1] - p_s;
+        p_code = img_code(ix, iy);
+      }
+      int incl = (p_len + 7) & ~7;  // every piece is padded to 8 with unreachable dummies
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+      }
+      p_off = incl - ((p_len + 7) & ~7);
+      nst = __shfl_sync(0xffffffffu, incl, 31);
+      if (nst > NCW) gbad = true;  // the union block does not fit the staging area
+    }
+    if (gbad) {
+      if (mine) { const int slot = atomicAdd(out.failCount, 1); out.failList[slot] = i; }
+      continue;
+    }
 
     // fp32 frame of this group: origin at the centre of the union block; V bounds every |relative coordinate|
     const double xref = g.ox + 0.5 * (double)(c0 + c1 + 1) * g.dx;
@@ -505,168 +533,236 @@ __global__ void __launch_bounds__(KNN_THREADS, 4) k_knn_tile(const double2* __re
     V = fmax(V, warp_max_d(mine ? fmax(fabs(xa - xref), fabs(ya - yref)) + rg : 0.0));
     const float qfx = (float)(xa - xref), qfy = (float)(ya - yref);
     const double delta = 3.0 * (2.384185791015625e-07 * V / fmax(rg, 1e-300) + 4.76837158203125e-07);
-    if (mine) deltaf = (float)delta;
-    if (mine && !(delta < 1e-3)) bad = true;  // tile far wider than this lane's radius: no useful fp32 bound
-    float thrf = (mine && !bad) ? (float)(rg2 * (1.0 + delta)) * 1.0000002f : -1.0f;
+    const float deltaf = (float)delta;
+    // tile far wider than this lane's radius: no useful fp32 bound (fp32 build: accuracy of h itself)
+    if (mine && !(delta < (F32 ? 1.5e-5 : 1e-3))) bad = true;
+    const float thr0 = (float)(rg2 * (1.0 + delta)) * 1.0000002f;
+    float thrf = (mine && !bad) ? thr0 : -1.0f;
     const float Vf = (float)V * 1.000001f;
 
-    for (int ru = r0; ru <= r1; ++ru) {
-      const int iy = g.wrapy ? floor_div(ru, g.ncy) : 0;
-      const int row = ru - iy * g.ncy;
-      const int ix0 = g.wrapx ? floor_div(c0, g.ncx) : 0, ix1 = g.wrapx ? floor_div(c1, g.ncx) : 0;
-      for (int ix = ix0; ix <= ix1; ++ix) {  // up to three x pieces (images -1, 0, +1)
-        const int a = max(c0, ix * g.ncx) - ix * g.ncx, b = min(c1, ix * g.ncx + g.ncx - 1) - ix * g.ncx;
-        const uint32_t code = img_code(ix, iy) << IMG_SHIFT;
-        anyimg |= (ix != 0) | (iy != 0);
-        // candidate position in the query frame: b + img * L  (the reference shifts the query by -img * L)
-        const double sx = (double)ix * g.Lx - xref, sy = (double)iy * g.Ly - yref;
-        const int s = (int)cellStart[row * g.ncx + a], e = (int)cellStart[row * g.ncx + b + 1];
-        for (int base = s; base < e; base += KNN_CMAX) {
-          const int len = min(KNN_CMAX, e - base);
-          const int len8 = (len + 7) & ~7;
-          __syncwarp();
-          for (int t = lane; t < len8; t += 32) {  // stage (coalesced); padded with unreachable dummies
-            float fx = 3.0e18f, fy = 3.0e18f;
-            if (t < len) {
-              const double2 pb = spos[base + t];
-              fx = (float)(pb.x + sx); fy = (float)(pb.y + sy);
-              // beyond the bounded block (clamped border cell): farther than every lane's reach, drop it
-              if (!(fabsf(fx) <= Vf && fabsf(fy) <= Vf)) { fx = 3.0e18f; fy = 3.0e18f; }
-            }
-            candF[t] = make_float2(fx, fy);
-          }
-          __syncwarp();
-          const uint32_t en0 = (uint32_t)base | code;
-          for (int c = 0; c < len8; c += 8) {  // phase 1: fp32 filter, shared-memory broadcast, branch-free
-            float4 v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = candF4[(c >> 1) + u];
-            float d2f[8];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const float ax = v[u].x - qfx, ay = v[u].y - qfy, bx = v[u].z - qfx, by = v[u].w - qfy;
-              d2f[2 * u] = fmaf(ay, ay, ax * ax);
-              d2f[2 * u + 1] = fmaf(by, by, bx * bx);
-            }
-            if (kp > klim) { ovf = true; thrf = -1.0f; }
-            const uint32_t enb = en0 + (uint32_t)c;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) knn_append(kp, d2f[u], enb + (uint32_t)u, thrf);
-          }
+    // stage the whole union block (coalesced loads, all pieces in flight)
+    bool anyimg = false;  // some staged piece is a periodic image (warp-uniform)
+    int self_slot = -1;
+    __syncwarp();
+    for (int pc_ = 0; pc_ < npc; ++pc_) {
+      const int s = __shfl_sync(0xffffffffu, p_s, pc_), len = __shfl_sync(0xffffffffu, p_len, pc_);
+      const int off = __shfl_sync(0xffffffffu, p_off, pc_);
+      const uint32_t code = __shfl_sync(0xffffffffu, p_code, pc_);
+      const int ix = (int)(code >> 2) - 1, iy = (int)(code & 3u) - 1;
+      anyimg |= (code != 5u);
+      // candidate position in the query frame: b + img * L  (the reference shifts the query by -img * L)
+      const double sx = (double)ix * g.Lx - xref, sy = (double)iy * g.Ly - yref;
+      const int len8 = (len + 7) & ~7;
+      for (int t = lane; t < len8; t += 32) {
+        float fx = 3.0e18f, fy = 3.0e18f;
+        if (t < len) {
+          const double2 pb = spos[s + t];
+          fx = (float)(pb.x + sx); fy = (float)(pb.y + sy);
+          // beyond the bounded block (clamped border cell): farther than every lane's reach, drop it
+          if (!(fabsf(fx) <= Vf && fabsf(fy) <= Vf)) { fx = 3.0e18f; fy = 3.0e18f; }
+          if (!F32) candD[off + t] = pb;
+          candE[off + t] = (uint32_t)(s + t) | (code << IMG_SHIFT);
         }
+        candF[off + t] = make_float2(fx, fy);
       }
+      if (mine && code == 5u && i >= s && i < s + len) self_slot = off + (i - s);
     }
-  }
-  __syncwarp();
+    __syncwarp();
 
-  // The column holds cnt entries, one of them the lane itself (d2f = 0, centre image; self is excluded in
-  // every image, nearest-neighbour.go:79).  m = cnt - 33 entries with the largest keys must be dropped.
-  const int cnt = (int)((kp - kbase) >> 8);
-  bool ok = valid && !bad && !ovf && cnt >= SPHB_K + 1;
-  // select A: the 4 largest keys below `bound` per pass (a max/min insertion network on the fp32 bit patterns).
-  // T = smallest dropped key, akey = largest kept key.
-  int mrem = ok ? cnt - (SPHB_K + 1) : 0;
-  uint32_t bound = 0xffffffffu, T = 0xffffffffu, akey = 0u;
-  bool sel_done = !ok;
-  while (__any_sync(0xffffffffu, !sel_done)) {
-    uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;
-    const int lim = sel_done ? 0 : cnt;
-    for (int s = 0; s < lim; ++s) {
-      uint32_t k = col[s * 32].x;
-      k = k < bound ? k : 0u;
-      uint32_t a;
-      a = max(t0, k); k = min(t0, k); t0 = a;
-      a = max(t1, k); k = min(t1, k); t1 = a;
-      a = max(t2, k); k = min(t2, k); t2 = a;
-      t3 = max(t3, k);
-    }
-    if (!sel_done) {
-      if (mrem <= 3) {
-        T = mrem == 0 ? bound : (mrem == 1 ? t0 : (mrem == 2 ? t1 : t2));
-        akey = mrem == 0 ? t0 : (mrem == 1 ? t1 : (mrem == 2 ? t2 : t3));
-        sel_done = true;
-      } else {
-        mrem -= 4;
-        bound = t3;
+    uint32_t kp = kbase;
+    bool ovf = false;  // column (nearly) full: stop appending, the lane goes to the fallback
+    for (int c = 0; c < nst; c += 8) {  // phase 1: fp32 filter, shared-memory broadcast, branch-free
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = candF4[(c >> 1) + u];
+      float d2f[8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float ax = v[u].x - qfx, ay = v[u].y - qfy, bx = v[u].z - qfx, by = v[u].w - qfy;
+        d2f[2 * u] = fmaf(ay, ay, ax * ax);
+        d2f[2 * u + 1] = fmaf(by, by, bx * bx);
       }
+      if (kp > klim) { ovf = true; thrf = -1.0f; }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) knn_append(kp, d2f[u], (uint32_t)(c + u), thrf);
     }
-  }
-  // rank ambiguity (includes exact ties): the smallest dropped key must exceed the largest kept one by more
-  // than the fp32 error; with nothing dropped the bound is the acceptance threshold itself (checked as h^2 <= rg^2)
-  if (ok && T != 0xffffffffu && !(__uint_as_float(T) > __uint_as_float(akey) * (1.0f + deltaf) * 1.000001f)) ok = false;
+    __syncwarp();
 
-  // select B + exact phase: kept entries get d^2 exactly as the reference computes it; the list entry goes to
-  // global memory, the slot is reused for the exact d^2
-  double h2 = 0.0;
-  uint32_t* np = out.nn + (size_t)tile * 32 * 32 + lane;  // next list slot of this lane (stride 32 words)
-  uint32_t wp = kbase;                                   // next d^2 slot (shared-space address, stride 256 B)
-  const uint32_t wend = kbase + 32u * 256u;
-  bool self_seen = false;
-  {
-    const int lim = ok ? cnt : 0;
-    if (!anyimg) {  // warp-uniform: no periodic image in this tile's block, the query is never shifted
-#pragma unroll 2
+    // The column holds cnt entries, one of them the lane itself (d2f = 0, centre image; self is excluded in
+    // every image, nearest-neighbour.go:79).  m = cnt - 33 entries with the largest keys must be dropped.
+    const int cnt = (int)((kp - kbase) >> 8);
+    bool ok = mine && !bad && !ovf && cnt >= SPHB_K + 1;
+    // select A: the 4 largest keys below `bound` per pass (a max/min insertion network on the fp32 bit patterns).
+    // T = smallest dropped key, akey = largest kept key.
+    int mrem = ok ? cnt - (SPHB_K + 1) : 0;
+    uint32_t bound = 0xffffffffu, T = 0xffffffffu, akey = 0u;
+    bool sel_done = !ok;
+    while (__any_sync(0xffffffffu, !sel_done)) {
+      uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+      const int lim = sel_done ? 0 : cnt;
       for (int s = 0; s < lim; ++s) {
-        const uint2 ke = col[s * 32];
-        const uint32_t j = ke.y & IDX_MASK;
-        self_seen |= (j == (uint32_t)i);
-        if (ke.x < T && j != (uint32_t)i && wp != wend) {
-          const double2 pb = spos[j];
-          const double d2 = dist_sq(xa - pb.x, ya - pb.y);
-          h2 = fmax(h2, d2);
-          *np = ke.y;
-          np += 32;
-          asm volatile("st.shared.f64 [%0], %1;" ::"r"(wp), "d"(d2));
-          wp += 256;
-        }
+        uint32_t k = col[s * 32].x;
+        k = k < bound ? k : 0u;
+        uint32_t a;
+        a = max(t0, k); k = min(t0, k); t0 = a;
+        a = max(t1, k); k = min(t1, k); t1 = a;
+        a = max(t2, k); k = min(t2, k); t2 = a;
+        t3 = max(t3, k);
       }
-    } else {
-      const double qxm = __dadd_rn(xa, g.Lx), qxp = __dadd_rn(xa, -g.Lx);  // ix = -1 / +1: query + (-ix * L)
-      const double qym = __dadd_rn(ya, g.Ly), qyp = __dadd_rn(ya, -g.Ly);
-      for (int s = 0; s < lim; ++s) {
-        const uint2 ke = col[s * 32];
-        const uint32_t j = ke.y & IDX_MASK;
-        self_seen |= (j == (uint32_t)i);
-        if (ke.x < T && j != (uint32_t)i && wp != wend) {
-          const double2 pb = spos[j];
-          const uint32_t cx = (ke.y >> (IMG_SHIFT + 2)) & 3u, cy = (ke.y >> IMG_SHIFT) & 3u;
-          const double qx = cx == 1u ? xa : (cx == 0u ? qxm : qxp);
-          const double qy = cy == 1u ? ya : (cy == 0u ? qym : qyp);
-          const double d2 = dist_sq(qx - pb.x, qy - pb.y);
-          h2 = fmax(h2, d2);
-          *np = ke.y;
-          np += 32;
-          asm volatile("st.shared.f64 [%0], %1;" ::"r"(wp), "d"(d2));
-          wp += 256;
+      if (!sel_done) {
+        if (mrem <= 3) {
+          T = mrem == 0 ? bound : (mrem == 1 ? t0 : (mrem == 2 ? t1 : t2));
+          akey = mrem == 0 ? t0 : (mrem == 1 ? t1 : (mrem == 2 ? t2 : t3));
+          sel_done = true;
+        } else {
+          mrem -= 4;
+          bound = t3;
         }
       }
     }
-  }
-  __syncwarp();
-  // exactly 32 kept (fails on key ties at a pass boundary; more than 32 cannot happen: at most cnt - 1 - m),
-  // and nothing within h can have been missed
-  if (ok && !(wp == wend && self_seen && h2 <= rg2)) ok = false;
-  if (valid && !ok) {
-    const int slot = atomicAdd(out.failCount, 1);
-    out.failList[slot] = i;
-  }
-  if (ok) {
-    const double inv_h = fast_rsqrt(h2);
-    const double h = fast_sqrt(h2, inv_h);
-    if (g.sides && (((g.sides & 1) && xa - g.ox < h) || ((g.sides & 2) && g.ox + (double)g.ncx * g.dx - xa < h)))
-      atomicOr(dflags, DFLAG_GHOST_THIN);
-    double acc = 0.0;
+    // fp64 build, rank ambiguity (includes exact ties): the smallest dropped key must exceed the largest kept one
+    // by more than the fp32 error; with nothing dropped the bound is the acceptance threshold itself (checked
+    // as h^2 <= rg^2).  fp32 build: the fp32 keys are the distances, ties may fall either way.
+    if (!F32 && ok && T != 0xffffffffu && !(__uint_as_float(T) > __uint_as_float(akey) * (1.0f + deltaf) * 1.000001f)) ok = false;
+
+    // select B: compact the kept entries (key < T, not self) to the head of the column, so that the next phase
+    // runs over exactly 32 slots with independent loads in flight
+    int kept = 0;
+    bool self_seen = false;
+    {
+      const int lim = ok ? cnt : 0;
 #pragma unroll 4
-    for (int s = 0; s < SPHB_K; ++s) {
-      const double d2 = *reinterpret_cast<const double*>(&col[s * 32]);
-      const double d = d2 * fast_rsqrt(d2 + 1e-300);  // coincident particles: d = 0
-      acc += kern_F<KERNEL>(d * inv_h);                    // d <= h up to rounding
+      for (int s = 0; s < lim; ++s) {
+        const uint2 ke = col[s * 32];
+        const bool self = ke.y == (uint32_t)self_slot;
+        self_seen |= self;
+        if (ke.x < T && !self && kept < SPHB_K) {
+          col[kept * 32] = ke;  // kept <= s: never overwrites an unread slot
+          ++kept;
+        }
+      }
     }
-    // Density2D (sph.go:322), sound speed (sph.go:426-428), pressure term c^2/(gamma rho) (sph.go:332,360)
-    const double rho = ph.Fpref * ph.mass * acc * (inv_h * inv_h);
-    const double c2 = ph.cfac * epred[i];
-    const double c = c2 > 0.0 ? fast_sqrt(c2, fast_rsqrt(c2)) : sqrt(c2);
-    out.pc[i] = make_double4(rho, c, h, c * c * fast_rcp(ph.gamma * rho));
+    // exactly 32 kept (fails on key ties at a pass boundary; more than 32 cannot happen: at most cnt - 1 - m)
+    if (ok && !(kept == SPHB_K && self_seen)) ok = false;
+    uint32_t* np = out.nn + (size_t)tile * 32 * 32 + lane;  // list slots of this lane (stride 32 words)
+    if (F32) {
+      // ---- fp32 build: the keys are the squared distances; list, h, density straight from the column
+      float h2f = 0.0f;
+      if (ok) {
+#pragma unroll 8
+        for (int s = 0; s < SPHB_K; ++s) h2f = fmaxf(h2f, __uint_as_float(col[s * 32].x));
+        if (!(h2f < thr0)) ok = false;  // everything below the acceptance threshold was seen
+      }
+      if (mine && !ok) {
+        const int slot = atomicAdd(out.failCount, 1);
+        out.failList[slot] = i;
+      }
+      if (ok) {
+        float inv_h;
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv_h) : "f"(h2f));
+        const float hf = h2f * inv_h;
+        float acc = 0.0f;
+#pragma unroll 8
+        for (int s = 0; s < SPHB_K; ++s) {
+          const uint2 ke = col[s * 32];
+          np[s * 32] = candE[ke.y];
+          const float q2 = __uint_as_float(ke.x) * (inv_h * inv_h);
+          float rq;
+          asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rq) : "f"(fmaxf(q2, 1e-30f)));
+          const float q = fminf(q2 * rq, 1.0f);
+          if (KERNEL == 0) acc += 1.0f;
+          else if (KERNEL == 1) {
+            const float lo = fmaf(q * q, q - 1.0f, 1.0f / 6.0f);
+            const float t = 1.0f - q;
+            acc += q < 0.5f ? lo : t * t * t * (1.0f / 3.0f);
+          } else {
+            const float t = 1.0f - q, t2 = t * t;
+            acc += t2 * t2 * fmaf(4.0f, q, 1.0f);
+          }
+        }
+        const double h = (double)hf;
+        if (g.sides && (((g.sides & 1) && xa - g.ox < h) || ((g.sides & 2) && g.ox + (double)g.ncx * g.dx - xa < h)))
+          atomicOr(dflags, DFLAG_GHOST_THIN);
+        // Density2D (sph.go:322), sound speed (sph.go:426-428), pressure term c^2/(gamma rho) (sph.go:332,360)
+        const float rho = (float)(ph.Fpref * ph.mass) * acc * (inv_h * inv_h);
+        const float c = sqrtf((float)(ph.cfac * ep));
+        out.pc[i] = make_double4((double)rho, (double)c, h, (double)(c * c / ((float)ph.gamma * rho)));
+      }
+      continue;
+    }
+    // ---- fp64 build, exact phase: d^2 exactly as the reference computes it; the list entry goes to global
+    // memory, the slot is reused for the exact d^2
+    double h2 = 0.0;
+    if (ok) {
+      if (!anyimg) {  // warp-uniform: no periodic image in this tile's block, the query is never shifted
+#pragma unroll
+        for (int s0 = 0; s0 < SPHB_K; s0 += 8) {
+          uint32_t en[8];
+          double2 pb[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const uint32_t sl = col[(s0 + u) * 32].y;
+            pb[u] = candD[sl];
+            en[u] = candE[sl];
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const double d2 = dist_sq(xa - pb[u].x, ya - pb[u].y);
+            h2 = fmax(h2, d2);
+            np[(s0 + u) * 32] = en[u];
+            *reinterpret_cast<double*>(&col[(s0 + u) * 32]) = d2;
+          }
+        }
+      } else {
+        const double qxm = __dadd_rn(xa, g.Lx), qxp = __dadd_rn(xa, -g.Lx);  // ix = -1 / +1: query + (-ix * L)
+        const double qym = __dadd_rn(ya, g.Ly), qyp = __dadd_rn(ya, -g.Ly);
+#pragma unroll
+        for (int s0 = 0; s0 < SPHB_K; s0 += 8) {
+          uint32_t en[8];
+          double2 pb[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const uint32_t sl = col[(s0 + u) * 32].y;
+            pb[u] = candD[sl];
+            en[u] = candE[sl];
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const uint32_t cx = (en[u] >> (IMG_SHIFT + 2)) & 3u, cy = (en[u] >> IMG_SHIFT) & 3u;
+            const double qx = cx == 1u ? xa : (cx == 0u ? qxm : qxp);
+            const double qy = cy == 1u ? ya : (cy == 0u ? qym : qyp);
+            const double d2 = dist_sq(qx - pb[u].x, qy - pb[u].y);
+            h2 = fmax(h2, d2);
+            np[(s0 + u) * 32] = en[u];
+            *reinterpret_cast<double*>(&col[(s0 + u) * 32]) = d2;
+          }
+        }
+      }
+      // nothing within h can have been missed
+      if (!(h2 <= rg2)) ok = false;
+    }
+    if (mine && !ok) {
+      const int slot = atomicAdd(out.failCount, 1);
+      out.failList[slot] = i;
+    }
+    if (ok) {
+      const double inv_h = fast_rsqrt(h2);
+      const double h = fast_sqrt(h2, inv_h);
+      if (g.sides && (((g.sides & 1) && xa - g.ox < h) || ((g.sides & 2) && g.ox + (double)g.ncx * g.dx - xa < h)))
+        atomicOr(dflags, DFLAG_GHOST_THIN);
+      double acc = 0.0;
+#pragma unroll 4
+      for (int s = 0; s < SPHB_K; ++s) {
+        const double d2 = *reinterpret_cast<const double*>(&col[s * 32]);
+        const double d = d2 * fast_rsqrt(d2 + 1e-300);  // coincident particles: d = 0
+        acc += kern_F<KERNEL>(d * inv_h);                    // d <= h up to rounding
+      }
+      // Density2D (sph.go:322), sound speed (sph.go:426-428), pressure term c^2/(gamma rho) (sph.go:332,360)
+      const double rho = ph.Fpref * ph.mass * acc * (inv_h * inv_h);
+      const double c2 = ph.cfac * ep;
+      const double c = c2 > 0.0 ? fast_sqrt(c2, fast_rsqrt(c2)) : sqrt(c2);
+      out.pc[i] = make_double4(rho, c, h, c * c * fast_rcp(ph.gamma * rho));
+    }
   }
 }
 
@@ -714,10 +810,10 @@ __global__ void __launch_bounds__(128) k_knn_fallback(const double2* __restrict_
       // image order: the reference loops the x image outermost (nearest-neighbour.go:57-61); only the
       // relative order of exactly equal keys depends on it, which parity excludes
       for (int ru = r0; ru <= r1; ++ru) {
-        const int iy = g.wrapy ? floor_div(ru, g.ncy) : 0;
+        const int iy = g.wrapy ? img_idx(ru, g.ncy) : 0;
         const int row = ru - iy * g.ncy;
         const double qy = (iy == 0) ? pa.y : __dadd_rn(pa.y, -(double)iy * g.Ly);
-        const int ix0 = g.wrapx ? floor_div(c0, g.ncx) : 0, ix1 = g.wrapx ? floor_div(c1, g.ncx) : 0;
+        const int ix0 = g.wrapx ? img_idx(c0, g.ncx) : 0, ix1 = g.wrapx ? img_idx(c1, g.ncx) : 0;
         for (int ix = ix0; ix <= ix1; ++ix) {
           const int a = max(c0, ix * g.ncx) - ix * g.ncx, b = min(c1, ix * g.ncx + g.ncx - 1) - ix * g.ncx;
           const double qx = (ix == 0) ? pa.x : __dadd_rn(pa.x, -(double)ix * g.Lx);
@@ -838,6 +934,8 @@ struct ForceIO {
   const double2* vpred;
   const double4* pc;
   const uint32_t* nn;
+  const uint32_t* keys;       // cell key of every particle (sorted order)
+  const uint32_t* cellStart;
   double2* pos;
   double2* vel;
   double* e;
@@ -902,6 +1000,337 @@ __global__ void __launch_bounds__(128) k_force(ForceIO io, int n, const GridP* _
   const double f = ph.mass * ph.DFpref / (h * h * h);
   double2 a = make_double2(ax * f + ph.gx, ay * f + ph.gy);
   const double ed = qa.w * aed * ph.mass;  // Benz formulation, sph.go:400
+  double2 p = io.pos[i], v = io.vel[i];
+  double e = io.e[i];
+  if (INTEGRATE) {
+    const double dt = 2.0 * ph.dtH;
+    // kick (sph.go:122-127), drift 2 (sph.go:130-135): unfused like the reference
+    v.x = __dadd_rn(v.x, __dmul_rn(a.x, dt));
+    v.y = __dadd_rn(v.y, __dmul_rn(a.y, dt));
+    e = __dadd_rn(e, __dmul_rn(__dmul_rn(ed, 2.0), ph.dtH));
+    p.x = __dadd_rn(p.x, __dmul_rn(v.x, ph.dtH));
+    p.y = __dadd_rn(p.y, __dmul_rn(v.y, ph.dtH));
+    // periodic wrap, single shift, X shift skips the Y test (sph.go:147-167)
+    if (p.x < ph.hor0) p.x = __dadd_rn(p.x, ph.hor1 - ph.hor0);
+    else if (p.x > ph.hor1) p.x = __dsub_rn(p.x, ph.hor1 - ph.hor0);
+    else if (p.y < ph.ver0) p.y = __dadd_rn(p.y, ph.ver1 - ph.ver0);
+    else if (p.y > ph.ver1) p.y = __dsub_rn(p.y, ph.ver1 - ph.ver0);
+    // reflections L, R, U, D: pos -= pos - wall (sph.go:170-193)
+    if (p.x < ph.rL) { p.x = __dsub_rn(p.x, __dsub_rn(p.x, ph.rL)); v.x = -v.x; }
+    if (p.x > ph.rR) { p.x = __dsub_rn(p.x, __dsub_rn(p.x, ph.rR)); v.x = -v.x; }
+    if (p.y < ph.rU) { p.y = __dsub_rn(p.y, __dsub_rn(p.y, ph.rU)); v.y = -v.y; }
+    if (p.y > ph.rD) { p.y = __dsub_rn(p.y, __dsub_rn(p.y, ph.rD)); v.y = -v.y; }
+  }
+  if (!SLAB) {
+    io.vdot[i] = a;
+    io.edot[i] = ed;
+    if (INTEGRATE) {
+      io.pos[i] = p;
+      io.vel[i] = v;
+      io.e[i] = e;
+    }
+  } else {
+    const uint32_t o = io.ownIdx[i];
+    io.o_pos[o] = p;
+    io.o_vel[o] = v;
+    io.o_e[o] = e;
+    io.o_vdot[o] = a;
+    io.o_edot[o] = ed;
+    io.o_vpred[o] = va;
+    io.o_epred[o] = io.epred[i];
+    io.o_id[o] = io.id[i];
+    io.o_pc[o] = qa;
+    io.o_gflag[o] = GF_OWNED;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// K4 (staged): the same computation with the neighbour records staged in shared memory.
+//
+// A block is FORCE_THREADS consecutive particles of the cell-sorted order (a strip of a grid row), one thread
+// per particle.  Their neighbours lie in a few contiguous ranges of the sorted order ("pieces": the strip
+// widened by h in the rows above / below, plus periodic-image pieces at the box edges).  The block finds
+// the pieces (per-thread cell ranges -> cellStart -> warp + shared-memory min/max per class), copies the
+// records {position, predicted velocity, rho, c, h, P} of every piece into shared memory with coalesced
+// loads, and the 32 x FORCE_THREADS gathers of the pair loop become shared-memory loads.  The staging area is
+// a cache keyed by the sorted index: a list entry that is not covered (piece table full, staging area full,
+// rows farther than FORCE_RMAX, mixed periodic images) is read from global memory instead, so the result
+// never depends on what was staged.
+//
+// R = double: reference arithmetic (sph.go:327-401), staged positions are the raw fp64 search positions.
+// R = float : the fp32 build.  Positions are staged as fp32 offsets from a block-local origin (the fp64
+//             difference is formed before the conversion), already shifted to the periodic image of the
+//             piece; everything per pair is fp32.  Integration stays fp64.
+// -------------------------------------------------------------------------------------------------
+#define FORCE_THREADS 128
+#define FORCE_NPIECE 6
+#define FORCE_RMAX 2
+#define FORCE_NCLS ((2 * FORCE_RMAX + 1) * 3)
+#define FORCE_CODE_MIXED 15
+
+template <typename R> struct Real2 { typedef double2 T; };
+template <> struct Real2<float> { typedef float2 T; };
+__device__ __forceinline__ double2 mk2(double a, double b) { return make_double2(a, b); }
+__device__ __forceinline__ float2 mk2(float a, float b) { return make_float2(a, b); }
+
+__device__ __forceinline__ double pair_rsqrt(double x) { return fast_rsqrt(x); }
+__device__ __forceinline__ float pair_rsqrt(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ double pair_rcp(double x) { return fast_rcp(x); }
+__device__ __forceinline__ float pair_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+template <int KERNEL, typename R>
+__device__ __forceinline__ R kern_DF_r(R q) {
+  if (KERNEL == 1) {
+    const R lo = q * (R(3.0) * q - R(2.0));
+    const R t = R(1.0) - q;
+    return q < R(0.5) ? lo : -t * t;
+  }
+  const R t = R(1.0) - q;
+  return R(-10.0) * q * t * t * t;
+}
+
+struct ForceSt {           // block tables of the staged kernel
+  int cls_s[FORCE_NCLS], cls_e[FORCE_NCLS], cls_cmin[FORCE_NCLS], cls_cmax[FORCE_NCLS];
+  int st[FORCE_NPIECE];                 // piece starts, ascending; unused = INT_MAX
+  int2 tab[FORCE_NPIECE + 1];           // [t] = {start - staged offset, end (exclusive)} of piece t - 1; [0] = {0, 0}: "not staged"
+  int tab_code[FORCE_NPIECE + 1];       // periodic image code of the piece (fp32 build)
+  int p_len[FORCE_NPIECE], p_off[FORCE_NPIECE];
+  int np;
+};
+
+// the 32 pair interactions of one particle; NP = number of staged pieces the lookup distinguishes
+template <int KERNEL, bool SLAB, typename R, int NP>
+__device__ __forceinline__ void force_pairs(const ForceIO& io, int n, const GridP& g, const ForceSt& T,
+                                            const typename Real2<R>::T* __restrict__ s_sp, const typename Real2<R>::T* __restrict__ s_vp,
+                                            const typename Real2<R>::T* __restrict__ s_ra, const typename Real2<R>::T* __restrict__ s_rb,
+                                            int i, double2 pa, double2 va, double4 qa, R pax, R pay, const uint32_t (&ent0)[8],
+                                            R& ax, R& ay, R& aed, bool& thin) {
+  typedef typename Real2<R>::T R2;
+  constexpr bool F32 = sizeof(R) == 4;
+  int st[NP];
+#pragma unroll
+  for (int m = 0; m < NP; ++m) st[m] = T.st[m];
+  const R vax = (R)va.x, vay = (R)va.y;
+  const R rhoa = (R)qa.x, ca = (R)qa.y, ha = (R)qa.z, Pa = (R)qa.w;
+  const R inv_h = pair_rcp(ha);
+  const uint32_t* col = io.nn + (size_t)(i >> 5) * 1024 + (i & 31);
+  uint32_t cur[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) cur[u] = ent0[u];
+#pragma unroll 1
+  for (int s0 = 0; s0 < SPHB_K; s0 += 8) {
+    uint32_t nxt[8];  // the next eight list entries are in flight while these eight are processed
+    if (s0 + 8 < SPHB_K) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) nxt[u] = col[(s0 + 8 + u) * 32];
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const uint32_t ent = cur[u];
+      const int j = (int)(ent & IDX_MASK);
+      const int code = (int)(ent >> IMG_SHIFT);
+      if ((uint32_t)j >= (uint32_t)n) continue;  // empty slot of an underfull list (reported as SPHB_E_KNN_UNDERFULL)
+      int t = 0;
+#pragma unroll
+      for (int m = 0; m < NP; ++m) t += (j >= st[m]) ? 1 : 0;
+      const int2 de = T.tab[t];
+      bool hit = j < de.y;
+      if (F32) hit = hit && (code == T.tab_code[t]);
+      R rx, ry, vbx, vby, rhob, cb, hb, Pb;
+      if (__builtin_expect(hit, 1)) {
+        const int sl = j - de.x;
+        const R2 p = s_sp[sl], v = s_vp[sl], a2 = s_ra[sl], b2 = s_rb[sl];
+        rx = p.x - pax; ry = p.y - pay;
+        if (!F32) {
+          if (__builtin_expect(code != 5, 0)) {  // periodic image: the reference shifts the query (nearest-neighbour.go:57-61)
+            rx = (R)(((double)p.x + (double)((code >> 2) - 1) * g.Lx) - pa.x);
+            ry = (R)(((double)p.y + (double)((code & 3) - 1) * g.Ly) - pa.y);
+          }
+        }
+        vbx = v.x; vby = v.y; rhob = a2.x; cb = a2.y; hb = b2.x; Pb = b2.y;
+      } else {
+        const double2 pb = io.spos[j];
+        const double2 vb = io.vpred[j];
+        const double4 qb = io.pc[j];
+        // rAB = NNPos - Pos with NNPos = neighbour - offset (nearest-neighbour.go:80, sph.go:372)
+        rx = (R)((pb.x + (double)((code >> 2) - 1) * g.Lx) - pa.x);
+        ry = (R)((pb.y + (double)((code & 3) - 1) * g.Ly) - pa.y);
+        vbx = (R)vb.x; vby = (R)vb.y; rhob = (R)qb.x; cb = (R)qb.y; hb = (R)qb.z; Pb = (R)qb.w;
+        if (SLAB && io.gflag[j] == GF_OUTER) rhob = R(-1.0);
+      }
+      if (SLAB) thin |= rhob < R(0.0);  // its rho, c, h were not evaluated
+      const R vx = vbx - vax, vy = vby - vay;
+      const R r2 = fma(ry, ry, rx * rx);
+      const R dot = fma(vy, ry, vx * rx);
+      const R rinv = pair_rsqrt(r2);  // coincident particles give Inf/NaN like the reference (sph.go:391)
+      const R q = fmin(r2 * rinv * inv_h, R(1.0));
+      const R dk = kern_DF_r<KERNEL, R>(q);
+      R pi = R(0.0);
+      if (dot < R(0.0)) {  // artificial viscosity, sph.go:375-388; the two divisions share one reciprocal
+        const R c2 = ca + cb, rho2 = rhoa + rhob, h2 = ha + hb;  // twice the arithmetic means
+        const R den = r2 + R(0.01);
+        const R inv = pair_rcp(den * rho2);
+        const R mu = (R(0.5) * dot) * h2 * (rho2 * inv);
+        pi = mu * fma(R(1.5), mu, R(-0.375) * c2) * (R(2.0) * den * inv);
+      }
+      const R w = (pi + Pa + Pb) * dk * rinv;
+      ax = fma(rx, w, ax);
+      ay = fma(ry, w, ay);
+      aed = fma(dot, dk, aed);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) cur[u] = nxt[u];
+  }
+}
+
+template <int KERNEL, bool INTEGRATE, bool SLAB, typename R>
+__global__ void __launch_bounds__(FORCE_THREADS) k_force_st(ForceIO io, int n, const GridP* __restrict__ gp, PhysP ph,
+                                                            int nrec, uint32_t* __restrict__ dflags) {
+  typedef typename Real2<R>::T R2;
+  constexpr bool F32 = sizeof(R) == 4;
+  const GridP g = *gp;
+  __shared__ ForceSt T;
+  extern __shared__ __align__(16) unsigned char fsm[];
+  R2* s_sp = reinterpret_cast<R2*>(fsm);  // position
+  R2* s_vp = s_sp + nrec;                 // predicted velocity
+  R2* s_ra = s_vp + nrec;                 // {rho, c}; rho < 0 marks an unevaluated (outer) ghost
+  R2* s_rb = s_ra + nrec;                 // {h, P}
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int i0 = blockIdx.x * FORCE_THREADS;
+  const int i = i0 + tid;
+  const bool active = i < n && (!SLAB || io.gflag[i] == GF_OWNED);
+  if (tid < FORCE_NCLS) { T.cls_s[tid] = 0x7fffffff; T.cls_e[tid] = 0; T.cls_cmin[tid] = FORCE_CODE_MIXED; T.cls_cmax[tid] = 0; }
+  __syncthreads();
+
+  double2 pa = make_double2(0.0, 0.0), va = make_double2(0.0, 0.0);
+  double4 qa = make_double4(1.0, 0.0, 0.0, 0.0);
+  int cxa = 0, cya = 0, clo = 0, chi = -1, rlo = 0, rhi = -1;
+  uint32_t ent0[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (active) {
+    pa = io.spos[i]; va = io.vpred[i]; qa = io.pc[i];
+    const uint32_t k = io.keys[i];
+    const uint32_t* col = io.nn + (size_t)(i >> 5) * 1024 + (i & 31);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) ent0[u] = col[u * 32];  // in flight during the staging phase
+    cya = (int)(k / (uint32_t)g.ncx);
+    cxa = (int)(k - (uint32_t)cya * (uint32_t)g.ncx);
+    const double rw = qa.z * (1.0 + 1e-6);
+    clo = (int)floor((pa.x - rw - g.ox) * g.inv_dx); chi = (int)floor((pa.x + rw - g.ox) * g.inv_dx);
+    rlo = (int)floor((pa.y - rw - g.oy) * g.inv_dy); rhi = (int)floor((pa.y + rw - g.oy) * g.inv_dy);
+    clo = max(min(clo, cxa), -g.ncx); chi = min(max(chi, cxa), 2 * g.ncx - 1);
+    rlo = max(min(rlo, cya), cya - g.ncy + 1); rhi = min(max(rhi, cya), cya + g.ncy - 1);
+  }
+  // piece classes: (row offset dr, x piece: centre / image -1 / image +1); every class is a contiguous range of
+  // the sorted order when taken over consecutive particles (the end of one row abuts the start of the next)
+#pragma unroll
+  for (int dr = -FORCE_RMAX; dr <= FORCE_RMAX; ++dr) {
+    const int ru = cya + dr;
+    int iy = 0;
+    if (g.wrapy) iy = img_idx(ru, g.ncy);
+    const int row = ru - iy * g.ncy;
+    const bool has = active && ru >= rlo && ru <= rhi && row >= 0 && row < g.ncy;
+#pragma unroll
+    for (int ty = 0; ty < 3; ++ty) {
+      int a, b;
+      bool okp;
+      if (ty == 0) { a = max(clo, 0); b = min(chi, g.ncx - 1); okp = a <= b; }
+      else if (ty == 1) { a = max(clo + g.ncx, 0); b = g.ncx - 1; okp = g.wrapx && clo < 0; }
+      else { a = 0; b = min(chi - g.ncx, g.ncx - 1); okp = g.wrapx && chi >= g.ncx; }
+      const bool hv = has && okp;
+      if (!__any_sync(0xffffffffu, hv)) continue;
+      int s = 0x7fffffff, e = 0;
+      const int code = (int)img_code(ty == 0 ? 0 : (ty == 1 ? -1 : 1), iy);
+      if (hv) { s = (int)io.cellStart[row * g.ncx + a]; e = (int)io.cellStart[row * g.ncx + b + 1]; }
+      const int smin = __reduce_min_sync(0xffffffffu, s), emax = __reduce_max_sync(0xffffffffu, e);
+      const int cmin = __reduce_min_sync(0xffffffffu, hv ? code : FORCE_CODE_MIXED), cmax = __reduce_max_sync(0xffffffffu, hv ? code : 0);
+      if (lane == 0) {
+        const int c = (dr + FORCE_RMAX) * 3 + ty;
+        atomicMin(&T.cls_s[c], smin); atomicMax(&T.cls_e[c], emax);
+        atomicMin(&T.cls_cmin[c], cmin); atomicMax(&T.cls_cmax[c], cmax);
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {  // piece table: nearest rows first, sorted by start, clipped to the staging area
+    int np = 0, off = 0;
+    int ps[FORCE_NPIECE], pl[FORCE_NPIECE], po[FORCE_NPIECE], pc_[FORCE_NPIECE];
+    for (int pr = 0; pr < FORCE_NCLS; ++pr) {
+      const int rr = pr / 3, ty = pr - rr * 3;
+      const int dr = (rr == 0) ? 0 : ((rr & 1) ? -((rr + 1) >> 1) : (rr >> 1));  // 0, -1, +1, -2, +2
+      const int c = (dr + FORCE_RMAX) * 3 + ty;
+      const int s = T.cls_s[c], e = T.cls_e[c];
+      if (e <= s || np == FORCE_NPIECE) continue;
+      const int code = (T.cls_cmin[c] == T.cls_cmax[c]) ? T.cls_cmin[c] : FORCE_CODE_MIXED;
+      if (F32 && code == FORCE_CODE_MIXED) continue;
+      const int len = min(e - s, nrec - off);
+      if (len <= 0) continue;
+      int m = np;
+      for (; m > 0 && ps[m - 1] > s; --m) { ps[m] = ps[m - 1]; pl[m] = pl[m - 1]; po[m] = po[m - 1]; pc_[m] = pc_[m - 1]; }
+      ps[m] = s; pl[m] = len; po[m] = off; pc_[m] = code;
+      off += len;
+      ++np;
+    }
+    T.np = np;
+    T.tab[0] = make_int2(0, 0); T.tab_code[0] = FORCE_CODE_MIXED;
+    for (int m = 0; m < FORCE_NPIECE; ++m) {
+      const bool u = m < np;
+      T.st[m] = u ? ps[m] : 0x7fffffff;
+      T.tab[m + 1] = u ? make_int2(ps[m] - po[m], ps[m] + pl[m]) : make_int2(0, 0);
+      T.tab_code[m + 1] = u ? pc_[m] : FORCE_CODE_MIXED;
+      T.p_len[m] = u ? pl[m] : 0;
+      T.p_off[m] = u ? po[m] : 0;
+    }
+  }
+  __syncthreads();
+  // block-local origin of the fp32 frame: the middle particle of the block
+  double xref = 0.0, yref = 0.0;
+  if (F32) {
+    const double2 pr = io.spos[min(i0 + FORCE_THREADS / 2, n - 1)];
+    xref = pr.x; yref = pr.y;
+  }
+  const int np = T.np;
+  for (int m = 0; m < np; ++m) {  // stage (coalesced)
+    const int s = T.st[m], len = T.p_len[m], off = T.p_off[m];
+    double sx = 0.0, sy = 0.0;
+    if (F32) {
+      const int code = T.tab_code[m + 1];
+      sx = (double)((code >> 2) - 1) * g.Lx - xref;
+      sy = (double)((code & 3) - 1) * g.Ly - yref;
+    }
+    for (int t = tid; t < len; t += FORCE_THREADS) {
+      const int j = s + t;
+      const double2 pb = io.spos[j];
+      const double2 vb = io.vpred[j];
+      const double4 qb = io.pc[j];
+      double rho = qb.x;
+      if (SLAB && io.gflag[j] == GF_OUTER) rho = -1.0;
+      if (F32) s_sp[off + t] = mk2((R)(pb.x + sx), (R)(pb.y + sy));
+      else s_sp[off + t] = mk2((R)pb.x, (R)pb.y);
+      s_vp[off + t] = mk2((R)vb.x, (R)vb.y);
+      s_ra[off + t] = mk2((R)rho, (R)qb.y);
+      s_rb[off + t] = mk2((R)qb.z, (R)qb.w);
+    }
+  }
+  __syncthreads();
+  if (!active) return;
+
+  const R pax = F32 ? (R)(pa.x - xref) : (R)pa.x, pay = F32 ? (R)(pa.y - yref) : (R)pa.y;
+  R ax = R(0.0), ay = R(0.0), aed = R(0.0);
+  bool thin = false;
+  if (np <= 3) force_pairs<KERNEL, SLAB, R, 3>(io, n, g, T, s_sp, s_vp, s_ra, s_rb, i, pa, va, qa, pax, pay, ent0, ax, ay, aed, thin);
+  else force_pairs<KERNEL, SLAB, R, FORCE_NPIECE>(io, n, g, T, s_sp, s_vp, s_ra, s_rb, i, pa, va, qa, pax, pay, ent0, ax, ay, aed, thin);
+  if (SLAB && thin) atomicOr(dflags, DFLAG_GHOST_THIN);
+  const double h = qa.z;
+  const double f = ph.mass * ph.DFpref / (h * h * h);
+  double2 a = make_double2((double)ax * f + ph.gx, (double)ay * f + ph.gy);
+  const double ed = qa.w * (double)aed * ph.mass;  // Benz formulation, sph.go:400
   double2 p = io.pos[i], v = io.vel[i];
   double e = io.e[i];
   if (INTEGRATE) {
