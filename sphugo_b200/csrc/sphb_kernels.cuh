@@ -1052,15 +1052,18 @@ __global__ void __launch_bounds__(128) k_force(ForceIO io, int n, const GridP* _
 // widened by h in the rows above / below, plus periodic-image pieces at the box edges).  The block finds
 // the pieces (per-thread cell ranges -> cellStart -> warp + shared-memory min/max per class), copies the
 // records {position, predicted velocity, rho, c, h, P} of every piece into shared memory with coalesced
-// loads, and the 32 x FORCE_THREADS gathers of the pair loop become shared-memory loads.  The staging area is
-// a cache keyed by the sorted index: a list entry that is not covered (piece table full, staging area full,
-// rows farther than FORCE_RMAX, mixed periodic images) is read from global memory instead, so the result
-// never depends on what was staged.
+// loads, and the 32 x FORCE_THREADS gathers of the pair loop become shared-memory loads.  A piece is keyed by
+// (image code << 28 | sorted index), the same word as a neighbour-list entry, so the lookup of an entry is a
+// few unsigned compares against the sorted piece starts.  The staging area is a cache: an entry that is
+// not covered (piece table full, staging area full, rows farther than FORCE_RMAX, mixed periodic images) is
+// evaluated from global memory after the main loop, so the result never depends on what was staged.
 //
-// R = double: reference arithmetic (sph.go:327-401), staged positions are the raw fp64 search positions.
+// Staged positions are already shifted to the periodic image of their piece: b + img * L, the same first
+// operation as the reference's NNPos = b - offset (nearest-neighbour.go:80), so rAB is bit-identical.
+// R = double: reference arithmetic (sph.go:327-401).
 // R = float : the fp32 build.  Positions are staged as fp32 offsets from a block-local origin (the fp64
-//             difference is formed before the conversion), already shifted to the periodic image of the
-//             piece; everything per pair is fp32.  Integration stays fp64.
+//             difference is formed before the conversion); everything per pair is fp32.  Integration stays fp64.
+// The viscosity means are staged pre-scaled: rho/2, -0.375 c, h/2 (sph.go:379-386 with alpha = 0.75).
 // -------------------------------------------------------------------------------------------------
 #define FORCE_THREADS 128
 #define FORCE_NPIECE 6
@@ -1068,10 +1071,8 @@ __global__ void __launch_bounds__(128) k_force(ForceIO io, int n, const GridP* _
 #define FORCE_NCLS ((2 * FORCE_RMAX + 1) * 3)
 #define FORCE_CODE_MIXED 15
 
-template <typename R> struct Real2 { typedef double2 T; };
-template <> struct Real2<float> { typedef float2 T; };
-__device__ __forceinline__ double2 mk2(double a, double b) { return make_double2(a, b); }
-__device__ __forceinline__ float2 mk2(float a, float b) { return make_float2(a, b); }
+template <typename R> struct RealV { typedef double2 T; static constexpr int N = 4; };  // vectors of 16 bytes
+template <> struct RealV<float> { typedef float4 T; static constexpr int N = 2; };
 
 __device__ __forceinline__ double pair_rsqrt(double x) { return fast_rsqrt(x); }
 __device__ __forceinline__ float pair_rsqrt(float x) {
@@ -1096,34 +1097,99 @@ __device__ __forceinline__ R kern_DF_r(R q) {
   return R(-10.0) * q * t * t * t;
 }
 
+// one neighbour record as the pair loop consumes it
+template <typename R> struct NbrRec { R x, y, vx, vy, rhoh, cs, hh, P; };  // rhoh = rho/2, cs = -0.375 c, hh = h/2
+
+__device__ __forceinline__ NbrRec<double> load_rec(const double2* __restrict__ sm, int nrec, int sl) {
+  const double2 a = sm[sl], b = sm[nrec + sl], c = sm[2 * nrec + sl], d = sm[3 * nrec + sl];
+  return NbrRec<double>{a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+}
+__device__ __forceinline__ NbrRec<float> load_rec(const float4* __restrict__ sm, int nrec, int sl) {
+  const float4 a = sm[sl], b = sm[nrec + sl];
+  return NbrRec<float>{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+}
+__device__ __forceinline__ void store_rec(double2* __restrict__ sm, int nrec, int sl, const NbrRec<double>& r) {
+  sm[sl] = make_double2(r.x, r.y); sm[nrec + sl] = make_double2(r.vx, r.vy);
+  sm[2 * nrec + sl] = make_double2(r.rhoh, r.cs); sm[3 * nrec + sl] = make_double2(r.hh, r.P);
+}
+__device__ __forceinline__ void store_rec(float4* __restrict__ sm, int nrec, int sl, const NbrRec<float>& r) {
+  sm[sl] = make_float4(r.x, r.y, r.vx, r.vy); sm[nrec + sl] = make_float4(r.rhoh, r.cs, r.hh, r.P);
+}
+
+// record of particle j as seen through periodic image `code`; the fp32 build takes position and velocity
+// relative to a block-local reference `ref` = {x, y, vx, vy} before converting (the pair terms only use
+// differences, so the fp32 error scales with the block's spread, not with |x| or a bulk flow velocity)
+template <typename R, bool SLAB>
+__device__ __forceinline__ NbrRec<R> make_rec(const ForceIO& io, const GridP& g, int j, int code, const double4& ref) {
+  const double2 pb = io.spos[j];
+  const double2 vb = io.vpred[j];
+  const double4 qb = io.pc[j];
+  double rho = 0.5 * qb.x;
+  if (SLAB && io.gflag[j] == GF_OUTER) rho = -1.0;  // its rho, c, h were not evaluated
+  const double x = pb.x + (double)((code >> 2) - 1) * g.Lx, y = pb.y + (double)((code & 3) - 1) * g.Ly;
+  NbrRec<R> r;
+  r.x = (R)(x - ref.x); r.y = (R)(y - ref.y);  // ref = 0 in the fp64 build: x - 0 is exact
+  r.vx = (R)(vb.x - ref.z); r.vy = (R)(vb.y - ref.w);
+  r.rhoh = (R)rho; r.cs = (R)(-0.375 * qb.y); r.hh = (R)(0.5 * qb.z); r.P = (R)qb.w;
+  return r;
+}
+
+// own quantities of the particle a thread evaluates
+template <typename R> struct OwnRec { R x, y, vx, vy, rhoh, cs, hh, P, inv_h; };
+
+// one pair of AccelerationAndEDot2D (sph.go:357-397): adds to (ax, ay, aed); sel = 0 discards the pair
+template <int KERNEL, typename R>
+__device__ __forceinline__ void pair_term(const OwnRec<R>& o, const NbrRec<R>& b, bool sel, R& ax, R& ay, R& aed) {
+  const R rx = b.x - o.x, ry = b.y - o.y;
+  const R vx = b.vx - o.vx, vy = b.vy - o.vy;
+  const R r2 = fma(ry, ry, rx * rx);
+  const R dot = fma(vy, ry, vx * rx);
+  const R rinv = pair_rsqrt(r2);  // coincident particles give Inf/NaN like the reference (sph.go:391)
+  const R q = fmin(r2 * rinv * o.inv_h, R(1.0));
+  R dk = kern_DF_r<KERNEL, R>(q);
+  // artificial viscosity, sph.go:375-388: mu = vr hAB / (r^2 + eta^2), Pi = (-alpha cAB mu + beta mu^2) / rhoAB
+  const R cs = o.cs + b.cs, rs = o.rhoh + b.rhoh, hs = o.hh + b.hh;  // -0.75 cAB, rhoAB, hAB
+  const R den = r2 + R(0.01);
+  R mu, pi;
+  if (sizeof(R) == 4) {
+    mu = dot * hs * pair_rcp(den);
+    pi = mu * fma(R(1.5), mu, cs) * pair_rcp(rs);
+  } else {  // the two divisions share one reciprocal
+    const R inv = pair_rcp(den * rs);
+    mu = dot * hs * (rs * inv);
+    pi = mu * fma(R(1.5), mu, cs) * (den * inv);
+  }
+  pi = dot < R(0.0) ? pi : R(0.0);
+  R w = (pi + o.P + b.P) * dk * rinv;
+  w = sel ? w : R(0.0);
+  dk = sel ? dk : R(0.0);
+  ax = fma(rx, w, ax);
+  ay = fma(ry, w, ay);
+  aed = fma(dot, dk, aed);
+}
+
 struct ForceSt {           // block tables of the staged kernel
   int cls_s[FORCE_NCLS], cls_e[FORCE_NCLS], cls_cmin[FORCE_NCLS], cls_cmax[FORCE_NCLS];
-  int st[FORCE_NPIECE];                 // piece starts, ascending; unused = INT_MAX
-  int2 tab[FORCE_NPIECE + 1];           // [t] = {start - staged offset, end (exclusive)} of piece t - 1; [0] = {0, 0}: "not staged"
-  int tab_code[FORCE_NPIECE + 1];       // periodic image code of the piece (fp32 build)
-  int p_len[FORCE_NPIECE], p_off[FORCE_NPIECE];
+  uint32_t stc[FORCE_NPIECE];           // piece keys (code << 28 | start), ascending; unused = 0xffffffff
+  uint2 tab[FORCE_NPIECE + 1];          // [t] = {key - staged offset, key + length} of piece t - 1; [0] = {0, 0}: "not staged"
+  int p_s[FORCE_NPIECE], p_len[FORCE_NPIECE], p_off[FORCE_NPIECE], p_code[FORCE_NPIECE];
   int np;
 };
 
 // the 32 pair interactions of one particle; NP = number of staged pieces the lookup distinguishes
 template <int KERNEL, bool SLAB, typename R, int NP>
 __device__ __forceinline__ void force_pairs(const ForceIO& io, int n, const GridP& g, const ForceSt& T,
-                                            const typename Real2<R>::T* __restrict__ s_sp, const typename Real2<R>::T* __restrict__ s_vp,
-                                            const typename Real2<R>::T* __restrict__ s_ra, const typename Real2<R>::T* __restrict__ s_rb,
-                                            int i, double2 pa, double2 va, double4 qa, R pax, R pay, const uint32_t (&ent0)[8],
+                                            const typename RealV<R>::T* __restrict__ sm, int nrec, int i,
+                                            const OwnRec<R>& own, const double4& ref, const uint32_t (&ent0)[8],
                                             R& ax, R& ay, R& aed, bool& thin) {
-  typedef typename Real2<R>::T R2;
-  constexpr bool F32 = sizeof(R) == 4;
-  int st[NP];
+  uint32_t stc[NP];
 #pragma unroll
-  for (int m = 0; m < NP; ++m) st[m] = T.st[m];
-  const R vax = (R)va.x, vay = (R)va.y;
-  const R rhoa = (R)qa.x, ca = (R)qa.y, ha = (R)qa.z, Pa = (R)qa.w;
-  const R inv_h = pair_rcp(ha);
+  for (int m = 0; m < NP; ++m) stc[m] = T.stc[m];
   const uint32_t* col = io.nn + (size_t)(i >> 5) * 1024 + (i & 31);
   uint32_t cur[8];
 #pragma unroll
   for (int u = 0; u < 8; ++u) cur[u] = ent0[u];
+  uint32_t miss = 0;
 #pragma unroll 1
   for (int s0 = 0; s0 < SPHB_K; s0 += 8) {
     uint32_t nxt[8];  // the next eight list entries are in flight while these eight are processed
@@ -1132,76 +1198,43 @@ __device__ __forceinline__ void force_pairs(const ForceIO& io, int n, const Grid
       for (int u = 0; u < 8; ++u) nxt[u] = col[(s0 + 8 + u) * 32];
     }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < 8; ++u) {  // branch-free: eight independent pairs for the scheduler to interleave
       const uint32_t ent = cur[u];
-      const int j = (int)(ent & IDX_MASK);
-      const int code = (int)(ent >> IMG_SHIFT);
-      if ((uint32_t)j >= (uint32_t)n) continue;  // empty slot of an underfull list (reported as SPHB_E_KNN_UNDERFULL)
       int t = 0;
 #pragma unroll
-      for (int m = 0; m < NP; ++m) t += (j >= st[m]) ? 1 : 0;
-      const int2 de = T.tab[t];
-      bool hit = j < de.y;
-      if (F32) hit = hit && (code == T.tab_code[t]);
-      R rx, ry, vbx, vby, rhob, cb, hb, Pb;
-      if (__builtin_expect(hit, 1)) {
-        const int sl = j - de.x;
-        const R2 p = s_sp[sl], v = s_vp[sl], a2 = s_ra[sl], b2 = s_rb[sl];
-        rx = p.x - pax; ry = p.y - pay;
-        if (!F32) {
-          if (__builtin_expect(code != 5, 0)) {  // periodic image: the reference shifts the query (nearest-neighbour.go:57-61)
-            rx = (R)(((double)p.x + (double)((code >> 2) - 1) * g.Lx) - pa.x);
-            ry = (R)(((double)p.y + (double)((code & 3) - 1) * g.Ly) - pa.y);
-          }
-        }
-        vbx = v.x; vby = v.y; rhob = a2.x; cb = a2.y; hb = b2.x; Pb = b2.y;
-      } else {
-        const double2 pb = io.spos[j];
-        const double2 vb = io.vpred[j];
-        const double4 qb = io.pc[j];
-        // rAB = NNPos - Pos with NNPos = neighbour - offset (nearest-neighbour.go:80, sph.go:372)
-        rx = (R)((pb.x + (double)((code >> 2) - 1) * g.Lx) - pa.x);
-        ry = (R)((pb.y + (double)((code & 3) - 1) * g.Ly) - pa.y);
-        vbx = (R)vb.x; vby = (R)vb.y; rhob = (R)qb.x; cb = (R)qb.y; hb = (R)qb.z; Pb = (R)qb.w;
-        if (SLAB && io.gflag[j] == GF_OUTER) rhob = R(-1.0);
-      }
-      if (SLAB) thin |= rhob < R(0.0);  // its rho, c, h were not evaluated
-      const R vx = vbx - vax, vy = vby - vay;
-      const R r2 = fma(ry, ry, rx * rx);
-      const R dot = fma(vy, ry, vx * rx);
-      const R rinv = pair_rsqrt(r2);  // coincident particles give Inf/NaN like the reference (sph.go:391)
-      const R q = fmin(r2 * rinv * inv_h, R(1.0));
-      const R dk = kern_DF_r<KERNEL, R>(q);
-      R pi = R(0.0);
-      if (dot < R(0.0)) {  // artificial viscosity, sph.go:375-388; the two divisions share one reciprocal
-        const R c2 = ca + cb, rho2 = rhoa + rhob, h2 = ha + hb;  // twice the arithmetic means
-        const R den = r2 + R(0.01);
-        const R inv = pair_rcp(den * rho2);
-        const R mu = (R(0.5) * dot) * h2 * (rho2 * inv);
-        pi = mu * fma(R(1.5), mu, R(-0.375) * c2) * (R(2.0) * den * inv);
-      }
-      const R w = (pi + Pa + Pb) * dk * rinv;
-      ax = fma(rx, w, ax);
-      ay = fma(ry, w, ay);
-      aed = fma(dot, dk, aed);
+      for (int m = 0; m < NP; ++m) t += (ent >= stc[m]) ? 1 : 0;
+      const uint2 de = T.tab[t];
+      const bool hit = ent < de.y;
+      const int sl = hit ? (int)(ent - de.x) : 0;
+      miss |= (hit ? 0u : 1u) << (s0 + u);
+      const NbrRec<R> b = load_rec(sm, nrec, sl);
+      if (SLAB) thin |= hit && b.rhoh < R(0.0);
+      pair_term<KERNEL, R>(own, b, hit, ax, ay, aed);
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) cur[u] = nxt[u];
+  }
+  while (miss) {  // entries that were not staged: the same pair from global memory
+    const int s = __ffs(miss) - 1;
+    miss &= miss - 1;
+    const uint32_t ent = col[s * 32];
+    const int j = (int)(ent & IDX_MASK);
+    if ((uint32_t)j >= (uint32_t)n) continue;  // empty slot of an underfull list (reported as SPHB_E_KNN_UNDERFULL)
+    const NbrRec<R> b = make_rec<R, SLAB>(io, g, j, (int)(ent >> IMG_SHIFT), ref);
+    if (SLAB) thin |= b.rhoh < R(0.0);
+    pair_term<KERNEL, R>(own, b, true, ax, ay, aed);
   }
 }
 
 template <int KERNEL, bool INTEGRATE, bool SLAB, typename R>
 __global__ void __launch_bounds__(FORCE_THREADS) k_force_st(ForceIO io, int n, const GridP* __restrict__ gp, PhysP ph,
                                                             int nrec, uint32_t* __restrict__ dflags) {
-  typedef typename Real2<R>::T R2;
+  typedef typename RealV<R>::T RV;
   constexpr bool F32 = sizeof(R) == 4;
   const GridP g = *gp;
   __shared__ ForceSt T;
   extern __shared__ __align__(16) unsigned char fsm[];
-  R2* s_sp = reinterpret_cast<R2*>(fsm);  // position
-  R2* s_vp = s_sp + nrec;                 // predicted velocity
-  R2* s_ra = s_vp + nrec;                 // {rho, c}; rho < 0 marks an unevaluated (outer) ghost
-  R2* s_rb = s_ra + nrec;                 // {h, P}
+  RV* sm = reinterpret_cast<RV*>(fsm);  // RealV<R>::N arrays of nrec vectors
   const int tid = threadIdx.x, lane = tid & 31;
   const int i0 = blockIdx.x * FORCE_THREADS;
   const int i = i0 + tid;
@@ -1236,6 +1269,7 @@ __global__ void __launch_bounds__(FORCE_THREADS) k_force_st(ForceIO io, int n, c
     if (g.wrapy) iy = img_idx(ru, g.ncy);
     const int row = ru - iy * g.ncy;
     const bool has = active && ru >= rlo && ru <= rhi && row >= 0 && row < g.ncy;
+    if (!__any_sync(0xffffffffu, has)) continue;
 #pragma unroll
     for (int ty = 0; ty < 3; ++ty) {
       int a, b;
@@ -1258,74 +1292,70 @@ __global__ void __launch_bounds__(FORCE_THREADS) k_force_st(ForceIO io, int n, c
     }
   }
   __syncthreads();
-  if (tid == 0) {  // piece table: nearest rows first, sorted by start, clipped to the staging area
-    int np = 0, off = 0;
-    int ps[FORCE_NPIECE], pl[FORCE_NPIECE], po[FORCE_NPIECE], pc_[FORCE_NPIECE];
-    for (int pr = 0; pr < FORCE_NCLS; ++pr) {
-      const int rr = pr / 3, ty = pr - rr * 3;
+  if (tid < 32) {  // piece table by one warp: lane = class in priority order (nearest rows first)
+    bool v = false;
+    int s = 0, e = 0, code = FORCE_CODE_MIXED;
+    if (lane < FORCE_NCLS) {
+      const int rr = lane / 3, ty = lane - rr * 3;
       const int dr = (rr == 0) ? 0 : ((rr & 1) ? -((rr + 1) >> 1) : (rr >> 1));  // 0, -1, +1, -2, +2
       const int c = (dr + FORCE_RMAX) * 3 + ty;
-      const int s = T.cls_s[c], e = T.cls_e[c];
-      if (e <= s || np == FORCE_NPIECE) continue;
-      const int code = (T.cls_cmin[c] == T.cls_cmax[c]) ? T.cls_cmin[c] : FORCE_CODE_MIXED;
-      if (F32 && code == FORCE_CODE_MIXED) continue;
-      const int len = min(e - s, nrec - off);
-      if (len <= 0) continue;
-      int m = np;
-      for (; m > 0 && ps[m - 1] > s; --m) { ps[m] = ps[m - 1]; pl[m] = pl[m - 1]; po[m] = po[m - 1]; pc_[m] = pc_[m - 1]; }
-      ps[m] = s; pl[m] = len; po[m] = off; pc_[m] = code;
-      off += len;
-      ++np;
+      s = T.cls_s[c]; e = T.cls_e[c];
+      code = (T.cls_cmin[c] == T.cls_cmax[c]) ? T.cls_cmin[c] : FORCE_CODE_MIXED;
+      v = e > s && code != FORCE_CODE_MIXED;
     }
-    T.np = np;
-    T.tab[0] = make_int2(0, 0); T.tab_code[0] = FORCE_CODE_MIXED;
-    for (int m = 0; m < FORCE_NPIECE; ++m) {
-      const bool u = m < np;
-      T.st[m] = u ? ps[m] : 0x7fffffff;
-      T.tab[m + 1] = u ? make_int2(ps[m] - po[m], ps[m] + pl[m]) : make_int2(0, 0);
-      T.tab_code[m + 1] = u ? pc_[m] : FORCE_CODE_MIXED;
-      T.p_len[m] = u ? pl[m] : 0;
-      T.p_off[m] = u ? po[m] : 0;
+    const uint32_t vm = __ballot_sync(0xffffffffu, v);
+    v = v && __popc(vm & ((1u << lane) - 1u)) < FORCE_NPIECE;
+    int len = v ? e - s : 0;
+    int incl = len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
     }
+    const int off = incl - len;
+    len = min(len, nrec - off);  // clipped to the staging area
+    v = v && len > 0;
+    const uint32_t key = v ? (((uint32_t)code << IMG_SHIFT) | (uint32_t)s) : 0xffffffffu;
+    int rk = 0;
+#pragma unroll
+    for (int o = 0; o < FORCE_NCLS; ++o) {
+      const uint32_t ko = __shfl_sync(0xffffffffu, key, o);
+      rk += (ko < key || (ko == key && o < lane)) ? 1 : 0;
+    }
+    const int np = __popc(__ballot_sync(0xffffffffu, v));
+    if (v) {
+      T.stc[rk] = key; T.tab[rk + 1] = make_uint2(key - (uint32_t)off, key + (uint32_t)len);
+      T.p_s[rk] = s; T.p_len[rk] = len; T.p_off[rk] = off; T.p_code[rk] = code;
+    }
+    if (lane >= np && lane < FORCE_NPIECE) { T.stc[lane] = 0xffffffffu; T.tab[lane + 1] = make_uint2(0u, 0u); }
+    if (lane == 0) { T.tab[0] = make_uint2(0u, 0u); T.np = np; }
   }
   __syncthreads();
-  // block-local origin of the fp32 frame: the middle particle of the block
-  double xref = 0.0, yref = 0.0;
+  // block-local origin of the fp32 frame: position and predicted velocity of the middle particle of the block
+  double4 ref = make_double4(0.0, 0.0, 0.0, 0.0);
   if (F32) {
-    const double2 pr = io.spos[min(i0 + FORCE_THREADS / 2, n - 1)];
-    xref = pr.x; yref = pr.y;
+    const int mid = min(i0 + FORCE_THREADS / 2, n - 1);
+    const double2 pr = io.spos[mid], vr = io.vpred[mid];
+    ref = make_double4(pr.x, pr.y, vr.x, vr.y);
   }
   const int np = T.np;
   for (int m = 0; m < np; ++m) {  // stage (coalesced)
-    const int s = T.st[m], len = T.p_len[m], off = T.p_off[m];
-    double sx = 0.0, sy = 0.0;
-    if (F32) {
-      const int code = T.tab_code[m + 1];
-      sx = (double)((code >> 2) - 1) * g.Lx - xref;
-      sy = (double)((code & 3) - 1) * g.Ly - yref;
-    }
-    for (int t = tid; t < len; t += FORCE_THREADS) {
-      const int j = s + t;
-      const double2 pb = io.spos[j];
-      const double2 vb = io.vpred[j];
-      const double4 qb = io.pc[j];
-      double rho = qb.x;
-      if (SLAB && io.gflag[j] == GF_OUTER) rho = -1.0;
-      if (F32) s_sp[off + t] = mk2((R)(pb.x + sx), (R)(pb.y + sy));
-      else s_sp[off + t] = mk2((R)pb.x, (R)pb.y);
-      s_vp[off + t] = mk2((R)vb.x, (R)vb.y);
-      s_ra[off + t] = mk2((R)rho, (R)qb.y);
-      s_rb[off + t] = mk2((R)qb.z, (R)qb.w);
-    }
+    const int s = T.p_s[m], len = T.p_len[m], off = T.p_off[m], code = T.p_code[m];
+    for (int t = tid; t < len; t += FORCE_THREADS)
+      store_rec(sm, nrec, off + t, make_rec<R, SLAB>(io, g, s + t, code, ref));
   }
   __syncthreads();
   if (!active) return;
 
-  const R pax = F32 ? (R)(pa.x - xref) : (R)pa.x, pay = F32 ? (R)(pa.y - yref) : (R)pa.y;
+  OwnRec<R> own;
+  own.x = (R)(pa.x - ref.x); own.y = (R)(pa.y - ref.y);
+  own.vx = (R)(va.x - ref.z); own.vy = (R)(va.y - ref.w);
+  own.rhoh = (R)(0.5 * qa.x); own.cs = (R)(-0.375 * qa.y); own.hh = (R)(0.5 * qa.z); own.P = (R)qa.w;
+  own.inv_h = pair_rcp((R)qa.z);
   R ax = R(0.0), ay = R(0.0), aed = R(0.0);
   bool thin = false;
-  if (np <= 3) force_pairs<KERNEL, SLAB, R, 3>(io, n, g, T, s_sp, s_vp, s_ra, s_rb, i, pa, va, qa, pax, pay, ent0, ax, ay, aed, thin);
-  else force_pairs<KERNEL, SLAB, R, FORCE_NPIECE>(io, n, g, T, s_sp, s_vp, s_ra, s_rb, i, pa, va, qa, pax, pay, ent0, ax, ay, aed, thin);
+  if (np <= 3) force_pairs<KERNEL, SLAB, R, 3>(io, n, g, T, sm, nrec, i, own, ref, ent0, ax, ay, aed, thin);
+  else force_pairs<KERNEL, SLAB, R, FORCE_NPIECE>(io, n, g, T, sm, nrec, i, own, ref, ent0, ax, ay, aed, thin);
   if (SLAB && thin) atomicOr(dflags, DFLAG_GHOST_THIN);
   const double h = qa.z;
   const double f = ph.mass * ph.DFpref / (h * h * h);

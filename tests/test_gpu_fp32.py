@@ -1,0 +1,129 @@
+"""-m gpu parity tests of the fp32 build (sphb_params.precision = 32) against the fp64 CPU oracle.
+
+Bar (north_star): smoothing lengths, densities, accelerations and energies within 1e-5 relative; neighbour
+index sets identical except where the fp32 distances cannot separate the candidates ("neighbour
+sets in fp32 can legitimately differ from the fp64 oracle at near-ties"): a differing neighbour is excused
+only if it sits within TIE32 * h of the k-th distance in both lists.  Accelerations / EDot are measured
+relative to sum|term| like in the fp64 tests.  State and integration stay fp64 in this build, so positions
+and velocities after one step inherit only the error of the accelerations."""
+import numpy as np
+import pytest
+
+from tests import util as U
+from oracle import oracle as orc
+from sphugo_b200 import _lib as L
+from sphugo_b200 import gen
+
+pytestmark = pytest.mark.gpu
+TOL32 = 1e-5
+TIE32 = 2e-6  # relative distance gap below which fp32 tile-relative coordinates may rank two candidates either way
+
+
+def _knn_density32(ic, hor, ver, kernels=(1, 2)):
+    po, pg = U.params_pair(hor=hor, ver=ver)
+    pg.precision = 32
+    o = orc.Oracle(po, ic["pos"], ids=ic["id"])
+    o.knn(hor, ver, mode=1)
+    g = L.Handle(pg, ic["pos"], ids=ic["id"])
+    g.knn(hor, ver)
+    ref = o.state(neighbours=True)
+    got = g.state(U.FIELDS_STATE + U.FIELDS_NN)
+    hard, excused = U.neighbour_sets_equal(got, ref, tie_rel=TIE32)
+    assert hard == 0, f"{hard} particles with different neighbour sets ({excused} near-ties excused)"
+    assert excused <= max(2, len(ic["pos"]) // 500), "too many near-tie differences for fp32 round-off"
+    assert U.rel_err(got["h"], ref["h"]) <= TOL32
+    for k in kernels:
+        o.density(k)
+        g.density(k)
+        assert U.rel_err(g.state(["rho"])["rho"], o.state()["rho"]) <= TOL32, f"density kernel {k}"
+    c = g.counters()
+    g.close(); o.close()
+    return c
+
+
+def test_fp32_knn_density_c1():
+    """examples/density shape (density.go:41-97), periodic [0,1]^2."""
+    _knn_density32(U.c1_density(), (0.0, 1.0), (0.0, 1.0))
+
+
+def test_fp32_knn_density_open_and_mixed():
+    ic = U.c1_periodic_visual()
+    _knn_density32(ic, U.OPEN, U.OPEN, kernels=(1,))
+    _knn_density32(ic, (0.1, 0.9), U.OPEN, kernels=(2,))
+
+
+def test_fp32_knn_large_lattice_uses_tile_kernel():
+    """2^16 jittered lattice at a realistic spacing: nearly every particle is served by the fp32 tile kernel
+    (not by the fp64 ring-expansion fallback), and still meets the bar."""
+    pos = gen.jittered_lattice(256, 256)
+    ic = dict(pos=pos, id=np.arange(len(pos), dtype=np.int64))
+    c = _knn_density32(ic, (0.0, 1.0), (0.0, 1.0), kernels=(1,))
+    assert c["knn_fallback"] < 0.2 * len(pos)  # first evaluation: radius from a density estimate
+
+
+def _step32(ic, steps, **cfg):
+    po, pg = U.params_pair(**cfg)
+    pg.precision = 32
+    o = orc.Oracle(po, ic["pos"], ic.get("vel"), ic.get("e"), None, ic["id"])
+    g = L.Handle(pg, ic["pos"], ic.get("vel"), ic.get("e"), None, ic["id"])
+    for done in range(1, steps + 1):
+        o.step(1)
+        g.step(1)
+        ref = o.state(neighbours=True)
+        got = g.state(U.FIELDS_STATE)
+        tol = TOL32 * (1 if done == 1 else 10)  # round-off grows along the trajectory
+        asc, esc = U.force_scales(ref, po)
+        L_ = max(1.0, float(np.abs(ref["pos"]).max()))
+        assert np.abs(got["pos"] - ref["pos"]).max() <= tol * L_, f"pos step {done}"
+        assert U.rel_err(got["h"], ref["h"]) <= tol, f"h step {done}"
+        assert U.rel_err(got["rho"], ref["rho"]) <= tol, f"rho step {done}"
+        assert U.rel_err(got["c"], ref["c"]) <= tol, f"c step {done}"
+        assert U.rel_err(got["vdot"], ref["vdot"], asc) <= tol, f"vdot step {done}"
+        assert U.rel_err(got["edot"], ref["edot"], esc) <= tol, f"edot step {done}"
+        vs = np.abs(ref["vel"]).max() + asc.max() * 2 * po.dt_half
+        assert np.abs(got["vel"] - ref["vel"]).max() <= tol * vs, f"vel step {done}"
+        assert U.rel_err(got["e"], ref["e"], esc * 2 * po.dt_half) <= tol, f"e step {done}"
+        assert abs(g.reduce(L.SUM_E) - o.total_energy()) <= tol * abs(o.total_energy())
+    g.close(); o.close()
+
+
+def test_fp32_default_simulation_steps():
+    """sim.MakeSimulation() shape: 1000 U([0,1]^2), open boundaries (sph.go:23-30)."""
+    _step32(gen.spawn([(1000, (0, 0), (1, 1))]), steps=4)
+
+
+def test_fp32_example_config_steps():
+    """example.sph-config (config-parser.go:872-924): Wendland, periodic x, gravity, floor."""
+    ic = gen.spawn([(260, (0.2, 0.3), (0.8, 0.4)), (700, (0.2, 0.6), (0.8, 0.99))])
+    _step32(ic, steps=3, gamma=4.666, particle_mass=1e6, accel=(0.0, 0.55), dt_half=0.00324, kernel=2,
+            hor=(0.2, 0.8), ver=(-100.0, 100.0), refl=(L.OPEN_LO, L.OPEN_HI, L.OPEN_LO, 0.99))
+
+
+def test_fp32_periodic_box_steps_with_wrap():
+    """C3 shape at reduced N: periodic [0,1]^2 jittered lattice, drifting so that particles wrap."""
+    pos = gen.jittered_lattice(128, 128)
+    n = len(pos)
+    vel = np.tile(np.array([[3.0, -2.0]]), (n, 1))
+    ic = dict(pos=pos, vel=vel, e=np.full(n, 0.01), id=np.arange(n, dtype=np.int64))
+    _step32(ic, steps=3, hor=(0.0, 1.0), ver=(0.0, 1.0), accel=(0.0, 0.2), dt_half=0.001)
+
+
+def test_fp32_and_fp64_builds_agree_at_c3_size():
+    """2^20 particles (BASELINE configs[2]): the two builds of the library against each other after two
+    steps, through size-independent measures (max relative difference of h, rho; energy sum)."""
+    pos = gen.jittered_lattice(1024, 1024)
+    n = len(pos)
+    kw = dict(hor=(0.0, 1.0), ver=(0.0, 1.0), accel=(0.0, 0.2), dt_half=0.001)
+    out = {}
+    for prec in (64, 32):
+        p = L.make_params(precision=prec, **kw)
+        g = L.Handle(p, pos, None, np.full(n, 0.01))
+        g.step(2)
+        out[prec] = U.by_id(g.state(["id", "h", "rho", "e", "pos"]))
+        out[prec]["sum_e"] = g.reduce(L.SUM_E)
+        g.close()
+    assert U.rel_err(out[32]["h"], out[64]["h"]) <= TOL32
+    assert U.rel_err(out[32]["rho"], out[64]["rho"]) <= TOL32
+    assert abs(out[32]["sum_e"] - out[64]["sum_e"]) <= TOL32 * abs(out[64]["sum_e"])
+    # positions inherit the acceleration error times dt^2: |a| ~ 1e2 here, so 1e-5 * 1e2 * (2e-3)^2 * steps
+    assert np.abs(out[32]["pos"] - out[64]["pos"]).max() <= 1e-8
