@@ -631,14 +631,19 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
     bool self_seen = false;
     {
       const int lim = ok ? cnt : 0;
-#pragma unroll 4
-      for (int s = 0; s < lim; ++s) {
-        const uint2 ke = col[s * 32];
-        const bool self = ke.y == (uint32_t)self_slot;
-        self_seen |= self;
-        if (ke.x < T && !self && kept < SPHB_K) {
-          col[kept * 32] = ke;  // kept <= s: never overwrites an unread slot
-          ++kept;
+      for (int s0 = 0; s0 < lim; s0 += 8) {  // eight loads in flight, then the (aliasing) compacted stores
+        uint2 ke[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) ke[u] = col[(s0 + u) * 32];  // slots up to cnt + 7 <= CAP - 1 exist (ovf bound)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const bool self = ke[u].y == (uint32_t)self_slot;
+          const bool in = s0 + u < lim;
+          self_seen |= self && in;
+          if (in && ke[u].x < T && !self && kept < SPHB_K) {
+            col[kept * 32] = ke[u];  // kept <= s0 + u: only slots that were already read
+            ++kept;
+          }
         }
       }
     }
@@ -1135,12 +1140,13 @@ __device__ __forceinline__ NbrRec<R> make_rec(const ForceIO& io, const GridP& g,
 }
 
 // own quantities of the particle a thread evaluates
-template <typename R> struct OwnRec { R x, y, vx, vy, rhoh, cs, hh, P, inv_h; };
+template <typename R> struct OwnRec { R x, y, xl, yl, vx, vy, rhoh, cs, hh, P, inv_h; };  // (xl, yl): fp32 residual of (x, y)
 
 // one pair of AccelerationAndEDot2D (sph.go:357-397): adds to (ax, ay, aed); sel = 0 discards the pair
 template <int KERNEL, typename R>
 __device__ __forceinline__ void pair_term(const OwnRec<R>& o, const NbrRec<R>& b, bool sel, R& ax, R& ay, R& aed) {
-  const R rx = b.x - o.x, ry = b.y - o.y;
+  R rx = b.x - o.x, ry = b.y - o.y;
+  if (sizeof(R) == 4) { rx -= o.xl; ry -= o.yl; }  // own position to full precision: only the neighbour's rounding is left
   const R vx = b.vx - o.vx, vy = b.vy - o.vy;
   const R r2 = fma(ry, ry, rx * rx);
   const R dot = fma(vy, ry, vx * rx);
@@ -1349,6 +1355,7 @@ __global__ void __launch_bounds__(FORCE_THREADS) k_force_st(ForceIO io, int n, c
 
   OwnRec<R> own;
   own.x = (R)(pa.x - ref.x); own.y = (R)(pa.y - ref.y);
+  own.xl = (R)((pa.x - ref.x) - (double)own.x); own.yl = (R)((pa.y - ref.y) - (double)own.y);
   own.vx = (R)(va.x - ref.z); own.vy = (R)(va.y - ref.w);
   own.rhoh = (R)(0.5 * qa.x); own.cs = (R)(-0.375 * qa.y); own.hh = (R)(0.5 * qa.z); own.P = (R)qa.w;
   own.inv_h = pair_rcp((R)qa.z);
