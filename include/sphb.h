@@ -173,8 +173,8 @@ int sphb_create_device(const sphb_params* p, int64_t n, int64_t capacity, const 
  * [x_lo, x_hi).  The exchange itself (NCCL send/recv over NVLink) is done by the caller on device buffers; see
  * sphugo_b200/slab.py.  One force evaluation:
  *     sphb_slab_set            ghost widths for this evaluation (from the all-reduced max h)
- *     sphb_slab_step_begin     drift-1 + predict on the owned particles               (sph.go:108-117)
- *     sphb_slab_pack_halo x2   owned particles within ghost_w of an edge -> records   -> exchange
+ *     sphb_slab_step_begin     selects the evaluation mode (drift-1 + predict run inside step_end, sph.go:108-117)
+ *     sphb_slab_pack_halo      owned particles within ghost_w of an edge -> records   -> exchange
  *     sphb_slab_add_ghosts x2  append the neighbour's records as ghosts
  *     sphb_slab_step_end       sort, kNN, density on owned + inner ghosts, forces + kick + drift-2 + boundaries on
  *                              owned, ghosts dropped                                   (sph.go:119-193)
@@ -197,12 +197,18 @@ typedef struct {
 int sphb_slab_set(sphb_sim* s, const sphb_slab* slab);
 /* max smoothing length of the owned particles after the last evaluation (device reduction; the caller all-reduces) */
 int sphb_max_h(sphb_sim* s, double* out);
+/* largest |Vel| of the owned particles (device reduction): bounds how far a particle can leave its slab per step,
+ * so the caller can migrate only when the accumulated excursion approaches the ghost-layer slack */
+int sphb_max_speed(sphb_sim* s, double* out);
 /* mode 0: CalculateForces on the state as is; 1: step-0 initialisation VPred = Vel, EPred = E (sph.go:97-100);
- * 2: drift-1 + predict (sph.go:108-117).  Owned particles only, in place. */
+ * 2: drift-1 + predict (sph.go:108-117).  The mode applies to the pack / add_ghosts / step_end calls that follow:
+ * ghosts travel with the predictor's inputs and are drifted and predicted by the receiver together with its owned
+ * particles, with identical arithmetic. */
 int sphb_slab_step_begin(sphb_sim* s, int32_t mode);
-/* pack owned particles within ghost_w of the low (side 0) / high (side 1) edge as ghost records
- * {x, y, vpx, vpy, epred, id (int64 bits), h_prev} = 7 x 8 bytes into d_buf (device); *count_out = records written */
-int sphb_slab_pack_halo(sphb_sim* s, int32_t side, void* d_buf, int64_t cap_records, int64_t* count_out);
+/* one pass: pack the owned particles that will lie within ghost_w of the low / high edge at evaluation time as ghost
+ * records {x, y, vx, vy, vdotx, vdoty, e, edot, id (int64 bits), h_prev} = 10 x 8 bytes (mode 0: VPred / EPred in the
+ * velocity / energy slots, zero derivatives) into d_buf_lo / d_buf_hi (device); count_out[0..1] = records written */
+int sphb_slab_pack_halo(sphb_sim* s, void* d_buf_lo, void* d_buf_hi, int64_t cap_records, int64_t* count_out);
 int sphb_slab_add_ghosts(sphb_sim* s, const void* d_buf, int64_t count);
 /* integrate != 0: kick + drift-2 + wrap + reflections on the owned particles and CurrentStep += 1 */
 int sphb_slab_step_end(sphb_sim* s, int32_t integrate);
@@ -212,7 +218,7 @@ int sphb_slab_pack_migrants(sphb_sim* s, int32_t side, void* d_buf, int64_t cap_
 int sphb_slab_add_migrants(sphb_sim* s, const void* d_buf, int64_t count);
 int sphb_slab_finish_migration(sphb_sim* s);
 
-#define SPHB_HALO_RECORD_DOUBLES 7
+#define SPHB_HALO_RECORD_DOUBLES 10
 #define SPHB_MIGRANT_RECORD_DOUBLES 12
 
 #ifdef __cplusplus

@@ -31,13 +31,13 @@ FIELD_SHAPE = {  # trailing shape, dtype
 SUM_E, SUM_RHO, LAST_VEL_NORM = 0, 1, 2
 PHASES = ["keys", "sort", "reorder", "knn", "force", "total"]
 COUNTERS = ["steps", "kernel_launches", "knn_fallback", "regrids"]
-HALO_RECORD_DOUBLES, MIGRANT_RECORD_DOUBLES = 7, 12
+HALO_RECORD_DOUBLES, MIGRANT_RECORD_DOUBLES = 10, 12
 
 EXPORTS = [
     "sphb_create", "sphb_destroy", "sphb_last_error", "sphb_set_params", "sphb_get_params", "sphb_count",
     "sphb_current_step", "sphb_append", "sphb_step", "sphb_calc_forces", "sphb_knn", "sphb_density", "sphb_stream", "sphb_sync",
     "sphb_download", "sphb_upload", "sphb_reduce", "sphb_phase_times", "sphb_counters", "sphb_create_device",
-    "sphb_slab_set", "sphb_max_h", "sphb_slab_step_begin", "sphb_slab_pack_halo", "sphb_slab_add_ghosts",
+    "sphb_slab_set", "sphb_max_h", "sphb_max_speed", "sphb_slab_step_begin", "sphb_slab_pack_halo", "sphb_slab_add_ghosts",
     "sphb_slab_step_end", "sphb_slab_pack_migrants", "sphb_slab_add_migrants", "sphb_slab_finish_migration",
 ]
 
@@ -124,10 +124,12 @@ def lib():
     L.sphb_slab_set.argtypes = [vp, C.POINTER(Slab)]
     L.sphb_max_h.restype = C.c_int
     L.sphb_max_h.argtypes = [vp, dp]
+    L.sphb_max_speed.restype = C.c_int
+    L.sphb_max_speed.argtypes = [vp, dp]
     L.sphb_slab_step_begin.restype = C.c_int
     L.sphb_slab_step_begin.argtypes = [vp, C.c_int32]
     L.sphb_slab_pack_halo.restype = C.c_int
-    L.sphb_slab_pack_halo.argtypes = [vp, C.c_int32, vp, C.c_int64, ip]
+    L.sphb_slab_pack_halo.argtypes = [vp, vp, vp, C.c_int64, ip]
     L.sphb_slab_add_ghosts.restype = C.c_int
     L.sphb_slab_add_ghosts.argtypes = [vp, vp, C.c_int64]
     L.sphb_slab_step_end.restype = C.c_int
@@ -285,6 +287,11 @@ class Handle:
     def max_h(self):
         out = C.c_double()
         self._chk(lib().sphb_max_h(self._h, C.byref(out)))
+        return out.value
+
+    def max_speed(self):
+        out = C.c_double()
+        self._chk(lib().sphb_max_speed(self._h, C.byref(out)))
         return out.value
 
     def phase_times(self):

@@ -65,6 +65,7 @@ struct sphb_sim {
   // slab mode
   bool slab_on = false;
   sphb_slab slab{};
+  int slab_mode = 0;           // mode of the evaluation in progress (sphb_slab_step_begin)
   uint32_t* ownTile = nullptr; // tile sums of the owned-particle scan
   int* packCount = nullptr;    // device counter of the pack kernels
   int64_t nleaving = 0;        // particles packed for migration and not yet compacted away
@@ -193,7 +194,7 @@ enum { MODE_ASIS = 0, MODE_INIT = 1, MODE_DRIFT = 2 };
 int refresh_stats(sphb_sim* s) {
   const int ntot = (int)(s->n + s->nghost);
   const int nb = ntot > 0 ? std::min(STAT_BLOCKS, cdiv(ntot, 256)) : 1;
-  k_stats_partial<<<nb, 256, 0, s->st>>>(s->a.pos, s->a.pc, s->a.e, (int)s->n, s->statPart);
+  k_stats_partial<<<nb, 256, 0, s->st>>>(s->a.pos, s->a.vel, s->a.pc, s->a.e, (int)s->n, s->statPart);
   k_stats_final<<<1, 32 * STAT_N, 0, s->st>>>(s->statPart, nb, s->stats);
   s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 2;
   CKL(s);
@@ -444,7 +445,7 @@ int create_common(const sphb_params* p, int64_t n, int64_t capacity, const doubl
   CKC(dalloc(s->failList, cap));
   CKC(dalloc(s->failCount, 2));
   CKC(dalloc(s->ownTile, (size_t)cdiv(capacity, SC_TILE) + 1));
-  CKC(dalloc(s->packCount, 1));
+  CKC(dalloc(s->packCount, 2));
   CKC(dalloc(s->dflags, 1));
   CKC(dalloc(s->statPart, (size_t)STAT_BLOCKS * STAT_N));
   CKC(dalloc(s->stats, STAT_N));
@@ -732,6 +733,18 @@ int sphb_max_h(sphb_sim* s, double* out) {
   CK(s, cudaMemcpyAsync(st, s->stats, sizeof st, cudaMemcpyDeviceToHost, s->st));
   CK(s, cudaStreamSynchronize(s->st));
   *out = st[8] > 0.0 ? st[5] : 0.0;
+  return SPHB_OK;
+}
+
+int sphb_max_speed(sphb_sim* s, double* out) {
+  int rc = enter(s); if (rc) return rc;
+  if (!out) return fail(s, SPHB_E_INVALID, "out is NULL");
+  if (s->n == 0) { *out = 0.0; return SPHB_OK; }
+  if (s->stats_dirty) { rc = refresh_stats(s); if (rc) return rc; }
+  double st[STAT_N];
+  CK(s, cudaMemcpyAsync(st, s->stats, sizeof st, cudaMemcpyDeviceToHost, s->st));
+  CK(s, cudaStreamSynchronize(s->st));
+  *out = st[9] > 0.0 ? std::sqrt(st[9]) : 0.0;
   return SPHB_OK;
 }
 

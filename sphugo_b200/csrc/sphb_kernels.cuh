@@ -1425,32 +1425,6 @@ __device__ __forceinline__ double slab_frame_x(double x, const SlabP& sl) {
   return sl.Lx > 0.0 ? wrap_coord(x, sl.frame_lo, sl.Lx) : x;
 }
 
-// drift-1 + predict in place on the owned particles (sph.go:108-117) / step-0 initialisation (sph.go:97-100)
-template <int MODE>
-__global__ void __launch_bounds__(256) k_slab_predict(double2* __restrict__ pos, const double2* __restrict__ vel,
-                                                     const double2* __restrict__ vdot, double2* __restrict__ vpred,
-                                                     const double* __restrict__ e, const double* __restrict__ edot,
-                                                     double* __restrict__ epred, uint8_t* __restrict__ gflag, int n,
-                                                     double dtH) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  gflag[i] = GF_OWNED;
-  if (MODE == 0) return;
-  const double2 v = vel[i];
-  if (MODE == 2) {
-    double2 p = pos[i];
-    const double2 a = vdot[i];
-    p.x = __dadd_rn(p.x, __dmul_rn(v.x, dtH));
-    p.y = __dadd_rn(p.y, __dmul_rn(v.y, dtH));
-    pos[i] = p;
-    vpred[i] = make_double2(__dadd_rn(v.x, __dmul_rn(a.x, dtH)), __dadd_rn(v.y, __dmul_rn(a.y, dtH)));
-    epred[i] = __dadd_rn(e[i], __dmul_rn(edot[i], dtH));
-  } else {
-    vpred[i] = v;
-    epred[i] = e[i];
-  }
-}
-
 // append with one atomic per warp; returns the slot of this lane or -1
 __device__ __forceinline__ int warp_append_slot(bool want, int* counter) {
   const uint32_t m = __ballot_sync(0xffffffffu, want);
@@ -1462,31 +1436,50 @@ __device__ __forceinline__ int warp_append_slot(bool want, int* counter) {
   return want ? base + __popc(m & ((1u << lane) - 1u)) : -1;
 }
 
-// ghost records {x, y, vpx, vpy, epred, id, h}
-__global__ void __launch_bounds__(256) k_pack_halo(const double2* __restrict__ pos, const double2* __restrict__ vpred,
+// Ghost records carry the predictor's inputs, {x, y, vx, vy, vdotx, vdoty, e, edot, id, h}: the receiving slab
+// drifts and predicts its ghosts in the same reorder kernel and with the same arithmetic as its owned
+// particles (sph.go:108-117), so no separate predict pass over the state is needed and a ghost is bit-identical
+// to the owner's copy.  mode 0 (CalculateForces on the state as is) sends {VPred, EPred} in the velocity / energy
+// slots with zero derivatives.  The width test uses the position the evaluation will see (after drift-1).
+#define HALO_REC 10
+__global__ void __launch_bounds__(256) k_pack_halo(const double2* __restrict__ pos, const double2* __restrict__ vel,
+                                                  const double2* __restrict__ vdot, const double2* __restrict__ vpred,
+                                                  const double* __restrict__ e, const double* __restrict__ edot,
                                                   const double* __restrict__ epred, const int64_t* __restrict__ id,
-                                                  const double4* __restrict__ pc, int n, SlabP sl, int side,
-                                                  double* __restrict__ buf, int cap, int* __restrict__ counter,
-                                                  uint32_t* __restrict__ dflags) {
+                                                  const double4* __restrict__ pc, int n, SlabP sl, int mode, double dtH,
+                                                  double* __restrict__ buf_lo, double* __restrict__ buf_hi, int cap,
+                                                  int* __restrict__ counters, uint32_t* __restrict__ dflags) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  bool want = false;
-  double2 p = make_double2(0, 0);
+  bool want_lo = false, want_hi = false;
+  double2 p = make_double2(0, 0), v = make_double2(0, 0);
   if (i < n) {
     p = pos[i];
-    const double xl = slab_frame_x(p.x, sl);
-    want = side == 0 ? (xl - sl.x_lo < sl.ghost_w) : (sl.x_hi - xl <= sl.ghost_w);
+    v = vel[i];
+    const double xe = mode == 2 ? __dadd_rn(p.x, __dmul_rn(v.x, dtH)) : p.x;
+    const double xl = slab_frame_x(xe, sl);
+    want_lo = sl.has_left && (xl - sl.x_lo < sl.ghost_w);
+    want_hi = sl.has_right && (sl.x_hi - xl <= sl.ghost_w);
   }
-  const int slot = warp_append_slot(want, counter);
-  if (slot < 0) return;
-  if (slot >= cap) { atomicOr(dflags, DFLAG_BUF_FULL); return; }
-  double* r = buf + (size_t)slot * 7;
-  const double2 vp = vpred[i];
-  r[0] = p.x; r[1] = p.y; r[2] = vp.x; r[3] = vp.y; r[4] = epred[i];
-  r[5] = __longlong_as_double(id[i]);
-  r[6] = pc[i].z;
+#pragma unroll
+  for (int side = 0; side < 2; ++side) {
+    const int slot = warp_append_slot(side == 0 ? want_lo : want_hi, counters + side);
+    if (slot < 0) continue;
+    if (slot >= cap) { atomicOr(dflags, DFLAG_BUF_FULL); continue; }
+    double* r = (side == 0 ? buf_lo : buf_hi) + (size_t)slot * HALO_REC;
+    r[0] = p.x; r[1] = p.y;
+    if (mode == 0) {
+      const double2 vp = vpred[i];
+      r[2] = vp.x; r[3] = vp.y; r[4] = 0.0; r[5] = 0.0; r[6] = epred[i]; r[7] = 0.0;
+    } else {
+      const double2 a = vdot[i];
+      r[2] = v.x; r[3] = v.y; r[4] = a.x; r[5] = a.y; r[6] = e[i]; r[7] = edot[i];
+    }
+    r[8] = __longlong_as_double(id[i]);
+    r[9] = pc[i].z;
+  }
 }
 
-__global__ void __launch_bounds__(256) k_add_ghosts(const double* __restrict__ buf, int count, SlabP sl,
+__global__ void __launch_bounds__(256) k_add_ghosts(const double* __restrict__ buf, int count, SlabP sl, int mode, double dtH,
                                                    double2* __restrict__ pos, double2* __restrict__ vel,
                                                    double2* __restrict__ vdot, double2* __restrict__ vpred,
                                                    double* __restrict__ e, double* __restrict__ edot,
@@ -1494,17 +1487,18 @@ __global__ void __launch_bounds__(256) k_add_ghosts(const double* __restrict__ b
                                                    double4* __restrict__ pc, uint8_t* __restrict__ gflag) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= count) return;
-  const double* r = buf + (size_t)k * 7;
+  const double* r = buf + (size_t)k * HALO_REC;
   const double x = r[0];
   pos[k] = make_double2(x, r[1]);
-  vel[k] = make_double2(0, 0);
-  vdot[k] = make_double2(0, 0);
-  vpred[k] = make_double2(r[2], r[3]);
-  e[k] = 0.0; edot[k] = 0.0;
-  epred[k] = r[4];
-  id[k] = __double_as_longlong(r[5]);
-  pc[k] = make_double4(0.0, 0.0, r[6], 0.0);
-  const double xl = slab_frame_x(x, sl);
+  vel[k] = make_double2(r[2], r[3]);
+  vdot[k] = make_double2(r[4], r[5]);
+  vpred[k] = make_double2(r[2], r[3]);  // read by the mode-0 reorder only
+  e[k] = r[6]; edot[k] = r[7];
+  epred[k] = r[6];
+  id[k] = __double_as_longlong(r[8]);
+  pc[k] = make_double4(0.0, 0.0, r[9], 0.0);
+  const double xe = mode == 2 ? __dadd_rn(x, __dmul_rn(r[2], dtH)) : x;
+  const double xl = slab_frame_x(xe, sl);
   gflag[k] = (xl >= sl.x_lo - sl.inner_w && xl < sl.x_hi + sl.inner_w) ? GF_INNER : GF_OUTER;
 }
 
@@ -1601,18 +1595,19 @@ __global__ void __launch_bounds__(256) k_compact(StateIn in, StateOut out, const
 // -------------------------------------------------------------------------------------------------
 // reductions and statistics
 // -------------------------------------------------------------------------------------------------
-// per-block partials of {min x, max x, min y, max y, sum h, max h, sum e, sum rho, #(h > 0)}; one block folds them
-#define STAT_N 9
+// per-block partials of {min x, max x, min y, max y, sum h, max h, sum e, sum rho, #(h > 0), max |v|^2}; one block folds them
+#define STAT_N 10
 #define STAT_BLOCKS 592
 __device__ __forceinline__ double stat_comb(int k, double a, double b) {
-  return (k == 0 || k == 2) ? fmin(a, b) : ((k == 1 || k == 3 || k == 5) ? fmax(a, b) : a + b);
+  return (k == 0 || k == 2) ? fmin(a, b) : ((k == 1 || k == 3 || k == 5 || k == 9) ? fmax(a, b) : a + b);
 }
 __device__ __forceinline__ double stat_init(int k) {
-  return (k == 0 || k == 2) ? 1.7976931348623157e308 : ((k == 1 || k == 3 || k == 5) ? -1.7976931348623157e308 : 0.0);
+  return (k == 0 || k == 2) ? 1.7976931348623157e308 : ((k == 1 || k == 3 || k == 5 || k == 9) ? -1.7976931348623157e308 : 0.0);
 }
 
-__global__ void __launch_bounds__(256) k_stats_partial(const double2* __restrict__ pos, const double4* __restrict__ pc,
-                                                      const double* __restrict__ e, int n, double* __restrict__ part) {
+__global__ void __launch_bounds__(256) k_stats_partial(const double2* __restrict__ pos, const double2* __restrict__ vel,
+                                                      const double4* __restrict__ pc, const double* __restrict__ e, int n,
+                                                      double* __restrict__ part) {
   __shared__ double sh[8][STAT_N];
   double v[STAT_N];
 #pragma unroll
@@ -1620,6 +1615,8 @@ __global__ void __launch_bounds__(256) k_stats_partial(const double2* __restrict
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     double2 p = pos[i];
     double4 q = pc[i];
+    const double2 u = vel[i];
+    v[9] = fmax(v[9], u.x * u.x + u.y * u.y);
     v[0] = fmin(v[0], p.x); v[1] = fmax(v[1], p.x);
     v[2] = fmin(v[2], p.y); v[3] = fmax(v[3], p.y);
     v[4] += q.z; v[5] = fmax(v[5], q.z);

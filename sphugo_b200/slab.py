@@ -23,7 +23,7 @@ from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
-HALO_DOUBLES = 7
+HALO_DOUBLES = 10
 MIGRANT_DOUBLES = 12
 OPEN_LO = -1.7976931348623157e308
 
@@ -158,10 +158,11 @@ class DistExchange:
             torch.cuda.current_stream(self.device).synchronize()  # libsphb reads the buffers on its own stream
         return recv_left, k_left, recv_right, k_right
 
-    def allreduce_max(self, v: float) -> float:
-        t = self.torch.tensor([v], dtype=self.torch.float64, device=self.device)
+    def allreduce_max(self, *vals: float):
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.device)
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
-        return float(t.item())
+        out = [float(v) for v in t.tolist()]
+        return out[0] if len(out) == 1 else out
 
 
 class LocalExchange:
@@ -228,12 +229,13 @@ class Slab:
         return cnt.value
 
     def pack_halo(self):
-        """-> (buf_left, n_left, buf_right, n_right); buffers are [cap, 7] views"""
+        """-> (buf_left, n_left, buf_right, n_right); buffers are [cap, HALO_DOUBLES] views; one pass, one readback"""
         lib = self.L.lib()
         views = [self.buf[s].view(-1)[: self.halo_cap * HALO_DOUBLES].view(self.halo_cap, HALO_DOUBLES) for s in range(2)]
-        n0 = self._pack(lib.sphb_slab_pack_halo, 0, views[0])
-        n1 = self._pack(lib.sphb_slab_pack_halo, 1, views[1])
-        return views[0], n0, views[1], n1
+        cnt = (C.c_int64 * 2)()
+        self._chk(lib.sphb_slab_pack_halo(self.h._h, C.c_void_p(views[0].data_ptr()), C.c_void_p(views[1].data_ptr()),
+                                          self.halo_cap, cnt))
+        return views[0], int(cnt[0]), views[1], int(cnt[1])
 
     def add_ghosts(self, buf, count):
         if count:
@@ -264,6 +266,42 @@ class Slab:
     def local_max_h(self):
         return self.h.max_h()
 
+    def local_max_speed(self):
+        return self.h.max_speed()
+
+
+GHOST_SLACK = 0.5  # ghost_widths(): an owned particle may sit this many h_max outside its slab
+
+
+class MigrationSchedule:
+    """When to migrate.  `every` = k > 0: after every k-th step (1 = the plain protocol).  `every` = 0: only when
+    it is needed - the ghost layer tolerates owned particles up to GHOST_SLACK * h_max outside their slab, and a
+    particle moves at most (|v_before| + |v_after|) * dt_half per step, so the run keeps an upper bound of the
+    excursion since the last migration (from the all-reduced max speed) and migrates before the bound, plus the
+    next step's movement, could reach `fraction` of the slack."""
+
+    def __init__(self, every: int, dt_half: float, fraction: float = 0.8):
+        self.every, self.dt_half, self.fraction = int(every or 0), float(dt_half), fraction
+        self.excursion = 0.0
+        self.v_prev = 0.0
+        self.steps = 0
+        self.migrations = 0
+
+    def after_step(self, v_max: float, h_max: float) -> bool:
+        """called once per completed step with the global max speed / max h; True = migrate now"""
+        self.steps += 1
+        self.excursion += (self.v_prev + v_max) * self.dt_half
+        self.v_prev = v_max
+        if self.every > 0:
+            due = self.steps % self.every == 0
+        else:
+            nxt = 2.0 * v_max * self.dt_half * 1.5  # the coming step (speeds may grow a little through the kick)
+            due = self.excursion + nxt > self.fraction * GHOST_SLACK * h_max
+        if due:
+            self.excursion = 0.0
+            self.migrations += 1
+        return due
+
 
 def default_h_hint(n_total: int, area: float) -> float:
     """first-evaluation guess of the largest smoothing length: 32 neighbours at the mean density, x1.6"""
@@ -278,20 +316,43 @@ class DistSlabSim:
         self.slab = Slab(params, topo, rank, pos, vel, e, ids, capacity, halo_cap, h_max_hint, safety)
         self.ex = DistExchange(topo, rank, self.slab.device)
         self.h_max = float(h_max_hint or 0.0)
-        self.migrate_every = migrate_every
+        self.v_max = 0.0
+        self.schedule = MigrationSchedule(migrate_every, params.dt_half)
         self.steps_done = 0
         self.h_growth = 1.0
+        import os
+        self.profile = os.environ.get("SPHB_SLAB_PROFILE") == "1"
+        self.prof = {}
+
+    def _tick(self, name):
+        """SPHB_SLAB_PROFILE=1: wall time per protocol phase with a device sync after each (diagnostic only)"""
+        import time
+        self.slab.h.sync()
+        t = time.perf_counter()
+        self.prof[name] = self.prof.get(name, 0.0) + (t - self._t0)
+        self._t0 = t
 
     def _evaluate(self, mode, integrate):
         s = self.slab
+        if self.profile:
+            import time
+            s.h.sync()
+            self._t0 = time.perf_counter()
         s.set_widths(self.h_max * self.h_growth)
         s.begin(mode)
+        if self.profile: self._tick("begin")
         bl, nl, br, nr = s.pack_halo()
+        if self.profile: self._tick("pack_halo")
         rl, kl, rr, kr = self.ex.exchange(bl, nl, br, nr, HALO_DOUBLES)
+        if self.profile: self._tick("exchange")
         s.add_ghosts(rl, kl)
         s.add_ghosts(rr, kr)
+        if self.profile: self._tick("add_ghosts")
         s.end(integrate)
-        self.h_max = self.ex.allreduce_max(s.local_max_h())  # also surfaces GHOST_THIN / overflow errors
+        if self.profile: self._tick("end")
+        # one tiny all-reduce per evaluation (also surfaces GHOST_THIN / overflow errors)
+        self.h_max, self.v_max = self.ex.allreduce_max(s.local_max_h(), s.local_max_speed())
+        if self.profile: self._tick("allreduce")
 
     def _migrate(self):
         s = self.slab
@@ -307,7 +368,7 @@ class DistSlabSim:
                 self._evaluate(1, False)
             self._evaluate(2, True)
             self.steps_done += 1
-            if self.migrate_every and self.steps_done % self.migrate_every == 0:
+            if self.schedule.after_step(self.v_max, self.h_max):
                 self._migrate()
 
     @property
@@ -334,8 +395,9 @@ class LocalSlabSim:
             self.slabs.append(Slab(params, topo, r, pos[m], vel[m], e[m], ids[m], capacity=n, halo_cap=halo_cap or n,
                                    h_max_hint=h_max_hint, safety=safety))
         self.h_max = float(h_max_hint or 0.0)
+        self.v_max = 0.0
         self.steps_done = 0
-        self.migrate_every = migrate_every
+        self.schedule = MigrationSchedule(migrate_every, params.dt_half)
 
     def _evaluate(self, mode, integrate):
         for s in self.slabs:
@@ -349,6 +411,7 @@ class LocalSlabSim:
         for s in self.slabs:
             s.end(integrate)
         self.h_max = max(s.local_max_h() for s in self.slabs)
+        self.v_max = max(s.local_max_speed() for s in self.slabs)
 
     def _migrate(self):
         for s in self.slabs:
@@ -366,7 +429,7 @@ class LocalSlabSim:
                 self._evaluate(1, False)
             self._evaluate(2, True)
             self.steps_done += 1
-            if self.migrate_every and self.steps_done % self.migrate_every == 0:
+            if self.schedule.after_step(self.v_max, self.h_max):
                 self._migrate()
 
     def state(self, fields):
@@ -404,7 +467,8 @@ def bench(args, nx, ny, box, phys, desc, rank, world, local):
     ids = np.arange(n_local, dtype=np.int64) + rank * n_local
     h_hint = default_h_hint(n_total, box[0] * box[1])
     sim = DistSlabSim(prm, topo, rank, pos, None, np.full(n_local, 0.01), ids, h_max_hint=h_hint,
-                      capacity=n_local + max(1 << 20, n_local // 8), halo_cap=max(1 << 18, n_local // 16))
+                      capacity=n_local + max(1 << 20, n_local // 8), halo_cap=max(1 << 18, n_local // 16),
+                      migrate_every=0)
     del pos
     K, W = args.steps, max(args.warmup, 3)
     sim.step(1 + W)
@@ -432,6 +496,10 @@ def bench(args, nx, ny, box, phys, desc, rank, world, local):
     cnt = torch.tensor([sim.handle.n], dtype=torch.int64, device=torch.device("cuda", local))
     dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     dev_ms, wall_ms = float(t[0]), float(t[1])
+    if rank == 0 and sim.profile:
+        import sys
+        print("slab phases, ms per step (wall, synchronised):",
+              {k: round(v * 1e3 / (K + 1 + W), 3) for k, v in sim.prof.items()}, file=sys.stderr)
     if rank == 0:
         peak, peak_src = B.measured_peak()
         ms_per_step = dev_ms / K
@@ -440,9 +508,10 @@ def bench(args, nx, ny, box, phys, desc, rank, world, local):
         line = {
             "metric": B.METRIC, "value": value, "unit": B.UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
+            "dtype": "f64" if args.precision == 64 else "f32", "data": "synthetic",
             "config": {"workload": desc, "particles": n_total, "particles_after": int(cnt.item()),
-                       "decomposition": f"{world} x-slabs, periodic ring, one ghost exchange per evaluation (NCCL send/recv), migration every step",
+                       "decomposition": f"{world} x-slabs, periodic ring, one ghost exchange per evaluation (NCCL send/recv), "
+                                        f"migration when the excursion bound nears the ghost slack ({sim.schedule.migrations} in {sim.schedule.steps} steps)",
                        "timing": "CUDA events on each rank's library stream around K steps, max over ranks",
                        "wall_ms_per_step": wall_ms / K},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

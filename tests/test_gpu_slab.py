@@ -92,6 +92,33 @@ def test_slab_matches_single_handle_bitwise_inside():
     g.close(); sim.close()
 
 
+def test_adaptive_migration_matches_every_step_migration():
+    """migration only when the excursion bound nears the ghost slack (slab.MigrationSchedule): particles that have
+    left their nominal slab stay with their owner for a few steps; results must not depend on the schedule"""
+    pos = gen.jittered_lattice(96, 96)
+    n = len(pos)
+    vel = np.tile([[0.9, -0.4]], (n, 1))  # ~0.07 h per step: a migration every few steps
+    kw = dict(hor=(0.0, 1.0), ver=(0.0, 1.0), accel=(0.0, 0.2), dt_half=0.001)
+    pg = L.make_params(**kw)
+    topo = slab.Topology(3, [0.0, 0.3, 0.7, 1.0], True)
+    out, migs = {}, {}
+    for every in (1, 0):
+        sim = slab.LocalSlabSim(pg, topo, pos, vel, np.full(n, 0.01), h_max_hint=slab.default_h_hint(n, 1.0),
+                                migrate_every=every)
+        sim.step(12)
+        out[every] = sim.state(FIELDS)
+        migs[every] = sim.schedule.migrations
+        assert sum(sim.counts()) == n
+        sim.close()
+    assert migs[1] == 12 and 1 <= migs[0] < 8
+    a, b = out[1], out[0]
+    assert (a["id"] == b["id"]).all()
+    assert np.abs(a["pos"] - b["pos"]).max() <= 1e-12
+    assert U.rel_err(b["h"], a["h"]) <= 1e-12
+    assert U.rel_err(b["rho"], a["rho"]) <= 1e-11
+    assert U.rel_err(b["e"], a["e"]) <= 1e-11
+
+
 def test_ghost_layer_too_thin_is_reported():
     pos = gen.jittered_lattice(64, 64)
     n = len(pos)

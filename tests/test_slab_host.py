@@ -36,6 +36,31 @@ def test_ghost_widths_cover_the_stencil():
     assert iw >= 0.01 and gw >= iw + 0.01
 
 
+def test_migration_schedule_bounds_the_excursion():
+    """adaptive schedule: migrate before the accumulated movement bound plus the coming step can reach the slack"""
+    h = 0.01
+    sch = slab.MigrationSchedule(0, dt_half=0.001)
+    # slow particles: 1e-3 * h per step -> hundreds of steps between migrations
+    due = [sch.after_step(v_max=0.005, h_max=h) for _ in range(700)]
+    assert 0 < sum(due) <= 2
+    # the bound never exceeded the slack at any evaluation
+    sch = slab.MigrationSchedule(0, dt_half=0.001)
+    exc, vprev = 0.0, 0.0
+    for k in range(200):
+        v = 0.2 + 0.1 * (k % 7)
+        exc += (vprev + v) * 0.001
+        vprev = v
+        if sch.after_step(v, h):
+            exc = 0.0
+        assert exc + 2 * v * 0.001 <= slab.GHOST_SLACK * h
+    # fast flow (a third of h per step): every step
+    sch = slab.MigrationSchedule(0, dt_half=0.001)
+    assert all(sch.after_step(v_max=1.7, h_max=h) for _ in range(5))
+    # fixed period
+    sch = slab.MigrationSchedule(3, dt_half=0.001)
+    assert [sch.after_step(1.0, h) for _ in range(6)] == [False, False, True, False, False, True]
+
+
 def test_reference_halo_selection_periodic_frame():
     pos = np.array([[0.01, 0.5], [0.26, 0.5], [0.49, 0.5], [0.74, 0.5], [0.99, 0.5]])
     # slab [0, 0.25) of a ring: the particle at 0.99 is owned-looking from the frame (x - 1 = -0.01 < x_lo)
