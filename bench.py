@@ -8,8 +8,8 @@ GPU in a periodic box (BASELINE.json configs[4]: 256 M on 8 GPUs = 32 M per GPU)
 selects the 2^20-particle single-GPU box (configs[2]).
 
 value   : device-resident state, CUDA events around K asynchronous sphb_step calls (max over ranks)
-e2e     : the same K steps through the C ABI with HOST buffers: per step upload of the persistent state from
-          pinned memory, sphb_step, download of the results
+e2e     : the same steps through the C ABI with HOST buffers: per step upload of the caller-set fields (Pos, Vel, E)
+          from pinned memory, sphb_step, download of the fields the per-step consumer reads (Pos, Rho, h, Z)
 roofline: whole step as the dominant "kernel" chain, algorithmic bytes 652 B/particle, plus
           per-phase fractions from the library's CUDA-event phase timers
 cpu_baseline / --impl reference: the CPU restatement of the reference Go path (oracle/, 1 core: package
@@ -37,6 +37,16 @@ B_ALG = B_ALG_BY_PREC[64]
 B_ALG_TOTAL = 652
 METRIC = "particle-updates/s per SPH step (k=32)"
 UNIT = "particle-updates/s"
+
+
+def ncu_traffic(kernel_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at this workload, from the
+    committed `ncu --set full` capture (profiles/traffic.json, written by tools/ncu_traffic.py); None if absent"""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p)).get(kernel_key)
+    except Exception:
+        return None
 
 
 def measured_peak():
@@ -242,27 +252,33 @@ def run_ours(args):
             phase_acc[k] += pt[k]
     value = n * K / (dev_ms * 1e-3)
     peak, peak_src = measured_peak()
-    achieved = n * B_ALG_TOTAL / (ms_per_step * 1e-3) / 1e9
+    step_achieved = n * B_ALG_TOTAL / (ms_per_step * 1e-3) / 1e9
     phases = {}
     for k in ("keys", "sort", "reorder", "knn", "force"):
         ms = phase_acc[k] / KP
         gbs = n * B_ALG[k] / (ms * 1e-3) / 1e9 if ms > 0 else None
         phases[k] = {"ms": ms, "alg_GBps": gbs, "frac": gbs / peak if gbs else None}
     dom = max(("keys", "sort", "reorder", "knn", "force"), key=lambda k: phase_acc[k])
+    dom_kernel = {"knn": "k_knn_tile (+ k_knn_fallback for refused particles)", "force": "k_force_st",
+                  "reorder": "k_reorder", "keys": "k_keys", "sort": "counting-sort kernels"}[dom]
+    traffic = ncu_traffic(f"{dom}_{args.workload}_f{args.precision}")
 
     h2d = d2h = 0
     e2e_val, Ke = 0.0, 0
     if not args.no_e2e:
         # ---- e2e: host buffers through the C ABI, every step: upload state, step, download results
         import ctypes as C
-        up_fields = ["pos", "vel", "e", "vdot", "edot"]
-        down_fields = ["pos", "vel", "e", "vdot", "edot", "rho", "h", "id"]
+        # inputs: the particle fields a caller sets (spawners / examples write Pos, Vel, E: config-parser.go:68-77,
+        # density.go:12-15); outputs: the fields the per-step consumer reads (animator.Frame: Pos, Rho, Z, NNDists[0],
+        # animator.go:60-101).  VDot / EDot of the previous step stay on the device.
+        up_fields = ["pos", "vel", "e"]
+        down_fields = ["pos", "rho", "h", "id"]
         host = {}
         for f in set(up_fields + down_fields):
             shp, dt = L.FIELD_SHAPE[f]
             t = torch.empty((n,) + shp, dtype=torch.float64 if dt == np.float64 else torch.int64).pin_memory()
             host[f] = t.numpy()
-        g.download(down_fields, out=host)
+        g.download(sorted(set(up_fields + down_fields)), out=host)  # every host buffer holds the current state
         h2d = sum(host[f].nbytes for f in up_fields)
         d2h = sum(host[f].nbytes for f in down_fields)
         Ke = max(3, min(K, 10))
@@ -280,6 +296,30 @@ def run_ours(args):
 
     g.close()
 
+    other = None
+    if not args.no_other_build:
+        # the other build of the library on the same workload (device-resident steps only), for the record
+        op = 32 if args.precision == 64 else 64
+        prm2 = L.make_params(hor=(0.0, box[0]), ver=(0.0, box[1]), device=local, **dict(phys, precision=op))
+        pos2, _ = make_ic(nx, ny, box, 0, 1)
+        g2 = L.Handle(prm2, pos2, None, e0)
+        del pos2
+        g2.step(1 + W)
+        g2.sync()
+        ext2 = torch.cuda.ExternalStream(g2.stream, device=torch.device("cuda", local))
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(ext2)
+        g2.step(K)
+        a1.record(ext2)
+        g2.sync()
+        torch.cuda.synchronize()
+        ms2 = a0.elapsed_time(a1) / K
+        b2 = sum(B_ALG_BY_PREC[op].values())
+        other = {"dtype": "f32" if op == 32 else "f64", "value": n / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2,
+                 "step_roofline_frac": n * b2 / (ms2 * 1e-3) / 1e9 / peak, "alg_bytes_per_particle": b2,
+                 "tolerance_vs_reference": 1e-5 if op == 32 else 1e-12}
+        g2.close()
+
     cb_v, cb_n, cb_s = cpu_baseline(steps=2, nx=512) if not args.no_cpu else (None, 0, 0)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W,
@@ -287,17 +327,22 @@ def run_ours(args):
         "dtype": "f64" if args.precision == 64 else "f32", "data": "synthetic",
         "config": {"workload": desc, "particles": n, "l2": "state (>= 280 B/particle) exceeds the 126 MB L2; no flush needed",
                    "timing": "CUDA events on the library stream around K asynchronous steps", "wall_ms_per_step": wall / K * 1e3},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "whole step (5 phases); dominant phase: " + dom,
-                     "alg_bytes_per_particle": B_ALG_TOTAL, "phases": phases},
+        # dominant kernel: algorithmic bytes of its phase x particles per launch / its launch time (CUDA
+        # events of the library's phase timers); "step" is the same for the whole 5-phase chain (north_star's figure)
+        "roofline": {"bound": "hbm", "achieved": phases[dom]["alg_GBps"], "peak": peak, "unit": "GB/s",
+                     "frac": phases[dom]["frac"], "traffic": traffic, "peak_source": peak_src, "kernel": dom_kernel,
+                     "alg_bytes_per_particle": B_ALG[dom], "launch_ms": phases[dom]["ms"],
+                     "step": {"achieved": step_achieved, "frac": step_achieved / peak, "alg_bytes_per_particle": B_ALG_TOTAL},
+                     "phases": phases},
         "cpu_baseline": None if cb_v is None else {
             "value": cb_v, "unit": UNIT, "cores": 1, "kind": "port",
             "sample": f"2 Step() calls on a {cb_n}-particle periodic jittered lattice ({cb_s:.2f} s/step); C restatement of the serial Go path"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
-                "what": "sphb_upload(pos,vel,e,vdot,edot) + sphb_step(1) + sphb_download(pos,vel,e,vdot,edot,rho,h,id), pinned host buffers"},
+                "what": "per step: sphb_upload(pos,vel,e) + sphb_step(1) + sphb_download(pos,rho,h,id), pinned host buffers, wall clock"},
         "gpu_launches": c1["kernel_launches"] - c0["kernel_launches"],
         "knn_fallback_particles": c1["knn_fallback"] - c0["knn_fallback"],
         "clocks": clocks,
+        "other_build": other,
     }
     print(json.dumps(line), flush=True)
 
@@ -312,6 +357,7 @@ def main():
     ap.add_argument("--precision", type=int, default=64, choices=[64, 32], help="64: reference arithmetic; 32: the fp32 build")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (tuning sweeps only)")
+    ap.add_argument("--no-other-build", action="store_true", help="skip the extra leg that times the other precision build")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

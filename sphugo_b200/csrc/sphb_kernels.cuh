@@ -473,8 +473,9 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
   const double rw = rg * (1.0 + 1e-6);
   int clo = (int)floor((xa - rw - g.ox) * g.inv_dx), chi = (int)floor((xa + rw - g.ox) * g.inv_dx);
   int rlo = (int)floor((ya - rw - g.oy) * g.inv_dy), rhi = (int)floor((ya + rw - g.oy) * g.inv_dy);
-  clo = min(clo, cxa); chi = max(chi, cxa);
-  rlo = min(rlo, cya); rhi = max(rhi, cya);
+  // (clamped to one period either side: non-finite or absurd positions must not overflow the range arithmetic)
+  clo = max(min(clo, cxa), -g.ncx); chi = min(max(chi, cxa), 2 * g.ncx - 1);
+  rlo = max(min(rlo, cya), -g.ncy); rhi = min(max(rhi, cya), 2 * g.ncy - 1);
 
   // One pass of the whole pipeline per group of lanes that sit in the same grid row (a tile is a strip of one
   // row, so there is one group unless the tile straddles the end of a row).

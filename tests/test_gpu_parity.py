@@ -242,3 +242,26 @@ def test_full_size_properties_c3():
     # mean neighbour count check: pi h^2 n ~ 33
     assert abs(np.mean(np.pi * st["h"] ** 2 * n) - 33) < 1.5
     assert np.isfinite(h.reduce(L.SUM_E)) and h.reduce(L.SUM_RHO) > 0
+
+
+def test_non_finite_input_does_not_fault_the_device():
+    """garbage in the mutable fields (Root.Particles is public: density.go:12-15) may give garbage results or a
+    status code, but never an illegal memory access: the next handle on the same device must work."""
+    pos = gen.jittered_lattice(64, 64)
+    n = len(pos)
+    vel = np.zeros((n, 2))
+    vel[::7] = [1e300, -1e300]
+    vel[5] = [np.nan, np.inf]
+    for prec in (64, 32):
+        pg = L.make_params(hor=(0.0, 1.0), ver=(0.0, 1.0), dt_half=0.001, precision=prec)
+        g = L.Handle(pg, pos, vel, np.full(n, 0.01))
+        try:
+            g.step(2)
+            g.sync()
+        except L.SphbError as ex:
+            assert ex.code != L.E_CUDA, ex
+        g.close()
+        g2 = L.Handle(pg, pos, None, np.full(n, 0.01))
+        g2.step(1)
+        assert np.isfinite(g2.state(["rho"])["rho"]).all()
+        g2.close()
