@@ -25,6 +25,7 @@ import "C"
 
 import (
 	"fmt"
+	"os"
 	"math"
 	"unsafe"
 )
@@ -65,7 +66,10 @@ func paramsOf(c *SphConfig) C.sphb_params {
 	p.refl_L, p.refl_R = C.double(c.Reflections.L), C.double(c.Reflections.R)
 	p.refl_U, p.refl_D = C.double(c.Reflections.U), C.double(c.Reflections.D)
 	p.kernel = kernelID(c.Kernel)
-	p.precision = 64
+	p.precision = 64 // SPHB_PRECISION=32 selects the fp32 build (results within 1e-5 instead of 1e-12)
+	if os.Getenv("SPHB_PRECISION") == "32" {
+		p.precision = 32
+	}
 	p.device = 0
 	return p
 }
