@@ -311,9 +311,14 @@ int build_neighbours(sphb_sim* s, int mode, const double hor[2], const double ve
   StateIn in{s->a.pos, s->a.vel, s->a.vdot, s->a.vpred, s->a.e, s->a.edot, s->a.epred, s->a.id, s->a.pc, s->a.ghost};
   StateOut out{s->b.pos, s->b.vel, s->b.vdot, s->b.vpred, s->b.e, s->b.edot, s->b.epred, s->b.id, s->b.pc, s->b.ghost, s->spos, s->hguess};
   const int rb = cdiv(ntot, 256);
-  if (mode == MODE_DRIFT) k_reorder<2><<<rb, 256, 0, s->st>>>(in, out, s->keys, s->perm, ntot, s->grid, dtH, s->cellStart, s->keysSorted);
-  else if (mode == MODE_INIT) k_reorder<1><<<rb, 256, 0, s->st>>>(in, out, s->keys, s->perm, ntot, s->grid, dtH, s->cellStart, s->keysSorted);
-  else k_reorder<0><<<rb, 256, 0, s->st>>>(in, out, s->keys, s->perm, ntot, s->grid, dtH, s->cellStart, s->keysSorted);
+#define REORDER(MODE, LEAN) k_reorder<MODE, LEAN><<<rb, 256, 0, s->st>>>(in, out, s->keys, s->perm, ntot, s->grid, dtH, s->cellStart, s->keysSorted)
+  // `timed` = called from forces(): a force evaluation follows and overwrites VDot, EDot; kNN rewrites {rho, c, h, P}
+  if (timed) {
+    if (mode == MODE_DRIFT) REORDER(2, true); else if (mode == MODE_INIT) REORDER(1, true); else REORDER(0, true);
+  } else {
+    if (mode == MODE_DRIFT) REORDER(2, false); else if (mode == MODE_INIT) REORDER(1, false); else REORDER(0, false);
+  }
+#undef REORDER
   std::swap(s->a, s->b);
   cudaMemsetAsync(s->failCount, 0, sizeof(int), s->st);
   if (timed) cudaEventRecord(s->ev[SPHB_PH_KNN], s->st);
@@ -462,11 +467,11 @@ int create_common(const sphb_params* p, int64_t n, int64_t capacity, const doubl
   s->gtune.force_nc = 0;
   s->ktune.guess_margin = 0.02;
   s->ktune.k_target = 46.0;
-  // column of cap - 8 entries + 8 slack (overflow is checked once per 8 candidates); ncw staged candidates per
+  // column of cap - 8 entries + 8 slack (overflow is checked once per 8 candidates, the compaction pads to 8); ncw staged candidates per
   // tile: a 32-particle strip of one row needs ~190 at 32 neighbours.  The fp64 build stages 28 B per candidate
   // and is occupancy-bound by shared memory: slightly tighter buffers buy two more warps per SM (measured
   // 9.6 -> 8.8 ms per evaluation at 2^25 particles for 0.05 % more fallback particles).
-  s->ktune.cap = p->precision == 32 ? 50 : 46;
+  s->ktune.cap = p->precision == 32 ? 50 : 47;
   s->ktune.cap0 = 80;
   s->ktune.ncw = p->precision == 32 ? 256 : 224;
   s->ktune.ncw0 = 512;

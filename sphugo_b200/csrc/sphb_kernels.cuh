@@ -299,7 +299,9 @@ struct StateOut {
   double* hguess;  // h of the previous evaluation in the new order (0 = unknown)
 };
 
-template <int MODE>
+// LEAN: a force evaluation follows (it overwrites VDot / EDot, and the kNN kernel overwrites {rho, c, h, P}), so those
+// fields are neither copied nor, unless the predictor needs them, read.
+template <int MODE, bool LEAN>
 __global__ void __launch_bounds__(256) k_reorder(StateIn in, StateOut out, const uint32_t* __restrict__ keys,
                                                 const uint32_t* __restrict__ perm, int n, const GridP* __restrict__ gp, double dtH,
                                                 const uint32_t* __restrict__ cellStart, uint32_t* __restrict__ keysSorted) {
@@ -316,8 +318,9 @@ __global__ void __launch_bounds__(256) k_reorder(StateIn in, StateOut out, const
     j = s;
     for (uint32_t u = s; u < e; ++u) j += (perm[u] < i) ? 1u : 0u;
   }
-  double2 p = in.pos[i], v = in.vel[i], a = in.vdot[i];
-  double e_ = in.e[i], ed = in.edot[i];
+  double2 p = in.pos[i], v = in.vel[i], a = make_double2(0.0, 0.0);
+  double e_ = in.e[i], ed = 0.0;
+  if (MODE == 2 || !LEAN) { a = in.vdot[i]; ed = in.edot[i]; }
   double4 pc = in.pc[i];
   double2 vp;
   double ep;
@@ -336,13 +339,11 @@ __global__ void __launch_bounds__(256) k_reorder(StateIn in, StateOut out, const
   }
   out.pos[j] = p;
   out.vel[j] = v;
-  out.vdot[j] = a;
   out.e[j] = e_;
-  out.edot[j] = ed;
+  if (!LEAN) { out.vdot[j] = a; out.edot[j] = ed; out.pc[j] = pc; }
   out.vpred[j] = vp;
   out.epred[j] = ep;
   out.id[j] = in.id[i];
-  out.pc[j] = pc;
   out.ghost[j] = in.ghost[i];
   out.hguess[j] = pc.z;
   double2 sp;
@@ -469,8 +470,10 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
     }
   }
   const double rg2 = rg * rg;
-  // unwrapped cell range that contains every point within rg (slightly widened)
-  const double rw = rg * (1.0 + 1e-6);
+  // unwrapped cell range that contains every point within rw = rg (1 + 1e-4): the lane scans only these cells.
+  // The widening matters in the fp32 build: a candidate outside them has a true d^2 > rg^2 (1 + 2e-4), so even
+  // with its fp32 key error (< 1.5e-5 relative, enforced below) it cannot undercut an accepted h^2 < thr.
+  const double rw = rg * (1.0 + 1e-4);
   int clo = (int)floor((xa - rw - g.ox) * g.inv_dx), chi = (int)floor((xa + rw - g.ox) * g.inv_dx);
   int rlo = (int)floor((ya - rw - g.oy) * g.inv_dy), rhi = (int)floor((ya + rw - g.oy) * g.inv_dy);
   // (clamped to one period either side: non-finite or absurd positions must not overflow the range arithmetic)
@@ -572,27 +575,62 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
 
     uint32_t kp = kbase;
     bool ovf = false;  // column (nearly) full: stop appending, the lane goes to the fallback
-    for (int c = 0; c < nst; c += 8) {  // phase 1: fp32 filter, shared-memory broadcast, branch-free
-      float4 v[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = candF4[(c >> 1) + u];
-      float d2f[8];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float ax = v[u].x - qfx, ay = v[u].y - qfy, bx = v[u].z - qfx, by = v[u].w - qfy;
-        d2f[2 * u] = fmaf(ay, ay, ax * ax);
-        d2f[2 * u + 1] = fmaf(by, by, bx * bx);
+    // phase 1: fp32 filter, branch-free.  A lane only scans its own window of every piece: the candidates in the
+    // cells its search disc touches (a contiguous slot range, from two cellStart lookups per piece, fetched one
+    // piece ahead).  The trip count is the longest window of the warp; a window that would run past the end of
+    // its piece is shifted back, so every staged slot is seen at most once per lane.
+    int w_lo = 0, w_hi = 0;  // window of the piece being fetched (staged slots)
+    {
+      const int ru = r0, ix = ix0;  // piece 0
+      const int iy = g.wrapy ? img_idx(ru, g.ncy) : 0, row = ru - iy * g.ncy, uL = ix * g.ncx;
+      const int a = max(c0, uL) - uL, b = min(c1, uL + g.ncx - 1) - uL;
+      const int ca = max(clo, a + uL) - uL, cb = min(chi, b + uL) - uL;
+      const int ps = __shfl_sync(0xffffffffu, p_s, 0), po = __shfl_sync(0xffffffffu, p_off, 0);
+      if (mine && ru >= rlo && ru <= rhi && ca <= cb) {
+        w_lo = (int)cellStart[row * g.ncx + ca] - ps + po;
+        w_hi = (int)cellStart[row * g.ncx + cb + 1] - ps + po;
+      } else { w_lo = po; w_hi = po; }
+    }
+    for (int pc_ = 0; pc_ < npc; ++pc_) {
+      const int ws = w_lo, we = w_hi;
+      const int po = __shfl_sync(0xffffffffu, p_off, pc_), pl = __shfl_sync(0xffffffffu, p_len, pc_);
+      if (pc_ + 1 < npc) {  // fetch the window of the next piece while this one is scanned
+        const int q = pc_ + 1, rr = q / nix, ix = ix0 + (q - rr * nix), ru = r0 + rr;
+        const int iy = g.wrapy ? img_idx(ru, g.ncy) : 0, row = ru - iy * g.ncy, uL = ix * g.ncx;
+        const int a = max(c0, uL) - uL, b = min(c1, uL + g.ncx - 1) - uL;
+        const int ca = max(clo, a + uL) - uL, cb = min(chi, b + uL) - uL;
+        const int ps = __shfl_sync(0xffffffffu, p_s, q), pq = __shfl_sync(0xffffffffu, p_off, q);
+        if (mine && ru >= rlo && ru <= rhi && ca <= cb) {
+          w_lo = (int)cellStart[row * g.ncx + ca] - ps + pq;
+          w_hi = (int)cellStart[row * g.ncx + cb + 1] - ps + pq;
+        } else { w_lo = pq; w_hi = pq; }
       }
-      if (kp > klim) { ovf = true; thrf = -1.0f; }
+      const int wal = ws & ~1;  // two candidates per 16-byte load
+      const int trips = __reduce_max_sync(0xffffffffu, (we - wal + 7) >> 3);
+      const int pend8 = po + ((pl + 7) & ~7);
+      int c = min(wal, pend8 - 8 * trips);  // >= po: a window lies inside its piece
+      for (int k = 0; k < trips; ++k, c += 8) {
+        float4 v[4];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) knn_append(kp, d2f[u], (uint32_t)(c + u), thrf);
+        for (int u = 0; u < 4; ++u) v[u] = candF4[(c >> 1) + u];
+        float d2f[8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float ax = v[u].x - qfx, ay = v[u].y - qfy, bx = v[u].z - qfx, by = v[u].w - qfy;
+          d2f[2 * u] = fmaf(ay, ay, ax * ax);
+          d2f[2 * u + 1] = fmaf(by, by, bx * bx);
+        }
+        if (kp > klim) { ovf = true; thrf = -1.0f; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) knn_append(kp, d2f[u], (uint32_t)(c + u), thrf);
+      }
     }
     __syncwarp();
 
     // The column holds cnt entries, one of them the lane itself (d2f = 0, centre image; self is excluded in
     // every image, nearest-neighbour.go:79).  m = cnt - 33 entries with the largest keys must be dropped.
     const int cnt = (int)((kp - kbase) >> 8);
-    bool ok = mine && !bad && !ovf && cnt >= SPHB_K + 1;
+    bool ok = mine && !bad && !ovf && cnt >= SPHB_K + 1 && cnt <= CAP - 8;  // (the compaction pads up to cnt + 7)
     // select A: the 4 largest keys below `bound` per pass (a max/min insertion network on the fp32 bit patterns).
     // T = smallest dropped key, akey = largest kept key.
     int mrem = ok ? cnt - (SPHB_K + 1) : 0;
@@ -632,17 +670,22 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
     bool self_seen = false;
     {
       const int lim = ok ? cnt : 0;
+      // pad the column to a multiple of eight with keys that are never kept (slots up to cnt + 7 <= CAP - 1 exist:
+      // the overflow test of the filter leaves that room)
+      if (ok) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) col[(cnt + u) * 32].x = 0xffffffffu;
+      }
       for (int s0 = 0; s0 < lim; s0 += 8) {  // eight loads in flight, then the (aliasing) compacted stores
         uint2 ke[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) ke[u] = col[(s0 + u) * 32];  // slots up to cnt + 7 <= CAP - 1 exist (ovf bound)
+        for (int u = 0; u < 8; ++u) ke[u] = col[(s0 + u) * 32];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          const bool self = ke[u].y == (uint32_t)self_slot;
-          const bool in = s0 + u < lim;
-          self_seen |= self && in;
-          if (in && ke[u].x < T && !self && kept < SPHB_K) {
-            col[kept * 32] = ke[u];  // kept <= s0 + u: only slots that were already read
+          const bool self = ke[u].y == (uint32_t)self_slot;  // (a padding slot holds a stale slot id but the lane's own
+          self_seen |= self && ke[u].x != 0xffffffffu;        //  entry is always inside the first cnt)
+          if (ke[u].x < T && !self) {  // at most cnt - 1 - m = 32 entries qualify; kept <= s0 + u: only slots already read
+            col[kept * 32] = ke[u];
             ++kept;
           }
         }
@@ -1196,7 +1239,7 @@ __device__ __forceinline__ void force_pairs(const ForceIO& io, int n, const Grid
   uint32_t cur[8];
 #pragma unroll
   for (int u = 0; u < 8; ++u) cur[u] = ent0[u];
-  uint32_t miss = 0;
+  bool allhit = true;
 #pragma unroll 1
   for (int s0 = 0; s0 < SPHB_K; s0 += 8) {
     uint32_t nxt[8];  // the next eight list entries are in flight while these eight are processed
@@ -1213,7 +1256,7 @@ __device__ __forceinline__ void force_pairs(const ForceIO& io, int n, const Grid
       const uint2 de = T.tab[t];
       const bool hit = ent < de.y;
       const int sl = hit ? (int)(ent - de.x) : 0;
-      miss |= (hit ? 0u : 1u) << (s0 + u);
+      allhit = allhit && hit;
       const NbrRec<R> b = load_rec(sm, nrec, sl);
       if (SLAB) thin |= hit && b.rhoh < R(0.0);
       pair_term<KERNEL, R>(own, b, hit, ax, ay, aed);
@@ -1221,10 +1264,15 @@ __device__ __forceinline__ void force_pairs(const ForceIO& io, int n, const Grid
 #pragma unroll
     for (int u = 0; u < 8; ++u) cur[u] = nxt[u];
   }
-  while (miss) {  // entries that were not staged: the same pair from global memory
-    const int s = __ffs(miss) - 1;
-    miss &= miss - 1;
+  if (allhit) return;
+  // some entries were not staged (rare: box edges, very non-uniform blocks): the same pairs from global memory
+#pragma unroll 1
+  for (int s = 0; s < SPHB_K; ++s) {
     const uint32_t ent = col[s * 32];
+    int t = 0;
+#pragma unroll
+    for (int m = 0; m < NP; ++m) t += (ent >= stc[m]) ? 1 : 0;
+    if (ent < T.tab[t].y) continue;  // was staged
     const int j = (int)(ent & IDX_MASK);
     if ((uint32_t)j >= (uint32_t)n) continue;  // empty slot of an underfull list (reported as SPHB_E_KNN_UNDERFULL)
     const NbrRec<R> b = make_rec<R, SLAB>(io, g, j, (int)(ent >> IMG_SHIFT), ref);
