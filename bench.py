@@ -75,6 +75,14 @@ def workload(name: str, n_gpus: int):
         phys["dt_half"] = 6e-5
         desc = (f"C5 share (BASELINE configs[4]): 2^25 jittered-lattice particles per GPU x {n_gpus} GPU(s) = {nx}x{ny} "
                 f"sites at spacing 2^-14, periodic box {box[0]}x{box[1]}, Monaghan, g=(0,0.2), fp64")
+    elif name == "c4":
+        # BASELINE configs[3]: 2^24 particles, shock tube (number-density ratio 4:1 across x = 0.5), strong scaling
+        nx = ny = 4096
+        box = (1.0, 1.0)
+        phys["dt_half"] = 2.5e-4
+        phys["accel"] = (0.0, 0.0)
+        desc = ("C4 (BASELINE configs[3]): 2^24-particle shock tube, jittered lattices with number-density ratio 4:1 left/right "
+                f"of x = 0.5, periodic [0,1]^2, Monaghan, g = 0, fp64; {n_gpus} GPU(s), equal-count x-slabs")
     else:
         raise SystemExit(f"unknown workload {name}")
     return nx, ny, box, phys, desc
@@ -181,6 +189,15 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def make_ic_c4(rank, world):
+    """this rank's equal-count x-slab of the 2^24-particle shock tube: (pos, ids, bounds)"""
+    from sphugo_b200 import gen, slab
+    pos = gen.shock_tube(1 << 24)
+    bounds = slab.equal_count_bounds(pos[:, 0], world, 0.0, 1.0)
+    m = (pos[:, 0] >= bounds[rank]) & (pos[:, 0] < bounds[rank + 1])
+    return np.ascontiguousarray(pos[m]), np.nonzero(m)[0].astype(np.int64), bounds
+
+
 def make_ic(nx, ny, box, rank, world):
     """this rank's x-slab (equal site count) of the global nx x ny jittered lattice on [0,box]"""
     from sphugo_b200 import gen
@@ -216,7 +233,10 @@ def run_ours(args):
         from sphugo_b200 import slab
         return slab.bench(args, nx, ny, box, phys, desc, rank, world, local)
 
-    pos, _ = make_ic(nx, ny, box, 0, 1)
+    if args.workload == "c4":
+        pos, _, _ = make_ic_c4(0, 1)
+    else:
+        pos, _ = make_ic(nx, ny, box, 0, 1)
     n = len(pos)
     prm = L.make_params(hor=(0.0, box[0]), ver=(0.0, box[1]), device=local, **phys)
     e0 = np.full(n, 0.01)
@@ -301,7 +321,7 @@ def run_ours(args):
         # the other build of the library on the same workload (device-resident steps only), for the record
         op = 32 if args.precision == 64 else 64
         prm2 = L.make_params(hor=(0.0, box[0]), ver=(0.0, box[1]), device=local, **dict(phys, precision=op))
-        pos2, _ = make_ic(nx, ny, box, 0, 1)
+        pos2 = make_ic_c4(0, 1)[0] if args.workload == "c4" else make_ic(nx, ny, box, 0, 1)[0]
         g2 = L.Handle(prm2, pos2, None, e0)
         del pos2
         g2.step(1 + W)
@@ -323,7 +343,7 @@ def run_ours(args):
     cb_v, cb_n, cb_s = cpu_baseline(steps=2, nx=512) if not args.no_cpu else (None, 0, 0)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if args.workload == "c4" else "weak", "vs_baseline": None,
         "dtype": "f64" if args.precision == 64 else "f32", "data": "synthetic",
         "config": {"workload": desc, "particles": n, "l2": "state (>= 280 B/particle) exceeds the 126 MB L2; no flush needed",
                    "timing": "CUDA events on the library stream around K asynchronous steps", "wall_ms_per_step": wall / K * 1e3},
@@ -353,7 +373,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c5", choices=["c3", "c5"])
+    ap.add_argument("--workload", default="c5", choices=["c3", "c4", "c5"])
     ap.add_argument("--precision", type=int, default=64, choices=[64, 32], help="64: reference arithmetic; 32: the fp32 build")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (tuning sweeps only)")

@@ -482,11 +482,15 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
 
   // One pass of the whole pipeline per group of lanes that sit in the same grid row (a tile is a strip of one
   // row, so there is one group unless the tile straddles the end of a row).
+  // Where the particles are sparse for the grid (h well above the mean) the union block of 32 lanes may not fit
+  // the staging area: the group is then halved (lanes are ordered along the strip) and retried.
   uint32_t todo = __ballot_sync(0xffffffffu, valid);
+  int maxlanes = 32;
   while (todo) {
     const int lead = __ffs(todo) - 1;
     const int grow = __shfl_sync(0xffffffffu, cya, lead);
-    const uint32_t grp = __ballot_sync(0xffffffffu, valid && cya == grow) & todo;
+    const uint32_t cand = __ballot_sync(0xffffffffu, valid && cya == grow) & todo;
+    const uint32_t grp = __ballot_sync(0xffffffffu, ((cand >> lane) & 1u) && __popc(cand & ((1u << lane) - 1u)) < maxlanes);
     todo &= ~grp;
     const bool mine = (grp >> lane) & 1u;
     bool bad = false;  // stencil wider than the period / fp32 bound not applicable / staging area full: fallback
@@ -501,10 +505,10 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
     // the pieces of the union block: (row, x image) -> a contiguous range of the sorted order; lane p fetches piece p
     const int ix0 = g.wrapx ? img_idx(c0, g.ncx) : 0, ix1 = g.wrapx ? img_idx(c1, g.ncx) : 0;
     const int nix = ix1 - ix0 + 1, npc = (r1 - r0 + 1) * nix;
-    if (npc > 32) gbad = true;
+    bool big = !gbad && npc > 32;  // does not fit: more pieces than lanes / more candidates than staging slots
     int p_s = 0, p_len = 0, p_off = 0, nst = 0;
     uint32_t p_code = 0;
-    if (!gbad) {
+    if (!gbad && !big) {
       if (lane < npc) {
         const int rr = lane / nix, ix = ix0 + (lane - rr * nix), ru = r0 + rr;
         const int iy = g.wrapy ? img_idx(ru, g.ncy) : 0;
@@ -522,7 +526,12 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
       }
       p_off = incl - ((p_len + 7) & ~7);
       nst = __shfl_sync(0xffffffffu, incl, 31);
-      if (nst > NCW) gbad = true;  // the union block does not fit the staging area
+      if (nst > NCW) big = true;
+    }
+    if (big) {
+      const int nl = __popc(grp);
+      if (nl > 1) { todo |= grp; maxlanes = nl >> 1; continue; }  // retry with half the lanes
+      gbad = true;  // a single query whose stencil does not fit: ring-expansion fallback
     }
     if (gbad) {
       if (mine) { const int slot = atomicAdd(out.failCount, 1); out.failList[slot] = i; }

@@ -458,14 +458,19 @@ def bench(args, nx, ny, box, phys, desc, rank, world, local):
     from . import _lib as L
     import bench as B  # repo-root bench.py (helpers: make_ic, ClockSampler, measured_peak)
 
-    pos, (x0, x1) = B.make_ic(nx, ny, box, rank, world)
-    n_local = len(pos)
-    n_total = nx * ny
-    bounds = [box[0] * k / world for k in range(world + 1)]
+    if args.workload == "c4":  # strong scaling, non-uniform density: equal-count slabs
+        pos, ids, bounds = B.make_ic_c4(rank, world)
+        n_local, n_total = len(pos), 1 << 24
+        h_hint = 2.0 * default_h_hint(n_total, 1.0)  # the dilute half has twice the mean spacing
+    else:
+        pos, (x0, x1) = B.make_ic(nx, ny, box, rank, world)
+        n_local = len(pos)
+        n_total = nx * ny
+        bounds = [box[0] * k / world for k in range(world + 1)]
+        ids = np.arange(n_local, dtype=np.int64) + rank * n_local
+        h_hint = default_h_hint(n_total, box[0] * box[1])
     topo = Topology(world, bounds, periodic=True)
     prm = L.make_params(hor=(0.0, box[0]), ver=(0.0, box[1]), device=local, **phys)
-    ids = np.arange(n_local, dtype=np.int64) + rank * n_local
-    h_hint = default_h_hint(n_total, box[0] * box[1])
     sim = DistSlabSim(prm, topo, rank, pos, None, np.full(n_local, 0.01), ids, h_max_hint=h_hint,
                       capacity=n_local + max(1 << 20, n_local // 8), halo_cap=max(1 << 18, n_local // 16),
                       migrate_every=0)
@@ -509,7 +514,8 @@ def bench(args, nx, ny, box, phys, desc, rank, world, local):
         achieved = n_total * B.B_ALG_TOTAL / (ms_per_step * 1e-3) / 1e9 / world  # per GPU
         line = {
             "metric": B.METRIC, "value": value, "unit": B.UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong" if args.workload == "c4" else "weak", "vs_baseline": None,
             "dtype": "f64" if args.precision == 64 else "f32", "data": "synthetic",
             "config": {"workload": desc, "particles": n_total, "particles_after": int(cnt.item()),
                        "decomposition": f"{world} x-slabs, periodic ring, one ghost exchange per evaluation (NCCL send/recv), "
