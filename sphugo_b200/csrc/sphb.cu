@@ -66,7 +66,6 @@ struct sphb_sim {
   bool slab_on = false;
   sphb_slab slab{};
   int slab_mode = 0;           // mode of the evaluation in progress (sphb_slab_step_begin)
-  uint32_t* ownTile = nullptr; // tile sums of the owned-particle scan
   int* packCount = nullptr;    // device counter of the pack kernels
   int64_t nleaving = 0;        // particles packed for migration and not yet compacted away
   cudaEvent_t ev[SPHB_PH_COUNT + 1] = {};
@@ -75,7 +74,6 @@ struct sphb_sim {
   GridTune gtune{};
   KnnTune ktune{};
   int force_nrec = 672;       // staged neighbour records per force block (shared memory)
-  bool force_gather = false;  // A/B switch: the unstaged gather kernel
   std::string err;
 };
 
@@ -256,7 +254,6 @@ void launch_force_st(sphb_sim* s, const ForceIO& io, int ntot, const PhysP& ph) 
 template <int KERNEL, bool INTEGRATE, bool SLAB>
 void launch_force_p(sphb_sim* s, const ForceIO& io, int ntot, const PhysP& ph) {
   if (s->prm.precision == 32) launch_force_st<KERNEL, INTEGRATE, SLAB, float>(s, io, ntot, ph);
-  else if (s->force_gather) k_force<KERNEL, INTEGRATE, SLAB><<<cdiv(ntot, 128), 128, 0, s->st>>>(io, ntot, s->grid, ph, s->dflags);
   else launch_force_st<KERNEL, INTEGRATE, SLAB, double>(s, io, ntot, ph);
 }
 
@@ -271,21 +268,21 @@ void launch_force(sphb_sim* s, int ntot, const PhysP& ph, bool integrate) {
     else launch_force_p<KERNEL, false, false>(s, io, ntot, ph);
     return;
   }
-  io.gflag = s->a.ghost; io.ownIdx = s->perm; io.epred = s->a.epred; io.id = s->a.id;
-  io.o_pos = s->b.pos; io.o_vel = s->b.vel; io.o_vdot = s->b.vdot; io.o_vpred = s->b.vpred;
-  io.o_e = s->b.e; io.o_edot = s->b.edot; io.o_epred = s->b.epred; io.o_id = s->b.id; io.o_pc = s->b.pc;
-  io.o_gflag = s->b.ghost;
+  io.gflag = s->a.ghost;
   if (integrate) launch_force_p<KERNEL, true, true>(s, io, ntot, ph);
   else launch_force_p<KERNEL, false, true>(s, io, ntot, ph);
 }
 
-// exclusive prefix of (flag == owned) over [0, ntot) into s->perm (free once the reorder is done)
-void own_scan(sphb_sim* s, int ntot) {
-  const int nt = cdiv(ntot, SC_TILE);
-  k_flag_tiles<<<nt, SC_THREADS, 0, s->st>>>(s->a.ghost, ntot, s->ownTile);
-  k_excl_scan<<<1, 1024, 0, s->st>>>(s->ownTile, nt, nullptr);
-  k_flag_apply<<<nt, SC_THREADS, 0, s->st>>>(s->a.ghost, ntot, s->ownTile, s->perm);
-  s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 3;
+// keep the entries of [0, nslots) flagged GF_OWNED, in place, in [0, nkeep) (nkeep = their number); failList / rank
+// are free outside the kNN / sort phases and serve as the hole / filler lists
+void compact_in_place(sphb_sim* s, int nslots, int nkeep) {
+  if (nslots <= 0) return;
+  cudaMemsetAsync(s->packCount, 0, 2 * sizeof(int), s->st);
+  k_find_holes<<<cdiv(nslots, 256), 256, 0, s->st>>>(s->a.ghost, nslots, nkeep, s->failList, s->rank, s->packCount);
+  SoaPtr a{s->a.pos, s->a.vel, s->a.vdot, s->a.vpred, s->a.e, s->a.edot, s->a.epred, s->a.id, s->a.pc, s->a.ghost};
+  const int moved_max = std::max(1, nslots - nkeep);  // fillers sit in [nkeep, nslots)
+  k_fill_holes<<<std::min(cdiv(moved_max, 256), 148 * 8), 256, 0, s->st>>>(a, s->failList, s->rank, s->packCount, s->dflags);
+  s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 2;
 }
 
 // sort + reorder + kNN (+ density with `kernel`); the neighbour list, spos and grid then describe s->a
@@ -343,12 +340,11 @@ int forces(sphb_sim* s, int mode, bool integrate) {
   const int ntot = (int)(s->n + s->nghost);
   const PhysP ph = make_phys(s->prm, s->prm.kernel);
   cudaEventRecord(s->ev[SPHB_PH_FORCE], s->st);
-  if (s->slab_on) own_scan(s, ntot);
   if (s->prm.kernel == 1) launch_force<1>(s, ntot, ph, integrate);
   else launch_force<2>(s, ntot, ph, integrate);
   s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 1;
-  if (s->slab_on) {  // the force kernel wrote the owned particles compacted into the other copy: ghosts are gone
-    std::swap(s->a, s->b);
+  if (s->slab_on) {  // drop the ghosts: the few owned particles sorted behind index n move into the ghosts' slots
+    compact_in_place(s, ntot, (int)s->n);
     s->nghost = 0;
     s->have_list = false;
   }
@@ -449,7 +445,6 @@ int create_common(const sphb_params* p, int64_t n, int64_t capacity, const doubl
   CKC(dalloc(s->nn, cap32 * SPHB_K));
   CKC(dalloc(s->failList, cap));
   CKC(dalloc(s->failCount, 2));
-  CKC(dalloc(s->ownTile, (size_t)cdiv(capacity, SC_TILE) + 1));
   CKC(dalloc(s->packCount, 2));
   CKC(dalloc(s->dflags, 1));
   CKC(dalloc(s->statPart, (size_t)STAT_BLOCKS * STAT_N));
@@ -484,7 +479,6 @@ int create_common(const sphb_params* p, int64_t n, int64_t capacity, const doubl
   if (const char* ev = getenv("SPHB_KNN_NCW")) s->ktune.ncw = std::max(128, std::min(1024, atoi(ev) / 8 * 8));
   if (const char* ev = getenv("SPHB_CELL_ASPECT")) s->gtune.aspect = atof(ev);
   if (const char* ev = getenv("SPHB_FORCE_NREC")) s->force_nrec = std::max(64, std::min(3072, atoi(ev)));
-  if (const char* ev = getenv("SPHB_FORCE_GATHER")) s->force_gather = atoi(ev) != 0;
   if (n > 0) {
     rc = upload_common(s, 0, n, pos_xy, vel_xy, e, rho, id, kind, 0);
     if (rc) { g_create_error = s->err; sphb_destroy(s); return rc; }
@@ -516,7 +510,7 @@ void sphb_destroy(sphb_sim* s) {
   cudaFree(s->spos); cudaFree(s->hguess);
   cudaFree(s->keys); cudaFree(s->keysSorted); cudaFree(s->rank); cudaFree(s->perm);
   cudaFree(s->cellCount); cudaFree(s->tileSum); cudaFree(s->cellStart); cudaFree(s->nn); cudaFree(s->failList); cudaFree(s->failCount);
-  cudaFree(s->ownTile); cudaFree(s->packCount);
+  cudaFree(s->packCount);
   cudaFree(s->dflags); cudaFree(s->statPart); cudaFree(s->stats); cudaFree(s->grid); cudaFree(s->scratch);
   for (auto& ev : s->ev) if (ev) cudaEventDestroy(ev);
   if (s->st) cudaStreamDestroy(s->st);

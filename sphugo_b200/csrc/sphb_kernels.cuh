@@ -999,108 +999,8 @@ struct ForceIO {
   double* e;
   double2* vdot;
   double* edot;
-  // slab mode: owned particles are written compacted (ghosts dropped) into the other state copy
-  const uint8_t* gflag;
-  const uint32_t* ownIdx;
-  const double* epred;
-  const int64_t* id;
-  double2 *o_pos, *o_vel, *o_vdot, *o_vpred;
-  double *o_e, *o_edot, *o_epred;
-  int64_t* o_id;
-  double4* o_pc;
-  uint8_t* o_gflag;
+  const uint8_t* gflag;  // slab mode: only owned particles are evaluated; ghosts are removed afterwards (k_fill_holes)
 };
-
-template <int KERNEL, bool INTEGRATE, bool SLAB>
-__global__ void __launch_bounds__(128) k_force(ForceIO io, int n, const GridP* __restrict__ gp, PhysP ph,
-                                               uint32_t* __restrict__ dflags) {
-  const GridP g = *gp;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  if (SLAB && io.gflag[i] != GF_OWNED) return;
-  const double2 pa = io.spos[i];
-  const double2 va = io.vpred[i];
-  const double4 qa = io.pc[i];  // rho, c, h, P
-  const double h = qa.z, inv_h = 1.0 / h;
-  const uint32_t* col = io.nn + (size_t)(i >> 5) * 1024 + (i & 31);
-  double ax = 0.0, ay = 0.0, aed = 0.0;
-#pragma unroll 4
-  for (int s = 0; s < SPHB_K; ++s) {
-    int j; double ox, oy;
-    decode_entry(col[s * 32], g, j, ox, oy);
-    const double2 pb = io.spos[j];
-    const double2 vb = io.vpred[j];
-    const double4 qb = io.pc[j];
-    if (SLAB && io.gflag[j] == GF_OUTER) atomicOr(dflags, DFLAG_GHOST_THIN);  // its rho, c, h were not evaluated
-    // rAB = NNPos - Pos with NNPos = neighbour - offset (nearest-neighbour.go:80, sph.go:372)
-    const double rx = (pb.x - ox) - pa.x, ry = (pb.y - oy) - pa.y;
-    const double vx = vb.x - va.x, vy = vb.y - va.y;
-    const double r2 = dist_sq(rx, ry);
-    const double rinv = rsqrt(r2);  // coincident particles give Inf/NaN like the reference (sph.go:391)
-    const double d = r2 * rinv;
-    const double dot = vx * rx + vy * ry;
-    double pi = 0.0;
-    if (dot < 0.0) {  // artificial viscosity, sph.go:375-388; the two divisions share one reciprocal
-      const double cAB = 0.5 * (qa.y + qb.y);
-      const double rhoAB = 0.5 * (qa.x + qb.x);
-      const double hAB = 0.5 * (qa.z + qb.z);
-      const double den = r2 + 0.01;
-      const double inv = 1.0 / (den * rhoAB);
-      const double mu = dot * hAB * (rhoAB * inv);
-      pi = (-0.75 * cAB * mu + 1.5 * mu * mu) * (den * inv);
-    }
-    const double dk = kern_DF<KERNEL>(fmin(d * inv_h, 1.0));
-    const double w = (pi + qa.w + qb.w) * dk * rinv;
-    ax += rx * w;
-    ay += ry * w;
-    aed += dot * dk;
-  }
-  const double f = ph.mass * ph.DFpref / (h * h * h);
-  double2 a = make_double2(ax * f + ph.gx, ay * f + ph.gy);
-  const double ed = qa.w * aed * ph.mass;  // Benz formulation, sph.go:400
-  double2 p = io.pos[i], v = io.vel[i];
-  double e = io.e[i];
-  if (INTEGRATE) {
-    const double dt = 2.0 * ph.dtH;
-    // kick (sph.go:122-127), drift 2 (sph.go:130-135): unfused like the reference
-    v.x = __dadd_rn(v.x, __dmul_rn(a.x, dt));
-    v.y = __dadd_rn(v.y, __dmul_rn(a.y, dt));
-    e = __dadd_rn(e, __dmul_rn(__dmul_rn(ed, 2.0), ph.dtH));
-    p.x = __dadd_rn(p.x, __dmul_rn(v.x, ph.dtH));
-    p.y = __dadd_rn(p.y, __dmul_rn(v.y, ph.dtH));
-    // periodic wrap, single shift, X shift skips the Y test (sph.go:147-167)
-    if (p.x < ph.hor0) p.x = __dadd_rn(p.x, ph.hor1 - ph.hor0);
-    else if (p.x > ph.hor1) p.x = __dsub_rn(p.x, ph.hor1 - ph.hor0);
-    else if (p.y < ph.ver0) p.y = __dadd_rn(p.y, ph.ver1 - ph.ver0);
-    else if (p.y > ph.ver1) p.y = __dsub_rn(p.y, ph.ver1 - ph.ver0);
-    // reflections L, R, U, D: pos -= pos - wall (sph.go:170-193)
-    if (p.x < ph.rL) { p.x = __dsub_rn(p.x, __dsub_rn(p.x, ph.rL)); v.x = -v.x; }
-    if (p.x > ph.rR) { p.x = __dsub_rn(p.x, __dsub_rn(p.x, ph.rR)); v.x = -v.x; }
-    if (p.y < ph.rU) { p.y = __dsub_rn(p.y, __dsub_rn(p.y, ph.rU)); v.y = -v.y; }
-    if (p.y > ph.rD) { p.y = __dsub_rn(p.y, __dsub_rn(p.y, ph.rD)); v.y = -v.y; }
-  }
-  if (!SLAB) {
-    io.vdot[i] = a;
-    io.edot[i] = ed;
-    if (INTEGRATE) {
-      io.pos[i] = p;
-      io.vel[i] = v;
-      io.e[i] = e;
-    }
-  } else {
-    const uint32_t o = io.ownIdx[i];
-    io.o_pos[o] = p;
-    io.o_vel[o] = v;
-    io.o_e[o] = e;
-    io.o_vdot[o] = a;
-    io.o_edot[o] = ed;
-    io.o_vpred[o] = va;
-    io.o_epred[o] = io.epred[i];
-    io.o_id[o] = io.id[i];
-    io.o_pc[o] = qa;
-    io.o_gflag[o] = GF_OWNED;
-  }
-}
 
 // -------------------------------------------------------------------------------------------------
 // K4 (staged): the same computation with the neighbour records staged in shared memory.
@@ -1291,7 +1191,7 @@ __device__ __forceinline__ void force_pairs(const ForceIO& io, int n, const Grid
 }
 
 template <int KERNEL, bool INTEGRATE, bool SLAB, typename R>
-__global__ void __launch_bounds__(FORCE_THREADS) k_force_st(ForceIO io, int n, const GridP* __restrict__ gp, PhysP ph,
+__global__ void __launch_bounds__(FORCE_THREADS, sizeof(R) == 4 ? 7 : 5) k_force_st(ForceIO io, int n, const GridP* __restrict__ gp, PhysP ph,
                                                             int nrec, uint32_t* __restrict__ dflags) {
   typedef typename RealV<R>::T RV;
   constexpr bool F32 = sizeof(R) == 4;
@@ -1447,26 +1347,12 @@ __global__ void __launch_bounds__(FORCE_THREADS) k_force_st(ForceIO io, int n, c
     if (p.y < ph.rU) { p.y = __dsub_rn(p.y, __dsub_rn(p.y, ph.rU)); v.y = -v.y; }
     if (p.y > ph.rD) { p.y = __dsub_rn(p.y, __dsub_rn(p.y, ph.rD)); v.y = -v.y; }
   }
-  if (!SLAB) {
-    io.vdot[i] = a;
-    io.edot[i] = ed;
-    if (INTEGRATE) {
-      io.pos[i] = p;
-      io.vel[i] = v;
-      io.e[i] = e;
-    }
-  } else {
-    const uint32_t o = io.ownIdx[i];
-    io.o_pos[o] = p;
-    io.o_vel[o] = v;
-    io.o_e[o] = e;
-    io.o_vdot[o] = a;
-    io.o_edot[o] = ed;
-    io.o_vpred[o] = va;
-    io.o_epred[o] = io.epred[i];
-    io.o_id[o] = io.id[i];
-    io.o_pc[o] = qa;
-    io.o_gflag[o] = GF_OWNED;
+  io.vdot[i] = a;
+  io.edot[i] = ed;
+  if (INTEGRATE) {
+    io.pos[i] = p;
+    io.vel[i] = v;
+    io.e[i] = e;
   }
 }
 
@@ -1608,46 +1494,41 @@ __global__ void __launch_bounds__(256) k_add_migrants(const double* __restrict__
   gflag[k] = GF_OWNED;
 }
 
-// keep-scan over the flags: tile counts of flag == GF_OWNED, then per-element exclusive prefix
-__global__ void __launch_bounds__(SC_THREADS) k_flag_tiles(const uint8_t* __restrict__ gflag, int n,
-                                                          uint32_t* __restrict__ tileSum) {
-  __shared__ uint32_t wsum[SC_THREADS / 32];
-  const int base = blockIdx.x * SC_TILE + threadIdx.x * SC_ITEMS;
-  uint32_t sum = 0;
-#pragma unroll
-  for (int k = 0; k < SC_ITEMS; ++k) sum += (base + k < n && gflag[base + k] == GF_OWNED) ? 1u : 0u;
-  uint32_t tot;
-  block_excl_scan_256(sum, wsum, tot);
-  if (threadIdx.x == 0) tileSum[blockIdx.x] = tot;
-}
-__global__ void __launch_bounds__(SC_THREADS) k_flag_apply(const uint8_t* __restrict__ gflag, int n,
-                                                          const uint32_t* __restrict__ tileOff,
-                                                          uint32_t* __restrict__ ownIdx) {
-  __shared__ uint32_t wsum[SC_THREADS / 32];
-  const int base = blockIdx.x * SC_TILE + threadIdx.x * SC_ITEMS;
-  uint32_t v[SC_ITEMS], sum = 0;
-#pragma unroll
-  for (int k = 0; k < SC_ITEMS; ++k) {
-    v[k] = (base + k < n && gflag[base + k] == GF_OWNED) ? 1u : 0u;
-    sum += v[k];
-  }
-  uint32_t tot;
-  uint32_t run = block_excl_scan_256(sum, wsum, tot) + tileOff[blockIdx.x];
-#pragma unroll
-  for (int k = 0; k < SC_ITEMS; ++k) {
-    if (base + k < n) ownIdx[base + k] = run;
-    run += v[k];
-  }
+// In-place compaction (ghost removal after an evaluation, departed particles after a migration): entries of
+// [0, nslots) flagged GF_OWNED are kept and must end up in [0, nkeep), nkeep = their number.  The order of the
+// particles is irrelevant (the next evaluation sorts them), so it is enough to move the owned entries that sit at
+// or beyond nkeep ("fillers") into the non-owned slots below nkeep ("holes"): there are equally many of both,
+// a fraction of a percent of the particles, instead of a pass over the whole state.
+__global__ void __launch_bounds__(256) k_find_holes(const uint8_t* __restrict__ gflag, int nslots, int nkeep,
+                                                   int* __restrict__ holes, uint32_t* __restrict__ fillers,
+                                                   int* __restrict__ counters) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool owned = i < nslots && gflag[i] == GF_OWNED;
+  const bool hole = i < nkeep && !owned, filler = i >= nkeep && owned;
+  const int sh = warp_append_slot(hole, counters), sf = warp_append_slot(filler, counters + 1);
+  if (sh >= 0) holes[sh] = i;
+  if (sf >= 0) fillers[sf] = (uint32_t)i;
 }
 
-// stable compaction of the owned particles (drops GF_LEAVING) into the other state copy
-__global__ void __launch_bounds__(256) k_compact(StateIn in, StateOut out, const uint32_t* __restrict__ ownIdx, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n || in.ghost[i] != GF_OWNED) return;
-  const uint32_t o = ownIdx[i];
-  out.pos[o] = in.pos[i]; out.vel[o] = in.vel[i]; out.vdot[o] = in.vdot[i]; out.vpred[o] = in.vpred[i];
-  out.e[o] = in.e[i]; out.edot[o] = in.edot[i]; out.epred[o] = in.epred[i];
-  out.id[o] = in.id[i]; out.pc[o] = in.pc[i]; out.ghost[o] = GF_OWNED;
+struct SoaPtr {
+  double2 *pos, *vel, *vdot, *vpred;
+  double *e, *edot, *epred;
+  int64_t* id;
+  double4* pc;
+  uint8_t* ghost;
+};
+
+__global__ void __launch_bounds__(256) k_fill_holes(SoaPtr a, const int* __restrict__ holes, const uint32_t* __restrict__ fillers,
+                                                   const int* __restrict__ counters, uint32_t* __restrict__ dflags) {
+  const int nh = counters[0];
+  if (blockIdx.x == 0 && threadIdx.x == 0 && counters[1] != nh) atomicOr(dflags, DFLAG_BUF_FULL);  // cannot happen
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nh; k += gridDim.x * blockDim.x) {
+    const int d = holes[k];
+    const uint32_t f = fillers[k];
+    a.pos[d] = a.pos[f]; a.vel[d] = a.vel[f]; a.vdot[d] = a.vdot[f]; a.vpred[d] = a.vpred[f];
+    a.e[d] = a.e[f]; a.edot[d] = a.edot[f]; a.epred[d] = a.epred[f];
+    a.id[d] = a.id[f]; a.pc[d] = a.pc[f]; a.ghost[d] = GF_OWNED;
+  }
 }
 
 // -------------------------------------------------------------------------------------------------
