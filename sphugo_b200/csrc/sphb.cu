@@ -241,14 +241,18 @@ SlabP make_slabp(const sphb_sim* s) {
 
 template <int KERNEL, bool INTEGRATE, bool SLAB, typename R>
 void launch_force_st(sphb_sim* s, const ForceIO& io, int ntot, const PhysP& ph) {
+  constexpr bool F32 = sizeof(R) == 4;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(k_force_st<KERNEL, INTEGRATE, SLAB, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (F32) cudaFuncSetAttribute(k_force_st32<KERNEL, INTEGRATE, SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    else cudaFuncSetAttribute(k_force_st<KERNEL, INTEGRATE, SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_done = true;
   }
   const int nrec = s->force_nrec;
   const size_t smem = (size_t)nrec * 8 * sizeof(R);  // four arrays of two reals per staged record
-  k_force_st<KERNEL, INTEGRATE, SLAB, R><<<cdiv(ntot, FORCE_THREADS), FORCE_THREADS, smem, s->st>>>(io, ntot, s->grid, ph, nrec, s->dflags);
+  const int nb = cdiv(ntot, FORCE_THREADS);
+  if (F32) k_force_st32<KERNEL, INTEGRATE, SLAB><<<nb, FORCE_THREADS, smem, s->st>>>(io, ntot, s->grid, ph, nrec, s->dflags);
+  else k_force_st<KERNEL, INTEGRATE, SLAB><<<nb, FORCE_THREADS, smem, s->st>>>(io, ntot, s->grid, ph, nrec, s->dflags);
 }
 
 template <int KERNEL, bool INTEGRATE, bool SLAB>

@@ -553,7 +553,20 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
     float thrf = (mine && !bad) ? thr0 : -1.0f;
     const float Vf = (float)V * 1.000001f;
 
-    // stage the whole union block (coalesced loads, all pieces in flight)
+    // window of piece 0 (see the filter below): issued here so that its two lookups overlap the staging loads
+    int w_lo = 0, w_hi = 0;
+    {
+      const int ru = r0, ix = ix0;
+      const int iy = g.wrapy ? img_idx(ru, g.ncy) : 0, row = ru - iy * g.ncy, uL = ix * g.ncx;
+      const int a = max(c0, uL) - uL, b = min(c1, uL + g.ncx - 1) - uL;
+      const int ca = max(clo, a + uL) - uL, cb = min(chi, b + uL) - uL;
+      const int ps = __shfl_sync(0xffffffffu, p_s, 0), po = __shfl_sync(0xffffffffu, p_off, 0);
+      if (mine && ru >= rlo && ru <= rhi && ca <= cb) {
+        w_lo = (int)cellStart[row * g.ncx + ca] - ps + po;
+        w_hi = (int)cellStart[row * g.ncx + cb + 1] - ps + po;
+      } else { w_lo = po; w_hi = po; }
+    }
+    // stage the whole union block (coalesced loads within a piece)
     bool anyimg = false;  // some staged piece is a periodic image (warp-uniform)
     int self_slot = -1;
     __syncwarp();
@@ -588,18 +601,6 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
     // cells its search disc touches (a contiguous slot range, from two cellStart lookups per piece, fetched one
     // piece ahead).  The trip count is the longest window of the warp; a window that would run past the end of
     // its piece is shifted back, so every staged slot is seen at most once per lane.
-    int w_lo = 0, w_hi = 0;  // window of the piece being fetched (staged slots)
-    {
-      const int ru = r0, ix = ix0;  // piece 0
-      const int iy = g.wrapy ? img_idx(ru, g.ncy) : 0, row = ru - iy * g.ncy, uL = ix * g.ncx;
-      const int a = max(c0, uL) - uL, b = min(c1, uL + g.ncx - 1) - uL;
-      const int ca = max(clo, a + uL) - uL, cb = min(chi, b + uL) - uL;
-      const int ps = __shfl_sync(0xffffffffu, p_s, 0), po = __shfl_sync(0xffffffffu, p_off, 0);
-      if (mine && ru >= rlo && ru <= rhi && ca <= cb) {
-        w_lo = (int)cellStart[row * g.ncx + ca] - ps + po;
-        w_hi = (int)cellStart[row * g.ncx + cb + 1] - ps + po;
-      } else { w_lo = po; w_hi = po; }
-    }
     for (int pc_ = 0; pc_ < npc; ++pc_) {
       const int ws = w_lo, we = w_hi;
       const int po = __shfl_sync(0xffffffffu, p_off, pc_), pl = __shfl_sync(0xffffffffu, p_len, pc_);
@@ -640,13 +641,14 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
     // every image, nearest-neighbour.go:79).  m = cnt - 33 entries with the largest keys must be dropped.
     const int cnt = (int)((kp - kbase) >> 8);
     bool ok = mine && !bad && !ovf && cnt >= SPHB_K + 1 && cnt <= CAP - 8;  // (the compaction pads up to cnt + 7)
-    // select A: the 4 largest keys below `bound` per pass (a max/min insertion network on the fp32 bit patterns).
+    // select A: the 5 largest keys below `bound` per pass (a max/min insertion network on the fp32 bit patterns;
+    // the warp-wide maximum of m is 4 on average at a 2 % margin, so one pass usually does).
     // T = smallest dropped key, akey = largest kept key.
     int mrem = ok ? cnt - (SPHB_K + 1) : 0;
     uint32_t bound = 0xffffffffu, T = 0xffffffffu, akey = 0u;
     bool sel_done = !ok;
     while (__any_sync(0xffffffffu, !sel_done)) {
-      uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+      uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
       const int lim = sel_done ? 0 : cnt;
       for (int s = 0; s < lim; ++s) {
         uint32_t k = col[s * 32].x;
@@ -655,16 +657,17 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
         a = max(t0, k); k = min(t0, k); t0 = a;
         a = max(t1, k); k = min(t1, k); t1 = a;
         a = max(t2, k); k = min(t2, k); t2 = a;
-        t3 = max(t3, k);
+        a = max(t3, k); k = min(t3, k); t3 = a;
+        t4 = max(t4, k);
       }
       if (!sel_done) {
-        if (mrem <= 3) {
-          T = mrem == 0 ? bound : (mrem == 1 ? t0 : (mrem == 2 ? t1 : t2));
-          akey = mrem == 0 ? t0 : (mrem == 1 ? t1 : (mrem == 2 ? t2 : t3));
+        if (mrem <= 4) {
+          T = mrem == 0 ? bound : (mrem == 1 ? t0 : (mrem == 2 ? t1 : (mrem == 3 ? t2 : t3)));
+          akey = mrem == 0 ? t0 : (mrem == 1 ? t1 : (mrem == 2 ? t2 : (mrem == 3 ? t3 : t4)));
           sel_done = true;
         } else {
-          mrem -= 4;
-          bound = t3;
+          mrem -= 5;
+          bound = t4;
         }
       }
     }
@@ -1191,8 +1194,8 @@ __device__ __forceinline__ void force_pairs(const ForceIO& io, int n, const Grid
 }
 
 template <int KERNEL, bool INTEGRATE, bool SLAB, typename R>
-__global__ void __launch_bounds__(FORCE_THREADS, sizeof(R) == 4 ? 7 : 5) k_force_st(ForceIO io, int n, const GridP* __restrict__ gp, PhysP ph,
-                                                            int nrec, uint32_t* __restrict__ dflags) {
+__device__ __forceinline__ void force_block(const ForceIO& io, int n, const GridP* __restrict__ gp, const PhysP& ph,
+                                            int nrec, uint32_t* __restrict__ dflags) {
   typedef typename RealV<R>::T RV;
   constexpr bool F32 = sizeof(R) == 4;
   const GridP g = *gp;
@@ -1354,6 +1357,19 @@ __global__ void __launch_bounds__(FORCE_THREADS, sizeof(R) == 4 ? 7 : 5) k_force
     io.vel[i] = v;
     io.e[i] = e;
   }
+}
+
+// the two builds as separate kernels: the fp64 one is capped at 96 registers (5 blocks of 128 threads per SM, the
+// number the staging area allows), the fp32 one is left to ptxas (64 registers, 8 blocks)
+template <int KERNEL, bool INTEGRATE, bool SLAB>
+__global__ void __launch_bounds__(FORCE_THREADS, 5) k_force_st(ForceIO io, int n, const GridP* __restrict__ gp, PhysP ph, int nrec,
+                                                              uint32_t* __restrict__ dflags) {
+  force_block<KERNEL, INTEGRATE, SLAB, double>(io, n, gp, ph, nrec, dflags);
+}
+template <int KERNEL, bool INTEGRATE, bool SLAB>
+__global__ void __launch_bounds__(FORCE_THREADS) k_force_st32(ForceIO io, int n, const GridP* __restrict__ gp, PhysP ph, int nrec,
+                                                             uint32_t* __restrict__ dflags) {
+  force_block<KERNEL, INTEGRATE, SLAB, float>(io, n, gp, ph, nrec, dflags);
 }
 
 // -------------------------------------------------------------------------------------------------

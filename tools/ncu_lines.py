@@ -41,8 +41,13 @@ for r in rows:
         ln = int(r[0])
     except ValueError:
         continue
-    smp = int(r[hdr.index("# Samples")] or 0)
-    ins = int(r[hdr.index("Instructions Executed")] or 0)
+    def num(v):
+        try:
+            return int(v.replace(",", ""))
+        except ValueError:
+            return 0
+    smp = num(r[hdr.index("# Samples")])
+    ins = num(r[hdr.index("Instructions Executed")])
     cur.append((fname, ln, r[1].strip(), smp, ins))
 name, data = launches[which]
 agg = {}
