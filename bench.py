@@ -9,7 +9,7 @@ selects the 2^20-particle single-GPU box (configs[2]).
 
 value   : device-resident state, CUDA events around K asynchronous sphb_step calls (max over ranks)
 e2e     : the same steps through the C ABI with HOST buffers: per step upload of the caller-set fields (Pos, Vel, E)
-          from pinned memory, sphb_step, download of the fields the per-step consumer reads (Pos, Rho, h, Z)
+          from pinned memory, sphb_step, download of the frame data the per-step consumer draws (sphb_frame) + sum E
 roofline: whole step as the dominant "kernel" chain, algorithmic bytes 652 B/particle, plus
           per-phase fractions from the library's CUDA-event phase timers
 cpu_baseline / --impl reference: the CPU restatement of the reference Go path (oracle/, 1 core: package
@@ -289,27 +289,33 @@ def run_ours(args):
         # ---- e2e: host buffers through the C ABI, every step: upload state, step, download results
         import ctypes as C
         # inputs: the particle fields a caller sets (spawners / examples write Pos, Vel, E: config-parser.go:68-77,
-        # density.go:12-15); outputs: the fields the per-step consumer reads (animator.Frame: Pos, Rho, Z, NNDists[0],
-        # animator.go:60-101).  VDot / EDot of the previous step stay on the device.
+        # density.go:12-15); outputs: what the per-step consumer needs - the frame data of (*Animator).CurrentFrame
+        # (pixel coordinates, colour-ramp index, Z: animator.go:60-101), extracted on the device (sphb_frame) - and
+        # the energy sum simviewer plots (simviewer.go:302).  VDot / EDot of the previous step stay on the device.
+        # The caller keeps its particles in its own fixed order (element k = particle id k): sphb_upload_by_id and
+        # sphb_frame(id_out = NULL) translate to and from the device's cell order.
         up_fields = ["pos", "vel", "e"]
-        down_fields = ["pos", "rho", "h", "id"]
+        st = g.download(up_fields + ["id"])
         host = {}
-        for f in set(up_fields + down_fields):
+        for f in up_fields:
             shp, dt = L.FIELD_SHAPE[f]
-            t = torch.empty((n,) + shp, dtype=torch.float64 if dt == np.float64 else torch.int64).pin_memory()
-            host[f] = t.numpy()
-        g.download(sorted(set(up_fields + down_fields)), out=host)  # every host buffer holds the current state
+            host[f] = torch.empty((n,) + shp, dtype=torch.float64).pin_memory().numpy()
+            host[f][st["id"]] = st[f]  # the current state, in id order
+        del st
+        fr = {"xy": torch.empty((n, 2), dtype=torch.float32).pin_memory().numpy(),
+              "colour": torch.empty((n,), dtype=torch.uint8).pin_memory().numpy()}
         h2d = sum(host[f].nbytes for f in up_fields)
-        d2h = sum(host[f].nbytes for f in down_fields)
+        d2h = sum(a.nbytes for a in fr.values()) + 8
         Ke = max(3, min(K, 10))
         for _ in range(2):
-            g.upload(**{f: host[f] for f in up_fields}); g.step(1); g.download(down_fields, out=host)
+            g.upload_by_id(**host); g.step(1); g.frame(1280, 720, ids=False, out=fr); g.reduce(L.SUM_E)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(Ke):
-            g.upload(**{f: host[f] for f in up_fields})
+            g.upload_by_id(**host)
             g.step(1)
-            g.download(down_fields, out=host)
+            g.frame(1280, 720, ids=False, out=fr)
+            g.reduce(L.SUM_E)
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
         e2e_val = n * Ke / e2e_s
@@ -358,7 +364,7 @@ def run_ours(args):
             "value": cb_v, "unit": UNIT, "cores": 1, "kind": "port",
             "sample": f"2 Step() calls on a {cb_n}-particle periodic jittered lattice ({cb_s:.2f} s/step); C restatement of the serial Go path"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
-                "what": "per step: sphb_upload(pos,vel,e) + sphb_step(1) + sphb_download(pos,rho,h,id), pinned host buffers, wall clock"},
+                "what": "per step: sphb_upload_by_id(Pos,Vel,E) + sphb_step(1) + sphb_frame(xy f32, colour u8, caller's order) + sphb_reduce(sum E), pinned host buffers, wall clock"},
         "gpu_launches": c1["kernel_launches"] - c0["kernel_launches"],
         "knn_fallback_particles": c1["knn_fallback"] - c0["knn_fallback"],
         "clocks": clocks,

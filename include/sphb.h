@@ -159,8 +159,24 @@ int sphb_download(sphb_sim* s, uint32_t field_mask, void* const* host_ptrs, int6
 /* overwrite device state (same order as the last download) for POS, VEL, E, RHO, VDOT, EDOT:
  * Root.Particles is public and examples poke it directly (density.go:12-15). */
 int sphb_upload(sphb_sim* s, uint32_t field_mask, const void* const* host_ptrs, int64_t n);
+/* the same for a caller that keeps its particles in a fixed order of its own: host array element k belongs to the
+ * particle with id k.  Needs dense ids (a permutation of 0..N-1, e.g. the ids sphb_create assigns when id == NULL;
+ * verified on the device, SPHB_E_STATE otherwise).  POS, VEL, E only.  The device order changes with every sort, so
+ * this - not sphb_upload - is the call for "Go mutated Root.Particles between two steps". */
+int sphb_upload_by_id(sphb_sim* s, uint32_t field_mask, const void* const* host_ptrs, int64_t n);
 
 int sphb_reduce(sphb_sim* s, int32_t which, double* out); /* TotalEnergy / TotalDensity / TotalMomentum */
+
+/* Per-particle frame data as (*Animator).CurrentFrame derives it (sim/animator.go:75-101), computed on the device so
+ * that a frame costs 9 (+8 with ids) bytes per particle over the bus instead of the 40 of {Pos, Rho, NNDists[0], Z}:
+ *   xy_out[2 i], xy_out[2 i + 1] = float32(Pos.X) * float32(width), float32(Pos.Y) * float32(height)
+ *   colour_out[i]                = uint8(min(Rho / (ParticleMass * N * 10) * 256, 255))        (the ramp index)
+ *   id_out[i] (may be NULL)      = Z: the renderer draws in order of descending Z
+ * Host buffers sized for `capacity` particles; *n_out = N.  Order = current device order when id_out is given.
+ * id_out == NULL: element k describes the particle with id k (dense ids required, as for sphb_upload_by_id) - a
+ * caller that numbers its particles in drawing order receives the frame ready to rasterise, 9 bytes per particle. */
+int sphb_frame(sphb_sim* s, int32_t width, int32_t height, float* xy_out, uint8_t* colour_out, int64_t* id_out,
+               int64_t capacity, int64_t* n_out);
 int sphb_phase_times(sphb_sim* s, double* ms, int32_t n); /* n <= SPHB_PH_COUNT */
 int sphb_counters(const sphb_sim* s, int64_t* out, int32_t n); /* n <= SPHB_CNT_COUNT */
 

@@ -36,7 +36,7 @@ HALO_RECORD_DOUBLES, MIGRANT_RECORD_DOUBLES = 10, 12
 EXPORTS = [
     "sphb_create", "sphb_destroy", "sphb_last_error", "sphb_set_params", "sphb_get_params", "sphb_count",
     "sphb_current_step", "sphb_append", "sphb_step", "sphb_calc_forces", "sphb_knn", "sphb_density", "sphb_stream", "sphb_sync",
-    "sphb_download", "sphb_upload", "sphb_reduce", "sphb_phase_times", "sphb_counters", "sphb_create_device",
+    "sphb_download", "sphb_upload", "sphb_upload_by_id", "sphb_reduce", "sphb_frame", "sphb_phase_times", "sphb_counters", "sphb_create_device",
     "sphb_slab_set", "sphb_max_h", "sphb_max_speed", "sphb_slab_step_begin", "sphb_slab_pack_halo", "sphb_slab_add_ghosts",
     "sphb_slab_step_end", "sphb_slab_pack_migrants", "sphb_slab_add_migrants", "sphb_slab_finish_migration",
 ]
@@ -116,6 +116,10 @@ def lib():
     L.sphb_upload.argtypes = [vp, C.c_uint32, C.POINTER(vp), C.c_int64]
     L.sphb_reduce.restype = C.c_int
     L.sphb_reduce.argtypes = [vp, C.c_int32, dp]
+    L.sphb_upload_by_id.restype = C.c_int
+    L.sphb_upload_by_id.argtypes = L.sphb_upload.argtypes
+    L.sphb_frame.restype = C.c_int
+    L.sphb_frame.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp, C.c_int64, ip]
     L.sphb_phase_times.restype = C.c_int
     L.sphb_phase_times.argtypes = [vp, dp, C.c_int32]
     L.sphb_counters.restype = C.c_int
@@ -279,10 +283,35 @@ class Handle:
             mask |= 1 << FIELD_BIT[name]
         self._chk(lib().sphb_upload(self._h, mask, ptrs, n))
 
+    def upload_by_id(self, **fields):
+        """pos / vel / e arrays indexed by particle id (dense ids): the caller's own fixed order"""
+        n = self.n
+        ptrs, mask, keep = (C.c_void_p * len(FIELDS))(), 0, []
+        for name, a in fields.items():
+            shp, dt = FIELD_SHAPE[name]
+            a = np.ascontiguousarray(a, dtype=dt).reshape((n,) + shp)
+            keep.append(a)
+            ptrs[FIELD_BIT[name]] = a.ctypes.data
+            mask |= 1 << FIELD_BIT[name]
+        self._chk(lib().sphb_upload_by_id(self._h, mask, ptrs, n))
+
     def reduce(self, which):
         out = C.c_double()
         self._chk(lib().sphb_reduce(self._h, which, C.byref(out)))
         return out.value
+
+    def frame(self, width=1280, height=720, ids=True, out=None):
+        """frame data of (*Animator).CurrentFrame (animator.go:75-101): dict xy float32 [n, 2], colour uint8 [n],
+        id int64 [n] in current device order; `out` may hold preallocated (pinned) arrays"""
+        n = self.n
+        out = out or {}
+        xy = out.get("xy") if out.get("xy") is not None else np.empty((n, 2), np.float32)
+        col = out.get("colour") if out.get("colour") is not None else np.empty(n, np.uint8)
+        idv = (out.get("id") if out.get("id") is not None else np.empty(n, np.int64)) if ids else None
+        nout = C.c_int64()
+        self._chk(lib().sphb_frame(self._h, width, height, xy.ctypes.data, col.ctypes.data,
+                                   idv.ctypes.data if ids else None, n, C.byref(nout)))
+        return {"xy": xy, "colour": col, "id": idv}
 
     def max_h(self):
         out = C.c_double()

@@ -71,6 +71,7 @@ struct sphb_sim {
   cudaEvent_t ev[SPHB_PH_COUNT + 1] = {};
   bool ev_valid = false;
   int64_t counters[SPHB_CNT_COUNT] = {0, 0, 0, 0};
+  int ids_dense = -1;         // -1 unknown, 0 no, 1 the ids are a permutation of 0..n-1 (by-id upload / frame)
   GridTune gtune{};
   KnnTune ktune{};
   int force_nrec = 672;       // staged neighbour records per force block (shared memory)
@@ -491,6 +492,23 @@ int create_common(const sphb_params* p, int64_t n, int64_t capacity, const doubl
   return SPHB_OK;
 }
 
+// ids a permutation of 0..n-1?  (keys / packCount are free outside an evaluation)
+int require_dense_ids(sphb_sim* s) {
+  if (s->ids_dense < 0) {
+    const int n = (int)s->n;
+    int bad = 0;
+    CK(s, cudaMemsetAsync(s->keys, 0, (size_t)n * sizeof(uint32_t), s->st));
+    CK(s, cudaMemsetAsync(s->packCount, 0, sizeof(int), s->st));
+    k_check_dense<<<cdiv(n, 256), 256, 0, s->st>>>(s->a.id, n, s->keys, s->packCount);
+    CKL(s);
+    CK(s, cudaMemcpyAsync(&bad, s->packCount, sizeof(int), cudaMemcpyDeviceToHost, s->st));
+    CK(s, cudaStreamSynchronize(s->st));
+    s->ids_dense = bad ? 0 : 1;
+  }
+  if (!s->ids_dense) return fail(s, SPHB_E_STATE, "the particle ids are not a permutation of 0..N-1: by-id transfers need dense ids");
+  return SPHB_OK;
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -548,6 +566,7 @@ int sphb_append(sphb_sim* s, int64_t n, const double* pos_xy, const double* vel_
   rc = upload_common(s, s->n, n, pos_xy, vel_xy, e, rho, id, cudaMemcpyHostToDevice, s->n);
   if (rc) return rc;
   s->n += n;
+  s->ids_dense = -1;
   return SPHB_OK;
 }
 
@@ -705,6 +724,35 @@ int sphb_upload(sphb_sim* s, uint32_t mask, const void* const* hp, int64_t n) {
   return SPHB_OK;
 }
 
+int sphb_upload_by_id(sphb_sim* s, uint32_t mask, const void* const* hp, int64_t n) {
+  int rc = enter(s); if (rc) return rc;
+  if (n != s->n) return fail(s, SPHB_E_INVALID, "upload: n = %lld but the simulation holds %lld particles", (long long)n, (long long)s->n);
+  const uint32_t allowed = SPHB_MASK(SPHB_F_POS) | SPHB_MASK(SPHB_F_VEL) | SPHB_MASK(SPHB_F_E);
+  if (mask & ~allowed) return fail(s, SPHB_E_INVALID, "upload_by_id: POS, VEL, E only (mask 0x%x)", mask);
+  if (mask && !hp) return fail(s, SPHB_E_INVALID, "host_ptrs is NULL");
+  for (int f = 0; f < SPHB_F_COUNT; ++f)
+    if ((mask & SPHB_MASK(f)) && !hp[f]) return fail(s, SPHB_E_INVALID, "host_ptrs[%d] is NULL", f);
+  if (n == 0 || mask == 0) return SPHB_OK;
+  if (s->slab_on) return fail(s, SPHB_E_STATE, "upload_by_id: not available in slab mode (a handle owns a subset of the ids)");
+  rc = require_dense_ids(s); if (rc) return rc;
+  rc = ensure_scratch(s, (size_t)n * 40); if (rc) return rc;
+  double2* sp = (double2*)s->scratch;
+  double2* sv = sp + n;
+  double* se = (double*)(sv + n);
+  if (mask & SPHB_MASK(SPHB_F_POS)) CK(s, cudaMemcpyAsync(sp, hp[SPHB_F_POS], (size_t)n * 16, cudaMemcpyHostToDevice, s->st));
+  if (mask & SPHB_MASK(SPHB_F_VEL)) CK(s, cudaMemcpyAsync(sv, hp[SPHB_F_VEL], (size_t)n * 16, cudaMemcpyHostToDevice, s->st));
+  if (mask & SPHB_MASK(SPHB_F_E)) CK(s, cudaMemcpyAsync(se, hp[SPHB_F_E], (size_t)n * 8, cudaMemcpyHostToDevice, s->st));
+  k_gather_by_id<<<cdiv(n, 256), 256, 0, s->st>>>(s->a.id, (int)n, (mask & SPHB_MASK(SPHB_F_POS)) ? sp : nullptr,
+                                                 (mask & SPHB_MASK(SPHB_F_VEL)) ? sv : nullptr,
+                                                 (mask & SPHB_MASK(SPHB_F_E)) ? se : nullptr, s->a.pos, s->a.vel, s->a.e);
+  s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 1;
+  CKL(s);
+  if (mask & SPHB_MASK(SPHB_F_POS)) s->have_list = false;
+  s->stats_dirty = true;
+  CK(s, cudaStreamSynchronize(s->st));  // host buffers are borrowed for the duration of the call only
+  return SPHB_OK;
+}
+
 int sphb_reduce(sphb_sim* s, int32_t which, double* out) {
   int rc = enter(s); if (rc) return rc;
   if (!out) return fail(s, SPHB_E_INVALID, "out is NULL");
@@ -724,6 +772,31 @@ int sphb_reduce(sphb_sim* s, int32_t which, double* out) {
   CK(s, cudaMemcpyAsync(st, s->stats, sizeof st, cudaMemcpyDeviceToHost, s->st));
   CK(s, cudaStreamSynchronize(s->st));
   *out = which == SPHB_SUM_E ? st[6] : st[7];
+  return SPHB_OK;
+}
+
+int sphb_frame(sphb_sim* s, int32_t width, int32_t height, float* xy_out, uint8_t* colour_out, int64_t* id_out,
+               int64_t capacity, int64_t* n_out) {
+  int rc = enter(s); if (rc) return rc;
+  rc = check_async(s); if (rc) return rc;
+  const int64_t n = s->n;
+  if (n_out) *n_out = n;
+  if (!xy_out || !colour_out) return fail(s, SPHB_E_INVALID, "xy_out / colour_out is NULL");
+  if (capacity < n) return fail(s, SPHB_E_NOMEM, "frame: capacity %lld < %lld particles", (long long)capacity, (long long)n);
+  if (n == 0) return SPHB_OK;
+  rc = ensure_scratch(s, (size_t)n * (sizeof(float2) + 1) + 16); if (rc) return rc;
+  float2* xy = (float2*)s->scratch;
+  uint8_t* col = (uint8_t*)(xy + n);
+  // colorFormula = Rho / (m * float64(len(Particles) * 10)) * 256: the divisor is one rounded product
+  const double div = s->prm.particle_mass * (double)(n * 10);
+  if (!id_out) { rc = require_dense_ids(s); if (rc) return rc; }
+  k_frame<<<cdiv(n, 256), 256, 0, s->st>>>(s->a.pos, s->a.pc, id_out ? nullptr : s->a.id, (int)n, (float)width, (float)height, div, xy, col);
+  s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 1;
+  CKL(s);
+  CK(s, cudaMemcpyAsync(xy_out, xy, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost, s->st));
+  CK(s, cudaMemcpyAsync(colour_out, col, (size_t)n, cudaMemcpyDeviceToHost, s->st));
+  if (id_out) CK(s, cudaMemcpyAsync(id_out, s->a.id, (size_t)n * sizeof(int64_t), cudaMemcpyDeviceToHost, s->st));
+  CK(s, cudaStreamSynchronize(s->st));
   return SPHB_OK;
 }
 

@@ -1720,6 +1720,43 @@ __global__ void __launch_bounds__(256) k_split_pc(const double4* __restrict__ pc
   if (h) h[i] = q.z;
 }
 
+// dense-id check: every id in [0, n) exactly once (seen[] zeroed by the caller)
+__global__ void __launch_bounds__(256) k_check_dense(const int64_t* __restrict__ id, int n, uint32_t* __restrict__ seen,
+                                                    int* __restrict__ bad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t v = id[i];
+  if (v < 0 || v >= n || atomicExch(&seen[v], 1u) != 0u) *bad = 1;
+}
+
+// host-order (by id) staging arrays -> device order: field[i] = staged[id[i]]
+__global__ void __launch_bounds__(256) k_gather_by_id(const int64_t* __restrict__ id, int n, const double2* __restrict__ spos_,
+                                                     const double2* __restrict__ svel, const double* __restrict__ se,
+                                                     double2* __restrict__ pos, double2* __restrict__ vel, double* __restrict__ e) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t k = id[i];
+  if (spos_) pos[i] = spos_[k];
+  if (svel) vel[i] = svel[k];
+  if (se) e[i] = se[k];
+}
+
+// frame data of animator.go:75-101: pixel coordinates (float32 products like the reference) and the colour-ramp index;
+// id != nullptr: element id[i] of the outputs (the caller's own particle order), else element i
+__global__ void __launch_bounds__(256) k_frame(const double2* __restrict__ pos, const double4* __restrict__ pc,
+                                              const int64_t* __restrict__ id, int n,
+                                              float w, float h, double colour_div, float2* __restrict__ xy,
+                                              uint8_t* __restrict__ colour) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double2 p = pos[i];
+  const double rho = pc[i].x;
+  if (id) i = (int)id[i];
+  xy[i] = make_float2(__fmul_rn((float)p.x, w), __fmul_rn((float)p.y, h));
+  const double cf = fmin(__dmul_rn(__ddiv_rn(rho, colour_div), 256.0), 255.0);  // Rho / (m N 10) * 256, math.Min(., 255)
+  colour[i] = (uint8_t)(int)cf;                           // uint8(): truncation; negative / NaN do not occur (Rho >= 0)
+}
+
 // upload helpers: scatter host-provided rho into pc.x, invalidate h when positions are overwritten
 __global__ void __launch_bounds__(256) k_set_pc(double4* __restrict__ pc, int n, const double* __restrict__ rho,
                                                int zero_h) {

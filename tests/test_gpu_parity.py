@@ -265,3 +265,58 @@ def test_non_finite_input_does_not_fault_the_device():
         g2.step(1)
         assert np.isfinite(g2.state(["rho"])["rho"]).all()
         g2.close()
+
+
+def test_frame_extraction_matches_the_animator_formula():
+    """sphb_frame against (*Animator).CurrentFrame's per-particle arithmetic (animator.go:75-101) on oracle state"""
+    ic = gen.spawn([(260, (0.2, 0.3), (0.8, 0.4)), (700, (0.2, 0.6), (0.8, 0.99))])
+    kw = dict(gamma=4.666, particle_mass=1e6, accel=(0.0, 0.55), dt_half=0.00324, kernel=2,
+              hor=(0.2, 0.8), ver=(-100.0, 100.0), refl=(L.OPEN_LO, L.OPEN_HI, L.OPEN_LO, 0.99))
+    po, pg = U.params_pair(**kw)
+    o = orc.Oracle(po, ic["pos"], ic["vel"], ic["e"], None, ic["id"])
+    g = L.Handle(pg, ic["pos"], ic["vel"], ic["e"], None, ic["id"])
+    o.step(3); g.step(3)
+    ref = o.state()
+    fr = g.frame(1280, 720)
+    order = np.argsort(fr["id"], kind="stable")
+    n = len(ref["id"])
+    x = ref["pos"][:, 0].astype(np.float32) * np.float32(1280)
+    y = ref["pos"][:, 1].astype(np.float32) * np.float32(720)
+    cf = ref["rho"] / (po.particle_mass * float(n * 10)) * 256
+    ci = np.minimum(cf, 255).astype(np.uint8)
+    assert (fr["id"][order] == ref["id"]).all()
+    assert np.abs(fr["xy"][order, 0] - x).max() <= 1e-3 and np.abs(fr["xy"][order, 1] - y).max() <= 1e-3
+    # rho agrees to 1e-9 along the trajectory: the truncated index may differ only where cf sits on an integer
+    diff = fr["colour"][order].astype(int) - ci.astype(int)
+    near = np.abs(cf - np.round(cf)) < 1e-6
+    assert (diff[~near] == 0).all() and np.abs(diff).max() <= 1
+    assert ci.max() > ci.min()  # the scene spans several ramp entries
+    g.close(); o.close()
+
+
+def test_by_id_transfers_follow_the_callers_order():
+    """sphb_upload_by_id / sphb_frame(id_out = NULL): host arrays indexed by particle id, whatever the device order"""
+    pos = gen.jittered_lattice(48, 48)
+    n = len(pos)
+    kw = dict(hor=(0.0, 1.0), ver=(0.0, 1.0), accel=(0.0, 0.2), dt_half=0.002)
+    pg = L.make_params(**kw)
+    a = L.Handle(pg, pos, None, np.full(n, 0.01))   # ids = 0..n-1
+    b = L.Handle(pg, pos, None, np.full(n, 0.01))
+    a.step(3); b.step(3)
+    st = a.state(["pos", "vel", "e", "id"])          # sorted by id
+    # b receives a's state in id order although its own device order is a cell order
+    b.upload_by_id(pos=st["pos"], vel=st["vel"], e=st["e"])
+    a.step(2); b.step(2)
+    sa, sb = a.state(["pos", "vel", "e", "rho", "id"]), b.state(["pos", "vel", "e", "rho", "id"])
+    for f in ("pos", "vel", "e", "rho"):
+        assert np.array_equal(sa[f], sb[f]), f
+    f_dev, f_id = a.frame(640, 480, ids=True), a.frame(640, 480, ids=False)
+    o = np.argsort(f_dev["id"], kind="stable")
+    assert np.array_equal(f_dev["xy"][o], f_id["xy"]) and np.array_equal(f_dev["colour"][o], f_id["colour"])
+    a.close(); b.close()
+    # sparse ids are refused
+    c = L.Handle(pg, pos, None, np.full(n, 0.01), None, np.arange(n, dtype=np.int64) * 3 + 7)
+    with pytest.raises(L.SphbError) as ei:
+        c.frame(640, 480, ids=False)
+    assert ei.value.code == L.E_STATE
+    c.close()
