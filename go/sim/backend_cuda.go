@@ -248,6 +248,21 @@ func (sim *Simulation) Sync(withNeighbours bool) {
 	b.hostStale = false
 }
 
+// FrameData returns what (*Animator).CurrentFrame needs per particle (animator.go:75-101) without mirroring the whole
+// state: pixel coordinates (float32(Pos)*float32(size)), the colour-ramp index and Z, in device order.
+func (sim *Simulation) FrameData(width, height int) (xy []float32, colour []uint8, z []int64) {
+	b := sim.backend()
+	n := int(C.sphb_count(b.h))
+	if n == 0 {
+		return
+	}
+	xy, colour, z = make([]float32, 2*n), make([]uint8, n), make([]int64, n)
+	var nOut C.int64_t
+	check(b, C.sphb_frame(b.h, C.int32_t(width), C.int32_t(height), (*C.float)(unsafe.Pointer(&xy[0])),
+		(*C.uint8_t)(unsafe.Pointer(&colour[0])), (*C.int64_t)(unsafe.Pointer(&z[0])), C.int64_t(n), &nOut))
+	return
+}
+
 // FindAllNearestNeighboursPeriodic is the batch form of the per-particle loop the examples run
 // (examples/density/density.go:65-69): for i { Particles[i].FindNearestNeighboursPeriodic(root, hor, ver) }.
 func (sim *Simulation) FindAllNearestNeighboursPeriodic(hor, ver [2]float64) {
