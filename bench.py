@@ -101,7 +101,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -120,6 +120,14 @@ class ClockSampler:
             self.proc.wait(timeout=3)
         except Exception:
             self.proc.kill()
+        if not any(len(ln.split(",")) >= 8 for ln in self.lines):
+            # the timed region was shorter than nvidia-smi's first report: one synchronous sample right after it
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=10).stdout
+                self.lines += out.splitlines()
+            except Exception:
+                pass
         sm, mx, reasons = [], [], set()
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
