@@ -1107,21 +1107,23 @@ __device__ __forceinline__ void pair_term(const OwnRec<R>& o, const NbrRec<R>& b
   const R r2 = fma(ry, ry, rx * rx);
   const R dot = fma(vy, ry, vx * rx);
   const R rinv = pair_rsqrt(r2);  // coincident particles give Inf/NaN like the reference (sph.go:391)
-  const R q = fmin(r2 * rinv * o.inv_h, R(1.0));
+  // q = d / h <= 1 up to the rounding of the reciprocals: the kernels' derivatives are O(eps^2) there, no clamp
+  const R q = r2 * rinv * o.inv_h;
   R dk = kern_DF_r<KERNEL, R>(q);
-  // artificial viscosity, sph.go:375-388: mu = vr hAB / (r^2 + eta^2), Pi = (-alpha cAB mu + beta mu^2) / rhoAB
+  // artificial viscosity, sph.go:375-388: mu = vr hAB / (r^2 + eta^2), Pi = (-alpha cAB mu + beta mu^2) / rhoAB for
+  // approaching pairs (vr < 0): min(vr, 0) makes mu, hence Pi, vanish otherwise
   const R cs = o.cs + b.cs, rs = o.rhoh + b.rhoh, hs = o.hh + b.hh;  // -0.75 cAB, rhoAB, hAB
   const R den = r2 + R(0.01);
+  const R dneg = fmin(dot, R(0.0));
   R mu, pi;
   if (sizeof(R) == 4) {
-    mu = dot * hs * pair_rcp(den);
+    mu = dneg * hs * pair_rcp(den);
     pi = mu * fma(R(1.5), mu, cs) * pair_rcp(rs);
   } else {  // the two divisions share one reciprocal
     const R inv = pair_rcp(den * rs);
-    mu = dot * hs * (rs * inv);
+    mu = dneg * hs * (rs * inv);
     pi = mu * fma(R(1.5), mu, cs) * (den * inv);
   }
-  pi = dot < R(0.0) ? pi : R(0.0);
   R w = (pi + o.P + b.P) * dk * rinv;
   w = sel ? w : R(0.0);
   dk = sel ? dk : R(0.0);
@@ -1162,9 +1164,12 @@ __device__ __forceinline__ void force_pairs(const ForceIO& io, int n, const Grid
 #pragma unroll
     for (int u = 0; u < 8; ++u) {  // branch-free: eight independent pairs for the scheduler to interleave
       const uint32_t ent = cur[u];
-      int t = 0;
+      int t = NP;  // t = #{m : ent >= stc[m]}: one borrow-propagating subtraction pair per piece
 #pragma unroll
-      for (int m = 0; m < NP; ++m) t += (ent >= stc[m]) ? 1 : 0;
+      for (int m = 0; m < NP; ++m) {
+        uint32_t tmp;
+        asm("{sub.cc.u32 %1, %2, %3;\n\tsubc.u32 %0, %0, 0;}" : "+r"(t), "=r"(tmp) : "r"(ent), "r"(stc[m]));
+      }
       const uint2 de = T.tab[t];
       const bool hit = ent < de.y;
       const int sl = hit ? (int)(ent - de.x) : 0;
