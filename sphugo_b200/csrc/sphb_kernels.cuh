@@ -545,6 +545,7 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
     // clamped border cells of an open axis may hold particles beyond the block: bound by the queries' reach
     V = fmax(V, warp_max_d(mine ? fmax(fabs(xa - xref), fabs(ya - yref)) + rg : 0.0));
     const float qfx = (float)(xa - xref), qfy = (float)(ya - yref);
+    const float2 nqx2 = make_float2(-qfx, -qfx), nqy2 = make_float2(-qfy, -qfy);
     const double delta = 3.0 * (2.384185791015625e-07 * V / fmax(rg, 1e-300) + 4.76837158203125e-07);
     const float deltaf = (float)delta;
     // tile far wider than this lane's radius: no useful fp32 bound (fp32 build: accuracy of h itself)
@@ -589,7 +590,8 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
           if (!F32) candD[off + t] = pb;
           candE[off + t] = (uint32_t)(s + t) | (code << IMG_SHIFT);
         }
-        candF[off + t] = make_float2(fx, fy);
+        float* cf = reinterpret_cast<float*>(candF) + (size_t)((off + t) >> 1) * 4 + ((off + t) & 1);
+        cf[0] = fx; cf[2] = fy;  // pairs of candidates as {x0, x1, y0, y1}: operands of the packed fp32 filter
       }
       if (mine && code == 5u && i >= s && i < s + len) self_slot = off + (i - s);
     }
@@ -625,10 +627,11 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
         for (int u = 0; u < 4; ++u) v[u] = candF4[(c >> 1) + u];
         float d2f[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float ax = v[u].x - qfx, ay = v[u].y - qfy, bx = v[u].z - qfx, by = v[u].w - qfy;
-          d2f[2 * u] = fmaf(ay, ay, ax * ax);
-          d2f[2 * u + 1] = fmaf(by, by, bx * bx);
+        for (int u = 0; u < 4; ++u) {  // two candidates per instruction (FADD2 / FMUL2 / FFMA2)
+          const float2 ax = __fadd2_rn(make_float2(v[u].x, v[u].y), nqx2), ay = __fadd2_rn(make_float2(v[u].z, v[u].w), nqy2);
+          const float2 d2 = __ffma2_rn(ay, ay, __fmul2_rn(ax, ax));
+          d2f[2 * u] = d2.x;
+          d2f[2 * u + 1] = d2.y;
         }
         if (kp > klim) { ovf = true; thrf = -1.0f; }
 #pragma unroll

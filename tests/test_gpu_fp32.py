@@ -61,7 +61,7 @@ def test_fp32_knn_large_lattice_uses_tile_kernel():
     assert c["knn_fallback"] < 0.2 * len(pos)  # first evaluation: radius from a density estimate
 
 
-def _step32(ic, steps, **cfg):
+def _step32(ic, steps, edot_slack=1.0, **cfg):
     po, pg = U.params_pair(**cfg)
     pg.precision = 32
     o = orc.Oracle(po, ic["pos"], ic.get("vel"), ic.get("e"), None, ic["id"])
@@ -79,10 +79,11 @@ def _step32(ic, steps, **cfg):
         assert U.rel_err(got["rho"], ref["rho"]) <= tol, f"rho step {done}"
         assert U.rel_err(got["c"], ref["c"]) <= tol, f"c step {done}"
         assert U.rel_err(got["vdot"], ref["vdot"], asc) <= tol, f"vdot step {done}"
-        assert U.rel_err(got["edot"], ref["edot"], esc) <= tol, f"edot step {done}"
+        assert U.rel_err(got["edot"], ref["edot"], esc) <= tol * edot_slack, f"edot step {done}"
         vs = np.abs(ref["vel"]).max() + asc.max() * 2 * po.dt_half
         assert np.abs(got["vel"] - ref["vel"]).max() <= tol * vs, f"vel step {done}"
-        assert U.rel_err(got["e"], ref["e"], esc * 2 * po.dt_half) <= tol, f"e step {done}"
+        assert U.rel_err(got["e"], ref["e"], esc * 2 * po.dt_half) <= tol * edot_slack, f"e step {done}"
+        assert U.rel_err(got["e"], ref["e"]) <= TOL32 * 1e-2, f"e (relative to |E|, the north_star's bar) step {done}"
         assert abs(g.reduce(L.SUM_E) - o.total_energy()) <= tol * abs(o.total_energy())
     g.close(); o.close()
 
@@ -127,3 +128,16 @@ def test_fp32_and_fp64_builds_agree_at_c3_size():
     assert abs(out[32]["sum_e"] - out[64]["sum_e"]) <= TOL32 * abs(out[64]["sum_e"])
     # positions inherit the acceleration error times dt^2: |a| ~ 1e2 here, so 1e-5 * 1e2 * (2e-3)^2 * steps
     assert np.abs(out[32]["pos"] - out[64]["pos"]).max() <= 1e-8
+
+
+def test_fp32_shock_tube_density_contrast_steps():
+    """C4 shape at reduced N: 4:1 number-density contrast, periodic box (group halving, force rows -2..+2)."""
+    pos = gen.shock_tube(40000)
+    n = len(pos)
+    ic = dict(pos=pos, vel=np.zeros((n, 2)), e=np.full(n, 0.01), id=np.arange(n, dtype=np.int64))
+    # EDot sums (v_b - v_a).r_ab.  This run starts from rest, so all velocities are a dt and their differences between
+    # neighbours are tiny, while a 128-particle force block of the dilute half is a strip half a box long that also
+    # holds the fast particles at the density jump: the fp32 build resolves velocities to 2^-24 of the spread over
+    # a block, which shows as 5e-5 of sum|term| here (absolute 1e-16 against E = 0.01; accelerations, h, rho and
+    # the energies themselves stay inside the 1e-5 bar).  Hence the slack on this one measure.
+    _step32(ic, steps=2, edot_slack=10.0, hor=(0.0, 1.0), ver=(0.0, 1.0), dt_half=2e-3)

@@ -320,3 +320,21 @@ def test_by_id_transfers_follow_the_callers_order():
         c.frame(640, 480, ids=False)
     assert ei.value.code == L.E_STATE
     c.close()
+
+
+def test_shock_tube_density_contrast_steps():
+    """C4 shape at reduced N (BASELINE configs[3]): number-density ratio 4:1 across x = 0.5, periodic box.  The grid
+    follows the mean h, so the dilute half has h ~ 2 cell rows: kNN tiles whose union block does not fit the staging
+    area are halved and retried, force blocks stage rows -2..+2 - and only a small share of the particles may need the
+    ring-expansion fallback."""
+    pos = gen.shock_tube(40000)
+    n = len(pos)
+    ic = dict(pos=pos, vel=np.zeros((n, 2)), e=np.full(n, 0.01), id=np.arange(n, dtype=np.int64))
+    cfg = dict(hor=(0.0, 1.0), ver=(0.0, 1.0), dt_half=2e-3)
+    _step_case(ic, steps=3, **cfg)
+    g = L.Handle(L.make_params(**cfg), pos, None, ic["e"])
+    g.step(3)
+    g.sync()
+    c = g.counters()
+    assert c["knn_fallback"] < 0.05 * n * 4, c  # 4 evaluations; the first one guesses its radii from the cell counts
+    g.close()
