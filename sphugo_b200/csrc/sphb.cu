@@ -71,6 +71,9 @@ struct sphb_sim {
   cudaEvent_t ev[SPHB_PH_COUNT + 1] = {};
   bool ev_valid = false;
   int64_t counters[SPHB_CNT_COUNT] = {0, 0, 0, 0};
+  unsigned long long* hacc = nullptr;  // [HACC_N][2] smoothing-length accumulator written by the kNN kernels
+  bool hacc_valid = false;    // it describes the current particles (no upload / append since the evaluation that filled it)
+  double hscale = 0.0;        // fixed-point scale of the evaluation in progress (0: accumulator off)
   int ids_dense = -1;         // -1 unknown, 0 no, 1 the ids are a permutation of 0..n-1 (by-id upload / frame)
   GridTune gtune{};
   KnnTune ktune{};
@@ -203,7 +206,7 @@ int refresh_stats(sphb_sim* s) {
 
 template <int KERNEL, bool F32>
 void launch_knn_p(sphb_sim* s, int ntot, const PhysP& ph) {
-  KnnOut out{s->a.pc, s->nn, s->failList, s->failCount};
+  KnnOut out{s->hacc, s->hscale, s->a.pc, s->nn, s->failList, s->failCount};
   const int tiles = cdiv(ntot, 32);
   KnnTune kt = s->ktune;
   kt.cap = s->have_h ? s->ktune.cap : s->ktune.cap0;  // first evaluation: radius from a density estimate, wider spread
@@ -223,7 +226,7 @@ template <int KERNEL>
 void launch_knn(sphb_sim* s, int ntot, const PhysP& ph) {
   if (s->prm.precision == 32) launch_knn_p<KERNEL, true>(s, ntot, ph);
   else launch_knn_p<KERNEL, false>(s, ntot, ph);
-  KnnOut out{s->a.pc, s->nn, s->failList, s->failCount};
+  KnnOut out{s->hacc, s->hscale, s->a.pc, s->nn, s->failList, s->failCount};
   k_knn_fallback<KERNEL><<<148 * 4, 128, 0, s->st>>>(s->spos, s->keysSorted, s->cellStart, s->hguess,
                                                    s->a.epred, ntot, s->grid, ph, out, s->dflags);
   s->have_h = true;
@@ -294,12 +297,19 @@ void compact_in_place(sphb_sim* s, int nslots, int nkeep) {
 int build_neighbours(sphb_sim* s, int mode, const double hor[2], const double ver[2], int kernel, bool timed) {
   const int ntot = (int)(s->n + s->nghost);
   if (ntot <= 0) return fail(s, SPHB_E_STATE, "Simulation not initialized: no particles (sph.go:92-94)");
-  if (s->stats_dirty) { int rc = refresh_stats(s); if (rc) return rc; }
+  // Fully periodic single-handle runs need no statistics pass per evaluation: the box comes from hor / ver and the
+  // mean smoothing length from the accumulator the previous kNN filled.
+  const bool periodic = !axis_open(hor) && !axis_open(ver) && !s->slab_on;
+  const bool use_hacc = periodic && s->hacc_valid;
+  if (s->stats_dirty && !use_hacc) { int rc = refresh_stats(s); if (rc) return rc; }
+  const double hscale_prev = s->hscale;
+  s->hscale = periodic ? 16777216.0 / std::max(hor[1] - hor[0], ver[1] - ver[0]) : 0.0;  // h < L: 24-bit fixed point
   const PhysP ph = make_phys(s->prm, kernel);
   const double dtH = s->prm.dt_half;
   if (timed) cudaEventRecord(s->ev[SPHB_PH_KEYS], s->st);
   k_make_grid<<<1, 32, 0, s->st>>>(s->stats, ntot, hor[0], hor[1], ver[0], ver[1], make_slabp(s), s->slab_on ? 1 : 0,
-                                   s->gtune, s->grid);
+                                   s->gtune, s->grid, s->hacc, hscale_prev > 0.0 ? hscale_prev : 1.0, use_hacc ? 1 : 0);
+  s->hacc_valid = periodic;  // the kNN below refills the accumulator
   if (mode == MODE_DRIFT) k_keys<true><<<cdiv(ntot, 256), 256, 0, s->st>>>(s->a.pos, s->a.vel, ntot, s->grid, dtH, s->keys, s->rank, s->cellCount);
   else k_keys<false><<<cdiv(ntot, 256), 256, 0, s->st>>>(s->a.pos, s->a.vel, ntot, s->grid, dtH, s->keys, s->rank, s->cellCount);
   if (timed) cudaEventRecord(s->ev[SPHB_PH_SORT], s->st);
@@ -355,7 +365,8 @@ int forces(sphb_sim* s, int mode, bool integrate) {
   }
   cudaEventRecord(s->ev[SPHB_PH_TOTAL], s->st);
   s->ev_valid = true;
-  rc = refresh_stats(s); if (rc) return rc;
+  if (s->hacc_valid) s->stats_dirty = true;  // sums / bounds are refreshed on demand (sphb_reduce, open axes, slabs)
+  else { rc = refresh_stats(s); if (rc) return rc; }
   CKL(s);
   return SPHB_OK;
 }
@@ -399,6 +410,7 @@ int upload_common(sphb_sim* s, int64_t off, int64_t n, const double* pos_xy, con
   CKL(s);
   CK(s, cudaStreamSynchronize(s->st));  // host buffers are borrowed for the duration of the call only
   s->stats_dirty = true;
+  s->hacc_valid = false;  // new particles: the mean smoothing length must come from a statistics pass
   s->have_list = false;
   return SPHB_OK;
 }
@@ -451,6 +463,8 @@ int create_common(const sphb_params* p, int64_t n, int64_t capacity, const doubl
   CKC(dalloc(s->failList, cap));
   CKC(dalloc(s->failCount, 2));
   CKC(dalloc(s->packCount, 2));
+  CKC(dalloc(s->hacc, 2 * HACC_N));
+  CKC(cudaMemsetAsync(s->hacc, 0, 2 * HACC_N * sizeof(unsigned long long), s->st));
   CKC(dalloc(s->dflags, 1));
   CKC(dalloc(s->statPart, (size_t)STAT_BLOCKS * STAT_N));
   CKC(dalloc(s->stats, STAT_N));
@@ -532,7 +546,7 @@ void sphb_destroy(sphb_sim* s) {
   cudaFree(s->spos); cudaFree(s->hguess);
   cudaFree(s->keys); cudaFree(s->keysSorted); cudaFree(s->rank); cudaFree(s->perm);
   cudaFree(s->cellCount); cudaFree(s->tileSum); cudaFree(s->cellStart); cudaFree(s->nn); cudaFree(s->failList); cudaFree(s->failCount);
-  cudaFree(s->packCount);
+  cudaFree(s->packCount); cudaFree(s->hacc);
   cudaFree(s->dflags); cudaFree(s->statPart); cudaFree(s->stats); cudaFree(s->grid); cudaFree(s->scratch);
   for (auto& ev : s->ev) if (ev) cudaEventDestroy(ev);
   if (s->st) cudaStreamDestroy(s->st);

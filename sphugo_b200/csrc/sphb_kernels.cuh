@@ -375,7 +375,13 @@ __global__ void __launch_bounds__(256) k_reorder(StateIn in, StateOut out, const
 #define KNN_WARPS 2
 #define KNN_THREADS (KNN_WARPS * 32)
 
+#define HACC_N 256  // spread slots of the smoothing-length accumulator (keeps the atomics uncontended)
 struct KnnOut {
+  // fully periodic, single-handle runs: sum of h in fixed point (h * hscale, integer => order-independent, so the next
+  // grid is bit-reproducible) and particle count, [HACC_N][2]; the next k_make_grid takes the mean h from here
+  // instead of a statistics pass over the state.  hscale = 0: disabled.
+  unsigned long long* hacc;
+  double hscale;
   double4* pc;      // {rho, c, h, P = c^2/(gamma rho)}
   uint32_t* nn;     // [tile][slot][lane], entry = index | image code << 28
   int* failList;
@@ -417,6 +423,19 @@ __device__ __forceinline__ void knn_append(uint32_t& kp, float d2f, uint32_t en,
       "}\n"
       : "+r"(kp)
       : "f"(d2f), "r"(en), "f"(thr));
+}
+
+// warp-level contribution to the smoothing-length accumulator (all 32 lanes call): h * hscale < 2^24 per lane, so the
+// warp sum fits 32 bits and is one REDUX
+__device__ __forceinline__ void knn_accumulate_h(const KnnOut& out, bool ok, double h) {
+  if (out.hscale == 0.0) return;
+  const unsigned q = __reduce_add_sync(0xffffffffu, ok ? (unsigned)__double2uint_rn(h * out.hscale) : 0u);
+  const unsigned cnt = __popc(__ballot_sync(0xffffffffu, ok));
+  if ((threadIdx.x & 31) == 0 && cnt) {
+    unsigned long long* a = out.hacc + 2 * (blockIdx.x & (HACC_N - 1));
+    atomicAdd(a, (unsigned long long)q);
+    atomicAdd(a + 1, (unsigned long long)cnt);
+  }
 }
 
 template <int KERNEL, bool F32>
@@ -752,6 +771,7 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
         const float c = sqrtf((float)(ph.cfac * ep));
         out.pc[i] = make_double4((double)rho, (double)c, h, (double)(c * c / ((float)ph.gamma * rho)));
       }
+      knn_accumulate_h(out, ok, (double)(ok ? h2f * rsqrtf(fmaxf(h2f, 1e-37f)) : 0.0f));
       continue;
     }
     // ---- fp64 build, exact phase: d^2 exactly as the reference computes it; the list entry goes to global
@@ -827,6 +847,7 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
       const double c = c2 > 0.0 ? fast_sqrt(c2, fast_rsqrt(c2)) : sqrt(c2);
       out.pc[i] = make_double4(rho, c, h, c * c * fast_rcp(ph.gamma * rho));
     }
+    knn_accumulate_h(out, ok, ok ? sqrt(h2) : 0.0);
   }
 }
 
@@ -945,6 +966,11 @@ __global__ void __launch_bounds__(128) k_knn_fallback(const double2* __restrict_
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     nncol[lane * 32] = ti;
+    if (lane == 0 && out.hscale != 0.0) {
+      unsigned long long* a = out.hacc + 2 * (blockIdx.x & (HACC_N - 1));
+      atomicAdd(a, (unsigned long long)__double2uint_rn(h * out.hscale));
+      atomicAdd(a + 1, 1ull);
+    }
     if (lane == 0) {
       const double rho = ph.Fpref * ph.mass * acc / (h * h);
       const double c = sqrt(ph.cfac * epred[i]);
@@ -1626,7 +1652,13 @@ struct GridTune {
 };
 
 __global__ void k_make_grid(const double* __restrict__ stats, int n, double hor0, double hor1, double ver0, double ver1,
-                            SlabP sl, int slab_on, GridTune t, GridP* __restrict__ out) {
+                            SlabP sl, int slab_on, GridTune t, GridP* __restrict__ out, unsigned long long* __restrict__ hacc,
+                            double hscale, int use_hacc) {
+  // the smoothing-length accumulator of the previous evaluation (one warp sums the slots and clears them)
+  unsigned long long hs = 0, hc = 0;
+  for (int k = threadIdx.x; k < HACC_N; k += 32) { hs += hacc[2 * k]; hc += hacc[2 * k + 1]; hacc[2 * k] = 0; hacc[2 * k + 1] = 0; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { hs += __shfl_xor_sync(0xffffffffu, hs, o); hc += __shfl_xor_sync(0xffffffffu, hc, o); }
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   GridP g;
   g.wrapx = !(hor0 == -1.7976931348623157e308);
@@ -1653,8 +1685,9 @@ __global__ void k_make_grid(const double* __restrict__ stats, int n, double hor0
   if (!(ey > 1e-12 * scale)) ey = 1e-12 * scale;
   double d;  // row height dy; dx = aspect * dy
   const double asp = (t.aspect > 0.0) ? t.aspect : 1.0;
-  const double nh = stats[8];
-  if (nh > 0.0) d = t.cell_per_h * stats[4] / nh;
+  const double nh = use_hacc ? (double)hc : stats[8];
+  const double sumh = use_hacc ? (double)hs / hscale : stats[4];
+  if (nh > 0.0) d = t.cell_per_h * sumh / nh;
   else d = sqrt(t.ppc0 * ex * ey / ((double)(n > 0 ? n : 1) * asp));
   if (!(d > 0.0)) d = scale;
   double fx = fmin(fmax(floor(ex / (d * asp)), 1.0), 1.0e6), fy = fmin(fmax(floor(ey / d), 1.0), 1.0e6);
