@@ -22,7 +22,7 @@ for r in rows[2:]:
     name = re.sub(r"[<(].*", "", r[ik]).replace("void ", "")
     b = float(r[ir].replace(",", "")) * scale[units[ir]] + float(r[iw].replace(",", "")) * scale[units[iw]]
     acc.setdefault(name, []).append(b)
-phase = {"k_knn_tile": "knn", "k_force_st": "force", "k_force": "force", "k_reorder": "reorder"}
+phase = {"k_knn_tile": "knn", "k_force_st": "force", "k_force_st32": "force", "k_reorder": "reorder"}
 path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
 d = json.load(open(path)) if os.path.exists(path) else {}
 for k, v in acc.items():
