@@ -72,6 +72,8 @@ struct sphb_sim {
   bool ev_valid = false;
   int64_t counters[SPHB_CNT_COUNT] = {0, 0, 0, 0};
   unsigned long long* hacc = nullptr;  // [HACC_N][2] smoothing-length accumulator written by the kNN kernels
+  uint32_t* qmax = nullptr;   // {max h, max |v|^2} of the owned particles as float bits (kNN / force kernels)
+  bool qmax_valid = false;    // the statistics pass was skipped: sphb_max_h / sphb_max_speed read qmax
   bool hacc_valid = false;    // it describes the current particles (no upload / append since the evaluation that filled it)
   double hscale = 0.0;        // fixed-point scale of the evaluation in progress (0: accumulator off)
   int ids_dense = -1;         // -1 unknown, 0 no, 1 the ids are a permutation of 0..n-1 (by-id upload / frame)
@@ -206,7 +208,7 @@ int refresh_stats(sphb_sim* s) {
 
 template <int KERNEL, bool F32>
 void launch_knn_p(sphb_sim* s, int ntot, const PhysP& ph) {
-  KnnOut out{s->hacc, s->hscale, s->a.pc, s->nn, s->failList, s->failCount};
+  KnnOut out{s->hacc, s->hscale, s->qmax, s->a.pc, s->nn, s->failList, s->failCount};
   const int tiles = cdiv(ntot, 32);
   KnnTune kt = s->ktune;
   kt.cap = s->have_h ? s->ktune.cap : s->ktune.cap0;  // first evaluation: radius from a density estimate, wider spread
@@ -226,9 +228,9 @@ template <int KERNEL>
 void launch_knn(sphb_sim* s, int ntot, const PhysP& ph) {
   if (s->prm.precision == 32) launch_knn_p<KERNEL, true>(s, ntot, ph);
   else launch_knn_p<KERNEL, false>(s, ntot, ph);
-  KnnOut out{s->hacc, s->hscale, s->a.pc, s->nn, s->failList, s->failCount};
+  KnnOut out{s->hacc, s->hscale, s->qmax, s->a.pc, s->nn, s->failList, s->failCount};
   k_knn_fallback<KERNEL><<<148 * 4, 128, 0, s->st>>>(s->spos, s->keysSorted, s->cellStart, s->hguess,
-                                                   s->a.epred, ntot, s->grid, ph, out, s->dflags);
+                                                   s->a.epred, ntot, s->grid, ph, out, s->slab_on ? s->a.ghost : nullptr, s->dflags);
   s->have_h = true;
 }
 
@@ -269,7 +271,8 @@ template <int KERNEL>
 void launch_force(sphb_sim* s, int ntot, const PhysP& ph, bool integrate) {
   ForceIO io{};
   io.spos = s->spos; io.vpred = s->a.vpred; io.pc = s->a.pc; io.nn = s->nn;
-  io.keys = s->keysSorted; io.cellStart = s->cellStart;
+  io.keys = s->keysSorted; io.cellStart = s->cellStart; io.qmax = s->qmax;
+  if (integrate) cudaMemsetAsync(s->qmax + 1, 0, sizeof(uint32_t), s->st);  // max |v|^2 after this kick
   io.pos = s->a.pos; io.vel = s->a.vel; io.e = s->a.e; io.vdot = s->a.vdot; io.edot = s->a.edot;
   if (!s->slab_on) {
     if (integrate) launch_force_p<KERNEL, true, false>(s, io, ntot, ph);
@@ -297,9 +300,10 @@ void compact_in_place(sphb_sim* s, int nslots, int nkeep) {
 int build_neighbours(sphb_sim* s, int mode, const double hor[2], const double ver[2], int kernel, bool timed) {
   const int ntot = (int)(s->n + s->nghost);
   if (ntot <= 0) return fail(s, SPHB_E_STATE, "Simulation not initialized: no particles (sph.go:92-94)");
-  // Fully periodic single-handle runs need no statistics pass per evaluation: the box comes from hor / ver and the
-  // mean smoothing length from the accumulator the previous kNN filled.
-  const bool periodic = !axis_open(hor) && !axis_open(ver) && !s->slab_on;
+  // Fully periodic runs (single handle, or a slab of a periodic ring) need no statistics pass per evaluation: the box
+  // comes from hor / ver / the slab edges, the mean smoothing length from the accumulator the previous kNN filled,
+  // max h and max speed (slab driver) from qmax.
+  const bool periodic = !axis_open(ver) && !axis_open(hor) && (!s->slab_on || (s->slab.has_left && s->slab.has_right));
   const bool use_hacc = periodic && s->hacc_valid;
   if (s->stats_dirty && !use_hacc) { int rc = refresh_stats(s); if (rc) return rc; }
   const double hscale_prev = s->hscale;
@@ -310,6 +314,7 @@ int build_neighbours(sphb_sim* s, int mode, const double hor[2], const double ve
   k_make_grid<<<1, 32, 0, s->st>>>(s->stats, ntot, hor[0], hor[1], ver[0], ver[1], make_slabp(s), s->slab_on ? 1 : 0,
                                    s->gtune, s->grid, s->hacc, hscale_prev > 0.0 ? hscale_prev : 1.0, use_hacc ? 1 : 0);
   s->hacc_valid = periodic;  // the kNN below refills the accumulator
+  cudaMemsetAsync(s->qmax, 0, sizeof(uint32_t), s->st);  // max h of this evaluation
   if (mode == MODE_DRIFT) k_keys<true><<<cdiv(ntot, 256), 256, 0, s->st>>>(s->a.pos, s->a.vel, ntot, s->grid, dtH, s->keys, s->rank, s->cellCount);
   else k_keys<false><<<cdiv(ntot, 256), 256, 0, s->st>>>(s->a.pos, s->a.vel, ntot, s->grid, dtH, s->keys, s->rank, s->cellCount);
   if (timed) cudaEventRecord(s->ev[SPHB_PH_SORT], s->st);
@@ -365,7 +370,8 @@ int forces(sphb_sim* s, int mode, bool integrate) {
   }
   cudaEventRecord(s->ev[SPHB_PH_TOTAL], s->st);
   s->ev_valid = true;
-  if (s->hacc_valid) s->stats_dirty = true;  // sums / bounds are refreshed on demand (sphb_reduce, open axes, slabs)
+  s->qmax_valid = s->hacc_valid;
+  if (s->hacc_valid) s->stats_dirty = true;  // sums / bounds are refreshed on demand (sphb_reduce, open axes)
   else { rc = refresh_stats(s); if (rc) return rc; }
   CKL(s);
   return SPHB_OK;
@@ -411,6 +417,7 @@ int upload_common(sphb_sim* s, int64_t off, int64_t n, const double* pos_xy, con
   CK(s, cudaStreamSynchronize(s->st));  // host buffers are borrowed for the duration of the call only
   s->stats_dirty = true;
   s->hacc_valid = false;  // new particles: the mean smoothing length must come from a statistics pass
+  s->qmax_valid = false;
   s->have_list = false;
   return SPHB_OK;
 }
@@ -463,6 +470,8 @@ int create_common(const sphb_params* p, int64_t n, int64_t capacity, const doubl
   CKC(dalloc(s->failList, cap));
   CKC(dalloc(s->failCount, 2));
   CKC(dalloc(s->packCount, 2));
+  CKC(dalloc(s->qmax, 2));
+  CKC(cudaMemsetAsync(s->qmax, 0, 2 * sizeof(uint32_t), s->st));
   CKC(dalloc(s->hacc, 2 * HACC_N));
   CKC(cudaMemsetAsync(s->hacc, 0, 2 * HACC_N * sizeof(unsigned long long), s->st));
   CKC(dalloc(s->dflags, 1));
@@ -546,7 +555,7 @@ void sphb_destroy(sphb_sim* s) {
   cudaFree(s->spos); cudaFree(s->hguess);
   cudaFree(s->keys); cudaFree(s->keysSorted); cudaFree(s->rank); cudaFree(s->perm);
   cudaFree(s->cellCount); cudaFree(s->tileSum); cudaFree(s->cellStart); cudaFree(s->nn); cudaFree(s->failList); cudaFree(s->failCount);
-  cudaFree(s->packCount); cudaFree(s->hacc);
+  cudaFree(s->packCount); cudaFree(s->hacc); cudaFree(s->qmax);
   cudaFree(s->dflags); cudaFree(s->statPart); cudaFree(s->stats); cudaFree(s->grid); cudaFree(s->scratch);
   for (auto& ev : s->ev) if (ev) cudaEventDestroy(ev);
   if (s->st) cudaStreamDestroy(s->st);
@@ -818,6 +827,13 @@ int sphb_max_h(sphb_sim* s, double* out) {
   int rc = enter(s); if (rc) return rc;
   if (!out) return fail(s, SPHB_E_INVALID, "out is NULL");
   rc = check_async(s); if (rc) return rc;  // the slab driver calls this once per evaluation: surfaces GHOST_THIN etc.
+  if (s->qmax_valid) {
+    float q[2];
+    CK(s, cudaMemcpyAsync(q, s->qmax, sizeof q, cudaMemcpyDeviceToHost, s->st));
+    CK(s, cudaStreamSynchronize(s->st));
+    *out = (double)q[0];
+    return SPHB_OK;
+  }
   if (s->stats_dirty) { rc = refresh_stats(s); if (rc) return rc; }
   double st[STAT_N];
   CK(s, cudaMemcpyAsync(st, s->stats, sizeof st, cudaMemcpyDeviceToHost, s->st));
@@ -830,6 +846,13 @@ int sphb_max_speed(sphb_sim* s, double* out) {
   int rc = enter(s); if (rc) return rc;
   if (!out) return fail(s, SPHB_E_INVALID, "out is NULL");
   if (s->n == 0) { *out = 0.0; return SPHB_OK; }
+  if (s->qmax_valid) {
+    float q[2];
+    CK(s, cudaMemcpyAsync(q, s->qmax, sizeof q, cudaMemcpyDeviceToHost, s->st));
+    CK(s, cudaStreamSynchronize(s->st));
+    *out = std::sqrt((double)q[1]) * (1.0 + 1e-7);
+    return SPHB_OK;
+  }
   if (s->stats_dirty) { rc = refresh_stats(s); if (rc) return rc; }
   double st[STAT_N];
   CK(s, cudaMemcpyAsync(st, s->stats, sizeof st, cudaMemcpyDeviceToHost, s->st));

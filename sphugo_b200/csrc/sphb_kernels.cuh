@@ -382,6 +382,7 @@ struct KnnOut {
   // instead of a statistics pass over the state.  hscale = 0: disabled.
   unsigned long long* hacc;
   double hscale;
+  uint32_t* qmax;   // [0]: max h of the owned particles as float bits, rounded up (monotone for non-negative floats)
   double4* pc;      // {rho, c, h, P = c^2/(gamma rho)}
   uint32_t* nn;     // [tile][slot][lane], entry = index | image code << 28
   int* failList;
@@ -427,14 +428,16 @@ __device__ __forceinline__ void knn_append(uint32_t& kp, float d2f, uint32_t en,
 
 // warp-level contribution to the smoothing-length accumulator (all 32 lanes call): h * hscale < 2^24 per lane, so the
 // warp sum fits 32 bits and is one REDUX
-__device__ __forceinline__ void knn_accumulate_h(const KnnOut& out, bool ok, double h) {
+__device__ __forceinline__ void knn_accumulate_h(const KnnOut& out, bool ok, bool owned, double h) {
   if (out.hscale == 0.0) return;
   const unsigned q = __reduce_add_sync(0xffffffffu, ok ? (unsigned)__double2uint_rn(h * out.hscale) : 0u);
   const unsigned cnt = __popc(__ballot_sync(0xffffffffu, ok));
+  const unsigned hm = __reduce_max_sync(0xffffffffu, (ok && owned) ? __float_as_uint(__double2float_ru(h)) : 0u);
   if ((threadIdx.x & 31) == 0 && cnt) {
     unsigned long long* a = out.hacc + 2 * (blockIdx.x & (HACC_N - 1));
     atomicAdd(a, (unsigned long long)q);
     atomicAdd(a + 1, (unsigned long long)cnt);
+    if (hm) atomicMax(out.qmax, hm);
   }
 }
 
@@ -465,6 +468,7 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
   const int i = tile * 32 + lane;
   // queries: owned particles and (slab mode) inner ghosts; outer ghosts are candidates only
   const bool valid = i < n && (gflag == nullptr || gflag[i] != GF_OUTER);
+  const bool owned = i < n && (gflag == nullptr || gflag[i] == GF_OWNED);
 
   double xa = 0, ya = 0, rg = 0, ep = 0;
   int cxa = 0, cya = 0;
@@ -771,7 +775,7 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
         const float c = sqrtf((float)(ph.cfac * ep));
         out.pc[i] = make_double4((double)rho, (double)c, h, (double)(c * c / ((float)ph.gamma * rho)));
       }
-      knn_accumulate_h(out, ok, (double)(ok ? h2f * rsqrtf(fmaxf(h2f, 1e-37f)) : 0.0f));
+      knn_accumulate_h(out, ok, owned, (double)(ok ? h2f * rsqrtf(fmaxf(h2f, 1e-37f)) : 0.0f));
       continue;
     }
     // ---- fp64 build, exact phase: d^2 exactly as the reference computes it; the list entry goes to global
@@ -847,7 +851,7 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
       const double c = c2 > 0.0 ? fast_sqrt(c2, fast_rsqrt(c2)) : sqrt(c2);
       out.pc[i] = make_double4(rho, c, h, c * c * fast_rcp(ph.gamma * rho));
     }
-    knn_accumulate_h(out, ok, ok ? sqrt(h2) : 0.0);
+    knn_accumulate_h(out, ok, owned, ok ? sqrt(h2) : 0.0);
   }
 }
 
@@ -865,7 +869,7 @@ __global__ void __launch_bounds__(128) k_knn_fallback(const double2* __restrict_
                                                      const double* __restrict__ hguess,
                                                      const double* __restrict__ epred, int n,
                                                      const GridP* __restrict__ gp, PhysP ph, KnnOut out,
-                                                     uint32_t* __restrict__ dflags) {
+                                                     const uint8_t* __restrict__ gflag, uint32_t* __restrict__ dflags) {
   const GridP g = *gp;
   const int nfail = *out.failCount;
   if (blockIdx.x == 0 && threadIdx.x == 0) out.failCount[1] += nfail;  // cumulative, read by sphb_counters
@@ -970,6 +974,7 @@ __global__ void __launch_bounds__(128) k_knn_fallback(const double2* __restrict_
       unsigned long long* a = out.hacc + 2 * (blockIdx.x & (HACC_N - 1));
       atomicAdd(a, (unsigned long long)__double2uint_rn(h * out.hscale));
       atomicAdd(a + 1, 1ull);
+      if (gflag == nullptr || gflag[i] == GF_OWNED) atomicMax(out.qmax, __float_as_uint(__double2float_ru(h)));
     }
     if (lane == 0) {
       const double rho = ph.Fpref * ph.mass * acc / (h * h);
@@ -1032,6 +1037,7 @@ struct ForceIO {
   double2* vdot;
   double* edot;
   const uint8_t* gflag;  // slab mode: only owned particles are evaluated; ghosts are removed afterwards (k_fill_holes)
+  uint32_t* qmax;        // [1]: max |Vel|^2 of the evaluated particles after the kick, as float bits rounded up
 };
 
 // -------------------------------------------------------------------------------------------------
@@ -1390,6 +1396,10 @@ __device__ __forceinline__ void force_block(const ForceIO& io, int n, const Grid
     io.pos[i] = p;
     io.vel[i] = v;
     io.e[i] = e;
+    // max speed for the slab driver's migration schedule (whatever subset of the warp is converged here)
+    const unsigned m = __activemask();
+    const unsigned vm = __reduce_max_sync(m, __float_as_uint(__double2float_ru(v.x * v.x + v.y * v.y)));
+    if ((threadIdx.x & 31) == (__ffs(m) - 1)) atomicMax(io.qmax + 1, vm);
   }
 }
 

@@ -147,3 +147,22 @@ def test_reference_pruning_artefact_is_not_a_gpu_failure():
     assert artefacts > 0, "the reference artefact this test documents has disappeared"
     assert U.rel_err(sg["h"], se["h"]) <= 1e-12
     assert (sg["h"] <= sf["h"] * (1 + 1e-12)).all()  # exact kNN can only be tighter than the pruned walk
+
+
+def test_fp32_build_in_slab_mode():
+    """the fp32 build behind the slab protocol (ghosts, in-place ghost removal, migration) against the oracle"""
+    pos = gen.jittered_lattice(96, 96)
+    n = len(pos)
+    ic = dict(pos=pos, vel=np.tile([[1.5, -0.7]], (n, 1)), e=np.full(n, 0.01), id=np.arange(n, dtype=np.int64))
+    kw = dict(hor=(0.0, 1.0), ver=(0.0, 1.0), accel=(0.0, 0.2), dt_half=0.002)
+    po, pg = U.params_pair(**kw)
+    pg.precision = 32
+    topo = slab.Topology(3, [0.0, 0.35, 0.7, 1.0], True)
+    sim = slab.LocalSlabSim(pg, topo, ic["pos"], ic["vel"], ic["e"], ic["id"], h_max_hint=slab.default_h_hint(n, 1.0))
+    o = orc.Oracle(po, ic["pos"], ic["vel"], ic["e"], None, ic["id"])
+    for k in range(3):
+        sim.step(1)
+        o.step(1, knn_mode=1)
+        _compare(sim.state(FIELDS), o.state(neighbours=True), po, 1e-5 if k == 0 else 1e-4, f"fp32 slab step {k + 1}")
+    assert sum(sim.counts()) == n
+    sim.close(); o.close()
