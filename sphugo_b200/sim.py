@@ -15,6 +15,7 @@ Same names, argument meaning and error behaviour as the Go API that simviewer an
     p.FindNearestNeighboursPeriodic(root, hor, ver)  nearest-neighbour.go:28   Simulation.FindNearestNeighboursPeriodic(hor, ver)  (batch)
     Density2D(p, sim, kernel)        sph.go:306             Simulation.Density2D(kernel)                          (batch)
     sim.Root.Particles[i].{Pos,...}  core.go:17             Simulation.Particles()  (lazy, field-masked download)
+    (*Animator).CurrentFrame's per-particle arithmetic  animator.go:75-101   Simulation.FrameData()
 
 Reference panics become SimPanic (the Go shim re-panics); config errors stay ValueError.
 All numerics run in the CUDA library; this file only marshals SphConfig into sphb_params.
@@ -93,12 +94,12 @@ class SphConfig:  # config-parser.go:111-128
     Start: List[UniformRectSpawner] = dataclasses.field(default_factory=list)
     Viewport: Tuple[Tuple[float, float], Tuple[float, float]] = ((0.0, 0.0), (1.0, 1.0))
 
-    def to_params(self, device: int = 0) -> L.Params:
+    def to_params(self, device: int = 0, precision: int = 64) -> L.Params:
         r = self.Reflections
         return L.make_params(dt_half=self.DeltaTHalf, gamma=self.Gamma, particle_mass=self.ParticleMass,
                              accel=tuple(self.Acceleration), hor=tuple(self.HorPeriodicity),
                              ver=tuple(self.VertPeriodicity), refl=(r.L, r.R, r.U, r.D), kernel=self.Kernel.id,
-                             device=device)
+                             precision=precision, device=device)
 
 
 def MakeConfig() -> SphConfig:
@@ -246,6 +247,12 @@ class Simulation:
         """sim.Root.Particles as SoA numpy arrays: Pos, Vel, Rho, C, E, ..., NNDists[0] (= h); `nn_idx`, `nn_dist`,
         `nn_pos` fill NearestNeighbours / NNDists / NNPos on request only (descending distance, slot 0 = h)."""
         return self._call(self._h.state, tuple(fields), sort_by_id)
+
+    def FrameData(self, width: int = 1280, height: int = 720, by_id: bool = False) -> dict:
+        """what (*Animator).CurrentFrame derives per particle (animator.go:75-101), computed on the device: `xy`
+        float32 pixel coordinates, `colour` uint8 ramp index, `id` (Z; None with by_id, where element k belongs
+        to the particle with id k)"""
+        return self._call(self._h.frame, width, height, not by_id)
 
     def __len__(self):
         return self._h.n
