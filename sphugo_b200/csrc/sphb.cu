@@ -568,6 +568,7 @@ int sphb_set_params(sphb_sim* s, const sphb_params* p) {
   int rc = enter(s); if (rc) return rc;
   rc = check_params(s, p); if (rc) return rc;
   if (p->device != s->device) return fail(s, SPHB_E_INVALID, "device cannot change after create");
+  if (p->precision != s->prm.precision) return fail(s, SPHB_E_INVALID, "precision cannot change after create");
   s->prm = *p;
   return SPHB_OK;
 }

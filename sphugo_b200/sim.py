@@ -168,7 +168,8 @@ def MakeConfigFromText(text: str) -> SphConfig:
 class Simulation:
     """sim.Simulation (sph.go:14-21): Config is public and mutable; particle state lives on the GPU."""
 
-    def __init__(self, conf: SphConfig, particles: Optional[dict] = None, device: int = 0, capacity: Optional[int] = None):
+    def __init__(self, conf: SphConfig, particles: Optional[dict] = None, device: int = 0, capacity: Optional[int] = None,
+                 precision: int = 64):
         self.Config = conf
         self.device = device
         if particles is None:
@@ -180,7 +181,8 @@ class Simulation:
         n = len(particles["pos"])
         ids = particles.get("id", np.arange(n, dtype=np.int64))
         self._pushed = self._snapshot()
-        self._h = L.Handle(conf.to_params(device), particles["pos"], particles.get("vel"), particles.get("e"),
+        self.precision = precision  # 64: the reference's arithmetic; 32: the fp32 build (results within 1e-5)
+        self._h = L.Handle(conf.to_params(device, precision), particles["pos"], particles.get("vel"), particles.get("e"),
                            particles.get("rho"), ids, capacity=capacity or max(n, 1))
 
     # --- plumbing
@@ -193,7 +195,7 @@ class Simulation:
     def _push_config(self):
         snap = self._snapshot()
         if snap != self._pushed:  # sim.Config is a public field: callers edit it between steps
-            self._call(self._h.set_params, self.Config.to_params(self.device))
+            self._call(self._h.set_params, self.Config.to_params(self.device, self.precision))
             self._pushed = snap
 
     @staticmethod
