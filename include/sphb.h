@@ -100,7 +100,7 @@ enum { SPHB_SUM_E = 0, SPHB_SUM_RHO = 1, SPHB_LAST_VEL_NORM = 2 /* TotalMomentum
 /* phases reported by sphb_phase_times (milliseconds, CUDA events, last step) */
 enum {
   SPHB_PH_KEYS = 0,   /* drift-1 + cell keys                       (replaces Partition, core.go:126) */
-  SPHB_PH_SORT = 1,   /* radix sort of (key, index)                 (replaces Treebuild, core.go:172) */
+  SPHB_PH_SORT = 1,   /* counting sort by cell                      (replaces Treebuild, core.go:172) */
   SPHB_PH_REORDER = 2,/* SoA gather + predict + cell table                                         */
   SPHB_PH_KNN = 3,    /* kNN + density + sound speed (+ fallback)   (nearest-neighbour.go:28, sph.go:306,423) */
   SPHB_PH_FORCE = 4,  /* force + kick + drift-2 + boundaries        (sph.go:327, 122-193) */

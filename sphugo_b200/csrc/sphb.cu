@@ -458,7 +458,7 @@ int create_common(const sphb_params* p, int64_t n, int64_t capacity, const doubl
   CKC(dalloc(s->spos, cap));
   CKC(dalloc(s->hguess, cap));
   CKC(dalloc(s->keys, cap)); CKC(dalloc(s->keysSorted, cap)); CKC(dalloc(s->rank, cap)); CKC(dalloc(s->perm, cap));
-  // cell table: about 2 particles per cell at most; the radix sort covers ceil(log2(ncell)/8) digits
+  // cell table: about 2 particles per cell at most (the counting sort scans one counter per cell)
   int64_t ncm = std::max<int64_t>(64, std::min<int64_t>(capacity / 2 + 1, (int64_t)1 << 30));
   s->ncell_max = (int)ncm;
   s->ntiles_cap = cdiv(ncm + 1, SC_TILE);

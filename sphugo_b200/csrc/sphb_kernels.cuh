@@ -3,7 +3,7 @@
 // The hot path of bbeni/sphugo's (*Simulation).Step() (reference sim/sph.go:64-198), re-designed for a
 // B200: no tree, no per-particle priority queue in memory.  Pipeline per force evaluation
 //   K1 keys      drift-1 + uniform-cell key                 (replaces Partition      core.go:126-164)
-//   SORT         stable LSD radix sort of (key, index)      (replaces Treebuild      core.go:172-224)
+//   SORT         counting sort by cell (scan of the counts)  (replaces Treebuild      core.go:172-224)
 //   K2 reorder   SoA gather + predict + cell table          (replaces BoundingSpheres core.go:229-312)
 //   K3 knn       exact kNN(32) + density + sound speed      (nearest-neighbour.go:28-165, sph.go:306-323,423-429)
 //   K4 force     pressure + viscosity, kick, drift-2, walls (sph.go:327-401, 122-193)
