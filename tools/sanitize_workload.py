@@ -1,0 +1,33 @@
+#!/usr/bin/env python
+"""Small workload that touches every kernel of libsphb.so, for compute-sanitizer:
+
+  compute-sanitizer --tool memcheck  --error-exitcode 9 python tools/sanitize_workload.py
+  compute-sanitizer --tool racecheck --error-exitcode 9 python tools/sanitize_workload.py
+
+Both builds: non-uniform periodic box (group halving, force rows -2..+2, fallback), open box (statistics pass,
+clamped border cells), frame / neighbour-list download, and a 2-slab ring with migration (ghost packing, in-place
+ghost removal)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+
+from sphugo_b200 import _lib as L, gen, slab  # noqa: E402
+
+for prec in (64, 32):
+    pos = gen.shock_tube(6000)
+    g = L.Handle(L.make_params(hor=(0.0, 1.0), ver=(0.0, 1.0), dt_half=2e-3, precision=prec), pos, None, np.full(len(pos), 0.01))
+    g.step(2); g.sync(); g.frame(64, 64, ids=False); g.state(["pos", "rho", "nn_idx"]); g.close()
+    ic = gen.spawn([(1500, (0, 0), (1, 1))])
+    g = L.Handle(L.make_params(precision=prec, accel=(0.0, 0.2)), ic["pos"], None, ic["e"])
+    g.step(2); g.sync(); g.close()
+    pos = gen.jittered_lattice(96, 96)
+    n = len(pos)
+    pg = L.make_params(hor=(0.0, 1.0), ver=(0.0, 1.0), dt_half=0.002, precision=prec)
+    sim = slab.LocalSlabSim(pg, slab.Topology(2, [0.0, 0.5, 1.0], True), pos, np.tile([[3.0, 1.0]], (n, 1)), np.full(n, 0.01),
+                            h_max_hint=slab.default_h_hint(n, 1.0))
+    sim.step(3)
+    assert sum(sim.counts()) == n
+    sim.close()
+print("sanitizer workload done")
