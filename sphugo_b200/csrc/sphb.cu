@@ -55,6 +55,12 @@ struct sphb_sim {
   double* statPart = nullptr;
   double* stats = nullptr;    // STAT_N doubles
   GridP* grid = nullptr;
+  GridP* grid_next = nullptr;  // the next evaluation's grid, built right after the kNN of a fused step
+  bool grid_next_ready = false;
+  bool fuse_keys = false;      // the force launch in progress emits the next step's keys
+  bool keys_ready = false;     // keys / rank / cellCount already hold the next step's cell keys (force epilogue)
+  double keys_dtH = 0.0, next_hor[2] = {0, 0}, next_ver[2] = {0, 0};
+  int keys_n = 0;
   void* scratch = nullptr;    // download / upload staging
   size_t scratchBytes = 0;
   int ncell_max = 0;
@@ -192,6 +198,12 @@ int enter(sphb_sim* s) {
   return SPHB_OK;
 }
 
+// the force epilogue left the next step's cell counts in cellCount: forget them (the state changed under them)
+void drop_ready_keys(sphb_sim* s) {
+  if (s->keys_ready) cudaMemsetAsync(s->cellCount, 0, ((size_t)s->ntiles_cap * SC_TILE + 8) * sizeof(uint32_t), s->st);
+  s->keys_ready = false;
+}
+
 // ---- one force evaluation -----------------------------------------------------------------------
 enum { MODE_ASIS = 0, MODE_INIT = 1, MODE_DRIFT = 2 };
 
@@ -272,6 +284,8 @@ void launch_force(sphb_sim* s, int ntot, const PhysP& ph, bool integrate) {
   ForceIO io{};
   io.spos = s->spos; io.vpred = s->a.vpred; io.pc = s->a.pc; io.nn = s->nn;
   io.keys = s->keysSorted; io.cellStart = s->cellStart; io.qmax = s->qmax;
+  io.next_grid = s->fuse_keys ? s->grid_next : nullptr;
+  io.next_keys = s->keys; io.next_rank = s->rank; io.next_count = s->cellCount;
   if (integrate) cudaMemsetAsync(s->qmax + 1, 0, sizeof(uint32_t), s->st);  // max |v|^2 after this kick
   io.pos = s->a.pos; io.vel = s->a.vel; io.e = s->a.e; io.vdot = s->a.vdot; io.edot = s->a.edot;
   if (!s->slab_on) {
@@ -304,6 +318,11 @@ int build_neighbours(sphb_sim* s, int mode, const double hor[2], const double ve
   // comes from hor / ver / the slab edges, the mean smoothing length from the accumulator the previous kNN filled,
   // max h and max speed (slab driver) from qmax.
   const bool periodic = !axis_open(ver) && !axis_open(hor) && (!s->slab_on || (s->slab.has_left && s->slab.has_right));
+  // a fused step already built this evaluation's grid (and consumed the accumulator for it)
+  const bool same_box = s->grid_next_ready && periodic && !s->slab_on && hor[0] == s->next_hor[0] && hor[1] == s->next_hor[1] &&
+                        ver[0] == s->next_ver[0] && ver[1] == s->next_ver[1];
+  if (s->grid_next_ready && !same_box) s->hacc_valid = false;  // the accumulator went into a grid that does not apply
+  s->grid_next_ready = false;
   const bool use_hacc = periodic && s->hacc_valid;
   if (s->stats_dirty && !use_hacc) { int rc = refresh_stats(s); if (rc) return rc; }
   const double hscale_prev = s->hscale;
@@ -311,12 +330,18 @@ int build_neighbours(sphb_sim* s, int mode, const double hor[2], const double ve
   const PhysP ph = make_phys(s->prm, kernel);
   const double dtH = s->prm.dt_half;
   if (timed) cudaEventRecord(s->ev[SPHB_PH_KEYS], s->st);
-  k_make_grid<<<1, 32, 0, s->st>>>(s->stats, ntot, hor[0], hor[1], ver[0], ver[1], make_slabp(s), s->slab_on ? 1 : 0,
-                                   s->gtune, s->grid, s->hacc, hscale_prev > 0.0 ? hscale_prev : 1.0, use_hacc ? 1 : 0);
+  if (same_box) std::swap(s->grid, s->grid_next);
+  else k_make_grid<<<1, 32, 0, s->st>>>(s->stats, ntot, hor[0], hor[1], ver[0], ver[1], make_slabp(s), s->slab_on ? 1 : 0,
+                                        s->gtune, s->grid, s->hacc, hscale_prev > 0.0 ? hscale_prev : 1.0, use_hacc ? 1 : 0);
   s->hacc_valid = periodic;  // the kNN below refills the accumulator
   cudaMemsetAsync(s->qmax, 0, sizeof(uint32_t), s->st);  // max h of this evaluation
-  if (mode == MODE_DRIFT) k_keys<true><<<cdiv(ntot, 256), 256, 0, s->st>>>(s->a.pos, s->a.vel, ntot, s->grid, dtH, s->keys, s->rank, s->cellCount);
-  else k_keys<false><<<cdiv(ntot, 256), 256, 0, s->st>>>(s->a.pos, s->a.vel, ntot, s->grid, dtH, s->keys, s->rank, s->cellCount);
+  const bool keys_ok = same_box && s->keys_ready && mode == MODE_DRIFT && dtH == s->keys_dtH && ntot == s->keys_n;
+  if (keys_ok) s->keys_ready = false;  // consumed: the scan below zeroes cellCount again
+  else {
+    drop_ready_keys(s);
+    if (mode == MODE_DRIFT) k_keys<true><<<cdiv(ntot, 256), 256, 0, s->st>>>(s->a.pos, s->a.vel, ntot, s->grid, dtH, s->keys, s->rank, s->cellCount);
+    else k_keys<false><<<cdiv(ntot, 256), 256, 0, s->st>>>(s->a.pos, s->a.vel, ntot, s->grid, dtH, s->keys, s->rank, s->cellCount);
+  }
   if (timed) cudaEventRecord(s->ev[SPHB_PH_SORT], s->st);
   // counting sort: scan of the cell counts, then the permutation
   k_scan_tiles<<<s->ntiles_cap, SC_THREADS, 0, s->st>>>(s->cellCount, s->grid, s->tileSum);
@@ -360,9 +385,22 @@ int forces(sphb_sim* s, int mode, bool integrate) {
   const int ntot = (int)(s->n + s->nghost);
   const PhysP ph = make_phys(s->prm, s->prm.kernel);
   cudaEventRecord(s->ev[SPHB_PH_FORCE], s->st);
+  // Periodic single-handle steps: the next grid only depends on the mean h the kNN above produced, so it is built now
+  // and the force epilogue emits the next step's cell keys (no k_keys pass in the next step).
+  s->fuse_keys = integrate && !s->slab_on && s->hacc_valid && !axis_open(s->prm.hor) && !axis_open(s->prm.ver);
+  if (s->fuse_keys) {
+    k_make_grid<<<1, 32, 0, s->st>>>(s->stats, ntot, s->prm.hor[0], s->prm.hor[1], s->prm.ver[0], s->prm.ver[1], make_slabp(s), 0,
+                                     s->gtune, s->grid_next, s->hacc, s->hscale, 1);
+    s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 1;
+  }
   if (s->prm.kernel == 1) launch_force<1>(s, ntot, ph, integrate);
   else launch_force<2>(s, ntot, ph, integrate);
   s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 1;
+  if (s->fuse_keys) {
+    s->grid_next_ready = s->keys_ready = true;
+    s->keys_dtH = s->prm.dt_half; s->keys_n = ntot;
+    s->next_hor[0] = s->prm.hor[0]; s->next_hor[1] = s->prm.hor[1]; s->next_ver[0] = s->prm.ver[0]; s->next_ver[1] = s->prm.ver[1];
+  }
   if (s->slab_on) {  // drop the ghosts: the few owned particles sorted behind index n move into the ghosts' slots
     compact_in_place(s, ntot, (int)s->n);
     s->nghost = 0;
@@ -418,6 +456,8 @@ int upload_common(sphb_sim* s, int64_t off, int64_t n, const double* pos_xy, con
   s->stats_dirty = true;
   s->hacc_valid = false;  // new particles: the mean smoothing length must come from a statistics pass
   s->qmax_valid = false;
+  drop_ready_keys(s);
+  s->grid_next_ready = false;
   s->have_list = false;
   return SPHB_OK;
 }
@@ -478,6 +518,7 @@ int create_common(const sphb_params* p, int64_t n, int64_t capacity, const doubl
   CKC(dalloc(s->statPart, (size_t)STAT_BLOCKS * STAT_N));
   CKC(dalloc(s->stats, STAT_N));
   CKC(dalloc(s->grid, 1));
+  CKC(dalloc(s->grid_next, 1));
   for (auto& ev : s->ev) CKC(cudaEventCreate(&ev));
   CKC(cudaMemsetAsync(s->failCount, 0, 2 * sizeof(int), s->st));
   CKC(cudaMemsetAsync(s->dflags, 0, sizeof(uint32_t), s->st));
@@ -556,7 +597,7 @@ void sphb_destroy(sphb_sim* s) {
   cudaFree(s->keys); cudaFree(s->keysSorted); cudaFree(s->rank); cudaFree(s->perm);
   cudaFree(s->cellCount); cudaFree(s->tileSum); cudaFree(s->cellStart); cudaFree(s->nn); cudaFree(s->failList); cudaFree(s->failCount);
   cudaFree(s->packCount); cudaFree(s->hacc); cudaFree(s->qmax);
-  cudaFree(s->dflags); cudaFree(s->statPart); cudaFree(s->stats); cudaFree(s->grid); cudaFree(s->scratch);
+  cudaFree(s->dflags); cudaFree(s->statPart); cudaFree(s->stats); cudaFree(s->grid); cudaFree(s->grid_next); cudaFree(s->scratch);
   for (auto& ev : s->ev) if (ev) cudaEventDestroy(ev);
   if (s->st) cudaStreamDestroy(s->st);
   delete s;
@@ -743,6 +784,7 @@ int sphb_upload(sphb_sim* s, uint32_t mask, const void* const* hp, int64_t n) {
     CKL(s);
   }
   if (mask & SPHB_MASK(SPHB_F_POS)) s->have_list = false;  // the list describes the old positions; h stays a valid first guess
+  if (mask & (SPHB_MASK(SPHB_F_POS) | SPHB_MASK(SPHB_F_VEL))) drop_ready_keys(s);  // they were keys of the old state
   s->stats_dirty = true;
   CK(s, cudaStreamSynchronize(s->st));
   return SPHB_OK;
@@ -772,6 +814,7 @@ int sphb_upload_by_id(sphb_sim* s, uint32_t mask, const void* const* hp, int64_t
   s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 1;
   CKL(s);
   if (mask & SPHB_MASK(SPHB_F_POS)) s->have_list = false;
+  if (mask & (SPHB_MASK(SPHB_F_POS) | SPHB_MASK(SPHB_F_VEL))) drop_ready_keys(s);
   s->stats_dirty = true;
   CK(s, cudaStreamSynchronize(s->st));  // host buffers are borrowed for the duration of the call only
   return SPHB_OK;

@@ -63,11 +63,16 @@ struct KnnTune {
 // small helpers
 // -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double wrap_coord(double x, double lo, double L) {
-  // canonical image in [lo, lo+L); exact identity for lo <= x < lo+L
+  // canonical image in [lo, lo+L); exact identity for lo <= x < lo+L.  Step() keeps positions within one period of
+  // the box (sph.go:147-167), so the first three cases - no division - are the ones that run.
+  const double hi = lo + L;
+  if (x >= lo && x < hi) return x;
+  if (x < lo && x >= lo - L) { const double xs = __dadd_rn(x, L); return xs >= hi ? __dsub_rn(xs, L) : xs; }
+  if (x >= hi && x < hi + L) { const double xs = __dsub_rn(x, L); return xs < lo ? __dadd_rn(xs, L) : xs; }
   double w = floor((x - lo) / L);
-  double xs = (w == 0.0) ? x : __dsub_rn(x, __dmul_rn(w, L));
+  double xs = __dsub_rn(x, __dmul_rn(w, L));
   if (xs < lo) xs = __dadd_rn(xs, L);
-  else if (xs >= lo + L) xs = __dsub_rn(xs, L);
+  else if (xs >= hi) xs = __dsub_rn(xs, L);
   return xs;
 }
 
@@ -1038,6 +1043,11 @@ struct ForceIO {
   double* edot;
   const uint8_t* gflag;  // slab mode: only owned particles are evaluated; ghosts are removed afterwards (k_fill_holes)
   uint32_t* qmax;        // [1]: max |Vel|^2 of the evaluated particles after the kick, as float bits rounded up
+  // periodic single-handle steps: the cell keys of the NEXT step (drift-1 of the new state in the next grid, which is
+  // already known: it only depends on the mean h this evaluation's kNN produced) come out of the epilogue, so
+  // the next step needs no k_keys pass.  next_grid == nullptr: off.
+  const GridP* next_grid;
+  uint32_t *next_keys, *next_rank, *next_count;
 };
 
 // -------------------------------------------------------------------------------------------------
@@ -1396,6 +1406,14 @@ __device__ __forceinline__ void force_block(const ForceIO& io, int n, const Grid
     io.pos[i] = p;
     io.vel[i] = v;
     io.e[i] = e;
+    if (!SLAB && io.next_grid) {  // == k_keys<true> of the next step
+      const GridP gn = *io.next_grid;
+      const double xd = __dadd_rn(p.x, __dmul_rn(v.x, ph.dtH)), yd = __dadd_rn(p.y, __dmul_rn(v.y, ph.dtH));
+      const double xs = gn.wrapx ? wrap_coord(xd, gn.lox, gn.Lx) : xd, ys = gn.wrapy ? wrap_coord(yd, gn.loy, gn.Ly) : yd;
+      const uint32_t k = (uint32_t)cell_of(ys, gn.oy, gn.inv_dy, gn.ncy) * (uint32_t)gn.ncx + (uint32_t)cell_of(xs, gn.ox, gn.inv_dx, gn.ncx);
+      io.next_keys[i] = k;
+      io.next_rank[i] = atomicAdd(&io.next_count[k], 1u);
+    }
     // max speed for the slab driver's migration schedule (whatever subset of the warp is converged here)
     const unsigned m = __activemask();
     const unsigned vm = __reduce_max_sync(m, __float_as_uint(__double2float_ru(v.x * v.x + v.y * v.y)));
