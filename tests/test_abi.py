@@ -67,3 +67,16 @@ def test_sm100a_sass_only():
     from sphugo_b200 import build
     out = subprocess.run(["cuobjdump", "-lelf", build.build()], capture_output=True, text=True).stdout
     assert "sm_100a" in out and "sm_90" not in out
+
+
+def test_every_entry_point_is_mapped_in_integration_md():
+    """INTEGRATION.md names, for every declared entry point, the reference interface it replaces"""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [f for f in _declared() if f not in text]
+    assert not missing, missing
+
+
+def test_header_cites_the_reference_for_the_step_path():
+    src = open(os.path.join(ROOT, "include", "sphb.h")).read()
+    for cite in ("sph.go", "nearest-neighbour.go", "core.go", "config-parser.go", "animator.go"):
+        assert cite in src, cite
