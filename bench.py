@@ -382,6 +382,11 @@ def run_ours(args):
 
 
 def main():
+    # rank 0 prints exactly one JSON line on stdout: NCCL's own messages (version banner, warnings) go to stderr
+    # (NCCL_DEBUG=VERSION prints the banner with a bare printf to stdout; at WARN it goes through the debug file)
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
