@@ -556,14 +556,15 @@ int create_common(const sphb_params* p, int64_t n, int64_t capacity, const doubl
   return SPHB_OK;
 }
 
-// ids a permutation of 0..n-1?  (keys / packCount are free outside an evaluation)
+// ids a permutation of 0..n-1?  (perm / packCount are free outside an evaluation; keys / rank are not: after a fused
+// step they hold the next step's cell keys)
 int require_dense_ids(sphb_sim* s) {
   if (s->ids_dense < 0) {
     const int n = (int)s->n;
     int bad = 0;
-    CK(s, cudaMemsetAsync(s->keys, 0, (size_t)n * sizeof(uint32_t), s->st));
+    CK(s, cudaMemsetAsync(s->perm, 0, (size_t)n * sizeof(uint32_t), s->st));
     CK(s, cudaMemsetAsync(s->packCount, 0, sizeof(int), s->st));
-    k_check_dense<<<cdiv(n, 256), 256, 0, s->st>>>(s->a.id, n, s->keys, s->packCount);
+    k_check_dense<<<cdiv(n, 256), 256, 0, s->st>>>(s->a.id, n, s->perm, s->packCount);
     CKL(s);
     CK(s, cudaMemcpyAsync(&bad, s->packCount, sizeof(int), cudaMemcpyDeviceToHost, s->st));
     CK(s, cudaStreamSynchronize(s->st));

@@ -338,3 +338,32 @@ def test_shock_tube_density_contrast_steps():
     c = g.counters()
     assert c["knn_fallback"] < 0.05 * n * 4, c  # 4 evaluations; the first one guesses its radii from the cell counts
     g.close()
+
+
+def test_host_calls_between_steps_do_not_disturb_the_prepared_keys():
+    """after a periodic step the next step's cell keys are already on the device (force epilogue): read-only calls
+    in between (frame by id incl. its first-use dense-id check, reductions, downloads) must leave them intact, and
+    state-changing calls must discard them"""
+    pos = gen.jittered_lattice(64, 64)
+    n = len(pos)
+    kw = dict(hor=(0.0, 1.0), ver=(0.0, 1.0), accel=(0.0, 0.2), dt_half=0.002)
+    a = L.Handle(L.make_params(**kw), pos, None, np.full(n, 0.01))
+    b = L.Handle(L.make_params(**kw), pos, None, np.full(n, 0.01))
+    a.step(4)
+    for k in range(4):
+        b.step(1)
+        b.frame(320, 200, ids=False)        # first call runs the dense-id check
+        b.reduce(L.SUM_E); b.state(["pos", "nn_idx"])
+    sa, sb = a.state(), b.state()
+    for f in ("pos", "vel", "e", "rho", "h"):
+        assert np.array_equal(sa[f], sb[f]), f
+    # a parameter change (dt) and an upload invalidate the prepared keys
+    st = b.state(["pos", "vel", "e", "id"])
+    p2 = L.make_params(**dict(kw, dt_half=0.001))
+    a.set_params(p2); b.set_params(p2)
+    b.upload_by_id(pos=st["pos"], vel=st["vel"], e=st["e"])   # same values: only the bookkeeping differs
+    a.step(2); b.step(2)
+    sa, sb = a.state(), b.state()
+    for f in ("pos", "vel", "e", "rho", "h"):
+        assert np.array_equal(sa[f], sb[f]), f
+    a.close(); b.close()
