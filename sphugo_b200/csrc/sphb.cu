@@ -348,7 +348,7 @@ int build_neighbours(sphb_sim* s, int mode, const double hor[2], const double ve
   k_excl_scan<<<1, 1024, 0, s->st>>>(s->tileSum, s->ntiles_cap, s->grid);
   k_scan_apply<<<s->ntiles_cap, SC_THREADS, 0, s->st>>>(s->cellCount, s->grid, s->tileSum, s->cellStart);
   k_scatter_perm<<<cdiv(ntot, 256), 256, 0, s->st>>>(s->keys, s->rank, s->cellStart, ntot, s->perm);
-  s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 6;
+  s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 4 + (same_box ? 0 : 1) + (keys_ok ? 0 : 1);
   if (timed) cudaEventRecord(s->ev[SPHB_PH_REORDER], s->st);
   StateIn in{s->a.pos, s->a.vel, s->a.vdot, s->a.vpred, s->a.e, s->a.edot, s->a.epred, s->a.id, s->a.pc, s->a.ghost};
   StateOut out{s->b.pos, s->b.vel, s->b.vdot, s->b.vpred, s->b.e, s->b.edot, s->b.epred, s->b.id, s->b.pc, s->b.ghost, s->spos, s->hguess};
