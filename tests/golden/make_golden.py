@@ -61,7 +61,27 @@ def c2_example_config():
     save("c2_example_config", pos0=ic["pos"], id=ic["id"], **{f: st[f] for f in ("pos", "vel", "e", "rho", "h", "vdot", "edot")})
 
 
+def c3_c4_small():
+    """the two large BASELINE shapes at reduced N, exact-kNN mode (the GPU's contract): C3, a periodic
+    jittered lattice (64 x 64) drifting so that particles wrap, 3 steps; C4, a shock tube with a 4:1 number-density
+    contrast (8000 particles), 2 steps"""
+    pos = gen.jittered_lattice(64, 64)
+    n = len(pos)
+    vel = np.tile(np.array([[3.0, -2.0]]), (n, 1))
+    o = orc.Oracle(orc.make_params(hor=(0.0, 1.0), ver=(0.0, 1.0), accel=(0.0, 0.2), dt_half=0.001), pos, vel, np.full(n, 0.01))
+    o.step(3, 1)
+    st = o.state()
+    save("c3_small", pos0=pos, vel0=vel, **{f: st[f] for f in ("id", "pos", "vel", "e", "rho", "h")})
+    pos = gen.shock_tube(8000)
+    n = len(pos)
+    o = orc.Oracle(orc.make_params(hor=(0.0, 1.0), ver=(0.0, 1.0), dt_half=2e-3), pos, None, np.full(n, 0.01))
+    o.step(2, 1)
+    st = o.state()
+    save("c4_small", pos0=pos, **{f: st[f] for f in ("id", "pos", "vel", "e", "rho", "h")})
+
+
 if __name__ == "__main__":
     c1_density()
     c2_default()
     c2_example_config()
+    c3_c4_small()

@@ -367,3 +367,31 @@ def test_host_calls_between_steps_do_not_disturb_the_prepared_keys():
     for f in ("pos", "vel", "e", "rho", "h"):
         assert np.array_equal(sa[f], sb[f]), f
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("precision,tol", [(64, 1e-9), (32, 1e-4)])
+def test_golden_c3_c4_small(precision, tol):
+    """committed golden vectors of the two large BASELINE shapes at reduced N (tests/golden/make_golden.py), both
+    builds: fp64 to 1e-9 along the 2-3 step trajectory, fp32 to 1e-4 (ten times its one-step bar)"""
+    g = _golden("c3_small")
+    n = len(g["pos0"])
+    h = L.Handle(L.make_params(hor=(0.0, 1.0), ver=(0.0, 1.0), accel=(0.0, 0.2), dt_half=0.001, precision=precision),
+                 g["pos0"], g["vel0"], np.full(n, 0.01))
+    h.step(3)
+    st = h.state()
+    assert (st["id"] == g["id"]).all()
+    assert np.abs(st["pos"] - g["pos"]).max() <= tol
+    for f in ("vel", "e", "rho", "h"):
+        assert U.rel_err(st[f], g[f], np.abs(g[f]).max() * 1e-3) <= tol, ("c3", f)
+    h.close()
+    g = _golden("c4_small")
+    n = len(g["pos0"])
+    h = L.Handle(L.make_params(hor=(0.0, 1.0), ver=(0.0, 1.0), dt_half=2e-3, precision=precision), g["pos0"], None, np.full(n, 0.01))
+    h.step(2)
+    st = h.state()
+    assert np.abs(st["pos"] - g["pos"]).max() <= tol
+    for f in ("e", "rho", "h"):
+        assert U.rel_err(st[f], g[f], np.abs(g[f]).max() * 1e-3) <= tol, ("c4", f)
+    # velocities started at zero: measured against the largest one
+    assert np.abs(st["vel"] - g["vel"]).max() <= tol * np.abs(g["vel"]).max()
+    h.close()

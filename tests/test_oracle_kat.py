@@ -174,3 +174,18 @@ def test_golden_vectors_reproduce():
     o.knn(mode=1)  # the exact mode reproduces the faithful golden list
     s = o.state(neighbours=True)
     assert (np.sort(s["nn_id"], 1) == g["nn_id"]).all() and np.array_equal(s["h"], g["h"])
+
+
+def test_golden_c3_c4_small_reproduce():
+    """the reduced-size C3 / C4 fixtures are what the oracle (exact-kNN mode) produces today"""
+    import os
+    from sphugo_b200 import gen
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "c4_small.npz"))
+    pos = gen.shock_tube(8000)
+    assert np.array_equal(pos, g["pos0"])
+    o = orc.Oracle(orc.make_params(hor=(0.0, 1.0), ver=(0.0, 1.0), dt_half=2e-3), pos, None, np.full(len(pos), 0.01))
+    o.step(2, 1)
+    st = o.state()
+    for f in ("pos", "vel", "e", "rho", "h"):
+        assert np.array_equal(st[f], g[f]), f
+    o.close()
