@@ -226,10 +226,10 @@ void launch_knn_p(sphb_sim* s, int ntot, const PhysP& ph) {
   kt.cap = s->have_h ? s->ktune.cap : s->ktune.cap0;  // first evaluation: radius from a density estimate, wider spread
   kt.ncw = s->have_h ? s->ktune.ncw : s->ktune.ncw0;
   const size_t smem = (size_t)KNN_WARPS * knn_smem_bytes_per_warp(kt.cap, kt.ncw, F32);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[64] = {};  // function attributes are per device (one handle per GPU, maybe several per process)
+  if (!attr_done[s->device & 63]) {
     cudaFuncSetAttribute(k_knn_tile<KERNEL, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_done = true;
+    attr_done[s->device & 63] = true;
   }
   k_knn_tile<KERNEL, F32><<<cdiv(tiles, KNN_WARPS), KNN_THREADS, smem, s->st>>>(s->spos, s->keysSorted, s->cellStart,
                                                                               s->hguess, s->a.epred, ntot, s->grid, ph, kt, out,
@@ -260,11 +260,11 @@ SlabP make_slabp(const sphb_sim* s) {
 template <int KERNEL, bool INTEGRATE, bool SLAB, typename R>
 void launch_force_st(sphb_sim* s, const ForceIO& io, int ntot, const PhysP& ph) {
   constexpr bool F32 = sizeof(R) == 4;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[64] = {};  // per device
+  if (!attr_done[s->device & 63]) {
     if (F32) cudaFuncSetAttribute(k_force_st32<KERNEL, INTEGRATE, SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     else cudaFuncSetAttribute(k_force_st<KERNEL, INTEGRATE, SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_done = true;
+    attr_done[s->device & 63] = true;
   }
   const int nrec = s->force_nrec;
   const size_t smem = (size_t)nrec * 8 * sizeof(R);  // four arrays of two reals per staged record
