@@ -86,8 +86,9 @@ enum {
   SPHB_F_VPRED = 8,  /* double[2n]  Particle.VPred          */
   SPHB_F_H = 9,      /* double[n]   Particle.NNDists[0]     */
   SPHB_F_ID = 10,    /* int64[n]    Particle.Z              */
-  SPHB_F_NN_IDX = 11,/* int32[32n]  index (current device order) of Particle.NearestNeighbours[k];
-                                     slot order is ascending index, NOT the reference's descending distance */
+  SPHB_F_NN_IDX = 11,/* int32[32n]  index (current device order) of Particle.NearestNeighbours[k], -1 = none; slots in
+                                     the reference's order: descending distance, slot 0 = farthest = h
+                                     (nearest-neighbour.go:139-153) */
   SPHB_F_NN_DIST = 12,/* double[32n] Particle.NNDists[k] for the same slots */
   SPHB_F_NN_POS = 13, /* double[64n] Particle.NNPos[k] (neighbour image position in the query frame) */
   SPHB_F_COUNT = 14
