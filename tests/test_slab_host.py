@@ -99,6 +99,9 @@ def _worker(rank, world, port, q):
         ok = (kl == len(exp_l) and kr == len(exp_r) and np.array_equal(rl[:kl, :2].numpy(), exp_l)
               and np.array_equal(rr[:kr, :2].numpy(), exp_r) and (rl[:kl, 5] == L).all() and (rr[:kr, 5] == R).all())
         hm = ex.allreduce_max(float(rank + 1))
+        # the per-evaluation all-reduce of the slab driver: (max h, max speed) in one call
+        h2, v2 = ex.allreduce_max(0.01 * (rank + 1), 5.0 - rank)
+        ok = ok and h2 == 0.01 * world and v2 == 5.0
         q.put((rank, bool(ok), kl, kr, hm))
     finally:
         dist.destroy_process_group()
