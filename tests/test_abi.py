@@ -80,3 +80,18 @@ def test_header_cites_the_reference_for_the_step_path():
     src = open(os.path.join(ROOT, "include", "sphb.h")).read()
     for cite in ("sph.go", "nearest-neighbour.go", "core.go", "config-parser.go", "animator.go"):
         assert cite in src, cite
+
+
+def test_header_is_plain_c_and_a_c_client_links():
+    """include/sphb.h compiles as C99 and a C program (tests/c/abi_smoke.c, what cgo would build) links against
+    libsphb.so; on a box without a GPU it must see SPHB_E_CUDA from sphb_create, with a GPU one step must run"""
+    from sphugo_b200 import build
+    so = build.build()
+    inc = os.path.join(ROOT, "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", os.path.join(inc, "sphb.h")], check=True)
+    exe = os.path.join(ROOT, "tests", "c", "abi_smoke")
+    libdir = os.path.dirname(so)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", inc, os.path.join(ROOT, "tests", "c", "abi_smoke.c"),
+                    "-L", libdir, "-lsphb", "-Wl,-rpath," + libdir, "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
