@@ -1,0 +1,38 @@
+// C++ client of include/sphb_sim.hpp (the compiled-language mirror of the Go `sim` step API).  Without a GPU the
+// constructor must throw sim::Panic with SPHB_E_CUDA; with one, the speed-test shape (examples/speed-test/
+// speed-test.go:22-43 at reduced N) steps and conserves what it should.  Exit code 0 = behaved as specified.
+#include <cmath>
+#include <cstdio>
+#include "sphb_sim.hpp"
+
+int main() {
+  const int nx = 48;
+  std::vector<double> pos, e(nx * nx, 0.01);
+  uint64_t s = 12345678;  // splitmix64 jitter, like sphugo_b200/gen.py
+  auto next = [&]() { s += 0x9E3779B97F4A7C15ull; uint64_t z = s; z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return ((z ^ (z >> 31)) >> 11) * (1.0 / 9007199254740992.0); };
+  for (int j = 0; j < nx; ++j)
+    for (int i = 0; i < nx; ++i) { pos.push_back((i + 0.5 + 0.5 * (next() - 0.5)) / nx); pos.push_back((j + 0.5 + 0.5 * (next() - 0.5)) / nx); }
+  sim::SphConfig conf = sim::MakeConfig();
+  conf.HorPeriodicity[0] = 0; conf.HorPeriodicity[1] = 1; conf.VertPeriodicity[0] = 0; conf.VertPeriodicity[1] = 1;
+  conf.Acceleration = {0, 0.2};
+  conf.DeltaTHalf = 0.002;
+  try {
+    sim::Simulation simu = sim::MakeSimulationFromParticles(conf, pos, {}, e);
+    const double e0 = 0.01 * nx * nx;
+    for (int k = 0; k < 5; ++k) simu.Step();
+    const double e5 = simu.TotalEnergy();
+    auto ps = simu.Particles();
+    double rho = 0;
+    for (auto& p : ps) rho += p.Rho;
+    std::printf("gpu path: %lld particles, step %d, sum E %.12g (start %.12g), mean rho %.6g\n", (long long)simu.Len(), simu.CurrentStep,
+                e5, e0, rho / ps.size());
+    // a near-uniform box: the thermal energy barely moves in 5 steps, the mean density is N m within a few percent
+    if (!(std::fabs(e5 - e0) < 1e-2 * e0) || !(std::fabs(rho / ps.size() - nx * nx) < 0.1 * nx * nx) || ps.size() != (size_t)nx * nx) return 2;
+    bool thrown = false;
+    try { simu.Density2D(sim::Kernel::TopHat2D); simu.Config.kernel = sim::Kernel::TopHat2D; simu.Step(); } catch (const sim::Panic& p) { thrown = p.code == SPHB_E_KERNEL; }
+    return thrown ? 0 : 3;  // TopHat2D.DF panics in the reference (sph.go:251-253)
+  } catch (const sim::Panic& p) {
+    std::printf("no device: Panic(%d): %s\n", p.code, p.what());
+    return p.code == SPHB_E_CUDA ? 0 : 1;
+  }
+}

@@ -95,3 +95,16 @@ def test_header_is_plain_c_and_a_c_client_links():
                     "-L", libdir, "-lsphb", "-Wl,-rpath," + libdir, "-o", exe], check=True)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_cxx_mirror_of_the_sim_api_compiles_and_behaves():
+    """include/sphb_sim.hpp (C++ mirror of the Go `sim` step API) builds with g++ against libsphb.so; without a GPU
+    its constructor throws Panic(SPHB_E_CUDA), with one it steps the speed-test shape (tests/c/sim_smoke.cpp)"""
+    from sphugo_b200 import build
+    so = build.build()
+    inc, libdir = os.path.join(ROOT, "include"), os.path.dirname(so)
+    exe = os.path.join(ROOT, "tests", "c", "sim_smoke")
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-O1", "-I", inc, os.path.join(ROOT, "tests", "c", "sim_smoke.cpp"),
+                    "-L", libdir, "-lsphb", "-Wl,-rpath," + libdir, "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
