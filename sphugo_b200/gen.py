@@ -1,8 +1,9 @@
 """Synthetic initial conditions.
 
-The reference draws its particles from Go's math/rand (config-parser.go:58-80), whose lagged-Fibonacci
-seed table is not available here; initial conditions therefore always cross the boundary as explicit
-arrays and are generated by this documented generator instead:
+The reference draws its particles from Go's math/rand (config-parser.go:58-80); gorand.py reconstructs that
+stream bit for bit and the mirrored spawners of sim.py use it.  The benchmark workloads and most parity cases
+(large N, lattices, shock tubes: shapes the reference has no generator for) use this documented, vectorised
+generator instead; initial conditions always cross the boundary as explicit arrays either way:
 
     splitmix64, state0 = seed;  u = (next() >> 11) * 2**-53  in [0, 1)
 

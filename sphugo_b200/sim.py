@@ -30,6 +30,7 @@ import numpy as np
 
 from . import _lib as L
 from . import gen
+from . import gorand
 
 MaxFloat64 = 1.7976931348623157e308
 
@@ -69,10 +70,10 @@ class UniformRectSpawner:  # config-parser.go:37-41
     NParticles: int = 1000
 
     def Spawn(self, t: float = 0.0, seed: int = gen.DEFAULT_SEED):
-        """positions (x then y per particle), E = 0.01, everything else zero (config-parser.go:58-80).  The
-        uniform stream is splitmix64 (gen.py), not Go's math/rand: see DESIGN.md 'inputs'."""
-        pos = gen.uniform_rect(self.NParticles, self.UpperLeft, self.LowerRight, seed)
-        return dict(pos=pos, vel=np.zeros_like(pos), e=np.full(self.NParticles, 0.01))
+        """positions (x then y per particle), then Z per particle; E = 0.01, everything else zero
+        (config-parser.go:58-80).  The stream is Go's math/rand after rand.Seed(12345678), reconstructed bit for
+        bit in gorand.py, so the particles are the ones the Go binary spawns."""
+        return gorand.uniform_rect_spawn(self.NParticles, self.UpperLeft, self.LowerRight, seed)
 
 
 def MakeUniformRectSpawner() -> UniformRectSpawner:
@@ -179,7 +180,10 @@ class Simulation:
             else:
                 particles = dict(pos=np.zeros((0, 2)), vel=np.zeros((0, 2)), e=np.zeros(0))
         n = len(particles["pos"])
+        # the device id is the spawn index (dense, so the by-id transfers work); Particle.Z (core.go:41, a random
+        # 63-bit draw that two spawners can repeat because each re-seeds) is kept on the host: Z[id]
         ids = particles.get("id", np.arange(n, dtype=np.int64))
+        self.Z = particles.get("z")
         self._pushed = self._snapshot()
         self.precision = precision  # 64: the reference's arithmetic; 32: the fp32 build (results within 1e-5)
         self._h = L.Handle(conf.to_params(device, precision), particles["pos"], particles.get("vel"), particles.get("e"),

@@ -15,7 +15,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from oracle import oracle as orc  # noqa: E402
-from sphugo_b200 import gen  # noqa: E402
+from sphugo_b200 import gen, gorand  # noqa: E402
 
 
 def save(name, **arrs):
@@ -80,8 +80,38 @@ def c3_c4_small():
     save("c4_small", pos0=pos, **{f: st[f] for f in ("id", "pos", "vel", "e", "rho", "h")})
 
 
+def go_scenes():
+    """the same two scenes with the particles the Go binary itself spawns: Go's math/rand after rand.Seed(12345678)
+    (config-parser.go:60-64), reconstructed in sphugo_b200/gorand.py.  `z` is Particle.Z; ids are spawn indices."""
+    a, b = gorand.uniform_rect_spawn(1000), gorand.uniform_rect_spawn(200, (0.1, 0.0), (0.3, 0.4))  # density.go:50-63
+    pos, z = np.concatenate([a["pos"], b["pos"]]), np.concatenate([a["z"], b["z"]])
+    o = orc.Oracle(orc.make_params(hor=(0, 1), ver=(0, 1)), pos)
+    o.knn((0.0, 1.0), (0.0, 1.0), mode=0)
+    st = o.state(neighbours=True)
+    rho = []
+    for k in (0, 1, 2):
+        o.density(k)
+        rho.append(o.state()["rho"])
+    save("c1_density_go", pos=st["pos"], id=st["id"], z=z, h=st["h"], nn_id=np.sort(st["nn_id"], 1).astype(np.int32),
+         rho_tophat=rho[0], rho_monaghan=rho[1], rho_wendland=rho[2])
+    ic = gorand.uniform_rect_spawn(1000)  # sim.MakeSimulation(), sph.go:23-30
+    o = orc.Oracle(orc.make_params(), ic["pos"], ic["vel"], ic["e"])
+    out = dict(pos0=ic["pos"], z=ic["z"])
+    for steps in (1, 5):
+        o.step(steps - o.current_step)
+        st = o.state()
+        for f in ("pos", "vel", "e", "rho", "h", "vdot", "edot"):
+            out[f"{f}_{steps}"] = st[f]
+    out["id"] = st["id"]
+    save("c2_default_go", **out)
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["go"]:
+        go_scenes()
+        sys.exit(0)
     c1_density()
     c2_default()
     c2_example_config()
     c3_c4_small()
+    go_scenes()

@@ -1,0 +1,100 @@
+"""Known answers for the reconstruction of Go's math/rand (sphugo_b200/gorand.py): the values Go's own documentation,
+rng.go and the Go playground show for the Go 1 source.  The reference seeds it explicitly before every spawn
+(config-parser.go:60-64, core.go:78-80), so these pin the reference's initial conditions."""
+import numpy as np
+
+from sphugo_b200 import gorand
+
+
+def _s64(u):
+    return u - (1 << 64) if u >> 63 else u
+
+
+def test_cooked_table_head_and_tail():
+    c = gorand.rng_cooked()
+    assert len(c) == 607
+    assert _s64(c[0]) == -4181792142133755926 and _s64(c[1]) == -4576982950128230565  # first entries of rngCooked in rng.go
+    assert c[-1] == 4152330101494654406
+
+
+def test_jump_ahead_equals_stepping():
+    vec = gorand._lcg_fill(1, 20, 10)
+    n = 3000
+    v, tap, feed = list(vec), 0, gorand.RNG_LEN - gorand.RNG_TAP
+    for _ in range(n):  # Go's rngSource.Uint64, literally
+        tap = (tap - 1) % gorand.RNG_LEN
+        feed = (feed - 1) % gorand.RNG_LEN
+        v[feed] = (v[feed] + v[tap]) & ((1 << 64) - 1)
+    assert gorand._advance_state(vec, n) == v
+
+
+def test_seed_1_known_answers():
+    r = gorand.Rand(1)
+    assert [r.Int() for _ in range(10)] == [5577006791947779410, 8674665223082153551, 6129484611666145821, 4037200794235010051,
+                                            3916589616287113937, 6334824724549167320, 605394647632969758, 1443635317331776148,
+                                            894385949183117216, 2775422040480279449]
+    r = gorand.Rand(1)
+    assert [r.Float64() for _ in range(5)] == [0.6046602879796196, 0.9405090880450124, 0.6645600532184904, 0.4377141871869802,
+                                               0.4246374970712657]
+    r = gorand.Rand(1)
+    assert [r.Intn(100) for _ in range(10)] == [81, 87, 47, 59, 81, 18, 25, 40, 56, 0]
+
+
+def test_vector_forms_follow_the_scalar_stream():
+    a, b = gorand.Rand(12345678), gorand.Rand(12345678)
+    f = a.Float64s(5000)
+    z = a.Ints(3000)
+    assert [b.Float64() for _ in range(5000)] == list(f)
+    assert [b.Int() for _ in range(3000)] == list(z)
+    assert 0.0 <= f.min() and f.max() < 1.0
+
+
+def test_spawner_streams():
+    """every Spawn re-seeds (config-parser.go:60-64): two rectangles share their uniforms; Z follows the positions"""
+    a = gorand.uniform_rect_spawn(1000)
+    b = gorand.uniform_rect_spawn(200, (0.1, 0.0), (0.3, 0.4))  # density.go:56-60
+    u = (b["pos"] - [0.1, 0.0]) / [0.2, 0.4]
+    assert np.allclose(u, a["pos"][:200], rtol=0, atol=1e-15)
+    r = gorand.Rand(12345678)
+    r.Float64s(2000)
+    assert list(a["z"][:3]) == [r.Int() for _ in range(3)]
+    assert len(set(a["z"].tolist())) == 1000
+    c = gorand.init_uniformly(60)  # bounding-sphere_test.go:41-46 shape
+    r = gorand.Rand(12345678)
+    assert list(c["pos"][0]) == list(r.Float64s(4)[2:])
+
+
+def _golden(name):
+    import os
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+
+
+def test_go_scene_fixtures_are_the_go_streams_and_the_oracle_reproduces_them():
+    """tests/golden/c1_density_go.npz, c2_default_go.npz (make_golden.py go_scenes): inputs = what the Go binary spawns,
+    outputs = the oracle's; cross-checked against scipy's periodic cKDTree"""
+    from oracle import oracle as orc
+    from scipy.spatial import cKDTree
+    g = _golden("c2_default_go")
+    ic = gorand.uniform_rect_spawn(1000)
+    assert np.array_equal(ic["pos"], g["pos0"]) and np.array_equal(ic["z"], g["z"])
+    assert g["pos0"][0, 0] == gorand.Rand(12345678).Float64()
+    o = orc.Oracle(orc.make_params(), g["pos0"], None, np.full(1000, 0.01))
+    o.step(1)
+    s = o.state()
+    for f in ("pos", "vel", "e", "rho", "h", "vdot", "edot"):
+        assert np.array_equal(s[f], g[f + "_1"]), f
+    o.close()
+    g = _golden("c1_density_go")
+    o = orc.Oracle(orc.make_params(hor=(0, 1), ver=(0, 1)), g["pos"])
+    o.knn(mode=1)
+    s = o.state(neighbours=True)
+    assert (np.sort(s["nn_id"], 1) == g["nn_id"]).all() and np.array_equal(s["h"], g["h"])
+    d, j = cKDTree(g["pos"], boxsize=1.0).query(g["pos"], k=33)
+    assert (np.sort(j[:, 1:], 1) == g["nn_id"]).all() and np.allclose(d[:, -1], g["h"], rtol=1e-12, atol=0)
+    o.close()
+
+
+def test_python_spawners_use_the_go_stream():
+    from sphugo_b200 import sim
+    sp = sim.MakeUniformRectSpawner().Spawn(0)
+    assert np.array_equal(sp["pos"], _golden("c2_default_go")["pos0"]) and sp["z"].dtype == np.int64

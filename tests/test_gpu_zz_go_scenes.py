@@ -1,0 +1,51 @@
+"""-m gpu: the reference's two small scenes with the particles the Go binary itself spawns (Go's math/rand stream,
+sphugo_b200/gorand.py), through the mirrored `sim` API, against the committed golden vectors and the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import util as U
+from sphugo_b200 import sim
+
+pytestmark = pytest.mark.gpu
+
+
+def _golden(name):
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+
+
+def test_make_simulation_default_scene():
+    """sim.MakeSimulation() (sph.go:23-30): 1000 particles of the Go stream, MakeConfig defaults; 1 and 5 steps"""
+    g = _golden("c2_default_go")
+    s = sim.MakeSimulation()
+    assert len(s) == 1000 and np.array_equal(s.Z, g["z"])
+    p0 = s.Particles(("pos", "id"))
+    assert np.array_equal(p0["pos"], g["pos0"])
+    for steps, tol in ((1, U.TOL64), (5, 1e-9)):
+        while s.CurrentStep < steps:
+            s.Step()
+        st = s.Particles(("pos", "vel", "e", "rho", "h", "id"))
+        assert np.array_equal(st["id"], g["id"])
+        for f in ("pos", "vel", "e", "rho", "h"):
+            ref = g[f"{f}_{steps}"]
+            assert U.rel_err(st[f], ref, np.abs(ref).max() * 1e-3) <= tol, (f, steps)
+    s.Close()
+
+
+def test_density_example_scene():
+    """examples/density main (density.go:41-97) on the Go stream: kNN sets, h, three densities"""
+    g = _golden("c1_density_go")
+    conf = sim.MakeConfig()
+    conf.Start = [sim.UniformRectSpawner((0.0, 0.0), (1.0, 1.0), 1000), sim.UniformRectSpawner((0.1, 0.0), (0.3, 0.4), 200)]
+    s = sim.MakeSimulationFromConf(conf)
+    assert np.array_equal(s.Z, g["z"])
+    s.FindNearestNeighboursPeriodic((0.0, 1.0), (0.0, 1.0))
+    st = s.Particles(("pos", "h", "id", "nn_idx", "nn_dist", "nn_pos"))
+    assert np.array_equal(st["pos"], g["pos"])
+    assert (np.sort(st["nn_id"], 1) == g["nn_id"]).all()
+    assert U.rel_err(st["h"], g["h"]) <= U.TOL64
+    for k, name in ((sim.TopHat2D, "rho_tophat"), (sim.Monahan2D, "rho_monaghan"), (sim.Wendtland2D, "rho_wendland")):
+        s.Density2D(k)
+        assert U.rel_err(s.Particles(("rho",))["rho"], g[name]) <= U.TOL64, name
+    s.Close()

@@ -66,8 +66,9 @@ def test_sph_config_text():
 def test_simulation_api_against_oracle():
     from oracle import oracle as orc
     from tests import util as U
+    from sphugo_b200 import gen
     conf = sim.MakeConfigFromText(EXAMPLE)
-    s = sim.MakeSimulationFromConf(conf)
+    s = sim.Simulation(conf, gen.spawn([(sp.NParticles, sp.UpperLeft, sp.LowerRight) for sp in conf.Start]))
     assert len(s) == 960
     p0 = s.Particles(("pos", "vel", "e", "id"))
     kw = dict(gamma=4.666, particle_mass=1e6, accel=(0.0, 0.55), dt_half=0.00324, kernel=2, hor=(0.2, 0.8),
