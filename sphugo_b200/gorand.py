@@ -190,9 +190,14 @@ class Rand:
         return out
 
 
-def uniform_rect_spawn(n: int, upper_left=(0.0, 0.0), lower_right=(1.0, 1.0), seed: int = 12345678):
-    """UniformRectSpawner.Spawn (config-parser.go:58-80): re-seed, n x (x, y) positions, then n Z values; E = 0.01"""
-    r = Rand(seed)
+def uniform_rect_spawn(n: int, upper_left=(0.0, 0.0), lower_right=(1.0, 1.0), seed: int = 12345678, rand: "Rand" = None):
+    """UniformRectSpawner.Spawn (config-parser.go:58-80): re-seed, n x (x, y) positions, then n Z values; E = 0.01.
+    `rand`: the stream to re-seed and draw from (Go's spawners share the package-level source)"""
+    if rand is None:
+        r = Rand(seed)
+    else:
+        r = rand
+        r.Seed(seed)
     u = r.Float64s(2 * n).reshape(n, 2)
     ul, lr = np.asarray(upper_left, float), np.asarray(lower_right, float)
     pos = ul + u * (lr - ul)  # UpperLeft.X + rand.Float64()*(LowerRight.X-UpperLeft.X)

@@ -73,11 +73,32 @@ class UniformRectSpawner:  # config-parser.go:37-41
         """positions (x then y per particle), then Z per particle; E = 0.01, everything else zero
         (config-parser.go:58-80).  The stream is Go's math/rand after rand.Seed(12345678), reconstructed bit for
         bit in gorand.py, so the particles are the ones the Go binary spawns."""
-        return gorand.uniform_rect_spawn(self.NParticles, self.UpperLeft, self.LowerRight, seed)
+        return gorand.uniform_rect_spawn(self.NParticles, self.UpperLeft, self.LowerRight, seed, rand=GlobalRand)
 
 
 def MakeUniformRectSpawner() -> UniformRectSpawner:
     return UniformRectSpawner()
+
+
+# the package-level math/rand source every spawner draws from.  A Go >= 1.20 process that never calls rand.Seed starts
+# it from a random seed; every scene of the reference seeds it (each UniformRectSpawner.Spawn does), so it only matters
+# for a config with sources and no Start rectangle: seed 1 (Go's documented pre-1.20 default) is used then.
+GlobalRand = gorand.Rand(1)
+
+
+@dataclasses.dataclass
+class PointSource:  # config-parser.go:43-47
+    origin: Tuple[float, float] = (0.0, 0.0)
+    rate: float = 1.0
+    LastSpwned: float = 0.0
+
+    def Spawn(self, t: float):
+        """n = int((t - LastSpwned) * rate) particles jittered by +-0.01 around origin, Rho = 100, E = 0.002, drawn
+        from the running package-level stream without re-seeding (config-parser.go:82-102)"""
+        cooldown = 1 / self.rate
+        n = int((t - self.LastSpwned) / cooldown)
+        self.LastSpwned += float(n) * cooldown
+        return gorand.point_source_spawn(GlobalRand, n, self.origin)
 
 
 @dataclasses.dataclass
@@ -113,6 +134,7 @@ def MakeConfigFromText(text: str) -> SphConfig:
     conf = MakeConfig()
     title = sub = None
     pending = {}
+    src_pending = {}
 
     def flush_rect():
         nonlocal pending
@@ -158,11 +180,16 @@ def MakeConfigFromText(text: str) -> SphConfig:
             pending[name] = num[0] if name == "NParticles" else (num[0], num[1])
             if len(pending) == 3:
                 flush_rect()
-        elif title == "Sources":
-            raise ValueError(f"line {ln}: point sources are not supported by this reader")
+        elif title == "Sources" and sub == "Point" and name in ("Pos", "Rate"):  # config-parser.go:384-423: a Pos/Rate pair
+            src_pending[name] = (num[0], num[1]) if name == "Pos" else num[0]
+            if len(src_pending) == 2:
+                conf.Sources.append(PointSource(origin=src_pending["Pos"], rate=src_pending["Rate"]))
+                src_pending.clear()
         else:
             raise ValueError(f"line {ln}: unknown parameter {key}")
     flush_rect()
+    if src_pending:
+        raise ValueError(f"[Point] needs both Pos and Rate; got {sorted(src_pending)}")
     return conf
 
 
@@ -186,8 +213,10 @@ class Simulation:
         self.Z = particles.get("z")
         self._pushed = self._snapshot()
         self.precision = precision  # 64: the reference's arithmetic; 32: the fp32 build (results within 1e-5)
+        if capacity is None:  # sph.go:45 reserves 100000 more particles for the sources
+            capacity = max(n, 1) + (100000 if conf.Sources else 0)
         self._h = L.Handle(conf.to_params(device, precision), particles["pos"], particles.get("vel"), particles.get("e"),
-                           particles.get("rho"), ids, capacity=capacity or max(n, 1))
+                           particles.get("rho"), ids, capacity=capacity)
 
     # --- plumbing
     def _snapshot(self):
@@ -216,11 +245,31 @@ class Simulation:
     def CurrentStep(self) -> int:
         return self._h.current_step
 
+    def _spawn_sources(self):
+        """sph.go:72-86: every source spawns at t = CurrentStep * dtHalf * 2; the new particles join the state (the
+        reference re-makes its tree; here the next evaluation sorts them in).  Ids continue the spawn index."""
+        t = float(self.CurrentStep) * self.Config.DeltaTHalf * 2
+        for src in self.Config.Sources:
+            new = src.Spawn(t)
+            k = len(new["pos"])
+            if k:
+                n = len(self)
+                self._call(self._h.append, new["pos"], new["vel"], new["e"], new.get("rho"), np.arange(n, n + k, dtype=np.int64))
+                if self.Z is not None:
+                    self.Z = np.concatenate([self.Z, new["z"]])
+
     def Step(self):
         self._push_config()
+        self._spawn_sources()
+        if len(self) == 0:
+            raise SimPanic("int Run(): Simulation not initialized!")  # sph.go:92-94
         self._call(self._h.step, 1)
 
     def Run(self):
+        if self.Config.Sources:  # sources spawn between steps (sph.go:56-61 calls Step NSteps times)
+            for _ in range(self.Config.NSteps):
+                self.Step()
+            return
         self._push_config()
         self._call(self._h.step, self.Config.NSteps)
 

@@ -49,3 +49,36 @@ def test_density_example_scene():
         s.Density2D(k)
         assert U.rel_err(s.Particles(("rho",))["rho"], g[name]) <= U.TOL64, name
     s.Close()
+
+
+def test_point_source_appends_between_steps():
+    """sources (sph.go:72-86): particles spawned by a PointSource join the state before each step (sphb_append); the
+    oracle is fed the same particles through its own append"""
+    from oracle import oracle as orc
+
+    def config():
+        conf = sim.MakeConfig()
+        conf.Start = [sim.UniformRectSpawner((0.2, 0.25), (0.5, 0.5), 1500)]
+        conf.Sources = [sim.PointSource((0.35, 0.3), rate=1000.0)]
+        conf.DeltaTHalf, conf.Kernel, conf.Acceleration = 0.002, sim.Wendtland2D, (0.0, 0.05)
+        return conf
+
+    steps = 8
+    s = sim.MakeSimulationFromConf(config())
+    for _ in range(steps):
+        s.Step()
+    conf = config()  # the same streams again for the oracle: Start re-seeds, the source continues that stream
+    ic = conf.Start[0].Spawn(0)
+    o = orc.Oracle(orc.make_params(dt_half=0.002, kernel=2, accel=(0.0, 0.05)), ic["pos"], ic["vel"], ic["e"], capacity=len(ic["pos"]) + 1000)
+    for k in range(steps):
+        for src in conf.Sources:
+            new = src.Spawn(float(k) * conf.DeltaTHalf * 2)
+            if len(new["pos"]):
+                o.append(new["pos"], new["vel"], new["e"], new["rho"])
+        o.step(1, 1)
+    ref, got = o.state(), s.Particles(("pos", "vel", "e", "rho", "h", "id"))
+    assert len(s) == len(ref["pos"]) == 1500 + 28 and len(s.Z) == len(s)  # int(t * rate) particles by t = 7 * 0.004
+    assert np.array_equal(got["id"], ref["id"])
+    for f in ("pos", "vel", "e", "rho", "h"):
+        assert U.rel_err(got[f], ref[f], np.abs(ref[f]).max() * 1e-3) <= 1e-9, f
+    s.Close(); o.close()

@@ -114,3 +114,37 @@ def test_density_example_flow():
     with pytest.raises(sim.SimPanic):
         s.FindNearestNeighboursPeriodic((-sim.MaxFloat64, 1.0), (0, 1))
     s.Close()
+
+
+SOURCES = """[[Start]]
+[UniformRect]
+NParticles 10
+UpperLeft 0 0
+LowerRight 1 1
+[[Sources]]
+[Point]
+Pos 0.2 0.2
+Rate 100
+[Point]
+Rate 10
+Pos 0.5 0.5
+"""
+
+
+def test_point_sources_parse_and_spawn_from_the_running_go_stream():
+    """[[Sources]] [Point] (config-parser.go:384-423) and PointSource.Spawn (config-parser.go:82-102)"""
+    from sphugo_b200 import gorand
+    c = sim.MakeConfigFromText(SOURCES)
+    assert [(s.origin, s.rate) for s in c.Sources] == [((0.2, 0.2), 100.0), ((0.5, 0.5), 10.0)]
+    c.Start[0].Spawn(0)  # re-seeds the package-level stream and draws 20 uniforms + 10 Z
+    src = c.Sources[0]
+    assert len(src.Spawn(0.0)["pos"]) == 0  # t = 0: nothing yet
+    new = src.Spawn(0.035)  # int(0.035 * 100) = 3 particles, LastSpwned advances by 3 cooldowns
+    assert new["pos"].shape == (3, 2) and abs(src.LastSpwned - 0.03) < 1e-15
+    assert (new["rho"] == 100).all() and (new["e"] == 0.002).all()
+    r = gorand.Rand(12345678)
+    r.Float64s(20); r.Ints(10)
+    dy = 0.01 * (-1 + 2 * r.Float64()); dx = 0.01 * (-1 + 2 * r.Float64())  # dy is drawn first (config-parser.go:91-92)
+    assert tuple(new["pos"][0]) == (0.2 + dx, 0.2 + dy) and new["z"][0] == r.Int()
+    with pytest.raises(ValueError):
+        sim.MakeConfigFromText("[[Sources]]\n[Point]\nPos 0.1 0.1\n")
