@@ -108,3 +108,17 @@ def test_cxx_mirror_of_the_sim_api_compiles_and_behaves():
                     "-L", libdir, "-lsphb", "-Wl,-rpath," + libdir, "-o", exe], check=True)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_cxx_gorand_known_answers_and_python_twin():
+    """include/sphb_gorand.hpp: Go's math/rand in C++ for the compiled host side; same KATs as tests/test_gorand.py, and the
+    reference's seed 12345678 gives the same draws as sphugo_b200/gorand.py"""
+    from sphugo_b200 import gorand
+    exe = os.path.join(ROOT, "tests", "c", "gorand_kat")
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-O2", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c", "gorand_kat.cpp"), "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.returncode
+    f0, f1, z = r.stdout.split()
+    g = gorand.Rand(12345678)
+    assert (float(f0), float(f1), int(z)) == (g.Float64(), g.Float64(), g.Int())

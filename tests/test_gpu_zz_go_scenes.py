@@ -82,3 +82,17 @@ def test_point_source_appends_between_steps():
     for f in ("pos", "vel", "e", "rho", "h"):
         assert U.rel_err(got[f], ref[f], np.abs(ref[f]).max() * 1e-3) <= 1e-9, f
     s.Close(); o.close()
+
+
+def test_cxx_host_side_steps_on_the_device():
+    """tests/c/sim_smoke.cpp (C++ mirror of the Go step API, include/sphb_sim.hpp) on a GPU: MakeSimulation, a config
+    with a source, the speed-test shape, the TopHat panic"""
+    import subprocess
+    from sphugo_b200 import build
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = build.build()
+    exe = os.path.join(root, "tests", "c", "sim_smoke")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "c", "sim_smoke.cpp"),
+                    "-L", os.path.dirname(so), "-lsphb", "-Wl,-rpath," + os.path.dirname(so), "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "gpu path" in r.stdout, (r.returncode, r.stdout, r.stderr)
