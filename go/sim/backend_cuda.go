@@ -25,8 +25,10 @@ import "C"
 
 import (
 	"fmt"
-	"os"
 	"math"
+	"os"
+	"runtime"
+	"sync"
 	"unsafe"
 )
 
@@ -35,12 +37,20 @@ import (
 type gpuBackend struct {
 	h         *C.sphb_sim
 	n         int
-	hostStale bool  // Root.Particles is older than the device state
-	uploaded  int   // number of particles the device knows about (Sources append, sph.go:75-86)
-	idToIndex map[int]int
+	hostStale bool // Root.Particles is older than the device state
+	uploaded  int  // number of particles the device knows about (Sources append, sph.go:75-86)
 }
 
-var backends = map[*Simulation]*gpuBackend{}
+var (
+	backends   = map[*Simulation]*gpuBackend{}
+	backendsMu sync.Mutex // simviewer steps on one goroutine and replaces / closes simulations on another (simviewer.go:218-237)
+)
+
+func lookup(sim *Simulation) *gpuBackend {
+	backendsMu.Lock()
+	defer backendsMu.Unlock()
+	return backends[sim]
+}
 
 // kernelID identifies a Kernel by value: closures cannot cross the C ABI (sph.go:237-242).
 func kernelID(k Kernel) C.int32_t {
@@ -86,8 +96,10 @@ func check(b *gpuBackend, rc C.int) {
 	panic(fmt.Sprintf("libsphb %d: %s", int(rc), C.GoString(C.sphb_last_error(h))))
 }
 
-// soa flattens particles[from:] for sphb_create / sphb_append.
-func soa(ps []Particle) (pos, vel, e, rho []float64, id []int64) {
+// soa flattens ps (= Root.Particles[base:]) for sphb_create / sphb_append.  The device id of a particle is its index
+// in Root.Particles: with this backend the slice is never permuted (no Treebuild on the host), and Particle.Z is not a
+// safe key because every Spawn re-seeds math/rand, so two rectangles can repeat a Z (config-parser.go:60-64,75).
+func soa(ps []Particle, base int) (pos, vel, e, rho []float64, id []int64) {
 	n := len(ps)
 	pos, vel = make([]float64, 2*n), make([]float64, 2*n)
 	e, rho, id = make([]float64, n), make([]float64, n), make([]int64, n)
@@ -95,7 +107,7 @@ func soa(ps []Particle) (pos, vel, e, rho []float64, id []int64) {
 		p := &ps[i]
 		pos[2*i], pos[2*i+1] = p.Pos.X, p.Pos.Y
 		vel[2*i], vel[2*i+1] = p.Vel.X, p.Vel.Y
-		e[i], rho[i], id[i] = p.E, p.Rho, int64(p.Z)
+		e[i], rho[i], id[i] = p.E, p.Rho, int64(base+i)
 	}
 	return
 }
@@ -116,18 +128,20 @@ func iptr(s []int64) *C.int64_t {
 // backend creates the device copy on first use (== MakeCells, core.go:93-105) and appends particles that were
 // added to Root.Particles since (Sources).
 func (sim *Simulation) backend() *gpuBackend {
-	b := backends[sim]
+	b := lookup(sim)
 	ps := sim.Root.Particles
 	if b == nil {
 		b = &gpuBackend{}
 		prm := paramsOf(&sim.Config)
-		pos, vel, e, rho, id := soa(ps)
+		pos, vel, e, rho, id := soa(ps, 0)
 		capacity := len(ps) + 100000 // sph.go:45 reserves 100000 as well
 		check(nil, C.sphb_create(&prm, C.int64_t(len(ps)), C.int64_t(capacity), dptr(pos), dptr(vel), dptr(e), dptr(rho), iptr(id), &b.h))
 		b.uploaded = len(ps)
+		backendsMu.Lock()
 		backends[sim] = b
+		backendsMu.Unlock()
 	} else if len(ps) > b.uploaded {
-		pos, vel, e, rho, id := soa(ps[b.uploaded:])
+		pos, vel, e, rho, id := soa(ps[b.uploaded:], b.uploaded)
 		check(b, C.sphb_append(b.h, C.int64_t(len(id)), dptr(pos), dptr(vel), dptr(e), dptr(rho), iptr(id)))
 		b.uploaded = len(ps)
 	}
@@ -174,15 +188,19 @@ func (sim *Simulation) TotalDensity() float64  { return sim.reduce(C.SPHB_SUM_RH
 func (sim *Simulation) TotalMomentum() float64 { return sim.reduce(C.SPHB_LAST_VEL_NORM) } // keeps sph.go:460
 
 // Sync refreshes Root.Particles[i].{Pos,Vel,Rho,C,E,EDot,VDot,EPred,VPred,NNDists[0]} from the device.  The device
-// order is cell order; particles are matched by Z (core.go:41), so the host slice keeps its own order.
+// order is cell order; particles are matched by id (= index in Root.Particles), so the host slice keeps its own order.
 // withNeighbours additionally fills NearestNeighbours / NNDists / NNPos (descending distance like
 // nearest-neighbour.go:139-153) for the examples that draw them.
 func (sim *Simulation) Sync(withNeighbours bool) {
-	b := backends[sim]
+	b := lookup(sim)
 	if b == nil || !b.hostStale {
 		return
 	}
 	n := int(C.sphb_count(b.h))
+	if n == 0 {
+		b.hostStale = false
+		return
+	}
 	f2 := func() []float64 { return make([]float64, 2*n) }
 	f1 := func() []float64 { return make([]float64, n) }
 	pos, vel, vdot, vpred := f2(), f2(), f2(), f2()
@@ -191,7 +209,10 @@ func (sim *Simulation) Sync(withNeighbours bool) {
 	mask := C.uint32_t(0)
 	ptrs := (*[C.SPHB_F_COUNT]unsafe.Pointer)(C.calloc(C.SPHB_F_COUNT, C.size_t(unsafe.Sizeof(uintptr(0)))))
 	defer C.free(unsafe.Pointer(ptrs))
-	set := func(f int, p unsafe.Pointer) { ptrs[f] = p; mask |= 1 << uint(f) }
+	// the pointer table lives in C memory; a Go pointer may be stored there only while it is pinned (cgo rules, Go 1.21+)
+	var pinner runtime.Pinner
+	defer pinner.Unpin()
+	set := func(f int, p unsafe.Pointer) { pinner.Pin(p); ptrs[f] = p; mask |= 1 << uint(f) }
 	set(C.SPHB_F_POS, unsafe.Pointer(&pos[0]))
 	set(C.SPHB_F_VEL, unsafe.Pointer(&vel[0]))
 	set(C.SPHB_F_RHO, unsafe.Pointer(&rho[0]))
@@ -212,19 +233,12 @@ func (sim *Simulation) Sync(withNeighbours bool) {
 		set(C.SPHB_F_NN_POS, unsafe.Pointer(&nnPos[0]))
 	}
 	var nOut C.int64_t
-	// the pointer table lives in C memory and the Go buffers are pinned for the duration of the call (cgo rules)
 	check(b, C.sphb_download(b.h, mask, (*unsafe.Pointer)(unsafe.Pointer(ptrs)), C.int64_t(n), &nOut))
 
 	ps := sim.Root.Particles
-	if b.idToIndex == nil || len(b.idToIndex) != len(ps) {
-		b.idToIndex = make(map[int]int, len(ps))
-		for i := range ps {
-			b.idToIndex[ps[i].Z] = i
-		}
-	}
 	devToHost := make([]int, n)
 	for j := 0; j < n; j++ {
-		devToHost[j] = b.idToIndex[int(id[j])]
+		devToHost[j] = int(id[j])
 	}
 	for j := 0; j < n; j++ {
 		p := &ps[devToHost[j]]
@@ -260,6 +274,9 @@ func (sim *Simulation) FrameData(width, height int) (xy []float32, colour []uint
 	var nOut C.int64_t
 	check(b, C.sphb_frame(b.h, C.int32_t(width), C.int32_t(height), (*C.float)(unsafe.Pointer(&xy[0])),
 		(*C.uint8_t)(unsafe.Pointer(&colour[0])), (*C.int64_t)(unsafe.Pointer(&z[0])), C.int64_t(n), &nOut))
+	for j := range z { // device id -> Particle.Z, the key the renderer orders by (animator.go:71)
+		z[j] = int64(sim.Root.Particles[z[j]].Z)
+	}
 	return
 }
 
@@ -287,8 +304,13 @@ func (sim *Simulation) DensityAll(kernel Kernel) {
 
 // Close releases the device memory of a simulation that is being replaced (simviewer.go:218-237).
 func (sim *Simulation) Close() {
-	if b := backends[sim]; b != nil {
+	sim.IsBusy.Lock() // not while a step is being enqueued on this handle
+	defer sim.IsBusy.Unlock()
+	backendsMu.Lock()
+	b := backends[sim]
+	delete(backends, sim)
+	backendsMu.Unlock()
+	if b != nil {
 		C.sphb_destroy(b.h)
-		delete(backends, sim)
 	}
 }
