@@ -14,7 +14,12 @@
  * The reference has NO test that pins kNN, density, force, leapfrog or boundaries, so for
  * those functions parity is UNPINNED by the reference: they are restated line by line below
  * (same operation order, no FMA contraction: build with -ffp-contract=off) and cross-checked
- * against an independent exact brute-force kNN (mode 1) and scipy's cKDTree in tests/.
+ * against an independent exact brute-force kNN (mode 1) and scipy's cKDTree in tests/, and
+ * against a second restatement of the same Go functions written separately in numpy
+ * (tests/np_restatement.py), with which every field agrees bit for bit over several steps
+ * (tests/test_oracle_crosscheck.py).  The small scenes use the reference's own inputs: Go's
+ * math/rand stream, reconstructed and pinned by Go's published known answers
+ * (sphugo_b200/gorand.py, tests/test_gorand.py).
  *
  * Layout and algorithm follow the reference so that the timing of orc_step is an honest
  * "reference CPU path" figure: 1136-byte AoS particle (core.go:17-42), in-place Partition of
