@@ -34,9 +34,12 @@ def test_partition_kats(pts, ori, pivot, la, lb):
 
 
 @pytest.mark.parametrize("n", [1, 60, 6000])
-def test_inside_any_sphere(n):
-    """bounding-sphere_test.go:30-64: every particle lies inside some node circle"""
-    pos = gen.uniform_rect(n)
+@pytest.mark.parametrize("stream", ["go", "splitmix"])
+def test_inside_any_sphere(n, stream):
+    """bounding-sphere_test.go:30-64: every particle lies inside some node circle.  "go": the test's own particles,
+    MakeCellsUniform -> InitUniformly (core.go:76-91, 106-113) on Go's math/rand stream after rand.Seed(12345678)"""
+    from sphugo_b200 import gorand
+    pos = gorand.init_uniformly(n)["pos"] if stream == "go" else gen.uniform_rect(n)
     o = orc.Oracle(orc.make_params(), pos)
     assert o.outside_all_circles() == 0
     st = o.tree_stats()
