@@ -30,6 +30,11 @@ def test_make_simulation_default_scene():
         for f in ("pos", "vel", "e", "rho", "h"):
             ref = g[f"{f}_{steps}"]
             assert U.rel_err(st[f], ref, np.abs(ref).max() * 1e-3) <= tol, (f, steps)
+    # TotalMomentum assigns instead of accumulating (sph.go:457-463): the speed of whichever particle is last in the
+    # current order - tree order in the reference, cell order here - so it is some particle's |Vel|
+    speeds = np.sqrt((st["vel"] ** 2).sum(1))
+    assert np.isclose(speeds, s.TotalMomentum(), rtol=1e-14, atol=0).any()
+    assert abs(s.TotalEnergy() - g["e_5"].sum()) <= 1e-12 * g["e_5"].sum()
     s.Close()
 
 
