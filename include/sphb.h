@@ -120,7 +120,8 @@ enum {
 
 /* == sim.MakeSimulationFromConf + MakeCells (sph.go:40-54, core.go:93-105).
  * pos_xy, vel_xy: interleaved x,y. vel/e/rho/id may be NULL (zeros; id = index).
- * capacity >= n reserves room for sphb_append (Sources, sph.go:72-86). */
+ * capacity >= n reserves room for sphb_append (Sources, sph.go:72-86); an append beyond it reallocates at
+ * twice the size, like Go's append. */
 int sphb_create(const sphb_params* p, int64_t n, int64_t capacity, const double* pos_xy,
                 const double* vel_xy, const double* e, const double* rho, const int64_t* id,
                 sphb_sim** out);
@@ -133,7 +134,9 @@ int sphb_get_params(const sphb_sim* s, sphb_params* p);
 int64_t sphb_count(const sphb_sim* s);        /* len(sim.Root.Particles) */
 int64_t sphb_current_step(const sphb_sim* s); /* sim.CurrentStep */
 
-/* == append(sim.Root.Particles, spawned...) + MakeCells (sph.go:75-86) */
+/* == append(sim.Root.Particles, spawned...) + MakeCells (sph.go:75-86).  Beyond the capacity the device arrays are
+ * reallocated at twice the size (SPHB_E_NOMEM if that fails or 2^28-1 particles per device would be exceeded; the
+ * handle is unchanged then).  Not while ghosts are attached (slab mode, between step_begin and step_end). */
 int sphb_append(sphb_sim* s, int64_t n, const double* pos_xy, const double* vel_xy, const double* e,
                 const double* rho, const int64_t* id);
 

@@ -556,6 +556,92 @@ int create_common(const sphb_params* p, int64_t n, int64_t capacity, const doubl
   return SPHB_OK;
 }
 
+// append beyond the capacity: Go's append reallocates (sph.go:79).  Every per-capacity array is allocated anew at twice
+// the size BEFORE anything is released (a failed allocation leaves the handle as it was), the particle state is copied
+// over, and everything that described the old order (neighbour list, prepared keys, next grid) is forgotten.
+struct CapArrays {
+  Soa a, b;
+  double2* spos = nullptr;
+  double* hguess = nullptr;
+  uint32_t *keys = nullptr, *keysSorted = nullptr, *rank = nullptr, *perm = nullptr;
+  uint32_t *cellStart = nullptr, *cellCount = nullptr, *tileSum = nullptr, *nn = nullptr;
+  int* failList = nullptr;
+  void release() {
+    free_soa(a); free_soa(b);
+    cudaFree(spos); cudaFree(hguess); cudaFree(keys); cudaFree(keysSorted); cudaFree(rank); cudaFree(perm);
+    cudaFree(cellStart); cudaFree(cellCount); cudaFree(tileSum); cudaFree(nn); cudaFree(failList);
+    *this = CapArrays{};
+  }
+};
+
+int grow_capacity(sphb_sim* s, int64_t need) {
+  const int64_t limit = (int64_t)IDX_MASK - 1;
+  if (need > limit) return fail(s, SPHB_E_NOMEM, "append: %lld particles exceed 2^28-1 per device", (long long)need);
+  const int64_t ncap = std::min<int64_t>(std::max<int64_t>(need, 2 * s->cap), limit);
+  const size_t cap = (size_t)ncap, cap32 = (cap + 31) / 32 * 32;
+  const int64_t ncm = std::max<int64_t>(64, std::min<int64_t>(ncap / 2 + 1, (int64_t)1 << 30));
+  const int ntiles = cdiv(ncm + 1, SC_TILE);
+  const size_t ncount = (size_t)ntiles * SC_TILE + 8;
+  CK(s, cudaStreamSynchronize(s->st));
+  CapArrays t;
+#define CKG(call)                                                                                          \
+  do {                                                                                                     \
+    cudaError_t e__ = (call);                                                                              \
+    if (e__ != cudaSuccess) {                                                                              \
+      t.release();                                                                                         \
+      cudaGetLastError();                                                                                  \
+      return fail(s, e__ == cudaErrorMemoryAllocation ? SPHB_E_NOMEM : SPHB_E_CUDA,                         \
+                  "append: growing the capacity %lld -> %lld: %s failed: %s", (long long)s->cap, (long long)ncap, #call, \
+                  cudaGetErrorString(e__));                                                                \
+    }                                                                                                      \
+  } while (0)
+  CKG(alloc_soa(t.a, cap));
+  CKG(alloc_soa(t.b, cap));
+  CKG(dalloc(t.spos, cap));
+  CKG(dalloc(t.hguess, cap));
+  CKG(dalloc(t.keys, cap)); CKG(dalloc(t.keysSorted, cap)); CKG(dalloc(t.rank, cap)); CKG(dalloc(t.perm, cap));
+  CKG(dalloc(t.cellStart, ncount));
+  CKG(dalloc(t.cellCount, ncount));
+  CKG(dalloc(t.tileSum, (size_t)ntiles));
+  CKG(dalloc(t.nn, cap32 * SPHB_K));
+  CKG(dalloc(t.failList, cap));
+  const size_t n = (size_t)s->n;
+  const cudaMemcpyKind dd = cudaMemcpyDeviceToDevice;
+  CKG(cudaMemcpyAsync(t.a.pos, s->a.pos, n * sizeof(double2), dd, s->st));
+  CKG(cudaMemcpyAsync(t.a.vel, s->a.vel, n * sizeof(double2), dd, s->st));
+  CKG(cudaMemcpyAsync(t.a.vdot, s->a.vdot, n * sizeof(double2), dd, s->st));
+  CKG(cudaMemcpyAsync(t.a.vpred, s->a.vpred, n * sizeof(double2), dd, s->st));
+  CKG(cudaMemcpyAsync(t.a.e, s->a.e, n * sizeof(double), dd, s->st));
+  CKG(cudaMemcpyAsync(t.a.edot, s->a.edot, n * sizeof(double), dd, s->st));
+  CKG(cudaMemcpyAsync(t.a.epred, s->a.epred, n * sizeof(double), dd, s->st));
+  CKG(cudaMemcpyAsync(t.a.id, s->a.id, n * sizeof(int64_t), dd, s->st));
+  CKG(cudaMemcpyAsync(t.a.pc, s->a.pc, n * sizeof(double4), dd, s->st));
+  CKG(cudaMemcpyAsync(t.a.ghost, s->a.ghost, n * sizeof(uint8_t), dd, s->st));
+  CKG(cudaMemsetAsync(t.cellCount, 0, ncount * sizeof(uint32_t), s->st));
+  CKG(cudaMemsetAsync(t.nn, 0xff, cap32 * SPHB_K * sizeof(uint32_t), s->st));
+  CKG(cudaStreamSynchronize(s->st));
+#undef CKG
+  CapArrays old;
+  old.a = s->a; old.b = s->b; old.spos = s->spos; old.hguess = s->hguess; old.keys = s->keys; old.keysSorted = s->keysSorted;
+  old.rank = s->rank; old.perm = s->perm; old.cellStart = s->cellStart; old.cellCount = s->cellCount; old.tileSum = s->tileSum;
+  old.nn = s->nn; old.failList = s->failList;
+  s->a = t.a; s->b = t.b; s->spos = t.spos; s->hguess = t.hguess; s->keys = t.keys; s->keysSorted = t.keysSorted;
+  s->rank = t.rank; s->perm = t.perm; s->cellStart = t.cellStart; s->cellCount = t.cellCount; s->tileSum = t.tileSum;
+  s->nn = t.nn; s->failList = t.failList;
+  old.release();
+  s->cap = ncap;
+  s->ncell_max = (int)ncm;
+  s->ntiles_cap = ntiles;
+  s->gtune.ncell_max = s->ncell_max;
+  s->keys_ready = false;  // the new cellCount is already zero
+  s->grid_next_ready = false;
+  s->have_list = false;
+  s->hacc_valid = false;
+  s->qmax_valid = false;
+  s->stats_dirty = true;
+  return SPHB_OK;
+}
+
 // ids a permutation of 0..n-1?  (perm / packCount are free outside an evaluation; keys / rank are not: after a fused
 // step they hold the next step's cell keys)
 int require_dense_ids(sphb_sim* s) {
@@ -627,8 +713,11 @@ int sphb_append(sphb_sim* s, int64_t n, const double* pos_xy, const double* vel_
   int rc = enter(s); if (rc) return rc;
   if (n < 0 || (n > 0 && !pos_xy)) return fail(s, SPHB_E_INVALID, "bad particle arrays");
   if (s->nghost) return fail(s, SPHB_E_STATE, "append while ghosts are attached");
-  if (s->n + n > s->cap) return fail(s, SPHB_E_NOMEM, "append: %lld + %lld exceeds capacity %lld", (long long)s->n, (long long)n, (long long)s->cap);
   if (n == 0) return SPHB_OK;
+  if (s->n + n > s->cap) {  // Go's append reallocates (sph.go:79)
+    rc = grow_capacity(s, s->n + n);
+    if (rc) return rc;
+  }
   rc = upload_common(s, s->n, n, pos_xy, vel_xy, e, rho, id, cudaMemcpyHostToDevice, s->n);
   if (rc) return rc;
   s->n += n;

@@ -101,3 +101,28 @@ def test_cxx_host_side_steps_on_the_device():
                     "-L", os.path.dirname(so), "-lsphb", "-Wl,-rpath," + os.path.dirname(so), "-o", exe], check=True)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and "gpu path" in r.stdout, (r.returncode, r.stdout, r.stderr)
+
+
+def test_append_beyond_the_capacity_reallocates():
+    """Go's append grows Root.Particles without bound (sph.go:79): sphb_append past the capacity moves the state to
+    arrays of twice the size; the step after it matches the oracle fed the same particles"""
+    from oracle import oracle as orc
+    from sphugo_b200 import _lib as L
+    from sphugo_b200 import gen
+    ic = gen.spawn([(1500, (0, 0), (1, 1))])
+    extra = gen.uniform_rect(2500, (0.2, 0.2), (0.8, 0.8), seed=99)
+    kw = dict(accel=(0.0, 0.2), dt_half=0.002)
+    g = L.Handle(L.make_params(**kw), ic["pos"], ic["vel"], ic["e"], capacity=1500)
+    o = orc.Oracle(orc.make_params(**kw), ic["pos"], ic["vel"], ic["e"], capacity=8000)
+    g.step(2); o.step(2, 1)
+    for lo, hi in ((0, 700), (700, 2500)):  # 1500 -> 3000 (doubling), then 2200 + 1800 > 3000 -> 6000
+        part = extra[lo:hi]
+        ids = np.arange(1500 + lo, 1500 + hi, dtype=np.int64)
+        g.append(part, None, np.full(len(part), 0.01), None, ids)
+        o.append(part, None, np.full(len(part), 0.01), None, ids)
+        g.step(1); o.step(1, 1)
+        ref, got = o.state(), g.state()
+        assert g.n == len(ref["pos"]) == 1500 + hi and np.array_equal(got["id"], ref["id"])
+        for f in ("pos", "vel", "e", "rho", "h"):
+            assert U.rel_err(got[f], ref[f], np.abs(ref[f]).max() * 1e-3) <= 1e-9, (f, hi)
+    g.close(); o.close()
