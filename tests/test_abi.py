@@ -122,3 +122,17 @@ def test_cxx_gorand_known_answers_and_python_twin():
     f0, f1, z = r.stdout.split()
     g = gorand.Rand(12345678)
     assert (float(f0), float(f1), int(z)) == (g.Float64(), g.Float64(), g.Int())
+
+
+def test_cxx_examples_build_and_panic_without_a_device():
+    """examples/*.cpp: the reference's three BASELINE example mains over the C++ host side build warning-free; without a GPU
+    they end like a Go panic (message on stderr, exit status 2) - no CPU fallback"""
+    import torch
+    from sphugo_b200 import build
+    build.build()
+    subprocess.run(["make", "-C", os.path.join(ROOT, "examples"), "-s"], check=True)
+    if torch.cuda.is_available():
+        return
+    for exe in ("speed_test", "density", "sph_simulation"):
+        r = subprocess.run([os.path.join(ROOT, "examples", exe)], capture_output=True, text=True)
+        assert r.returncode == 2 and r.stderr.startswith("panic: no CUDA device"), (exe, r.returncode, r.stderr)

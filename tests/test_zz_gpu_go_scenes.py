@@ -126,3 +126,13 @@ def test_append_beyond_the_capacity_reallocates():
         for f in ("pos", "vel", "e", "rho", "h"):
             assert U.rel_err(got[f], ref[f], np.abs(ref[f]).max() * 1e-3) <= 1e-9, (f, hi)
     g.close(); o.close()
+
+
+def test_cxx_examples_run_on_the_device():
+    """examples/*.cpp (speed-test at reduced N, density, sph-simulation for a few steps) end to end"""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-C", os.path.join(root, "examples"), "-s"], check=True)
+    for cmd, expect in ((["speed_test", "20000"], "average FPS"), (["density"], "periodic [0.1,0.9]^2"), (["sph_simulation", "12"], "step   12")):
+        r = subprocess.run([os.path.join(root, "examples", cmd[0])] + cmd[1:], capture_output=True, text=True)
+        assert r.returncode == 0 and expect in r.stdout, (cmd, r.returncode, r.stdout[-400:], r.stderr[-400:])
