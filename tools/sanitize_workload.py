@@ -5,8 +5,8 @@
   compute-sanitizer --tool racecheck --error-exitcode 9 python tools/sanitize_workload.py
 
 Both builds: non-uniform periodic box (group halving, force rows -2..+2, fallback), open box (statistics pass,
-clamped border cells), frame / neighbour-list download, and a 2-slab ring with migration (ghost packing, in-place
-ghost removal)."""
+clamped border cells), frame / neighbour-list download, a 2-slab ring with migration (ghost packing, in-place
+ghost removal), and appends inside and past the capacity (sources)."""
 import os
 import sys
 
@@ -30,4 +30,14 @@ for prec in (64, 32):
     sim.step(3)
     assert sum(sim.counts()) == n
     sim.close()
+    # sources: append inside the capacity, then past it (reallocation at twice the size), a step after each
+    ic = gen.spawn([(1200, (0, 0), (1, 1))])
+    g = L.Handle(L.make_params(precision=prec, accel=(0.0, 0.2), dt_half=0.002), ic["pos"], None, ic["e"], capacity=1300)
+    g.step(2)
+    extra = gen.uniform_rect(1500, (0.2, 0.2), (0.8, 0.8), seed=99)
+    for lo, hi in ((0, 100), (100, 1500)):
+        g.append(extra[lo:hi], None, np.full(hi - lo, 0.01), None, np.arange(1200 + lo, 1200 + hi, dtype=np.int64))
+        g.step(1); g.sync()
+    assert g.n == 2700
+    g.frame(64, 64, ids=False); g.close()
 print("sanitizer workload done")
