@@ -37,8 +37,9 @@ import (
 type gpuBackend struct {
 	h         *C.sphb_sim
 	n         int
-	hostStale bool // Root.Particles is older than the device state
-	uploaded  int  // number of particles the device knows about (Sources append, sph.go:75-86)
+	hostStale bool  // Root.Particles is older than the device state
+	uploaded  int   // number of particles the device knows about (Sources append, sph.go:75-86)
+	root      *Cell // the Root this device copy was made from: a different Root = the Simulation value was replaced
 }
 
 var (
@@ -130,8 +131,16 @@ func iptr(s []int64) *C.int64_t {
 func (sim *Simulation) backend() *gpuBackend {
 	b := lookup(sim)
 	ps := sim.Root.Particles
+	if b != nil && b.root != sim.Root {
+		// simviewer assigns a new Simulation value to the same variable (simviewer.go:147,224): same key, new particles
+		backendsMu.Lock()
+		delete(backends, sim)
+		backendsMu.Unlock()
+		C.sphb_destroy(b.h)
+		b = nil
+	}
 	if b == nil {
-		b = &gpuBackend{}
+		b = &gpuBackend{root: sim.Root}
 		prm := paramsOf(&sim.Config)
 		pos, vel, e, rho, id := soa(ps, 0)
 		capacity := len(ps) + 100000 // sph.go:45 reserves 100000 as well
