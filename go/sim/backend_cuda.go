@@ -202,7 +202,7 @@ func (sim *Simulation) TotalMomentum() float64 { return sim.reduce(C.SPHB_LAST_V
 // nearest-neighbour.go:139-153) for the examples that draw them.
 func (sim *Simulation) Sync(withNeighbours bool) {
 	b := lookup(sim)
-	if b == nil || !b.hostStale {
+	if b == nil || b.root != sim.Root || !b.hostStale {
 		return
 	}
 	n := int(C.sphb_count(b.h))
