@@ -369,7 +369,12 @@ class DistSlabSim:
             self._evaluate(2, True)
             self.steps_done += 1
             if self.schedule.after_step(self.v_max, self.h_max):
+                if self.profile:
+                    import time
+                    self.slab.h.sync()
+                    self._t0 = time.perf_counter()
                 self._migrate()
+                if self.profile: self._tick("migrate")
 
     @property
     def handle(self):
@@ -502,6 +507,19 @@ def bench(args, nx, ny, box, phys, desc, rank, world, local):
     cnt = torch.tensor([sim.handle.n], dtype=torch.int64, device=torch.device("cuda", local))
     dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     dev_ms, wall_ms = float(t[0]), float(t[1])
+    # per-phase split, from separate untimed steps on every rank: wall time of each protocol phase with a
+    # device sync after it (halo pack, exchange, ghost insertion, the evaluation itself, all-reduce, migration) and the
+    # library's CUDA-event timers of the last evaluation (keys, sort, reorder, knn, force)
+    KP = min(K, 5)
+    was_profiling, prof_timed = sim.profile, dict(sim.prof)
+    migrations_before = sim.schedule.migrations
+    sim.profile, sim.prof = True, {}
+    sim.step(KP)
+    sim.handle.sync()
+    slab_phases = {k: v * 1e3 / KP for k, v in sim.prof.items()}
+    slab_phases["migrations_in_these_steps"] = sim.schedule.migrations - migrations_before
+    device_phases = dict(sim.handle.phase_times())
+    sim.profile, sim.prof = was_profiling, prof_timed
     if rank == 0 and sim.profile:
         import sys
         print("slab phases, ms per step (wall, synchronised):",
@@ -531,6 +549,8 @@ def bench(args, nx, ny, box, phys, desc, rank, world, local):
             "gpu_launches": c1["kernel_launches"] - c0["kernel_launches"],
             "knn_fallback_particles": c1["knn_fallback"] - c0["knn_fallback"],
             "clocks": clocks,
+            "phases": {"slab_wall_ms_per_step": slab_phases, "device_ms_last_evaluation": device_phases,
+                       "what": f"rank 0, {KP} separate untimed steps with a device sync after every protocol phase"},
         }
         print(json.dumps(line), flush=True)
     dist.barrier()

@@ -122,3 +122,52 @@ def test_gloo_neighbour_exchange(world):
     assert all(r[1] for r in res), res
     assert all(r[2] > 0 and r[3] > 0 for r in res)
     assert all(r[4] == float(world) for r in res)
+
+
+def test_dist_slab_step_protocol_order_and_profile_ticks():
+    """DistSlabSim.step over recording fakes: the per-evaluation call order of the protocol (slab.py header), migration when
+    the schedule asks for it, and the per-phase wall-time ticks bench.py --gpus N reports (profile mode)"""
+    calls = []
+
+    class H:
+        def sync(self):
+            pass
+
+    class FakeSlab:
+        h = H()
+
+        def __getattr__(self, name):
+            def f(*a):
+                calls.append(name)
+                if name in ("pack_halo", "pack_migrants"):
+                    return None, 0, None, 0
+                if name == "local_max_h":
+                    return 0.01
+                if name == "local_max_speed":
+                    return 1.0
+            return f
+
+    class FakeEx:
+        def exchange(self, bl, nl, br, nr, width):
+            calls.append(f"exchange{width}")
+            return None, 0, None, 0
+
+        def allreduce_max(self, *v):
+            calls.append("allreduce")
+            return list(v)
+
+    sim = slab.DistSlabSim.__new__(slab.DistSlabSim)
+    sim.slab, sim.ex, sim.h_max, sim.v_max, sim.steps_done, sim.h_growth = FakeSlab(), FakeEx(), 0.01, 0.0, 0, 1.0
+    sim.schedule = slab.MigrationSchedule(2, 1e-3)  # migrate after every second step
+    sim.profile, sim.prof = False, {}
+    sim.step(1)
+    ev = ["set_widths", "begin", "pack_halo", f"exchange{slab.HALO_DOUBLES}", "add_ghosts", "add_ghosts", "end", "local_max_h",
+          "local_max_speed", "allreduce"]
+    assert calls == ev + ev  # step 0: initialisation evaluation + the real one (sph.go:89-103)
+    calls.clear()
+    sim.profile = True
+    sim.step(1)
+    mig = ["pack_migrants", f"exchange{slab.MIGRANT_DOUBLES}", "add_migrants", "add_migrants", "finish_migration"]
+    assert calls == ev + mig
+    assert set(sim.prof) == {"begin", "pack_halo", "exchange", "add_ghosts", "end", "allreduce", "migrate"}
+    assert all(v >= 0.0 for v in sim.prof.values()) and sim.schedule.migrations == 1
