@@ -308,6 +308,21 @@ def default_h_hint(n_total: int, area: float) -> float:
     return 1.6 * math.sqrt(33.0 * area / (math.pi * max(n_total, 1)))
 
 
+def _route_to_owner(topo: "Topology", rank: int, pos, vel, e, rho, ids):
+    """the rows of a batch of spawned particles that belong to `rank`'s slab (x folded into the period on a ring)"""
+    pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 2)
+    if ids is None:
+        raise ValueError("slab append needs explicit global ids (every rank must number the new particles alike)")
+    x = pos[:, 0]
+    if topo.periodic:
+        lo, hi = float(topo.bounds[0]), float(topo.bounds[-1])
+        x = lo + np.mod(x - lo, hi - lo)
+    m = topo.owner_of(x) == rank
+    pick = lambda a, shape: None if a is None else np.ascontiguousarray(a, dtype=np.float64).reshape(shape)[m]  # noqa: E731
+    n = len(pos)
+    return pos[m], pick(vel, (n, 2)), pick(e, (n,)), pick(rho, (n,)), np.asarray(ids, dtype=np.int64).reshape(n)[m]
+
+
 class DistSlabSim:
     """one rank of a torch.distributed slab run: same step / state surface as a single libsphb handle"""
 
@@ -376,6 +391,13 @@ class DistSlabSim:
                 self._migrate()
                 if self.profile: self._tick("migrate")
 
+    def append(self, pos, vel=None, e=None, rho=None, ids=None):
+        """sources in a slab run (sph.go:72-86): every rank is handed the same spawned particles between
+        two steps and keeps those whose x lies in its slab (sphb_append; no ghosts are attached between steps)"""
+        part = _route_to_owner(self.slab.topo, self.slab.rank, pos, vel, e, rho, ids)
+        if len(part[0]):
+            self.slab.h.append(*part)
+
     @property
     def handle(self):
         return self.slab.h
@@ -436,6 +458,13 @@ class LocalSlabSim:
             self.steps_done += 1
             if self.schedule.after_step(self.v_max, self.h_max):
                 self._migrate()
+
+    def append(self, pos, vel=None, e=None, rho=None, ids=None):
+        """sources: the new particles go to the slab that owns their x (see DistSlabSim.append)"""
+        for sl in self.slabs:
+            part = _route_to_owner(self.topo, sl.rank, pos, vel, e, rho, ids)
+            if len(part[0]):
+                sl.h.append(*part)
 
     def state(self, fields):
         """concatenated over the slabs, sorted by id"""

@@ -171,3 +171,16 @@ def test_dist_slab_step_protocol_order_and_profile_ticks():
     assert calls == ev + mig
     assert set(sim.prof) == {"begin", "pack_halo", "exchange", "add_ghosts", "end", "allreduce", "migrate"}
     assert all(v >= 0.0 for v in sim.prof.values()) and sim.schedule.migrations == 1
+
+
+def test_spawned_particles_are_routed_to_the_owning_slab():
+    """slab append (sources in a multi-GPU run): every particle goes to exactly one rank, x folded into the period"""
+    topo = slab.Topology(3, [0.0, 0.3, 0.55, 1.0], True)
+    pos = np.array([[0.1, 0.5], [0.3, 0.1], [0.54, 0.2], [0.99, 0.3], [1.02, 0.4], [-0.01, 0.6]])
+    ids = np.arange(100, 106)
+    e = np.linspace(1.0, 2.0, 6)
+    got = [slab._route_to_owner(topo, r, pos, None, e, None, ids) for r in range(3)]
+    assert [g[4].tolist() for g in got] == [[100, 104], [101, 102], [103, 105]]
+    assert got[0][1] is None and np.array_equal(got[2][2], e[[3, 5]]) and np.array_equal(got[0][0], pos[[0, 4]])  # positions unchanged
+    with pytest.raises(ValueError):
+        slab._route_to_owner(topo, 0, pos, None, None, None, None)

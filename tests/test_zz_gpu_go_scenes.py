@@ -136,3 +136,29 @@ def test_cxx_examples_run_on_the_device():
     for cmd, expect in ((["speed_test", "20000"], "average FPS"), (["density"], "periodic [0.1,0.9]^2"), (["sph_simulation", "12"], "step   12")):
         r = subprocess.run([os.path.join(root, "examples", cmd[0])] + cmd[1:], capture_output=True, text=True)
         assert r.returncode == 0 and expect in r.stdout, (cmd, r.returncode, r.stdout[-400:], r.stderr[-400:])
+
+
+def test_slab_run_takes_spawned_particles():
+    """sources in a slab run: two slabs of a periodic ring on one GPU, particles appended between steps go to
+    the slab that owns their x; the run keeps matching the oracle fed the same particles"""
+    from oracle import oracle as orc
+    from sphugo_b200 import gen, slab
+    from tests.test_gpu_slab import FIELDS, _compare
+    pos = gen.jittered_lattice(64, 64)
+    n = len(pos)
+    cfg = dict(hor=(0.0, 1.0), ver=(0.0, 1.0), accel=(0.0, 0.2), dt_half=0.002)
+    po, pg = U.params_pair(**cfg)
+    vel = np.tile([[2.0, -1.0]], (n, 1))
+    sim = slab.LocalSlabSim(pg, slab.Topology(2, [0.0, 0.5, 1.0], True), pos, vel, np.full(n, 0.01), h_max_hint=slab.default_h_hint(n, 1.0))
+    o = orc.Oracle(po, pos, vel, np.full(n, 0.01), capacity=n + 400)
+    sim.step(2); o.step(2, 1)
+    new = gen.jittered_lattice(16, 16, jitter=0.45, seed=77)[:200]  # spread over both slabs, none on top of another
+    ids = np.arange(n, n + 200, dtype=np.int64)
+    nv, ne = np.tile([[2.0, -1.0]], (200, 1)), np.full(200, 0.01)
+    sim.append(new, nv, ne, None, ids)
+    o.append(new, nv, ne, None, ids)
+    for k in range(2):
+        sim.step(1); o.step(1, 1)
+        assert sum(sim.counts()) == n + 200
+        _compare(sim.state(FIELDS), o.state(neighbours=True), po, 1e-9, f"after append, step {k + 1}")
+    sim.close(); o.close()
