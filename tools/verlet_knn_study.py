@@ -69,12 +69,30 @@ def main():
     tile_of[order] = np.arange(N) // 32
     ntiles = tile_of.max() + 1
     print(f"N = {N}, spacing {s:.4g}, dt_half {dtH:.4g}, mean h {h_mean:.4g} = {h_mean / s:.3f} spacings; lists built at step {t0}")
-    print("steps since rebuild | D / h | " + " | ".join(f"K_ext={k}: particles, tiles" for k in kexts))
+    print("steps since rebuild | D / h | " + " | ".join(f"K_ext={k}: particles, tiles, particles with the local bound" for k in kexts))
+    # local bound: D_i = largest |cum_j - cum_i| over the 3x3 block of coarse cells (edge >= 2 h) around particle i, from
+    # per-cell bounding boxes of the cumulative displacement (valid while d_excl < one coarse cell)
+    nc = int(1.0 / (2.0 * h_mean))
+    cs = 1.0 / nc
+    cid = np.minimum((p0[:, 1] / cs).astype(int), nc - 1) * nc + np.minimum((p0[:, 0] / cs).astype(int), nc - 1)
+    cum = np.zeros((N, 2))
     D = 0.0
     for t in range(t0 + 1, a.steps):
         disp = min_image(evals[t] - evals[t - 1])
         dev = disp - disp.mean(0)
         D += 2.0 * np.sqrt((dev ** 2).sum(1)).max()
+        cum += disp
+        mn, mx = np.full((nc * nc, 2), np.inf), np.full((nc * nc, 2), -np.inf)
+        np.minimum.at(mn, cid, cum)
+        np.maximum.at(mx, cid, cum)
+        mn, mx = mn.reshape(nc, nc, 2), mx.reshape(nc, nc, 2)
+        bmn, bmx = mn.copy(), mx.copy()
+        for sy in (-1, 0, 1):
+            for sx in (-1, 0, 1):
+                bmn = np.minimum(bmn, np.roll(np.roll(mn, sy, 0), sx, 1))
+                bmx = np.maximum(bmx, np.roll(np.roll(mx, sy, 0), sx, 1))
+        ext = np.maximum(np.abs(cum - bmn.reshape(-1, 2)[cid]), np.abs(bmx.reshape(-1, 2)[cid] - cum))
+        d_loc = np.sqrt((ext ** 2).sum(1))
         pt = evals[t]
         row = [f"{t - t0:19d}", f"{D / h_mean:.4f}"]
         # exact answer for reference: the true 32nd-neighbour distance now
@@ -88,7 +106,9 @@ def main():
             ok = hnew < d0[:, k] - D  # d0[:, k] = the first neighbour not kept
             assert np.allclose(hnew[ok], dtrue[ok, 32], rtol=1e-12), "certified result is not the exact kNN"
             tiles_ok = np.bincount(tile_of, weights=(~ok).astype(float), minlength=ntiles) == 0
-            row.append(f"{ok.mean():.4f}, {tiles_ok.mean():.4f}")
+            ok_loc = (hnew < d0[:, k] - d_loc) & (d0[:, k] < cs)
+            assert np.allclose(hnew[ok_loc], dtrue[ok_loc, 32], rtol=1e-12), "locally certified result is not the exact kNN"
+            row.append(f"{ok.mean():.4f}, {tiles_ok.mean():.4f}, {ok_loc.mean():.4f}")
         print(" | ".join(row))
 
 
