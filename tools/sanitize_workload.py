@@ -40,4 +40,13 @@ for prec in (64, 32):
         g.step(1); g.sync()
     assert g.n == 2700
     g.frame(64, 64, ids=False); g.close()
+    # the same on a periodic box, where steps are fused (the force epilogue prepares the next step's keys and grid)
+    pos = gen.jittered_lattice(48, 48)
+    g = L.Handle(L.make_params(precision=prec, hor=(0.0, 1.0), ver=(0.0, 1.0), dt_half=0.002), pos, None, np.full(len(pos), 0.01))
+    g.step(3)
+    extra = gen.jittered_lattice(20, 20, jitter=0.4, seed=5)
+    g.append(extra, None, np.full(len(extra), 0.01), None, np.arange(len(pos), len(pos) + len(extra), dtype=np.int64))
+    g.step(2); g.sync()
+    assert g.n == len(pos) + len(extra)
+    g.close()
 print("sanitizer workload done")
