@@ -18,7 +18,8 @@
  * against a second restatement of the same Go functions written separately in numpy
  * (tests/np_restatement.py), with which every field agrees bit for bit over several steps
  * (tests/test_oracle_crosscheck.py).  The small scenes use the reference's own inputs: Go's
- * math/rand stream, reconstructed and pinned by Go's published known answers
+ * math/rand stream, reconstructed and pinned by the reference's recorded output (README.md:89,
+ * the rand.Seed(101) draws of examples/heap) and Go's published known answers
  * (sphugo_b200/gorand.py, tests/test_gorand.py).
  *
  * Layout and algorithm follow the reference so that the timing of orc_step is an honest

@@ -12,8 +12,9 @@ rng.go) into an LCG-filled vector; Go's sources are not in this container, so th
 its published definition (Go's gen_cooked.go: fill the vector from the same LCG with seed 1, run the generator
 7.8e12 times, print the vector).  7.8e12 steps are taken by jump-ahead: the recurrence is linear over Z/2^64, so
 the state after n steps is x^n modulo the characteristic polynomial x^607 - x^334 - 1 applied to the initial
-sequence (43 polynomial squarings, 0.2 s).  Pinned by known answers from Go's documentation and playground
-(tests/test_gorand.py): rngCooked[0] = -4181792142133755926, and after rand.Seed(1) rand.Int() =
+sequence (43 polynomial squarings, 0.2 s).  Pinned by the reference's own recorded output - README.md:89 prints the
+26 numbers examples/heap/heap.go:27-33 drew with rand.Seed(101), and this generator reproduces them - and by known
+answers from Go's documentation and playground (tests/test_gorand.py): rngCooked[0] = -4181792142133755926, and after rand.Seed(1) rand.Int() =
 5577006791947779410, 8674665223082153551, ..., rand.Float64() = 0.6046602879796196, 0.9405090880450124, ...,
 rand.Intn(100) = 81, 87, 47, 59, 81, 18, 25, 40, 56, 0.
 

@@ -29,6 +29,12 @@ int main() {
   r.Seed(1);
   for (int want : intn)
     if (r.Intn(100) != want) return 5;
+  {  // the reference's own recorded output: examples/heap/heap.go:27-33 with rand.Seed(101), printed in README.md:89
+    const int readme[26] = {31, 37, 82, 83, 33, 54, 39, 42, 62, 49, 84, 59, 88, 26, 27, 21, 92, 97, 87, 49, 33, 9, 42, 49, 88, 67};
+    r.Seed(101);
+    for (int want : readme)
+      if ((int)(r.Int() % 90 + 9) != want) return 6;
+  }
   r.Seed(12345678);  // the reference's seed (config-parser.go:63): printed for the Python twin to compare
   const double f0 = r.Float64(), f1 = r.Float64();
   const long long z = (long long)r.Int();

@@ -98,3 +98,11 @@ def test_python_spawners_use_the_go_stream():
     from sphugo_b200 import sim
     sp = sim.MakeUniformRectSpawner().Spawn(0)
     assert np.array_equal(sp["pos"], _golden("c2_default_go")["pos0"]) and sp["z"].dtype == np.int64
+
+
+def test_reference_readme_records_this_stream():
+    """The reference's own recorded output pins the generator: examples/heap seeds math/rand with 101 and fills 26 slots with
+    rand.Int()%90+9 (examples/heap/heap.go:27-33); README.md:89 prints the array that Go program produced"""
+    r = gorand.Rand(101)
+    assert [r.Int() % 90 + 9 for _ in range(26)] == [31, 37, 82, 83, 33, 54, 39, 42, 62, 49, 84, 59, 88, 26, 27, 21, 92, 97, 87, 49, 33,
+                                                     9, 42, 49, 88, 67]
