@@ -9,8 +9,9 @@
 // recomputed from its definition (Go's gen_cooked.go: LCG fill with seed 1, then 7.8e12 generator steps) by jump-ahead:
 // the recurrence is linear over Z/2^64, so 7.8e12 steps are x^n mod (x^607 - x^334 - 1), 43 polynomial squarings.
 // Pinned by the reference's own recorded output (README.md:89 prints what examples/heap/heap.go:27-33 drew after
-// rand.Seed(101); reproduced here) and by known answers (tests/c/gorand_kat.cpp, tests/test_gorand.py): rngCooked[0] = -4181792142133755926; after Seed(1):
-// Int() = 5577006791947779410, 8674665223082153551, ...; Float64() = 0.6046602879796196, ...; Intn(100) = 81, 87, 47, ...
+// rand.Seed(101); reproduced here) and by known answers (tests/c/gorand_kat.cpp, tests/test_gorand.py):
+// rngCooked[0] = -4181792142133755926; after Seed(1): Int() = 5577006791947779410, 8674665223082153551, ...;
+// Float64() = 0.6046602879796196, ...; Intn(100) = 81, 87, 47, ...
 // The Python twin is sphugo_b200/gorand.py.  Input generation only: nothing here is on the step path.
 #pragma once
 #include <array>
