@@ -11,8 +11,11 @@
  *   - sim/partition_test.go:11-160  (13 Partition half-length KATs)      -> orc_partition
  *   - sim/bounding-sphere_test.go:30-64 (inside-any-circle property)     -> orc_tree_all_inside_any
  *   - README.md:88-162 (heap BuildHeap/Insert/ExtractMin/Replace KAT)    -> orc_heap_*
- * The reference has NO test that pins kNN, density, force, leapfrog or boundaries, so for
- * those functions parity is UNPINNED by the reference: they are restated line by line below
+ * and against the reference's recorded OUTPUT for kNN and density: the PNGs its Go binary drew
+ * for examples/density (doc/density_compare.png, density_test.png, density_test_periodic.png)
+ * are reproduced pixel for pixel from this oracle's results (tests/test_reference_images.py).
+ * The reference has NO test and no recorded output that pins force, leapfrog or boundaries, so
+ * for those functions parity is UNPINNED by the reference: they are restated line by line below
  * (same operation order, no FMA contraction: build with -ffp-contract=off) and cross-checked
  * against an independent exact brute-force kNN (mode 1) and scipy's cKDTree in tests/, and
  * against a second restatement of the same Go functions written separately in numpy

@@ -1,0 +1,102 @@
+"""The reference's own recorded output pins the hot path: doc/density_compare.png, doc/density_test.png and
+doc/density_test_periodic.png are what the reference's Go binary drew for examples/density (README.md:201-206) - periodic and
+open kNN (k = 32) and Density2D with TopHat / Monaghan / Wendland on BASELINE configs[0].  Here the same scenes are built
+from the reconstructed Go math/rand stream, evaluated, drawn with a restatement of the example's drawing code
+(tests/gx_restatement.py) and compared PIXEL FOR PIXEL (SHA-256 of the RGB array, tests/golden/reference_images.json; against
+the PNG itself where /root/reference is present).  Every disk's colour is a 255-level quantisation of one particle's density
+and disks overdraw each other in Root.Particles order, so a match pins the particle stream, the tree permutation, the
+neighbour search and the three density kernels of the oracle - and, in the GPU twin of this test
+(tests/test_zz_gpu_go_scenes.py::test_cuda_path_reproduces_the_reference_pictures), of the CUDA path."""
+import json
+import os
+
+import numpy as np
+
+from oracle import oracle as orc
+from sphugo_b200 import gorand
+from tests import gx_restatement as gx
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+with open(os.path.join(HERE, "golden", "reference_images.json")) as _f:
+    REF = json.load(_f)
+SIDE = 420
+
+
+def check(name, canvas, look_at_the_png=True):
+    r = REF[name]
+    assert (canvas.W, canvas.H) == (r["width"], r["height"])
+    png = os.path.join("/root/reference", r["source"])
+    if look_at_the_png and os.path.exists(png):  # CPU tests in the build container: say how far the pictures differ
+        from PIL import Image
+        ref = np.array(Image.open(png).convert("RGB"))
+        bad = int((ref != canvas.img).any(2).sum())
+        assert bad == 0, f"{name}: {bad} of {ref.shape[0] * ref.shape[1]} pixels differ from the reference's picture"
+    assert canvas.sha256() == r["sha256_rgb"], name
+
+
+def density_scene():
+    """examples/density main (density.go:50-63): 1000 + 200 particles, each spawner re-seeding Go's math/rand"""
+    a, b = gorand.uniform_rect_spawn(1000), gorand.uniform_rect_spawn(200, (0.1, 0.0), (0.3, 0.4))
+    return np.concatenate([a["pos"], b["pos"]])
+
+
+def periodic_visual_scene():
+    """periodicVisualTest (density.go:103-118): 10000 + 1200 particles"""
+    a, b = gorand.uniform_rect_spawn(10000, (0.1, 0.1), (0.9, 0.9)), gorand.uniform_rect_spawn(1200, (0.85, 0.4), (0.9, 0.9))
+    return np.concatenate([a["pos"], b["pos"]])
+
+
+PANELS = [(0, gx.HeatRamp), (1, gx.HeatRamp), (2, gx.HeatRamp), (0, gx.ParaRamp), (1, gx.ParaRamp), (2, gx.ParaRamp)]  # density.go:81-87
+
+
+def draw_density_compare(order_pos, rho_of_kernel):
+    """density.go:74-94: six panels (three kernels x two ramps) and the white separator lines"""
+    w, h = 3 * SIDE, 2 * SIDE
+    c = gx.Canvas(w, h)
+    for k, (kernel, ramp) in enumerate(PANELS):
+        gx.draw_density_panel(c, order_pos, rho_of_kernel[kernel], SIDE, k, ramp)
+    c.DrawLine((SIDE, 0), (SIDE, h), gx.WHITE)
+    c.DrawLine((2 * SIDE, 0), (2 * SIDE, h), gx.WHITE)
+    c.DrawLine((0, SIDE), (w, SIDE), gx.WHITE)
+    return c
+
+
+def test_oracle_reproduces_density_compare_png():
+    pos = density_scene()
+    o = orc.Oracle(orc.make_params(hor=(0, 1), ver=(0, 1)), pos)  # MakeCells
+    o.knn((0.0, 1.0), (0.0, 1.0), mode=0)  # Treebuild + BoundingSpheres + the per-particle periodic search (density.go:65-72)
+    rho = {}
+    for kernel in (0, 1, 2):
+        o.density(kernel)
+        st = o.state(sort_by_id=False)  # Root.Particles order: the drawing order
+        rho[kernel] = st["rho"]
+    check("density_compare", draw_density_compare(st["pos"], rho))
+    o.close()
+
+
+def test_oracle_reproduces_density_test_pngs():
+    pos = periodic_visual_scene()
+    o = orc.Oracle(orc.make_params(), pos)
+    # the example re-makes the tree on the slice the first pass permuted (density.go:122-125): one oracle, two passes
+    for name, hor, ver in (("density_test", orc.OPEN, orc.OPEN), ("density_test_periodic", (0.1, 0.9), (0.1, 0.9))):
+        o.knn(hor, ver, mode=0)
+        o.density(0)
+        st = o.state(sort_by_id=False)
+        c = gx.Canvas(700, 350)
+        gx.draw_density_test(c, st["pos"], st["rho"])
+        check(name, c)
+    o.close()
+
+
+def test_a_wrong_density_would_show():
+    """sensitivity of the comparison: 0.2 % on the densities changes the picture"""
+    pos = density_scene()
+    o = orc.Oracle(orc.make_params(hor=(0, 1), ver=(0, 1)), pos)
+    o.knn((0.0, 1.0), (0.0, 1.0), mode=0)
+    rho = {}
+    for kernel in (0, 1, 2):
+        o.density(kernel)
+        st = o.state(sort_by_id=False)
+        rho[kernel] = st["rho"] * 1.002
+    assert draw_density_compare(st["pos"], rho).sha256() != REF["density_compare"]["sha256_rgb"]
+    o.close()

@@ -56,6 +56,38 @@ def test_density_example_scene():
     s.Close()
 
 
+def test_cuda_path_reproduces_the_reference_pictures():
+    """the same three pictures from the CUDA library's results (through the mirrored sim API); only the drawing ORDER -
+    the tree permutation of Root.Particles, which the device does not have - is taken from the oracle"""
+    from oracle import oracle as orc
+    from tests import gx_restatement as gx
+    from tests.test_reference_images import check, density_scene, draw_density_compare, periodic_visual_scene
+    pos = density_scene()
+    o = orc.Oracle(orc.make_params(hor=(0, 1), ver=(0, 1)), pos)
+    o.knn((0.0, 1.0), (0.0, 1.0), mode=0)
+    order = o.state(sort_by_id=False)["id"]
+    s = sim.Simulation(sim.MakeConfig(), dict(pos=pos))
+    s.FindNearestNeighboursPeriodic((0.0, 1.0), (0.0, 1.0))
+    rho = {}
+    for kernel, k in ((0, sim.TopHat2D), (1, sim.Monahan2D), (2, sim.Wendtland2D)):
+        s.Density2D(k)
+        rho[kernel] = s.Particles(("rho",))["rho"][order]
+    check("density_compare", draw_density_compare(pos[order], rho), look_at_the_png=False)  # GPU tests never read /root/reference
+    s.Close(); o.close()
+    pos = periodic_visual_scene()
+    o = orc.Oracle(orc.make_params(), pos)
+    s = sim.Simulation(sim.MakeConfig(), dict(pos=pos))
+    for name, hor, ver in (("density_test", orc.OPEN, orc.OPEN), ("density_test_periodic", (0.1, 0.9), (0.1, 0.9))):
+        o.knn(hor, ver, mode=0)
+        order = o.state(sort_by_id=False)["id"]
+        s.FindNearestNeighboursPeriodic(hor, ver)
+        s.Density2D(sim.TopHat2D)
+        c = gx.Canvas(700, 350)
+        gx.draw_density_test(c, pos[order], s.Particles(("rho",))["rho"][order])
+        check(name, c, look_at_the_png=False)
+    s.Close(); o.close()
+
+
 def test_point_source_appends_between_steps():
     """sources (sph.go:72-86): particles spawned by a PointSource join the state before each step (sphb_append); the
     oracle is fed the same particles through its own append"""
