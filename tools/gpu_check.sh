@@ -14,4 +14,6 @@ timeout 300 python bench.py --workload c3 --steps 20 --warmup 3 --no-e2e > gpuru
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_c5.csv \
   python bench.py --steps 2 --warmup 3 --no-e2e > gpurun_out/ncu_bench.log 2>&1
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/sanitize_workload.py > gpurun_out/sanitizer.txt 2>&1; echo "memcheck rc=$?"
+timeout 300 python tools/speed_test.py --impl gpu > gpurun_out/speed_test_gpu.json 2> gpurun_out/speed_test_gpu.err
+timeout 300 python tools/speed_test.py --impl cpu > gpurun_out/speed_test_cpu.json 2> gpurun_out/speed_test_cpu.err
 tail -3 gpurun_out/pytest_gpu.log; tail -2 gpurun_out/smoke.log; cut -c1-300 gpurun_out/bench_c5.json
