@@ -199,6 +199,17 @@ class Oracle:
         lib().orc_tree_stats(self._h, _ip(out))
         return dict(nodes=int(out[0]), leaves=int(out[1]), max_leaf=int(out[2]), depth=int(out[3]))
 
+    def tree(self):
+        """the tree as arrays in pre-order: geo [nodes, 7] = LowerLeft, UpperRight, BCenter, BRadius; link [nodes, 4] =
+        index of Lower, index of Upper (-1 = nil), first particle (current order), particle count"""
+        L = lib()
+        L.orc_tree_dump.restype = C.c_int64
+        L.orc_tree_dump.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+        n = L.orc_tree_dump(self._h, 0, None, None)
+        geo, link = np.zeros((n, 7)), np.zeros((n, 4), dtype=np.int64)
+        L.orc_tree_dump(self._h, n, _dp(geo), _ip(link))
+        return geo, link
+
     def state(self, neighbours=False, sort_by_id=True):
         """Dict of numpy arrays. With sort_by_id rows are ordered by particle id (ids must be unique)."""
         n = self.n

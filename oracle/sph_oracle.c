@@ -13,7 +13,9 @@
  *   - README.md:88-162 (heap BuildHeap/Insert/ExtractMin/Replace KAT)    -> orc_heap_*
  * and against the reference's recorded OUTPUT for kNN and density: the PNGs its Go binary drew
  * for examples/density (doc/density_compare.png, density_test.png, density_test_periodic.png)
- * are reproduced pixel for pixel from this oracle's results (tests/test_reference_images.py).
+ * are reproduced pixel for pixel from this oracle's results (tests/test_reference_images.py),
+ * as are doc/tree.png (Partition / Treebuild) and doc/nearest_neighbours*.png (leaf bounding
+ * circles, open and periodic neighbour sets of one particle).
  * The reference has NO test and no recorded output that pins force, leapfrog or boundaries, so
  * for those functions parity is UNPINNED by the reference: they are restated line by line below
  * (same operation order, no FMA contraction: build with -ffp-contract=off) and cross-checked
@@ -612,6 +614,29 @@ void orc_tree_stats(const orc_sim* s, int64_t* out4) {
   int64_t nodes = 0, leaves = 0, maxleaf = 0; int maxdepth = 0;
   tree_stats(&s->root, 1, &nodes, &leaves, &maxleaf, &maxdepth);
   out4[0] = nodes; out4[1] = leaves; out4[2] = maxleaf; out4[3] = maxdepth;
+}
+
+/* the tree in pre-order for the tests that redraw the reference's pictures (visualization.go:33-75): per node
+ * geo = {LowerLeft.X, .Y, UpperRight.X, .Y, BCenter.X, .Y, BRadius}, link = {index of Lower, index of Upper (-1 = nil),
+ * first particle (offset in the current order), particle count}.  Returns the node count (nothing is written past cap). */
+static int64_t tree_dump(const Cell* c, const Particle* base, int64_t cap, double* geo, int64_t* link, int64_t* next) {
+  const int64_t me = (*next)++;
+  int64_t lo = -1, up = -1;
+  if (c->Lower) lo = tree_dump(c->Lower, base, cap, geo, link, next);
+  if (c->Upper) up = tree_dump(c->Upper, base, cap, geo, link, next);
+  if (me < cap) {
+    double* g = geo + 7 * me;
+    g[0] = c->LowerLeft.X; g[1] = c->LowerLeft.Y; g[2] = c->UpperRight.X; g[3] = c->UpperRight.Y;
+    g[4] = c->BCenter.X; g[5] = c->BCenter.Y; g[6] = c->BRadius;
+    int64_t* l = link + 4 * me;
+    l[0] = lo; l[1] = up; l[2] = (int64_t)(c->Particles - base); l[3] = c->Len;
+  }
+  return me;
+}
+int64_t orc_tree_dump(const orc_sim* s, int64_t cap, double* geo, int64_t* link) {
+  int64_t next = 0;
+  tree_dump(&s->root, s->ps, cap, geo, link, &next);
+  return next;
 }
 
 /* generic min-heap on int64, heap.go:51-146 (not on the executed path; README KAT only) */

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """tests/golden/reference_images.json: size and SHA-256 of the decoded RGB pixels of the PNGs the reference keeps under
-doc/ for examples/density (README.md:201-206): the recorded output of the reference's Go binary on BASELINE configs[0].
+doc/ for examples/density (README.md:201-206: the recorded output of the reference's Go binary on BASELINE configs[0]),
+examples/tree-partition (README.md:65) and examples/nearest-neighbors (README.md:174-178).
 The images themselves stay in the reference; the hashes travel (the GPU box has no /root/reference).
     python tests/golden/make_reference_image_hashes.py [/root/reference]
 """
@@ -13,7 +14,7 @@ import numpy as np
 from PIL import Image
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-NAMES = ["density_compare", "density_test", "density_test_periodic"]
+NAMES = ["density_compare", "density_test", "density_test_periodic", "tree", "nearest_neighbours", "nearest_neighbours_periodic"]
 
 
 def main():

@@ -100,3 +100,58 @@ def test_a_wrong_density_would_show():
         rho[kernel] = st["rho"] * 1.002
     assert draw_density_compare(st["pos"], rho).sha256() != REF["density_compare"]["sha256_rgb"]
     o.close()
+
+
+def test_oracle_reproduces_tree_png():
+    """examples/tree-partition (tree-partition.go:33-47): InitUniformly(2200) on the Go stream, Treebuild, MakeTreePlot.  Every
+    cell rectangle (coloured by level) and every particle pixel matches: pins Partition / Treebuild (core.go:126-224)"""
+    ic = gorand.init_uniformly(2200)
+    o = orc.Oracle(orc.make_params(), ic["pos"])
+    check("tree", gx.MakeTreePlot(gx.Tree(*o.tree()), o.state(sort_by_id=False)["pos"], 1024, 1024))
+    o.close()
+
+
+def _nearest_neighbours_picture(periodic):
+    """examples/nearest-neighbors NonPeriodic / Periodic (nearest-neighbors.go:20-102): 220 particles, the tree's cells (open)
+    or the bounding circles of its leaves (periodic), all particles, then particle 14 of the tree order, its 32 neighbours
+    and the circle of radius NNDists[0] (periodic: in all nine images).  The example queries a COPY of the particle, and
+    self-exclusion is by address (nearest-neighbour.go:79): the original is found at distance 0 and takes a slot, so the
+    list is the original + the 31 nearest others and NNDists[0] is the 31st"""
+    f32 = gx.f32
+    ic = gorand.init_uniformly(220)
+    o = orc.Oracle(orc.make_params(), ic["pos"])  # MakeCellsUniform; BoundingSpheres again changes nothing
+    tree = gx.Tree(*o.tree())
+    w = h = 1000
+    c = gx.Canvas(w, h)
+    # the pictures were drawn by a gx.DrawCircle whose scan box covered radius + border; today's clips the ring at its four
+    # extreme points (130 pixels of either picture), everything else is identical
+    if periodic:
+        tree.PlotBoundingCircles(c, 0, 1, gx.WHITE, box_with_border=True)
+    else:
+        tree.PlotCells(c, 0, 1, 1)
+    hv = ((0.0, 1.0), (0.0, 1.0)) if periodic else (orc.OPEN, orc.OPEN)
+    o.knn(hv[0], hv[1], mode=0, rebuild=False)
+    st = o.state(neighbours=True, sort_by_id=False)
+    for p in st["pos"]:
+        c.DrawDisk(f32(p[0] * float(w)), f32(p[1] * float(h)), 3.4, gx.ORANGE)
+    p0 = st["pos"][14]
+    x, y = p0[0] * float(w), p0[1] * float(h)
+    c.DrawDisk(f32(x), f32(y), 10, gx.GREEN)
+    by_id = {int(i): p for i, p in zip(st["id"], st["pos"])}
+    for i in st["nn_id"][14][1:]:  # descending distance; slot 0 of the batch result (the 32nd other) is not in the copy's list
+        pn = by_id[int(i)]
+        c.DrawDisk(f32(pn[0] * float(w)), f32(pn[1] * float(h)), 4.4, gx.GREEN)
+    c.DrawDisk(f32(x), f32(y), 4.4, gx.GREEN)  # the original itself, last (distance 0)
+    radius = f32(st["nn_dist"][14][1] * float(w))
+    for i in ((-1.0, 0.0, 1.0) if periodic else (0.0,)):
+        for j in ((-1.0, 0.0, 1.0) if periodic else (0.0,)):
+            c.DrawCircle(f32(x) + f32(float(w) * i), f32(y) + f32(float(h) * j), radius, 2, gx.GREEN, box_with_border=True)
+    o.close()
+    return c
+
+
+def test_oracle_reproduces_nearest_neighbours_pngs():
+    """pins, against the Go program's pictures: the leaf bounding circles (core.go:229-298), the open and the periodic
+    neighbour search of a particle next to the box edge (its neighbours come through the periodic images) and h"""
+    check("nearest_neighbours", _nearest_neighbours_picture(False))
+    check("nearest_neighbours_periodic", _nearest_neighbours_picture(True))
