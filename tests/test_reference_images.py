@@ -111,12 +111,14 @@ def test_oracle_reproduces_tree_png():
     o.close()
 
 
-def _nearest_neighbours_picture(periodic):
+def _nearest_neighbours_picture(periodic, batch_knn=None):
     """examples/nearest-neighbors NonPeriodic / Periodic (nearest-neighbors.go:20-102): 220 particles, the tree's cells (open)
     or the bounding circles of its leaves (periodic), all particles, then particle 14 of the tree order, its 32 neighbours
     and the circle of radius NNDists[0] (periodic: in all nine images).  The example queries a COPY of the particle, and
     self-exclusion is by address (nearest-neighbour.go:79): the original is found at distance 0 and takes a slot, so the
-    list is the original + the 31 nearest others and NNDists[0] is the 31st"""
+    list is the original + the 31 nearest others and NNDists[0] is the 31st.
+    batch_knn(pos, hor, ver, particle_id) -> (neighbour ids, distances), both by descending distance: the source of the
+    neighbour list (default: the oracle; the GPU twin of this test passes the CUDA path's)"""
     f32 = gx.f32
     ic = gorand.init_uniformly(220)
     o = orc.Oracle(orc.make_params(), ic["pos"])  # MakeCellsUniform; BoundingSpheres again changes nothing
@@ -138,11 +140,12 @@ def _nearest_neighbours_picture(periodic):
     x, y = p0[0] * float(w), p0[1] * float(h)
     c.DrawDisk(f32(x), f32(y), 10, gx.GREEN)
     by_id = {int(i): p for i, p in zip(st["id"], st["pos"])}
-    for i in st["nn_id"][14][1:]:  # descending distance; slot 0 of the batch result (the 32nd other) is not in the copy's list
+    nn_id, nn_dist = (st["nn_id"][14], st["nn_dist"][14]) if batch_knn is None else batch_knn(ic["pos"], hv[0], hv[1], int(st["id"][14]))
+    for i in nn_id[1:]:  # descending distance; slot 0 of the batch result (the 32nd other) is not in the copy's list
         pn = by_id[int(i)]
         c.DrawDisk(f32(pn[0] * float(w)), f32(pn[1] * float(h)), 4.4, gx.GREEN)
     c.DrawDisk(f32(x), f32(y), 4.4, gx.GREEN)  # the original itself, last (distance 0)
-    radius = f32(st["nn_dist"][14][1] * float(w))
+    radius = f32(nn_dist[1] * float(w))
     for i in ((-1.0, 0.0, 1.0) if periodic else (0.0,)):
         for j in ((-1.0, 0.0, 1.0) if periodic else (0.0,)):
             c.DrawCircle(f32(x) + f32(float(w) * i), f32(y) + f32(float(h) * j), radius, 2, gx.GREEN, box_with_border=True)
@@ -150,8 +153,12 @@ def _nearest_neighbours_picture(periodic):
     return c
 
 
+def nearest_neighbours_pictures(batch_knn=None, look_at_the_png=True):
+    check("nearest_neighbours", _nearest_neighbours_picture(False, batch_knn), look_at_the_png)
+    check("nearest_neighbours_periodic", _nearest_neighbours_picture(True, batch_knn), look_at_the_png)
+
+
 def test_oracle_reproduces_nearest_neighbours_pngs():
     """pins, against the Go program's pictures: the leaf bounding circles (core.go:229-298), the open and the periodic
     neighbour search of a particle next to the box edge (its neighbours come through the periodic images) and h"""
-    check("nearest_neighbours", _nearest_neighbours_picture(False))
-    check("nearest_neighbours_periodic", _nearest_neighbours_picture(True))
+    nearest_neighbours_pictures()

@@ -88,6 +88,23 @@ def test_cuda_path_reproduces_the_reference_pictures():
     s.Close(); o.close()
 
 
+def test_cuda_neighbour_list_reproduces_the_reference_pictures():
+    """doc/nearest_neighbours.png and nearest_neighbours_periodic.png with the green part - the 32 neighbours and h of the
+    picked particle, open and through the periodic images - taken from the CUDA path's neighbour list (the tree cells and
+    leaf circles in the background are the oracle's: the device has no tree)"""
+    from sphugo_b200 import _lib as L
+    from tests.test_reference_images import nearest_neighbours_pictures
+
+    def gpu_knn(pos, hor, ver, particle_id):
+        g = L.Handle(L.make_params(), pos)
+        g.knn(tuple(hor), tuple(ver))
+        st = g.state(("id", "nn_idx", "nn_dist"))
+        g.close()
+        return st["nn_id"][particle_id], st["nn_dist"][particle_id]
+
+    nearest_neighbours_pictures(gpu_knn, look_at_the_png=False)
+
+
 def test_point_source_appends_between_steps():
     """sources (sph.go:72-86): particles spawned by a PointSource join the state before each step (sphb_append); the
     oracle is fed the same particles through its own append"""
