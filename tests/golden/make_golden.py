@@ -104,6 +104,38 @@ def go_scenes():
             out[f"{f}_{steps}"] = st[f]
     out["id"] = st["id"]
     save("c2_default_go", **out)
+    # the two .sph-config files the reference generates, with their own rectangles (config-parser.go:872-973) on the Go
+    # stream; 4 steps.  example: faithful mode (= exact here).  tube: EXACT mode, the GPU's contract - on this scene the
+    # reference's own tree walk misses neighbours within the first steps (non-enclosing circle merge, core.go:300-311);
+    # `n_faithful_differs` counts the particles whose neighbour set differs between the two modes in the INITIAL state
+    # (2 of 4700 on the tube scene; the difference then spreads through the forces)
+    for name, kw, rects in REAL_CONFIGS:
+        parts = [gorand.uniform_rect_spawn(n, ul, lr) for n, ul, lr in rects]
+        pos = np.concatenate([p["pos"] for p in parts])
+        z = np.concatenate([p["z"] for p in parts])
+        sets = []
+        for mode in (0, 1):
+            o = orc.Oracle(orc.make_params(**kw), pos, None, np.full(len(pos), 0.01))
+            o.knn(mode=mode)
+            sets.append(np.sort(o.state(neighbours=True)["nn_id"], 1))
+            o.close()
+        o = orc.Oracle(orc.make_params(**kw), pos, None, np.full(len(pos), 0.01))
+        o.step(4, 0 if name == "c2_example_config_go" else 1)
+        st = o.state()
+        o.close()
+        save(name, pos0=pos, z=z, n_faithful_differs=np.array(int((sets[0] != sets[1]).any(1).sum())),
+             **{f: st[f] for f in ("id", "pos", "vel", "e", "rho", "h", "vdot", "edot")})
+
+
+O = orc.OPEN
+REAL_CONFIGS = [
+    ("c2_example_config_go", dict(gamma=4.666, particle_mass=1e6, accel=(0.0, 0.55), dt_half=0.00324, kernel=2, hor=(0.2, 0.8),
+                                  ver=(-100.0, 100.0), refl=(O[0], O[1], O[0], 0.99)),
+     [(260, (0.6, 0.2), (0.79, 0.3)), (700, (0.27, 0.3), (0.4, 0.9))]),
+    ("c2_tube_config_go", dict(gamma=4.666, particle_mass=1e5, accel=(0.0, 0.05), dt_half=0.00424, kernel=2,
+                               refl=(0.2, O[1], 0.25, 0.5)),
+     [(4000, (0.3, 0.3), (0.7, 0.4)), (700, (0.3, 0.3), (0.7, 0.5))]),
+]
 
 
 if __name__ == "__main__":

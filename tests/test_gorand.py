@@ -106,3 +106,31 @@ def test_reference_readme_records_this_stream():
     r = gorand.Rand(101)
     assert [r.Int() % 90 + 9 for _ in range(26)] == [31, 37, 82, 83, 33, 54, 39, 42, 62, 49, 84, 59, 88, 26, 27, 21, 92, 97, 87, 49, 33,
                                                      9, 42, 49, 88, 67]
+
+
+REAL_CONFIGS = {  # the two .sph-config files the reference generates (config-parser.go:872-973): physics and rectangles
+    "c2_example_config_go": (dict(gamma=4.666, particle_mass=1e6, accel=(0.0, 0.55), dt_half=0.00324, kernel=2, hor=(0.2, 0.8),
+                                  ver=(-100.0, 100.0), refl=(-1.7976931348623157e308, 1.7976931348623157e308, -1.7976931348623157e308, 0.99)),
+                             [(260, (0.6, 0.2), (0.79, 0.3)), (700, (0.27, 0.3), (0.4, 0.9))], 0),
+    "c2_tube_config_go": (dict(gamma=4.666, particle_mass=1e5, accel=(0.0, 0.05), dt_half=0.00424, kernel=2,
+                               refl=(0.2, 1.7976931348623157e308, 0.25, 0.5)),
+                          [(4000, (0.3, 0.3), (0.7, 0.4)), (700, (0.3, 0.3), (0.7, 0.5))], 1),
+}
+
+
+def test_generated_config_scenes_reproduce():
+    """c2_example_config_go / c2_tube_config_go: the reference's generated configs with their own rectangles on the Go
+    stream, 4 steps.  The tube scene is frozen in exact-kNN mode: in its initial state the reference's tree walk already
+    returns a different neighbour set for 2 of the 4700 particles (non-enclosing circle merges, core.go:300-311)"""
+    from oracle import oracle as orc
+    for name, (kw, rects, mode) in REAL_CONFIGS.items():
+        g = _golden(name)
+        pos = np.concatenate([gorand.uniform_rect_spawn(n, ul, lr)["pos"] for n, ul, lr in rects])
+        assert np.array_equal(pos, g["pos0"])
+        o = orc.Oracle(orc.make_params(**kw), pos, None, np.full(len(pos), 0.01))
+        o.step(4, mode)
+        st = o.state()
+        for f in ("pos", "vel", "e", "rho", "h", "vdot", "edot"):
+            assert np.array_equal(st[f], g[f]), (name, f)
+        o.close()
+    assert int(_golden("c2_example_config_go")["n_faithful_differs"]) == 0 and int(_golden("c2_tube_config_go")["n_faithful_differs"]) == 2

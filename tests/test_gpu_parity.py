@@ -108,14 +108,16 @@ def test_c2_default_simulation_steps():
 
 
 def test_c2_example_config_steps():
-    """generated example.sph-config (config-parser.go:872-924): Wendland, periodic x, gravity, floor."""
+    """the physics of the generated example.sph-config (config-parser.go:872-924: Wendland, periodic x, gravity, floor) on
+    two wide rectangles; the config's own rectangles on the Go stream are tests/golden/c2_example_config_go.npz"""
     ic = gen.spawn([(260, (0.2, 0.3), (0.8, 0.4)), (700, (0.2, 0.6), (0.8, 0.99))])
     _step_case(ic, steps=8, gamma=4.666, particle_mass=1e6, accel=(0.0, 0.55), dt_half=0.00324, kernel=2,
                hor=(0.2, 0.8), ver=(-100.0, 100.0), refl=(L.OPEN_LO, L.OPEN_HI, L.OPEN_LO, 0.99))
 
 
 def test_c2_tube_config_steps():
-    """generated tube.sph-config (config-parser.go:926-973): reflections L, U, D."""
+    """the physics of the generated tube.sph-config (config-parser.go:926-973: reflections L, U, D) on a dense and a dilute
+    rectangle side by side; the config's own rectangles on the Go stream are tests/golden/c2_tube_config_go.npz"""
     ic = gen.spawn([(4000, (0.2, 0.25), (0.5, 0.5)), (700, (0.5, 0.25), (0.8, 0.5))])
     _step_case(ic, steps=6, particle_mass=1e5, accel=(0.0, 0.05), dt_half=0.00424, kernel=2,
                refl=(0.2, L.OPEN_HI, 0.25, 0.5))

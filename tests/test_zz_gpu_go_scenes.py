@@ -105,6 +105,24 @@ def test_cuda_neighbour_list_reproduces_the_reference_pictures():
     nearest_neighbours_pictures(gpu_knn, look_at_the_png=False)
 
 
+def test_generated_config_scenes():
+    """example.sph-config and tube.sph-config as the reference generates them (config-parser.go:872-973: their own
+    rectangles, the Go stream), 4 steps against the committed golden vectors (tube: exact-kNN mode, see make_golden.py).
+    These dense scenes amplify round-off quickly - a 1e-16 perturbation of the input grows to 4e-12 (example) and 4e-11
+    (tube) of the velocity scale within the 4 steps in the oracle itself - hence 1e-8 / 1e-7 instead of 1e-9"""
+    from sphugo_b200 import _lib as L
+    from tests.test_gorand import REAL_CONFIGS
+    for name, (kw, rects, mode) in REAL_CONFIGS.items():
+        g = _golden(name)
+        h = L.Handle(L.make_params(**kw), g["pos0"], None, np.full(len(g["pos0"]), 0.01))
+        h.step(4)
+        st = h.state()
+        assert np.array_equal(st["id"], g["id"])
+        for f in ("pos", "vel", "e", "rho", "h"):
+            assert U.rel_err(st[f], g[f], np.abs(g[f]).max() * 1e-3) <= (1e-8 if "example" in name else 1e-7), (name, f)
+        h.close()
+
+
 def test_point_source_appends_between_steps():
     """sources (sph.go:72-86): particles spawned by a PointSource join the state before each step (sphb_append); the
     oracle is fed the same particles through its own append"""
