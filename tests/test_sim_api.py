@@ -148,3 +148,12 @@ def test_point_sources_parse_and_spawn_from_the_running_go_stream():
     assert tuple(new["pos"][0]) == (0.2 + dx, 0.2 + dy) and new["z"][0] == r.Int()
     with pytest.raises(ValueError):
         sim.MakeConfigFromText("[[Sources]]\n[Point]\nPos 0.1 0.1\n")
+
+
+def test_config_text_spawns_the_golden_scene():
+    """the reader + the spawners on the Go stream give exactly the particles tests/golden/c2_example_config_go.npz was made from"""
+    import os
+    c = sim.MakeConfigFromText(EXAMPLE)
+    pos = np.concatenate([s.Spawn(0)["pos"] for s in c.Start])
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "c2_example_config_go.npz"))
+    assert np.array_equal(pos, g["pos0"])
