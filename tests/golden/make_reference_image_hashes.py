@@ -14,7 +14,8 @@ import numpy as np
 from PIL import Image
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-NAMES = ["density_compare", "density_test", "density_test_periodic", "tree", "nearest_neighbours", "nearest_neighbours_periodic"]
+NAMES = ["density_compare", "density_test", "density_test_periodic", "tree", "nearest_neighbours", "nearest_neighbours_periodic",
+         "customColorMaps"]
 
 
 def main():

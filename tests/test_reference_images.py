@@ -162,3 +162,12 @@ def test_oracle_reproduces_nearest_neighbours_pngs():
     """pins, against the Go program's pictures: the leaf bounding circles (core.go:229-298), the open and the periodic
     neighbour search of a particle next to the box edge (its neighbours come through the periodic images) and h"""
     nearest_neighbours_pictures()
+
+
+def test_colour_ramps_reproduce_custom_colour_maps_png():
+    """examples/color-ramp (color-ramp.go:7-23): the four ramps the other pictures are coloured with"""
+    c = gx.Canvas(80, 256)
+    for j, cmap in enumerate([gx.RainbowRamp, gx.ParaRamp, gx.HeatRamp, gx.ToxicRamp]):
+        for i in range(256):
+            c.DrawRect((j * 20, 255 - i), ((j + 1) * 20, 255 - i), cmap(i))
+    check("customColorMaps", c)
