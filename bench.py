@@ -35,6 +35,15 @@ B_ALG_BY_PREC = {64: {"keys": 40, "sort": 16, "reorder": 148, "knn": 176, "force
                  32: {"keys": 24, "sort": 16, "reorder": 84, "knn": 152, "force": 200}}
 B_ALG = B_ALG_BY_PREC[64]
 B_ALG_TOTAL = 652
+_JSON_OUT = None
+
+
+def emit(line: dict):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 METRIC = "particle-updates/s per SPH step (k=32)"
 UNIT = "particle-updates/s"
 
@@ -194,7 +203,7 @@ def run_reference(args):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t_all,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def make_ic_c4(rank, world):
@@ -284,8 +293,13 @@ def run_ours(args):
     phases = {}
     for k in ("keys", "sort", "reorder", "knn", "force"):
         ms = phase_acc[k] / KP
-        gbs = n * B_ALG[k] / (ms * 1e-3) / 1e9 if ms > 0 else None
+        # a phase fused into another kernel (keys: emitted by the force epilogue on periodic steps) has no launch of
+        # its own: the timer brackets nothing and a bandwidth figure would be meaningless
+        fused = ms < 0.02 and k == "keys"
+        gbs = n * B_ALG[k] / (ms * 1e-3) / 1e9 if ms > 0 and not fused else None
         phases[k] = {"ms": ms, "alg_GBps": gbs, "frac": gbs / peak if gbs else None}
+        if fused:
+            phases[k]["fused_into"] = "force epilogue of the previous step"
     dom = max(("keys", "sort", "reorder", "knn", "force"), key=lambda k: phase_acc[k])
     dom_kernel = {"knn": "k_knn_tile (+ k_knn_fallback for refused particles)", "force": "k_force_st",
                   "reorder": "k_reorder", "keys": "k_keys", "sort": "counting-sort kernels"}[dom]
@@ -378,15 +392,17 @@ def run_ours(args):
         "clocks": clocks,
         "other_build": other,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
-    # rank 0 prints exactly one JSON line on stdout: NCCL's own messages (version banner, warnings) go to stderr
-    # (NCCL_DEBUG=VERSION prints the banner with a bare printf to stdout; at WARN it goes through the debug file)
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # rank 0 prints exactly one JSON line on stdout.  Libraries may write to fd 1 on their own (NCCL_DEBUG=VERSION / INFO
+    # print with a bare printf): the process's fd 1 is pointed at stderr for the whole run and the JSON line goes to
+    # the saved original stdout.  The caller's NCCL_* environment is left as it is.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

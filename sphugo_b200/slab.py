@@ -581,7 +581,7 @@ def bench(args, nx, ny, box, phys, desc, rank, world, local):
             "phases": {"slab_wall_ms_per_step": slab_phases, "device_ms_last_evaluation": device_phases,
                        "what": f"rank 0, {KP} separate untimed steps with a device sync after every protocol phase"},
         }
-        print(json.dumps(line), flush=True)
+        B.emit(line)
     dist.barrier()
     sim.handle.close()
     dist.destroy_process_group()

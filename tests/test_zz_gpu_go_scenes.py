@@ -57,11 +57,21 @@ def test_density_example_scene():
 
 
 def test_cuda_path_reproduces_the_reference_pictures():
-    """the same three pictures from the CUDA library's results (through the mirrored sim API); only the drawing ORDER -
-    the tree permutation of Root.Particles, which the device does not have - is taken from the oracle"""
+    """The three examples/density pictures from the CUDA library's results (through the mirrored sim API); only the drawing
+    ORDER - the tree permutation of Root.Particles, which the device does not have - is taken from the oracle.
+
+    density_compare (1000 + 200, periodic): the reference's pruned tree walk finds the exact neighbours of every particle,
+    so the CUDA path redraws the reference's PNG pixel for pixel.
+    density_test / density_test_periodic (10000 + 1200): the reference's walk returns a NON-nearest neighbour for 3 / 1
+    particles next to the (0.9, 0.9) corner (non-enclosing two-circle merge, core.go:300-311 with the prune of
+    nearest-neighbour.go:86-107).  The CUDA path computes exact kNN (SURVEY 8c contract), so it must equal the oracle's
+    EXACT mode for every particle, and differ from the reference's recorded output on exactly the particles where the
+    oracle's faithful and exact modes differ (tests/golden/reference_images.json: pruning_artefact_ids) - the open
+    picture then has its own hash (two of the three particles change their 8-bit colour), the periodic one keeps the
+    reference's."""
     from oracle import oracle as orc
     from tests import gx_restatement as gx
-    from tests.test_reference_images import check, density_scene, draw_density_compare, periodic_visual_scene
+    from tests.test_reference_images import REF, check, density_scene, draw_density_compare, periodic_visual_scene
     pos = density_scene()
     o = orc.Oracle(orc.make_params(hor=(0, 1), ver=(0, 1)), pos)
     o.knn((0.0, 1.0), (0.0, 1.0), mode=0)
@@ -74,17 +84,38 @@ def test_cuda_path_reproduces_the_reference_pictures():
         rho[kernel] = s.Particles(("rho",))["rho"][order]
     check("density_compare", draw_density_compare(pos[order], rho), look_at_the_png=False)  # GPU tests never read /root/reference
     s.Close(); o.close()
+
     pos = periodic_visual_scene()
-    o = orc.Oracle(orc.make_params(), pos)
+    o = orc.Oracle(orc.make_params(), pos)  # faithful: one oracle, two passes, like the example (density.go:122-125)
     s = sim.Simulation(sim.MakeConfig(), dict(pos=pos))
     for name, hor, ver in (("density_test", orc.OPEN, orc.OPEN), ("density_test_periodic", (0.1, 0.9), (0.1, 0.9))):
         o.knn(hor, ver, mode=0)
+        o.density(0)
         order = o.state(sort_by_id=False)["id"]
+        faithful = o.state(sort_by_id=True)
+        ox = orc.Oracle(orc.make_params(), pos)
+        ox.knn(hor, ver, mode=1)
+        ox.density(0)
+        exact = ox.state(neighbours=True, sort_by_id=True)
+        ox.close()
         s.FindNearestNeighboursPeriodic(hor, ver)
         s.Density2D(sim.TopHat2D)
+        gpu = s.Particles(("rho", "h", "id", "nn_idx", "nn_dist"))
+        # (1) the CUDA path is the exact kNN, particle for particle
+        assert np.array_equal(gpu["id"], exact["id"])
+        assert U.neighbour_sets_equal(gpu, exact)[0] == 0, name
+        assert U.rel_err(gpu["h"], exact["h"]) <= U.TOL64 and U.rel_err(gpu["rho"], exact["rho"]) <= U.TOL64, name
+        # (2) it differs from the reference's recorded output on exactly the reference's pruning artefacts
+        artefacts = REF[name]["exact_knn"]["pruning_artefact_ids"]
+        assert np.nonzero(faithful["h"] != exact["h"])[0].tolist() == artefacts, name
+        assert np.nonzero(np.abs(gpu["h"] / faithful["h"] - 1.0) > 1e-9)[0].tolist() == artefacts, name
+        # (3) the reference's picture from the faithful oracle (the PNG's hash), the exact-kNN picture from the CUDA path
         c = gx.Canvas(700, 350)
-        gx.draw_density_test(c, pos[order], s.Particles(("rho",))["rho"][order])
+        gx.draw_density_test(c, pos[order], faithful["rho"][order])
         check(name, c, look_at_the_png=False)
+        c = gx.Canvas(700, 350)
+        gx.draw_density_test(c, pos[order], gpu["rho"][order])
+        assert c.sha256() == REF[name]["exact_knn"]["sha256_rgb"], name
     s.Close(); o.close()
 
 
