@@ -389,6 +389,11 @@ def run_ours(args):
                 "what": "per step: sphb_upload_by_id(Pos,Vel,E) + sphb_step(1) + sphb_frame(xy f32, colour u8, caller's order) + sphb_reduce(sum E), pinned host buffers, wall clock"},
         "gpu_launches": c1["kernel_launches"] - c0["kernel_launches"],
         "knn_fallback_particles": c1["knn_fallback"] - c0["knn_fallback"],
+        # certified reuse of the neighbour lists inside the timed region: evaluations that took the exact kNN from the
+        # stored candidates (no sort / reorder / tile search), rebuild evaluations, and the particles the certificate
+        # refused (they took the ring-expansion search; counted in knn_fallback_particles)
+        "reuse": {"reuse_steps": c1["reuse_steps"] - c0["reuse_steps"], "rebuild_steps": K - (c1["reuse_steps"] - c0["reuse_steps"]),
+                  "refused_fraction": (c1["knn_fallback"] - c0["knn_fallback"]) / (n * K)},
         "clocks": clocks,
         "other_build": other,
     }

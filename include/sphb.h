@@ -115,7 +115,8 @@ enum {
   SPHB_CNT_KERNEL_LAUNCHES = 1,
   SPHB_CNT_KNN_FALLBACK = 2, /* particles that needed the ring-expansion search */
   SPHB_CNT_REGRIDS = 3,
-  SPHB_CNT_COUNT = 4
+  SPHB_CNT_REUSE_STEPS = 4,  /* evaluations that took the exact kNN from the stored candidate lists (no sort, no search) */
+  SPHB_CNT_COUNT = 5
 };
 
 /* == sim.MakeSimulationFromConf + MakeCells (sph.go:40-54, core.go:93-105).

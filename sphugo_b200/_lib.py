@@ -30,7 +30,7 @@ FIELD_SHAPE = {  # trailing shape, dtype
 }
 SUM_E, SUM_RHO, LAST_VEL_NORM = 0, 1, 2
 PHASES = ["keys", "sort", "reorder", "knn", "force", "total"]
-COUNTERS = ["steps", "kernel_launches", "knn_fallback", "regrids"]
+COUNTERS = ["steps", "kernel_launches", "knn_fallback", "regrids", "reuse_steps"]
 HALO_RECORD_DOUBLES, MIGRANT_RECORD_DOUBLES = 10, 12
 
 EXPORTS = [

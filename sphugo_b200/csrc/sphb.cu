@@ -76,7 +76,7 @@ struct sphb_sim {
   int64_t nleaving = 0;        // particles packed for migration and not yet compacted away
   cudaEvent_t ev[SPHB_PH_COUNT + 1] = {};
   bool ev_valid = false;
-  int64_t counters[SPHB_CNT_COUNT] = {0, 0, 0, 0};
+  int64_t counters[SPHB_CNT_COUNT] = {};
   unsigned long long* hacc = nullptr;  // [HACC_N][2] smoothing-length accumulator written by the kNN kernels
   uint32_t* qmax = nullptr;   // {max h, max |v|^2} of the owned particles as float bits (kNN / force kernels)
   bool qmax_valid = false;    // the statistics pass was skipped: sphb_max_h / sphb_max_speed read qmax
@@ -86,8 +86,28 @@ struct sphb_sim {
   GridTune gtune{};
   KnnTune ktune{};
   int force_nrec = 672;       // staged neighbour records per force block (shared memory)
+  // certified reuse of the neighbour lists (sphb_kernels.cuh, ReuseState)
+  uint32_t* nx = nullptr;     // extended list [tile][SPHB_KX][lane]
+  double* dexcl = nullptr;    // exclusion radius per particle
+  ReuseState* rs = nullptr;   // device bookkeeping
+  ReuseStat* stat_dev = nullptr;
+  ReuseStat* stat_host = nullptr;  // pinned ring of REUSE_RING records (non-blocking feedback for the schedule)
+  bool reuse_on = true;       // SPHB_REUSE=0 switches it off
+  int reuse_period = 4;       // evaluations per cycle: one rebuild + (period - 1) reuse evaluations; 1 = never reuse
+  int reuse_period_max = 8, reuse_period_fixed = 0;
+  double reuse_skin = 0.25;   // extended candidates are collected up to h (1 + skin)
+  int reuse_capb = 32, reuse_ncw = 320;
+  ReuseState* force_rs = nullptr;  // arguments of the force launch in progress
+  bool force_stale = false;
+  bool lists_ext = false;     // nn / nx / dexcl / rs describe the current particles (order and displacement chain)
+  int reuse_age = 0;          // reuse evaluations since the rebuild
+  sphb_params list_prm{};     // parameters of the rebuild (a change invalidates the displacement bookkeeping)
+  uint32_t stat_enq = 0, stat_seen = 0;  // records enqueued / read back
+  int reuse_cooldown = 0;
   std::string err;
 };
+
+#define REUSE_RING 64
 
 namespace {
 
@@ -198,6 +218,9 @@ int enter(sphb_sim* s) {
   return SPHB_OK;
 }
 
+// the state changed under the lists (upload, append, parameters): the next evaluation is a rebuild
+void invalidate_reuse(sphb_sim* s) { s->lists_ext = false; s->reuse_age = 0; }
+
 // the force epilogue left the next step's cell counts in cellCount: forget them (the state changed under them)
 void drop_ready_keys(sphb_sim* s) {
   if (s->keys_ready) cudaMemsetAsync(s->cellCount, 0, ((size_t)s->ntiles_cap * SC_TILE + 8) * sizeof(uint32_t), s->st);
@@ -218,32 +241,57 @@ int refresh_stats(sphb_sim* s) {
   return SPHB_OK;
 }
 
-template <int KERNEL, bool F32>
+template <int KERNEL, bool F32, bool EXT>
 void launch_knn_p(sphb_sim* s, int ntot, const PhysP& ph) {
   KnnOut out{s->hacc, s->hscale, s->qmax, s->a.pc, s->nn, s->failList, s->failCount};
   const int tiles = cdiv(ntot, 32);
   KnnTune kt = s->ktune;
   kt.cap = s->have_h ? s->ktune.cap : s->ktune.cap0;  // first evaluation: radius from a density estimate, wider spread
-  kt.ncw = s->have_h ? s->ktune.ncw : s->ktune.ncw0;
-  const size_t smem = (size_t)KNN_WARPS * knn_smem_bytes_per_warp(kt.cap, kt.ncw, F32);
+  kt.ncw = s->have_h ? (EXT ? s->reuse_ncw : s->ktune.ncw) : s->ktune.ncw0;
+  KnnExt ex{EXT ? s->nx : nullptr, EXT ? s->dexcl : nullptr, s->reuse_skin, EXT ? s->reuse_capb : 0};
+  const size_t smem = (size_t)KNN_WARPS * knn_smem_bytes_per_warp(kt.cap, kt.ncw, F32, ex.capb);
   static bool attr_done[64] = {};  // function attributes are per device (one handle per GPU, maybe several per process)
   if (!attr_done[s->device & 63]) {
-    cudaFuncSetAttribute(k_knn_tile<KERNEL, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_knn_tile<KERNEL, F32, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_done[s->device & 63] = true;
   }
-  k_knn_tile<KERNEL, F32><<<cdiv(tiles, KNN_WARPS), KNN_THREADS, smem, s->st>>>(s->spos, s->keysSorted, s->cellStart,
-                                                                              s->hguess, s->a.epred, ntot, s->grid, ph, kt, out,
-                                                                              s->slab_on ? s->a.ghost : nullptr, s->dflags);
+  k_knn_tile<KERNEL, F32, EXT><<<cdiv(tiles, KNN_WARPS), KNN_THREADS, smem, s->st>>>(s->spos, s->keysSorted, s->cellStart,
+                                                                                   s->hguess, s->a.epred, ntot, s->grid, ph, kt, out,
+                                                                                   s->slab_on ? s->a.ghost : nullptr, s->dflags, ex);
 }
 
+// ext: the evaluation starts a reuse cycle (extended lists + exclusion radii are written)
 template <int KERNEL>
-void launch_knn(sphb_sim* s, int ntot, const PhysP& ph) {
-  if (s->prm.precision == 32) launch_knn_p<KERNEL, true>(s, ntot, ph);
-  else launch_knn_p<KERNEL, false>(s, ntot, ph);
+void launch_knn(sphb_sim* s, int ntot, const PhysP& ph, bool ext) {
+  ext = ext && s->have_h;  // (the first evaluation has no previous h to take the skin from)
+  if (s->prm.precision == 32) { if (ext) launch_knn_p<KERNEL, true, true>(s, ntot, ph); else launch_knn_p<KERNEL, true, false>(s, ntot, ph); }
+  else { if (ext) launch_knn_p<KERNEL, false, true>(s, ntot, ph); else launch_knn_p<KERNEL, false, false>(s, ntot, ph); }
   KnnOut out{s->hacc, s->hscale, s->qmax, s->a.pc, s->nn, s->failList, s->failCount};
-  k_knn_fallback<KERNEL><<<148 * 4, 128, 0, s->st>>>(s->spos, s->keysSorted, s->cellStart, s->hguess,
-                                                   s->a.epred, ntot, s->grid, ph, out, s->slab_on ? s->a.ghost : nullptr, s->dflags);
+  FbExt fx{ext ? s->nx : nullptr, ext ? s->dexcl : nullptr, nullptr};
+  k_knn_fallback<KERNEL, false><<<148 * 4, 128, 0, s->st>>>(s->spos, s->keysSorted, s->cellStart, s->hguess,
+                                                          s->a.epred, ntot, s->grid, ph, out, s->slab_on ? s->a.ghost : nullptr, s->dflags, fx);
   s->have_h = true;
+  s->lists_ext = ext;  // (forces() completes the bookkeeping; any other caller leaves plain lists)
+}
+
+// REUSE evaluation: exact kNN from the stored candidates, refused particles to the ring-expansion search on the stale cells
+template <int KERNEL>
+void launch_knn_reuse(sphb_sim* s, int ntot, const PhysP& ph) {
+  KnnOut out{s->hacc, s->hscale, s->qmax, s->a.pc, s->nn, s->failList, s->failCount};
+  const bool f32 = s->prm.precision == 32;
+  const size_t smem = (size_t)REUSE_NC * REUSE_THREADS * (f32 ? 4 : 8);
+  static bool attr_done[64] = {};
+  if (!attr_done[s->device & 63]) {
+    cudaFuncSetAttribute(k_knn_reuse<KERNEL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(k_knn_reuse<KERNEL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    attr_done[s->device & 63] = true;
+  }
+  const uint8_t* gf = s->slab_on ? s->a.ghost : nullptr;
+  if (f32) k_knn_reuse<KERNEL, true><<<cdiv(ntot, REUSE_THREADS), REUSE_THREADS, smem, s->st>>>(s->spos, s->a.epred, ntot, s->grid, ph, out, s->nx, s->dexcl, s->rs, gf, s->dflags);
+  else k_knn_reuse<KERNEL, false><<<cdiv(ntot, REUSE_THREADS), REUSE_THREADS, smem, s->st>>>(s->spos, s->a.epred, ntot, s->grid, ph, out, s->nx, s->dexcl, s->rs, gf, s->dflags);
+  FbExt fx{s->nx, s->dexcl, s->rs};
+  k_knn_fallback<KERNEL, true><<<148 * 4, 128, 0, s->st>>>(s->spos, s->keysSorted, s->cellStart, s->hguess,
+                                                         s->a.epred, ntot, s->grid, ph, out, gf, s->dflags, fx);
 }
 
 SlabP make_slabp(const sphb_sim* s) {
@@ -286,6 +334,7 @@ void launch_force(sphb_sim* s, int ntot, const PhysP& ph, bool integrate) {
   io.keys = s->keysSorted; io.cellStart = s->cellStart; io.qmax = s->qmax;
   io.next_grid = s->fuse_keys ? s->grid_next : nullptr;
   io.next_keys = s->keys; io.next_rank = s->rank; io.next_count = s->cellCount;
+  io.rs = s->force_rs; io.stale = s->force_stale ? 1 : 0;
   if (integrate) cudaMemsetAsync(s->qmax + 1, 0, sizeof(uint32_t), s->st);  // max |v|^2 after this kick
   io.pos = s->a.pos; io.vel = s->a.vel; io.e = s->a.e; io.vdot = s->a.vdot; io.edot = s->a.edot;
   if (!s->slab_on) {
@@ -311,13 +360,17 @@ void compact_in_place(sphb_sim* s, int nslots, int nkeep) {
 }
 
 // sort + reorder + kNN (+ density with `kernel`); the neighbour list, spos and grid then describe s->a
-int build_neighbours(sphb_sim* s, int mode, const double hor[2], const double ver[2], int kernel, bool timed) {
+// ext: start a reuse cycle (extended lists); want_hacc: the smoothing-length accumulator will be consumed by the next
+// evaluation's grid (not when a reuse evaluation follows: it needs no grid)
+int build_neighbours(sphb_sim* s, int mode, const double hor[2], const double ver[2], int kernel, bool timed, bool ext = false,
+                     bool want_hacc = true) {
   const int ntot = (int)(s->n + s->nghost);
   if (ntot <= 0) return fail(s, SPHB_E_STATE, "Simulation not initialized: no particles (sph.go:92-94)");
   // Fully periodic runs (single handle, or a slab of a periodic ring) need no statistics pass per evaluation: the box
   // comes from hor / ver / the slab edges, the mean smoothing length from the accumulator the previous kNN filled,
   // max h and max speed (slab driver) from qmax.
   const bool periodic = !axis_open(ver) && !axis_open(hor) && (!s->slab_on || (s->slab.has_left && s->slab.has_right));
+  invalidate_reuse(s);
   // a fused step already built this evaluation's grid (and consumed the accumulator for it)
   const bool same_box = s->grid_next_ready && periodic && !s->slab_on && hor[0] == s->next_hor[0] && hor[1] == s->next_hor[1] &&
                         ver[0] == s->next_ver[0] && ver[1] == s->next_ver[1];
@@ -326,14 +379,14 @@ int build_neighbours(sphb_sim* s, int mode, const double hor[2], const double ve
   const bool use_hacc = periodic && s->hacc_valid;
   if (s->stats_dirty && !use_hacc) { int rc = refresh_stats(s); if (rc) return rc; }
   const double hscale_prev = s->hscale;
-  s->hscale = periodic ? 16777216.0 / std::max(hor[1] - hor[0], ver[1] - ver[0]) : 0.0;  // h < L: 24-bit fixed point
+  s->hscale = periodic && want_hacc ? 16777216.0 / std::max(hor[1] - hor[0], ver[1] - ver[0]) : 0.0;  // h < L: 24-bit fixed point
   const PhysP ph = make_phys(s->prm, kernel);
   const double dtH = s->prm.dt_half;
   if (timed) cudaEventRecord(s->ev[SPHB_PH_KEYS], s->st);
   if (same_box) std::swap(s->grid, s->grid_next);
   else k_make_grid<<<1, 32, 0, s->st>>>(s->stats, ntot, hor[0], hor[1], ver[0], ver[1], make_slabp(s), s->slab_on ? 1 : 0,
                                         s->gtune, s->grid, s->hacc, hscale_prev > 0.0 ? hscale_prev : 1.0, use_hacc ? 1 : 0);
-  s->hacc_valid = periodic;  // the kNN below refills the accumulator
+  s->hacc_valid = periodic && want_hacc;  // the kNN below refills the accumulator
   cudaMemsetAsync(s->qmax, 0, sizeof(uint32_t), s->st);  // max h of this evaluation
   const bool keys_ok = same_box && s->keys_ready && mode == MODE_DRIFT && dtH == s->keys_dtH && ntot == s->keys_n;
   if (keys_ok) s->keys_ready = false;  // consumed: the scan below zeroes cellCount again
@@ -365,9 +418,9 @@ int build_neighbours(sphb_sim* s, int mode, const double hor[2], const double ve
   cudaMemsetAsync(s->failCount, 0, sizeof(int), s->st);
   if (timed) cudaEventRecord(s->ev[SPHB_PH_KNN], s->st);
   switch (kernel) {
-    case 0: launch_knn<0>(s, ntot, ph); break;
-    case 1: launch_knn<1>(s, ntot, ph); break;
-    default: launch_knn<2>(s, ntot, ph); break;
+    case 0: launch_knn<0>(s, ntot, ph, ext); break;
+    case 1: launch_knn<1>(s, ntot, ph, ext); break;
+    default: launch_knn<2>(s, ntot, ph, ext); break;
   }
   s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 3;
   CKL(s);
@@ -376,26 +429,105 @@ int build_neighbours(sphb_sim* s, int mode, const double hor[2], const double ve
   return SPHB_OK;
 }
 
+// ---- schedule of the list reuse ------------------------------------------------------------------
+// Every evaluation that can be followed by a reuse evaluation ends with k_reuse_update, which also leaves a record
+// {age, refused particles, D} in a pinned host ring.  The host never waits for it: it reads whatever has arrived when it
+// plans the next step.  Policy: a reuse evaluation that refused more than 0.2 % of the particles ends the cycle one
+// evaluation earlier from now on; a cycle whose last evaluation refused fewer than 0.02 % is lengthened by one.
+void reuse_poll(sphb_sim* s) {
+  if (!s->stat_host || s->reuse_period_fixed) return;
+  while (s->stat_seen < s->stat_enq) {
+    const volatile ReuseStat* r = &s->stat_host[(s->stat_seen + 1) % REUSE_RING];
+    if (r->seq != s->stat_seen + 1 || r->seq2 != r->seq) {
+      if (s->stat_enq - s->stat_seen >= REUSE_RING) { s->stat_seen = s->stat_enq - REUSE_RING / 2; continue; }  // overwritten
+      break;  // not there yet
+    }
+    s->stat_seen += 1;
+    if (r->rebuild || r->n == 0) continue;
+    const double frac = (double)r->refused / (double)r->n;
+    if (frac > 2e-3) {
+      s->reuse_period = std::max(1, std::min(s->reuse_period, (int)r->age));
+      if (s->reuse_period == 1) s->reuse_cooldown = 64;  // not even one reuse evaluation pays: try again later
+    } else if (frac < 2e-4 && (int)r->age == s->reuse_period - 1 && s->reuse_period < s->reuse_period_max) {
+      s->reuse_period += 1;
+    }
+  }
+}
+
+bool same_params(const sphb_params& a, const sphb_params& b) { return std::memcmp(&a, &b, sizeof(sphb_params)) == 0; }
+
+void launch_reuse_update(sphb_sim* s, int ntot, bool rebuild) {
+  const sphb_params& p = s->prm;
+  double cs = 1.0;  // magnitude of the coordinates (rounding slack of the displacement bound)
+  if (!axis_open(p.hor)) cs = std::max(cs, std::max(std::fabs(p.hor[0]), std::fabs(p.hor[1])));
+  if (!axis_open(p.ver)) cs = std::max(cs, std::max(std::fabs(p.ver[0]), std::fabs(p.ver[1])));
+  k_reuse_update<<<1, 32, 0, s->st>>>(s->rs, s->grid, ntot, rebuild ? 1 : 0, s->failCount, s->hacc, s->hscale, cs, s->stat_dev);
+  s->stat_enq += 1;
+  cudaMemcpyAsync(&s->stat_host[s->stat_enq % REUSE_RING], s->stat_dev, sizeof(ReuseStat), cudaMemcpyDeviceToHost, s->st);
+  s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 1;
+}
+
 // CalculateForces (sph.go:403-435) [+ kick, drift-2, wrap, reflections when integrate (sph.go:122-193)]
 int forces(sphb_sim* s, int mode, bool integrate) {
   if (s->prm.kernel == SPHB_KERNEL_TOPHAT)
     return fail(s, SPHB_E_KERNEL, "TopHat2D.DF: not defined. derivative is delta distribution! (sph.go:251-253)");
-  int rc = build_neighbours(s, mode, s->prm.hor, s->prm.ver, s->prm.kernel, true);
-  if (rc) return rc;
   const int ntot = (int)(s->n + s->nghost);
   const PhysP ph = make_phys(s->prm, s->prm.kernel);
+  // ---- plan: rebuild (sort + tile search) or reuse (exact kNN from the stored candidates)
+  const bool cyc = s->reuse_on && !s->slab_on && mode == MODE_DRIFT && integrate;  // an ordinary step
+  if (cyc) {
+    reuse_poll(s);
+    if (s->reuse_cooldown > 0 && --s->reuse_cooldown == 0 && s->reuse_period == 1) s->reuse_period = 2;
+  }
+  const int period = s->reuse_period_fixed ? s->reuse_period_fixed : s->reuse_period;
+  const bool reuse = cyc && s->lists_ext && same_params(s->prm, s->list_prm) && s->reuse_age + 1 < period;
+  // may the NEXT evaluation be a reuse evaluation?  (then this one keeps the displacement books, and prepares no grid / keys)
+  const bool next_reuse = cyc && (reuse ? s->reuse_age + 2 < period : (period > 1 && s->have_h));
+  int rc;
+  if (!reuse) {
+    rc = build_neighbours(s, mode, s->prm.hor, s->prm.ver, s->prm.kernel, true, next_reuse, !next_reuse);
+    if (rc) return rc;
+    s->lists_ext = s->lists_ext && next_reuse;
+    s->reuse_age = 0;
+    if (s->lists_ext) s->list_prm = s->prm;
+  } else {
+    if (ntot <= 0) return fail(s, SPHB_E_STATE, "Simulation not initialized: no particles (sph.go:92-94)");
+    const bool periodic = !axis_open(s->prm.ver) && !axis_open(s->prm.hor);
+    s->grid_next_ready = false;
+    s->hscale = periodic && !next_reuse ? 16777216.0 / std::max(s->prm.hor[1] - s->prm.hor[0], s->prm.ver[1] - s->prm.ver[0]) : 0.0;
+    s->hacc_valid = periodic && !next_reuse;
+    drop_ready_keys(s);
+    cudaEventRecord(s->ev[SPHB_PH_KEYS], s->st);
+    cudaEventRecord(s->ev[SPHB_PH_SORT], s->st);
+    cudaEventRecord(s->ev[SPHB_PH_REORDER], s->st);
+    Soa& a = s->a;
+    k_predict<<<cdiv(ntot, 256), 256, 0, s->st>>>(a.pos, a.vel, a.vdot, a.e, a.edot, a.vpred, a.epred, s->spos, ntot, s->grid,
+                                                  s->prm.dt_half, nullptr);
+    cudaMemsetAsync(s->failCount, 0, sizeof(int), s->st);
+    cudaMemsetAsync(s->qmax, 0, sizeof(uint32_t), s->st);
+    cudaEventRecord(s->ev[SPHB_PH_KNN], s->st);
+    if (s->prm.kernel == 1) launch_knn_reuse<1>(s, ntot, ph); else launch_knn_reuse<2>(s, ntot, ph);
+    s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 3;
+    s->counters[SPHB_CNT_REUSE_STEPS] += 1;
+    s->reuse_age += 1;
+    CKL(s);
+  }
   cudaEventRecord(s->ev[SPHB_PH_FORCE], s->st);
   // Periodic single-handle steps: the next grid only depends on the mean h the kNN above produced, so it is built now
   // and the force epilogue emits the next step's cell keys (no k_keys pass in the next step).
-  s->fuse_keys = integrate && !s->slab_on && s->hacc_valid && !axis_open(s->prm.hor) && !axis_open(s->prm.ver);
+  s->fuse_keys = integrate && !s->slab_on && s->hacc_valid && !next_reuse && !axis_open(s->prm.hor) && !axis_open(s->prm.ver);
   if (s->fuse_keys) {
     k_make_grid<<<1, 32, 0, s->st>>>(s->stats, ntot, s->prm.hor[0], s->prm.hor[1], s->prm.ver[0], s->prm.ver[1], make_slabp(s), 0,
                                      s->gtune, s->grid_next, s->hacc, s->hscale, 1);
     s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 1;
   }
+  s->force_rs = (next_reuse && s->lists_ext) ? s->rs : nullptr;
+  s->force_stale = reuse;
   if (s->prm.kernel == 1) launch_force<1>(s, ntot, ph, integrate);
   else launch_force<2>(s, ntot, ph, integrate);
   s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 1;
+  if (s->force_rs || reuse) launch_reuse_update(s, ntot, !reuse);  // (the last evaluation of a cycle: for the record only)
+  if (!next_reuse) invalidate_reuse(s);  // the cycle ends here
   if (s->fuse_keys) {
     s->grid_next_ready = s->keys_ready = true;
     s->keys_dtH = s->prm.dt_half; s->keys_n = ntot;
@@ -409,7 +541,7 @@ int forces(sphb_sim* s, int mode, bool integrate) {
   cudaEventRecord(s->ev[SPHB_PH_TOTAL], s->st);
   s->ev_valid = true;
   s->qmax_valid = s->hacc_valid;
-  if (s->hacc_valid) s->stats_dirty = true;  // sums / bounds are refreshed on demand (sphb_reduce, open axes)
+  if (s->hacc_valid || next_reuse || reuse) s->stats_dirty = true;  // sums / bounds are refreshed on demand (sphb_reduce, open axes)
   else { rc = refresh_stats(s); if (rc) return rc; }
   CKL(s);
   return SPHB_OK;
@@ -459,6 +591,7 @@ int upload_common(sphb_sim* s, int64_t off, int64_t n, const double* pos_xy, con
   drop_ready_keys(s);
   s->grid_next_ready = false;
   s->have_list = false;
+  invalidate_reuse(s);
   return SPHB_OK;
 }
 
@@ -507,6 +640,13 @@ int create_common(const sphb_params* p, int64_t n, int64_t capacity, const doubl
   CKC(dalloc(s->tileSum, (size_t)s->ntiles_cap));
   CKC(cudaMemsetAsync(s->cellCount, 0, ((size_t)s->ntiles_cap * SC_TILE + 8) * sizeof(uint32_t), s->st));
   CKC(dalloc(s->nn, cap32 * SPHB_K));
+  CKC(dalloc(s->nx, cap32 * SPHB_KX));
+  CKC(dalloc(s->dexcl, cap));
+  CKC(dalloc(s->rs, 1));
+  CKC(cudaMemsetAsync(s->rs, 0, sizeof(ReuseState), s->st));
+  CKC(dalloc(s->stat_dev, 1));
+  CKC(cudaHostAlloc((void**)&s->stat_host, REUSE_RING * sizeof(ReuseStat), cudaHostAllocDefault));
+  std::memset(s->stat_host, 0, REUSE_RING * sizeof(ReuseStat));
   CKC(dalloc(s->failList, cap));
   CKC(dalloc(s->failCount, 2));
   CKC(dalloc(s->packCount, 2));
@@ -539,6 +679,12 @@ int create_common(const sphb_params* p, int64_t n, int64_t capacity, const doubl
   s->ktune.cap0 = 80;
   s->ktune.ncw = p->precision == 32 ? 256 : 224;
   s->ktune.ncw0 = 512;
+  if (const char* ev = getenv("SPHB_REUSE")) s->reuse_on = atoi(ev) != 0;
+  if (const char* ev = getenv("SPHB_REUSE_PERIOD")) s->reuse_period_fixed = std::max(1, std::min(64, atoi(ev)));
+  if (const char* ev = getenv("SPHB_REUSE_MAX")) s->reuse_period_max = std::max(1, std::min(64, atoi(ev)));
+  if (const char* ev = getenv("SPHB_REUSE_SKIN")) s->reuse_skin = std::max(0.03, std::min(1.0, atof(ev)));
+  if (const char* ev = getenv("SPHB_REUSE_CAPB")) s->reuse_capb = std::max(24, std::min(96, atoi(ev)));
+  if (const char* ev = getenv("SPHB_REUSE_NCW")) s->reuse_ncw = std::max(128, std::min(1024, atoi(ev) / 8 * 8));
   if (const char* ev = getenv("SPHB_CELL_PER_H")) s->gtune.cell_per_h = atof(ev);
   if (const char* ev = getenv("SPHB_PPC0")) s->gtune.ppc0 = atof(ev);
   if (const char* ev = getenv("SPHB_FORCE_NC")) s->gtune.force_nc = atoi(ev);
@@ -564,10 +710,12 @@ struct CapArrays {
   double2* spos = nullptr;
   double* hguess = nullptr;
   uint32_t *keys = nullptr, *keysSorted = nullptr, *rank = nullptr, *perm = nullptr;
-  uint32_t *cellStart = nullptr, *cellCount = nullptr, *tileSum = nullptr, *nn = nullptr;
+  uint32_t *cellStart = nullptr, *cellCount = nullptr, *tileSum = nullptr, *nn = nullptr, *nx = nullptr;
+  double* dexcl = nullptr;
   int* failList = nullptr;
   void release() {
     free_soa(a); free_soa(b);
+    cudaFree(nx); cudaFree(dexcl);
     cudaFree(spos); cudaFree(hguess); cudaFree(keys); cudaFree(keysSorted); cudaFree(rank); cudaFree(perm);
     cudaFree(cellStart); cudaFree(cellCount); cudaFree(tileSum); cudaFree(nn); cudaFree(failList);
     *this = CapArrays{};
@@ -604,6 +752,8 @@ int grow_capacity(sphb_sim* s, int64_t need) {
   CKG(dalloc(t.cellCount, ncount));
   CKG(dalloc(t.tileSum, (size_t)ntiles));
   CKG(dalloc(t.nn, cap32 * SPHB_K));
+  CKG(dalloc(t.nx, cap32 * SPHB_KX));
+  CKG(dalloc(t.dexcl, cap));
   CKG(dalloc(t.failList, cap));
   const size_t n = (size_t)s->n;
   const cudaMemcpyKind dd = cudaMemcpyDeviceToDevice;
@@ -624,11 +774,12 @@ int grow_capacity(sphb_sim* s, int64_t need) {
   CapArrays old;
   old.a = s->a; old.b = s->b; old.spos = s->spos; old.hguess = s->hguess; old.keys = s->keys; old.keysSorted = s->keysSorted;
   old.rank = s->rank; old.perm = s->perm; old.cellStart = s->cellStart; old.cellCount = s->cellCount; old.tileSum = s->tileSum;
-  old.nn = s->nn; old.failList = s->failList;
+  old.nn = s->nn; old.failList = s->failList; old.nx = s->nx; old.dexcl = s->dexcl;
   s->a = t.a; s->b = t.b; s->spos = t.spos; s->hguess = t.hguess; s->keys = t.keys; s->keysSorted = t.keysSorted;
   s->rank = t.rank; s->perm = t.perm; s->cellStart = t.cellStart; s->cellCount = t.cellCount; s->tileSum = t.tileSum;
-  s->nn = t.nn; s->failList = t.failList;
+  s->nn = t.nn; s->failList = t.failList; s->nx = t.nx; s->dexcl = t.dexcl;
   old.release();
+  invalidate_reuse(s);
   s->cap = ncap;
   s->ncell_max = (int)ncm;
   s->ntiles_cap = ntiles;
@@ -684,6 +835,8 @@ void sphb_destroy(sphb_sim* s) {
   cudaFree(s->keys); cudaFree(s->keysSorted); cudaFree(s->rank); cudaFree(s->perm);
   cudaFree(s->cellCount); cudaFree(s->tileSum); cudaFree(s->cellStart); cudaFree(s->nn); cudaFree(s->failList); cudaFree(s->failCount);
   cudaFree(s->packCount); cudaFree(s->hacc); cudaFree(s->qmax);
+  cudaFree(s->nx); cudaFree(s->dexcl); cudaFree(s->rs); cudaFree(s->stat_dev);
+  if (s->stat_host) cudaFreeHost(s->stat_host);
   cudaFree(s->dflags); cudaFree(s->statPart); cudaFree(s->stats); cudaFree(s->grid); cudaFree(s->grid_next); cudaFree(s->scratch);
   for (auto& ev : s->ev) if (ev) cudaEventDestroy(ev);
   if (s->st) cudaStreamDestroy(s->st);
@@ -697,6 +850,7 @@ int sphb_set_params(sphb_sim* s, const sphb_params* p) {
   rc = check_params(s, p); if (rc) return rc;
   if (p->device != s->device) return fail(s, SPHB_E_INVALID, "device cannot change after create");
   if (p->precision != s->prm.precision) return fail(s, SPHB_E_INVALID, "precision cannot change after create");
+  if (!same_params(s->prm, *p)) invalidate_reuse(s);
   s->prm = *p;
   return SPHB_OK;
 }
@@ -875,6 +1029,7 @@ int sphb_upload(sphb_sim* s, uint32_t mask, const void* const* hp, int64_t n) {
   }
   if (mask & SPHB_MASK(SPHB_F_POS)) s->have_list = false;  // the list describes the old positions; h stays a valid first guess
   if (mask & (SPHB_MASK(SPHB_F_POS) | SPHB_MASK(SPHB_F_VEL))) drop_ready_keys(s);  // they were keys of the old state
+  if (mask) invalidate_reuse(s);
   s->stats_dirty = true;
   CK(s, cudaStreamSynchronize(s->st));
   return SPHB_OK;
@@ -905,6 +1060,7 @@ int sphb_upload_by_id(sphb_sim* s, uint32_t mask, const void* const* hp, int64_t
   CKL(s);
   if (mask & SPHB_MASK(SPHB_F_POS)) s->have_list = false;
   if (mask & (SPHB_MASK(SPHB_F_POS) | SPHB_MASK(SPHB_F_VEL))) drop_ready_keys(s);
+  invalidate_reuse(s);
   s->stats_dirty = true;
   CK(s, cudaStreamSynchronize(s->st));  // host buffers are borrowed for the duration of the call only
   return SPHB_OK;

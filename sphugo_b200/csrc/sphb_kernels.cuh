@@ -13,6 +13,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 
 #define SPHB_K 32
 #define IMG_SHIFT 28
@@ -39,6 +40,13 @@ struct PhysP {
   int kernel;
 };
 
+struct KnnExt {           // extended list of a rebuild evaluation (nx == nullptr: off)
+  uint32_t* nx;          // [tile][SPHB_KX][lane]
+  double* dexcl;
+  double skin;           // candidates are collected up to h_prev * (1 + skin)
+  int capb;              // slots of the second column
+};
+
 struct KnnTune {
   double guess_margin;   // search radius = h_prev * (1 + margin)
   double k_target;       // expected candidates inside the first-guess radius when no h_prev exists
@@ -46,6 +54,34 @@ struct KnnTune {
   int cap0;              // same for the first evaluation (no previous h)
   int ncw;               // staged candidates per tile (shared memory), multiple of 8
   int ncw0;              // same for the first evaluation
+};
+
+// -------------------------------------------------------------------------------------------------
+// Certified reuse of the neighbour lists (DESIGN "list reuse").  A REBUILD evaluation (sort + tile search) keeps, next to
+// the 32 neighbours, up to SPHB_KX further candidates per particle (`nx`) and an exclusion radius `dexcl`: every particle
+// that is neither in nn nor in nx was at least dexcl away when the lists were built.  A REUSE evaluation moves nothing in
+// memory (no sort, no reorder): it re-evaluates those <= 48 candidates at their new positions, h' = the 32nd smallest
+// distance, and the result is the exact kNN whenever  h' + D < dexcl, where D bounds |u_i - u_j| over all pairs (u =
+// displacement since the build): a particle outside the candidate set can have come closer by at most D.  Particles that
+// fail the test go to the ring-expansion search (on the stale cells, widened by D).  Accepted results are exact kNN, so
+// parity with the reference (nearest-neighbour.go:28-165) is untouched.
+// -------------------------------------------------------------------------------------------------
+#define SPHB_KX 16
+#define RS_SLOTS 64
+struct ReuseState {
+  double D;                       // bound of the relative displacement of any two particles since the build
+  double ubx, uby;                // mean displacement since the build: stale-cell lookups are shifted back by it
+  double mrx, mry;                // reference displacement of the coming step (the mean of the previous one); any value is valid
+  long long sum[RS_SLOTS][2];     // fixed-point sums of this step's displacements (integer: order independent)
+  unsigned int Mbits;             // max |delta - mref| of this step as float bits, rounded up
+  unsigned int age;               // reuse evaluations since the build
+  unsigned int seq;               // evaluations recorded so far (host feedback)
+  unsigned int pad;
+};
+struct ReuseStat {                // one record per evaluation, copied to pinned host memory (non-blocking feedback)
+  unsigned int seq, age, refused, n;
+  float D, hmean;
+  unsigned int rebuild, seq2;     // seq2 == seq marks a complete record
 };
 
 // device-side status word
@@ -396,8 +432,9 @@ struct KnnOut {
 
 // shared memory per warp: the staged candidates of the tile {fp64 position (exact phase), fp32 tile-relative
 // position (filter), list entry} = 28 B each, and a column of CAP slots x 32 lanes x {fp32 key, staged slot}
-__host__ __device__ inline size_t knn_smem_bytes_per_warp(int cap, int ncw, bool f32) {
-  return (size_t)cap * 256 + (size_t)ncw * (f32 ? 12 : 28);  // the fp32 build stages no fp64 positions
+__host__ __device__ inline size_t knn_smem_bytes_per_warp(int cap, int ncw, bool f32, int capb = 0) {
+  // the fp32 build stages no fp64 positions; capb = slots of the second column (extended list, rebuild evaluations)
+  return (size_t)(cap + capb) * 256 + (size_t)ncw * (f32 ? 12 : 28);
 }
 
 __device__ __forceinline__ int warp_min_i(int v, uint32_t mask) {
@@ -431,6 +468,57 @@ __device__ __forceinline__ void knn_append(uint32_t& kp, float d2f, uint32_t en,
       : "f"(d2f), "r"(en), "f"(thr));
 }
 
+// the same with a second column for the extended list: d2f < thr goes to column A (kp), thr <= d2f < thrx to column B (kq)
+__device__ __forceinline__ void knn_append2(uint32_t& kp, uint32_t& kq, float d2f, uint32_t en, float thr, float thrx) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      ".reg .b32 kb;\n\t"
+      "setp.lt.f32 p, %2, %4;\n\t"
+      "setp.lt.and.f32 q, %2, %5, !p;\n\t"
+      "mov.b32 kb, %2;\n\t"
+      "@p st.shared.v2.b32 [%0], {kb, %3};\n\t"
+      "@p add.u32 %0, %0, 256;\n\t"
+      "@q st.shared.v2.b32 [%1], {kb, %3};\n\t"
+      "@q add.u32 %1, %1, 256;\n\t"
+      "}\n"
+      : "+r"(kp), "+r"(kq)
+      : "f"(d2f), "r"(en), "f"(thr), "f"(thrx));
+}
+
+// Selection on a lane's column of fp32 keys (bit patterns): the mrem largest keys are to be dropped.  Five keys per pass
+// (a max/min insertion network); T = smallest dropped key (0xffffffff: none), akey = largest kept key.  Warp-collective:
+// lanes with active == false run along with zero trips.
+__device__ __forceinline__ void knn_select_drop(const uint2* col, int cnt, int mrem, bool active, uint32_t& T, uint32_t& akey) {
+  uint32_t bound = 0xffffffffu;
+  T = 0xffffffffu; akey = 0u;
+  bool sel_done = !active;
+  while (__any_sync(0xffffffffu, !sel_done)) {
+    uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+    const int lim = sel_done ? 0 : cnt;
+    for (int s = 0; s < lim; ++s) {
+      uint32_t k = col[s * 32].x;
+      k = k < bound ? k : 0u;
+      uint32_t a;
+      a = max(t0, k); k = min(t0, k); t0 = a;
+      a = max(t1, k); k = min(t1, k); t1 = a;
+      a = max(t2, k); k = min(t2, k); t2 = a;
+      a = max(t3, k); k = min(t3, k); t3 = a;
+      t4 = max(t4, k);
+    }
+    if (!sel_done) {
+      if (mrem <= 4) {
+        T = mrem == 0 ? bound : (mrem == 1 ? t0 : (mrem == 2 ? t1 : (mrem == 3 ? t2 : t3)));
+        akey = mrem == 0 ? t0 : (mrem == 1 ? t1 : (mrem == 2 ? t2 : (mrem == 3 ? t3 : t4)));
+        sel_done = true;
+      } else {
+        mrem -= 5;
+        bound = t4;
+      }
+    }
+  }
+}
+
 // warp-level contribution to the smoothing-length accumulator (all 32 lanes call): h * hscale < 2^24 per lane, so the
 // warp sum fits 32 bits and is one REDUX
 __device__ __forceinline__ void knn_accumulate_h(const KnnOut& out, bool ok, bool owned, double h) {
@@ -446,7 +534,32 @@ __device__ __forceinline__ void knn_accumulate_h(const KnnOut& out, bool ok, boo
   }
 }
 
-template <int KERNEL, bool F32>
+// extended list of an accepted lane (rebuild evaluations): the up to SPHB_KX nearest entries of column B and the exclusion
+// radius.  Every candidate the lane saw and did not keep has a key >= T, everything it did not see lies beyond rgx, and
+// fp32 keys are within delta of the true d^2: dexcl^2 = min(T (1 - 2 delta), rgx^2 (1 - 1e-5)).  Warp-collective.
+__device__ __forceinline__ void knn_write_ext(const KnnExt& ex, const uint2* colB, const uint32_t* candE, int nb, bool ok,
+                                              bool bovf, int tile, int lane, int i, double rgx, double delta, double h) {
+  const bool sel = ok && !bovf && nb > SPHB_KX;
+  uint32_t T, akey;
+  knn_select_drop(colB, nb, sel ? nb - SPHB_KX : 0, sel, T, akey);
+  if (!ok) return;  // refused lanes: the fallback kernel writes their (empty) extended list
+  uint32_t* xp = ex.nx + (size_t)tile * (SPHB_KX * 32) + lane;
+  int w = 0;
+  double dx = h;    // second column overflowed: unknown candidates were lost, nothing beyond h is certain
+  if (!bovf) {
+    double d2x = rgx * rgx * (1.0 - 1e-5);
+    if (T != 0xffffffffu) d2x = fmin(d2x, (double)__uint_as_float(T) * (1.0 - 2.0 * delta));
+    for (int s = 0; s < nb; ++s) {
+      const uint2 ke = colB[s * 32];
+      if (ke.x < T && w < SPHB_KX) { xp[w * 32] = candE[ke.y]; ++w; }
+    }
+    dx = sqrt(d2x);
+  }
+  for (; w < SPHB_KX; ++w) xp[w * 32] = 0xffffffffu;
+  ex.dexcl[i] = dx;
+}
+
+template <int KERNEL, bool F32, bool EXT>
 __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __restrict__ spos,
                                                          const uint32_t* __restrict__ keys,
                                                          const uint32_t* __restrict__ cellStart,
@@ -454,19 +567,23 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
                                                          const double* __restrict__ epred, int n,
                                                          const GridP* __restrict__ gp, PhysP ph, KnnTune tune,
                                                          KnnOut out, const uint8_t* __restrict__ gflag,
-                                                         uint32_t* __restrict__ dflags) {
+                                                         uint32_t* __restrict__ dflags, KnnExt ex) {
   const GridP g = *gp;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int CAP = tune.cap, NCW = tune.ncw;
-  unsigned char* wb = smem_raw + (size_t)warp * knn_smem_bytes_per_warp(CAP, NCW, F32);
+  const int CAP = tune.cap, NCW = tune.ncw, CAPB = EXT ? ex.capb : 0;
+  unsigned char* wb = smem_raw + (size_t)warp * knn_smem_bytes_per_warp(CAP, NCW, F32, CAPB);
   uint2* col = reinterpret_cast<uint2*>(wb) + lane;                                  // [slot * 32] = {key, staged slot}
-  float2* candF = reinterpret_cast<float2*>(wb + (size_t)CAP * 256);                 // fp32 tile-relative positions
+  uint2* colB = reinterpret_cast<uint2*>(wb + (size_t)CAP * 256) + lane;             // second column (EXT): rg <= d < rgx
+  const size_t cbase = (size_t)(CAP + CAPB) * 256;
+  float2* candF = reinterpret_cast<float2*>(wb + cbase);                             // fp32 tile-relative positions
   const float4* candF4 = reinterpret_cast<const float4*>(candF);                     // two staged candidates each
-  uint32_t* candE = reinterpret_cast<uint32_t*>(wb + (size_t)CAP * 256 + (size_t)NCW * 8);   // index | image code << 28
-  double2* candD = reinterpret_cast<double2*>(wb + (size_t)CAP * 256 + (size_t)NCW * 12);    // exact positions (fp64 build)
+  uint32_t* candE = reinterpret_cast<uint32_t*>(wb + cbase + (size_t)NCW * 8);       // index | image code << 28
+  double2* candD = reinterpret_cast<double2*>(wb + cbase + (size_t)NCW * 12);        // exact positions (fp64 build)
   const uint32_t kbase = (uint32_t)__cvta_generic_to_shared(col);
   const uint32_t klim = kbase + (uint32_t)(CAP - 8) * 256u;  // beyond this fewer than 8 free slots remain
+  const uint32_t qbase = (uint32_t)__cvta_generic_to_shared(colB);
+  const uint32_t qlim = qbase + (uint32_t)(CAPB - 8) * 256u;
 
   const int tile = blockIdx.x * KNN_WARPS + warp;
   if (tile * 32 >= n) return;  // whole warp out of range (warp-uniform)
@@ -498,10 +615,13 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
     }
   }
   const double rg2 = rg * rg;
-  // unwrapped cell range that contains every point within rw = rg (1 + 1e-4): the lane scans only these cells.
+  // EXT: the lane collects candidates up to rgx = rg-equivalent with the skin instead of the margin; those between rg
+  // and rgx feed the extended list
+  const double rgx = EXT ? rg * ((1.0 + ex.skin) / (1.0 + tune.guess_margin)) : rg;
+  // unwrapped cell range that contains every point within rw = rgx (1 + 1e-4): the lane scans only these cells.
   // The widening matters in the fp32 build: a candidate outside them has a true d^2 > rg^2 (1 + 2e-4), so even
   // with its fp32 key error (< 1.5e-5 relative, enforced below) it cannot undercut an accepted h^2 < thr.
-  const double rw = rg * (1.0 + 1e-4);
+  const double rw = rgx * (1.0 + 1e-4);
   int clo = (int)floor((xa - rw - g.ox) * g.inv_dx), chi = (int)floor((xa + rw - g.ox) * g.inv_dx);
   int rlo = (int)floor((ya - rw - g.oy) * g.inv_dy), rhi = (int)floor((ya + rw - g.oy) * g.inv_dy);
   // (clamped to one period either side: non-finite or absurd positions must not overflow the range arithmetic)
@@ -571,7 +691,7 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
     const double yref = g.oy + 0.5 * (double)(r0 + r1 + 1) * g.dy;
     double V = fmax(0.5 * (double)(c1 - c0 + 1) * g.dx, 0.5 * (double)(r1 - r0 + 1) * g.dy);
     // clamped border cells of an open axis may hold particles beyond the block: bound by the queries' reach
-    V = fmax(V, warp_max_d(mine ? fmax(fabs(xa - xref), fabs(ya - yref)) + rg : 0.0));
+    V = fmax(V, warp_max_d(mine ? fmax(fabs(xa - xref), fabs(ya - yref)) + rgx : 0.0));
     const float qfx = (float)(xa - xref), qfy = (float)(ya - yref);
     const float2 nqx2 = make_float2(-qfx, -qfx), nqy2 = make_float2(-qfy, -qfy);
     const double delta = 3.0 * (2.384185791015625e-07 * V / fmax(rg, 1e-300) + 4.76837158203125e-07);
@@ -580,6 +700,8 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
     if (mine && !(delta < (F32 ? 1.5e-5 : 1e-3))) bad = true;
     const float thr0 = (float)(rg2 * (1.0 + delta)) * 1.0000002f;
     float thrf = (mine && !bad) ? thr0 : -1.0f;
+    const float thrx0 = (float)(rgx * rgx * (1.0 + delta)) * 1.0000002f;
+    float thrxf = (EXT && mine && !bad) ? thrx0 : -1.0f;
     const float Vf = (float)V * 1.000001f;
 
     // window of piece 0 (see the filter below): issued here so that its two lookups overlap the staging loads
@@ -625,8 +747,9 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
     }
     __syncwarp();
 
-    uint32_t kp = kbase;
+    uint32_t kp = kbase, kq = qbase;
     bool ovf = false;  // column (nearly) full: stop appending, the lane goes to the fallback
+    bool bovf = false; // second column full: the lane keeps an empty extended list
     // phase 1: fp32 filter, branch-free.  A lane only scans its own window of every piece: the candidates in the
     // cells its search disc touches (a contiguous slot range, from two cellStart lookups per piece, fetched one
     // piece ahead).  The trip count is the longest window of the warp; a window that would run past the end of
@@ -661,9 +784,15 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
           d2f[2 * u] = d2.x;
           d2f[2 * u + 1] = d2.y;
         }
-        if (kp > klim) { ovf = true; thrf = -1.0f; }
+        if (kp > klim) { ovf = true; thrf = -1.0f; thrxf = -1.0f; }
+        if (EXT) {
+          if (kq > qlim) { bovf = true; thrxf = -1.0f; }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) knn_append(kp, d2f[u], (uint32_t)(c + u), thrf);
+          for (int u = 0; u < 8; ++u) knn_append2(kp, kq, d2f[u], (uint32_t)(c + u), thrf, thrxf);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) knn_append(kp, d2f[u], (uint32_t)(c + u), thrf);
+        }
       }
     }
     __syncwarp();
@@ -675,33 +804,8 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
     // select A: the 5 largest keys below `bound` per pass (a max/min insertion network on the fp32 bit patterns;
     // the warp-wide maximum of m is 4 on average at a 2 % margin, so one pass usually does).
     // T = smallest dropped key, akey = largest kept key.
-    int mrem = ok ? cnt - (SPHB_K + 1) : 0;
-    uint32_t bound = 0xffffffffu, T = 0xffffffffu, akey = 0u;
-    bool sel_done = !ok;
-    while (__any_sync(0xffffffffu, !sel_done)) {
-      uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
-      const int lim = sel_done ? 0 : cnt;
-      for (int s = 0; s < lim; ++s) {
-        uint32_t k = col[s * 32].x;
-        k = k < bound ? k : 0u;
-        uint32_t a;
-        a = max(t0, k); k = min(t0, k); t0 = a;
-        a = max(t1, k); k = min(t1, k); t1 = a;
-        a = max(t2, k); k = min(t2, k); t2 = a;
-        a = max(t3, k); k = min(t3, k); t3 = a;
-        t4 = max(t4, k);
-      }
-      if (!sel_done) {
-        if (mrem <= 4) {
-          T = mrem == 0 ? bound : (mrem == 1 ? t0 : (mrem == 2 ? t1 : (mrem == 3 ? t2 : t3)));
-          akey = mrem == 0 ? t0 : (mrem == 1 ? t1 : (mrem == 2 ? t2 : (mrem == 3 ? t3 : t4)));
-          sel_done = true;
-        } else {
-          mrem -= 5;
-          bound = t4;
-        }
-      }
-    }
+    uint32_t T, akey;
+    knn_select_drop(col, cnt, ok ? cnt - (SPHB_K + 1) : 0, ok, T, akey);
     // fp64 build, rank ambiguity (includes exact ties): the smallest dropped key must exceed the largest kept one
     // by more than the fp32 error; with nothing dropped the bound is the acceptance threshold itself (checked
     // as h^2 <= rg^2).  fp32 build: the fp32 keys are the distances, ties may fall either way.
@@ -730,6 +834,9 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
           if (ke[u].x < T && !self) {  // at most cnt - 1 - m = 32 entries qualify; kept <= s0 + u: only slots already read
             col[kept * 32] = ke[u];
             ++kept;
+          } else if (EXT && !self && ke[u].x != 0xffffffffu) {  // dropped by the selection: nearer than all of column B
+            if (kq < qbase + (uint32_t)CAPB * 256u) { colB[((kq - qbase) >> 8) * 32] = ke[u]; kq += 256u; }
+            else bovf = true;
           }
         }
       }
@@ -780,7 +887,9 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
         const float c = sqrtf((float)(ph.cfac * ep));
         out.pc[i] = make_double4((double)rho, (double)c, h, (double)(c * c / ((float)ph.gamma * rho)));
       }
-      knn_accumulate_h(out, ok, owned, (double)(ok ? h2f * rsqrtf(fmaxf(h2f, 1e-37f)) : 0.0f));
+      const double hacc_h = (double)(ok ? h2f * rsqrtf(fmaxf(h2f, 1e-37f)) : 0.0f);
+      if (EXT) knn_write_ext(ex, colB, candE, (int)((kq - qbase) >> 8), ok, bovf, tile, lane, i, rgx, delta, hacc_h * 1.000001);
+      knn_accumulate_h(out, ok, owned, hacc_h);
       continue;
     }
     // ---- fp64 build, exact phase: d^2 exactly as the reference computes it; the list entry goes to global
@@ -856,6 +965,7 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
       const double c = c2 > 0.0 ? fast_sqrt(c2, fast_rsqrt(c2)) : sqrt(c2);
       out.pc[i] = make_double4(rho, c, h, c * c * fast_rcp(ph.gamma * rho));
     }
+    if (EXT) knn_write_ext(ex, colB, candE, (int)((kq - qbase) >> 8), ok, bovf, tile, lane, i, rgx, delta, ok ? sqrt(h2) : 0.0);
     knn_accumulate_h(out, ok, owned, ok ? sqrt(h2) : 0.0);
   }
 }
@@ -867,20 +977,33 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
 // (nearest-neighbour.go:139-153) distributed over the warp: lane s holds slot s, descending, lane 0 = h^2;
 // an insertion is one ballot + one shuffle-down.  Candidates are inserted in scan order with the
 // reference's strict comparisons, so equal keys end up in the same relative order.
-template <int KERNEL>
+// STALE (reuse evaluations): the cell table describes the positions of the last rebuild.  The block of cells is then
+// taken around the query's own (stale) cell and widened by D, the bound of the relative displacement since the build:
+// a particle now within d of the query was within d + D of it then, and the query was inside its cell.  A particle may
+// have crossed the periodic seam since (its wrapped position jumped by a period while its cell did not): the image of a
+// candidate is therefore corrected to the nearest one - unless the block spans more than half a period, in which case
+// all three images of every cell are scanned (exact whatever the cells say: positions are the current ones).
+struct FbExt {
+  uint32_t* nx;            // extended list to clear (nullptr: none)
+  double* dexcl;
+  const ReuseState* rs;    // STALE: D
+};
+
+template <int KERNEL, bool STALE>
 __global__ void __launch_bounds__(128) k_knn_fallback(const double2* __restrict__ spos,
                                                      const uint32_t* __restrict__ keys,
                                                      const uint32_t* __restrict__ cellStart,
                                                      const double* __restrict__ hguess,
                                                      const double* __restrict__ epred, int n,
                                                      const GridP* __restrict__ gp, PhysP ph, KnnOut out,
-                                                     const uint8_t* __restrict__ gflag, uint32_t* __restrict__ dflags) {
+                                                     const uint8_t* __restrict__ gflag, uint32_t* __restrict__ dflags, FbExt fx) {
   const GridP g = *gp;
   const int nfail = *out.failCount;
   if (blockIdx.x == 0 && threadIdx.x == 0) out.failCount[1] += nfail;  // cumulative, read by sphb_counters
   const int lane = threadIdx.x & 31;
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   const double BIG = 1.7976931348623157e308;
+  const double D = STALE ? fx.rs->D : 0.0;
   for (int f = gwarp; f < nfail; f += nwarps) {
     const int i = out.failList[f];
     const double2 pa = spos[i];
@@ -893,9 +1016,23 @@ __global__ void __launch_bounds__(128) k_knn_fallback(const double2* __restrict_
     for (int iter = 0; iter < 64; ++iter) {
       td = BIG; ti = 0xffffffffu; found = 0;
       // unwrapped cell block covering [pa - R, pa + R]; sides that cannot hide anything are "complete"
-      int c0 = (int)floor((pa.x - R - g.ox) * g.inv_dx), c1 = (int)floor((pa.x + R - g.ox) * g.inv_dx);
-      int r0 = (int)floor((pa.y - R - g.oy) * g.inv_dy), r1 = (int)floor((pa.y + R - g.oy) * g.inv_dy);
-      c0 = min(c0, cxa); c1 = max(c1, cxa); r0 = min(r0, cya); r1 = max(r1, cya);
+      int c0, c1, r0, r1;
+      double spanx = 0.0, spany = 0.0;  // STALE: half width of the block around the query's cell
+      bool fullx = false, fully = false;
+      if (STALE) {
+        const int wx = (int)fmin(ceil((R + D) * g.inv_dx), 1.0e9), wy = (int)fmin(ceil((R + D) * g.inv_dy), 1.0e9);
+        fullx = g.wrapx && 2 * (2 * (long long)wx + 1) > (long long)g.ncx;
+        fully = g.wrapy && 2 * (2 * (long long)wy + 1) > (long long)g.ncy;
+        c0 = fullx ? -g.ncx : (int)max((long long)cxa - wx, -(long long)g.ncx);
+        c1 = fullx ? 2 * g.ncx - 1 : (int)min((long long)cxa + wx, 2 * (long long)g.ncx - 1);
+        r0 = fully ? -g.ncy : (int)max((long long)cya - wy, -(long long)g.ncy);
+        r1 = fully ? 2 * g.ncy - 1 : (int)min((long long)cya + wy, 2 * (long long)g.ncy - 1);
+        spanx = (double)wx * g.dx - D; spany = (double)wy * g.dy - D;
+      } else {
+        c0 = (int)floor((pa.x - R - g.ox) * g.inv_dx); c1 = (int)floor((pa.x + R - g.ox) * g.inv_dx);
+        r0 = (int)floor((pa.y - R - g.oy) * g.inv_dy); r1 = (int)floor((pa.y + R - g.oy) * g.inv_dy);
+        c0 = min(c0, cxa); c1 = max(c1, cxa); r0 = min(r0, cya); r1 = max(r1, cya);
+      }
       bool doneL, doneR, doneD, doneU;
       if (g.wrapx) { doneL = c0 <= -g.ncx; doneR = c1 >= 2 * g.ncx - 1; c0 = max(c0, -g.ncx); c1 = min(c1, 2 * g.ncx - 1); }
       else { doneL = c0 <= 0; doneR = c1 >= g.ncx - 1; c0 = min(max(c0, 0), g.ncx - 1); c1 = max(min(c1, g.ncx - 1), 0); }
@@ -906,21 +1043,33 @@ __global__ void __launch_bounds__(128) k_knn_fallback(const double2* __restrict_
       for (int ru = r0; ru <= r1; ++ru) {
         const int iy = g.wrapy ? img_idx(ru, g.ncy) : 0;
         const int row = ru - iy * g.ncy;
-        const double qy = (iy == 0) ? pa.y : __dadd_rn(pa.y, -(double)iy * g.Ly);
         const int ix0 = g.wrapx ? img_idx(c0, g.ncx) : 0, ix1 = g.wrapx ? img_idx(c1, g.ncx) : 0;
         for (int ix = ix0; ix <= ix1; ++ix) {
           const int a = max(c0, ix * g.ncx) - ix * g.ncx, b = min(c1, ix * g.ncx + g.ncx - 1) - ix * g.ncx;
-          const double qx = (ix == 0) ? pa.x : __dadd_rn(pa.x, -(double)ix * g.Lx);
-          const uint32_t code = img_code(ix, iy) << IMG_SHIFT;
           const int s = (int)cellStart[row * g.ncx + a], e = (int)cellStart[row * g.ncx + b + 1];
           for (int j0 = s; j0 < e; j0 += 32) {
             const int j = j0 + lane;
-            const bool have = j < e;
+            bool have = j < e;
             double d2 = BIG;
+            int sx = ix, sy = iy;  // image of the candidate: it is taken at pb + (sx Lx, sy Ly)
             if (have) {
               const double2 pb = spos[j];
-              d2 = dist_sq(qx - pb.x, qy - pb.y);
+              if (STALE) {  // nearest image, where the block is narrow enough for that to be the only one in reach
+                if (g.wrapx && !fullx) {
+                  const double d0 = (pa.x - (double)sx * g.Lx) - pb.x;
+                  sx += d0 > 0.5 * g.Lx ? 1 : (d0 < -0.5 * g.Lx ? -1 : 0);
+                }
+                if (g.wrapy && !fully) {
+                  const double d0 = (pa.y - (double)sy * g.Ly) - pb.y;
+                  sy += d0 > 0.5 * g.Ly ? 1 : (d0 < -0.5 * g.Ly ? -1 : 0);
+                }
+                if (sx < -1 || sx > 1 || sy < -1 || sy > 1) have = false;  // farther than a period: not a candidate
+              }
+              const double qx = (sx == 0) ? pa.x : __dadd_rn(pa.x, -(double)sx * g.Lx);
+              const double qy = (sy == 0) ? pa.y : __dadd_rn(pa.y, -(double)sy * g.Ly);
+              if (have) d2 = dist_sq(qx - pb.x, qy - pb.y);
             }
+            const uint32_t code = img_code(sx, sy) << IMG_SHIFT;
             const double thr = __shfl_sync(0xffffffffu, td, 0);
             // strict admission, self excluded in every image (nearest-neighbour.go:79)
             uint32_t pend = __ballot_sync(0xffffffffu, have && d2 < thr && j != i);
@@ -946,10 +1095,16 @@ __global__ void __launch_bounds__(128) k_knn_fallback(const double2* __restrict_
       if (found >= SPHB_K) {
         // certified if the 32nd distance does not reach past the scanned block on any open side
         const double d = sqrt(t0);
-        const double reachL = doneL ? 1e300 : pa.x - (g.ox + (double)c0 * g.dx);
-        const double reachR = doneR ? 1e300 : (g.ox + (double)(c1 + 1) * g.dx) - pa.x;
-        const double reachD = doneD ? 1e300 : pa.y - (g.oy + (double)r0 * g.dy);
-        const double reachU = doneU ? 1e300 : (g.oy + (double)(r1 + 1) * g.dy) - pa.y;
+        double reachL, reachR, reachD, reachU;
+        if (STALE) {
+          reachL = doneL ? 1e300 : spanx; reachR = doneR ? 1e300 : spanx;
+          reachD = doneD ? 1e300 : spany; reachU = doneU ? 1e300 : spany;
+        } else {
+          reachL = doneL ? 1e300 : pa.x - (g.ox + (double)c0 * g.dx);
+          reachR = doneR ? 1e300 : (g.ox + (double)(c1 + 1) * g.dx) - pa.x;
+          reachD = doneD ? 1e300 : pa.y - (g.oy + (double)r0 * g.dy);
+          reachU = doneU ? 1e300 : (g.oy + (double)(r1 + 1) * g.dy) - pa.y;
+        }
         const double reach = fmin(fmin(reachL, reachR), fmin(reachD, reachU));
         if (d * (1.0 + 1e-9) <= reach) break;
         R = d * (1.0 + 1e-6);  // guaranteed to suffice next time
@@ -960,15 +1115,17 @@ __global__ void __launch_bounds__(128) k_knn_fallback(const double2* __restrict_
     }
     const int tile = i >> 5, ql = i & 31;
     uint32_t* nncol = out.nn + (size_t)tile * 32 * 32 + ql;
+    if (fx.nx && lane < SPHB_KX) fx.nx[(size_t)tile * (SPHB_KX * 32) + lane * 32 + ql] = 0xffffffffu;  // no extended list
     if (found < SPHB_K) {
       if (lane == 0) atomicOr(dflags, DFLAG_UNDERFULL);
       nncol[lane * 32] = 0xffffffffu;
-      if (lane == 0) out.pc[i] = make_double4(0.0, 0.0, 0.0, 0.0);
+      if (lane == 0) { out.pc[i] = make_double4(0.0, 0.0, 0.0, 0.0); if (fx.dexcl) fx.dexcl[i] = 0.0; }
       continue;
     }
     const double h2 = __shfl_sync(0xffffffffu, td, 0);
     const double h = sqrt(h2);
     const double inv_h = 1.0 / h;
+    if (lane == 0 && fx.dexcl) fx.dexcl[i] = h;  // everything outside the list is at least h away, nothing more is known
     if (lane == 0 && g.sides && (((g.sides & 1) && pa.x - g.ox < h) || ((g.sides & 2) && g.ox + (double)g.ncx * g.dx - pa.x < h)))
       atomicOr(dflags, DFLAG_GHOST_THIN);
     double acc = kern_F<KERNEL>(fmin(sqrt(td) * inv_h, 1.0));
@@ -1048,6 +1205,11 @@ struct ForceIO {
   // the next step needs no k_keys pass.  next_grid == nullptr: off.
   const GridP* next_grid;
   uint32_t *next_keys, *next_rank, *next_count;
+  // list reuse (nullptr: off): the epilogue accumulates the displacement of every particle between this evaluation and
+  // the next one (max deviation from the reference displacement, fixed-point sum for the mean); stale != 0: the cell
+  // table is the last rebuild's, so the staging lookups are shifted back by the mean displacement and widened by D
+  ReuseState* rs;
+  int stale;
 };
 
 // -------------------------------------------------------------------------------------------------
@@ -1271,9 +1433,12 @@ __device__ __forceinline__ void force_block(const ForceIO& io, int n, const Grid
     for (int u = 0; u < 8; ++u) ent0[u] = col[u * 32];  // in flight during the staging phase
     cya = (int)(k / (uint32_t)g.ncx);
     cxa = (int)(k - (uint32_t)cya * (uint32_t)g.ncx);
-    const double rw = qa.z * (1.0 + 1e-6);
-    clo = (int)floor((pa.x - rw - g.ox) * g.inv_dx); chi = (int)floor((pa.x + rw - g.ox) * g.inv_dx);
-    rlo = (int)floor((pa.y - rw - g.oy) * g.inv_dy); rhi = (int)floor((pa.y + rw - g.oy) * g.inv_dy);
+    double rw = qa.z * (1.0 + 1e-6), lx = pa.x, ly = pa.y;
+    if (io.stale) {  // where the neighbours' (stale) cells are: only what gets staged depends on this, never the result
+      rw += io.rs->D; lx -= io.rs->ubx; ly -= io.rs->uby;
+    }
+    clo = (int)floor((lx - rw - g.ox) * g.inv_dx); chi = (int)floor((lx + rw - g.ox) * g.inv_dx);
+    rlo = (int)floor((ly - rw - g.oy) * g.inv_dy); rhi = (int)floor((ly + rw - g.oy) * g.inv_dy);
     clo = max(min(clo, cxa), -g.ncx); chi = min(max(chi, cxa), 2 * g.ncx - 1);
     rlo = max(min(rlo, cya), cya - g.ncy + 1); rhi = min(max(rhi, cya), cya + g.ncy - 1);
   }
@@ -1418,6 +1583,25 @@ __device__ __forceinline__ void force_block(const ForceIO& io, int n, const Grid
     const unsigned m = __activemask();
     const unsigned vm = __reduce_max_sync(m, __float_as_uint(__double2float_ru(v.x * v.x + v.y * v.y)));
     if ((threadIdx.x & 31) == (__ffs(m) - 1)) atomicMax(io.qmax + 1, vm);
+    if (io.rs) {
+      // displacement from this evaluation's position (pa, wrapped) to the next one's (drift-1 of the coming step), seam
+      // jumps removed; deviation from the reference displacement -> max (float bits, rounded up), fixed-point sum
+      double ddx = __dadd_rn(p.x, __dmul_rn(v.x, ph.dtH)) - pa.x, ddy = __dadd_rn(p.y, __dmul_rn(v.y, ph.dtH)) - pa.y;
+      if (g.Lx > 0.0) ddx -= g.Lx * rint(ddx / g.Lx);
+      if (g.Ly > 0.0) ddy -= g.Ly * rint(ddy / g.Ly);
+      const double ex_ = ddx - io.rs->mrx, ey_ = ddy - io.rs->mry;
+      const float dev = __double2float_ru(sqrt(ex_ * ex_ + ey_ * ey_) * (1.0 + 1e-9));
+      const unsigned dm = __reduce_max_sync(m, __float_as_uint(dev));
+      const double sc = 1048576.0 * g.inv_dy;  // fixed point: 2^-20 of a cell row (k_reuse_update divides by the same)
+      const int qx = (int)fmin(fmax(rint(ddx * sc), -1048576.0), 1048576.0), qy = (int)fmin(fmax(rint(ddy * sc), -1048576.0), 1048576.0);
+      const int sx_ = __reduce_add_sync(m, qx), sy_ = __reduce_add_sync(m, qy);
+      if ((threadIdx.x & 31) == (__ffs(m) - 1)) {
+        atomicMax(&io.rs->Mbits, dm);
+        long long* a = io.rs->sum[blockIdx.x & (RS_SLOTS - 1)];
+        atomicAdd((unsigned long long*)a, (unsigned long long)(long long)sx_);
+        atomicAdd((unsigned long long*)(a + 1), (unsigned long long)(long long)sy_);
+      }
+    }
   }
 }
 
@@ -1841,3 +2025,5 @@ __global__ void __launch_bounds__(256) k_iota64(int64_t* __restrict__ id, int n,
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) id[i] = base + i;
 }
+
+#include "sphb_reuse.cuh"
