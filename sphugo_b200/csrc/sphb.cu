@@ -334,7 +334,7 @@ void launch_force(sphb_sim* s, int ntot, const PhysP& ph, bool integrate) {
   io.keys = s->keysSorted; io.cellStart = s->cellStart; io.qmax = s->qmax;
   io.next_grid = s->fuse_keys ? s->grid_next : nullptr;
   io.next_keys = s->keys; io.next_rank = s->rank; io.next_count = s->cellCount;
-  io.rs = s->force_rs; io.stale = s->force_stale ? 1 : 0;
+  io.rs = s->force_rs; io.stale = s->force_stale ? s->rs : nullptr;
   if (integrate) cudaMemsetAsync(s->qmax + 1, 0, sizeof(uint32_t), s->st);  // max |v|^2 after this kick
   io.pos = s->a.pos; io.vel = s->a.vel; io.e = s->a.e; io.vdot = s->a.vdot; io.edot = s->a.edot;
   if (!s->slab_on) {

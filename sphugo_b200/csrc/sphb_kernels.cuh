@@ -1209,7 +1209,7 @@ struct ForceIO {
   // the next one (max deviation from the reference displacement, fixed-point sum for the mean); stale != 0: the cell
   // table is the last rebuild's, so the staging lookups are shifted back by the mean displacement and widened by D
   ReuseState* rs;
-  int stale;
+  const ReuseState* stale;
 };
 
 // -------------------------------------------------------------------------------------------------
@@ -1435,7 +1435,7 @@ __device__ __forceinline__ void force_block(const ForceIO& io, int n, const Grid
     cxa = (int)(k - (uint32_t)cya * (uint32_t)g.ncx);
     double rw = qa.z * (1.0 + 1e-6), lx = pa.x, ly = pa.y;
     if (io.stale) {  // where the neighbours' (stale) cells are: only what gets staged depends on this, never the result
-      rw += io.rs->D; lx -= io.rs->ubx; ly -= io.rs->uby;
+      rw += io.stale->D; lx -= io.stale->ubx; ly -= io.stale->uby;
     }
     clo = (int)floor((lx - rw - g.ox) * g.inv_dx); chi = (int)floor((lx + rw - g.ox) * g.inv_dx);
     rlo = (int)floor((ly - rw - g.oy) * g.inv_dy); rhi = (int)floor((ly + rw - g.oy) * g.inv_dy);
