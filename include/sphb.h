@@ -242,6 +242,38 @@ int sphb_slab_finish_migration(sphb_sim* s);
 #define SPHB_HALO_RECORD_DOUBLES 10
 #define SPHB_MIGRANT_RECORD_DOUBLES 12
 
+/* ---- the slab ring inside the library: multi-GPU behind this ABI (SURVEY §8b `n_devices`, §8e).
+ * One process and one handle per GPU; every rank creates its handle with the particles of its x-slab, describes the ring
+ * (sphb_ring_set), joins the communicator (sphb_comm_init: NCCL, loaded with dlopen - libsphb.so has no link-time NCCL
+ * dependency) and from then on calls sphb_ring_step where a single-GPU caller calls sphb_step: halo exchange, ghost
+ * handling, migration, the all-reduces and the schedule of the neighbour-list reuse all happen inside, on the handle's
+ * stream (ncclSend / ncclRecv / ncclAllReduce).  Only the rebuild evaluation of a cycle waits for the host (counts, max
+ * h / max speed); the reuse evaluations send fixed-size messages and are asynchronous like sphb_step.
+ * Collective contract: sphb_ring_step and every state-changing call (append, upload, set_params, knn, calc_forces) are
+ * made by all ranks between the same two steps; download / reduce / counters may be called by any rank at any time. */
+typedef struct {
+  int32_t rank, nranks;   /* position in the ring of x-slabs, ascending x */
+  int32_t periodic;       /* the x axis wraps: rank nranks-1 and rank 0 are neighbours */
+  int32_t migrate_every;  /* 0: migrate when the excursion bound nears the ghost-layer slack; 1: at every rebuild */
+  double x_lo, x_hi;      /* this rank's nominal slab */
+  double h_hint;          /* first guess of the largest smoothing length (until one has been measured) */
+  double safety;          /* ghost layer = safety x max h (+ slack); 0 = default 1.15 */
+  int64_t halo_cap;       /* records per side of the exchange buffers */
+} sphb_ring;
+
+#define SPHB_E_NCCL (-8) /* NCCL missing or a NCCL call failed */
+#define SPHB_NCCL_ID_BYTES 128
+int sphb_comm_unique_id(void* id_out /* SPHB_NCCL_ID_BYTES */); /* ncclGetUniqueId: rank 0 makes it, the caller distributes it */
+int sphb_comm_init(sphb_sim* s, const void* unique_id, int32_t rank, int32_t nranks); /* ncclCommInitRank on the handle's device */
+int sphb_ring_set(sphb_sim* s, const sphb_ring* ring);
+int sphb_ring_step(sphb_sim* s, int32_t nsteps); /* == Step() x nsteps of the whole ring; called by every rank */
+/* all slabs of the ring in one process (handles[k] = rank k, any devices): the exchange is a device copy.  Used by the
+ * single-GPU tests of the whole protocol. */
+int sphb_ring_step_local(sphb_sim* const* handles, int32_t n, int32_t nsteps);
+enum { SPHB_RING_H_MAX = 0, SPHB_RING_V_MAX = 1, SPHB_RING_MIGRATIONS = 2, SPHB_RING_GHOSTS = 3, SPHB_RING_PERIOD = 4,
+       SPHB_RING_EXCURSION = 5, SPHB_RING_INFO_COUNT = 6 };
+int sphb_ring_info(const sphb_sim* s, double* out, int32_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -39,7 +39,10 @@ EXPORTS = [
     "sphb_download", "sphb_upload", "sphb_upload_by_id", "sphb_reduce", "sphb_frame", "sphb_phase_times", "sphb_counters", "sphb_create_device",
     "sphb_slab_set", "sphb_max_h", "sphb_max_speed", "sphb_slab_step_begin", "sphb_slab_pack_halo", "sphb_slab_add_ghosts",
     "sphb_slab_step_end", "sphb_slab_pack_migrants", "sphb_slab_add_migrants", "sphb_slab_finish_migration",
+    "sphb_comm_unique_id", "sphb_comm_init", "sphb_ring_set", "sphb_ring_step", "sphb_ring_step_local", "sphb_ring_info",
 ]
+NCCL_ID_BYTES = 128
+RING_INFO = ["h_max", "v_max", "migrations", "ghosts", "period", "excursion"]
 
 
 class Params(C.Structure):
@@ -58,6 +61,14 @@ class Slab(C.Structure):
 
     _fields_ = [("x_lo", C.c_double), ("x_hi", C.c_double), ("ghost_w", C.c_double), ("inner_w", C.c_double),
                 ("has_left", C.c_int32), ("has_right", C.c_int32)]
+
+
+class Ring(C.Structure):
+    """sphb_ring"""
+
+    _fields_ = [("rank", C.c_int32), ("nranks", C.c_int32), ("periodic", C.c_int32), ("migrate_every", C.c_int32),
+                ("x_lo", C.c_double), ("x_hi", C.c_double), ("h_hint", C.c_double), ("safety", C.c_double),
+                ("halo_cap", C.c_int64)]
 
 
 class SphbError(RuntimeError):
@@ -144,6 +155,18 @@ def lib():
     L.sphb_slab_add_migrants.argtypes = [vp, vp, C.c_int64]
     L.sphb_slab_finish_migration.restype = C.c_int
     L.sphb_slab_finish_migration.argtypes = [vp]
+    L.sphb_comm_unique_id.restype = C.c_int
+    L.sphb_comm_unique_id.argtypes = [vp]
+    L.sphb_comm_init.restype = C.c_int
+    L.sphb_comm_init.argtypes = [vp, vp, C.c_int32, C.c_int32]
+    L.sphb_ring_set.restype = C.c_int
+    L.sphb_ring_set.argtypes = [vp, C.POINTER(Ring)]
+    L.sphb_ring_step.restype = C.c_int
+    L.sphb_ring_step.argtypes = [vp, C.c_int32]
+    L.sphb_ring_step_local.restype = C.c_int
+    L.sphb_ring_step_local.argtypes = [C.POINTER(vp), C.c_int32, C.c_int32]
+    L.sphb_ring_info.restype = C.c_int
+    L.sphb_ring_info.argtypes = [vp, dp, C.c_int32]
     _LIB = L
     return L
 
@@ -328,6 +351,23 @@ class Handle:
         self._chk(lib().sphb_phase_times(self._h, ms, len(PHASES)))
         return dict(zip(PHASES, list(ms)))
 
+    # ---- the slab ring inside the library (include/sphb.h "slab ring")
+    def ring_set(self, rank, nranks, periodic, x_lo, x_hi, h_hint, halo_cap, safety=0.0, migrate_every=0):
+        r = Ring(rank, nranks, int(bool(periodic)), int(migrate_every), x_lo, x_hi, h_hint, safety, int(halo_cap))
+        self._chk(lib().sphb_ring_set(self._h, C.byref(r)))
+
+    def comm_init(self, unique_id: bytes, rank: int, nranks: int):
+        buf = C.create_string_buffer(bytes(unique_id), NCCL_ID_BYTES)
+        self._chk(lib().sphb_comm_init(self._h, buf, rank, nranks))
+
+    def ring_step(self, nsteps=1):
+        self._chk(lib().sphb_ring_step(self._h, nsteps))
+
+    def ring_info(self):
+        out = (C.c_double * len(RING_INFO))()
+        self._chk(lib().sphb_ring_info(self._h, out, len(RING_INFO)))
+        return dict(zip(RING_INFO, [float(x) for x in out]))
+
     def counters(self):
         out = (C.c_int64 * len(COUNTERS))()
         self._chk(lib().sphb_counters(self._h, out, len(COUNTERS)))
@@ -343,3 +383,24 @@ class Handle:
             o = np.argsort(d["id"], kind="stable")
             d = {k: v[o] for k, v in d.items()}
         return d
+
+
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId through the library (rank 0 calls it and distributes the 128 bytes)"""
+    buf = C.create_string_buffer(NCCL_ID_BYTES)
+    rc = lib().sphb_comm_unique_id(buf)
+    if rc:
+        raise SphbError(rc, lib().sphb_last_error(None).decode())
+    return buf.raw
+
+
+def ring_step_local(handles, nsteps=1):
+    """Step() of a ring whose slabs all live in this process (handles[k] = rank k)"""
+    arr = (C.c_void_p * len(handles))(*[h._h for h in handles])
+    rc = lib().sphb_ring_step_local(arr, len(handles), nsteps)
+    if rc:
+        for h in handles:
+            msg = lib().sphb_last_error(h._h).decode()
+            if msg:
+                raise SphbError(rc, msg)
+        raise SphbError(rc, "sphb_ring_step_local failed")

@@ -15,10 +15,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsphb.so")
 SOURCES = ["sphb.cu"]
-DEPS = ["sphb.cu", "sphb_kernels.cuh", "sphb_reuse.cuh", "sphb_slab.inc", os.path.join("..", "..", "include", "sphb.h")]
+DEPS = ["sphb.cu", "sphb_kernels.cuh", "sphb_reuse.cuh", "sphb_ring.cuh", "sphb_slab.inc", "sphb_ring.inc", os.path.join("..", "..", "include", "sphb.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-shared", "-Xcompiler", "-fPIC", "-diag-suppress", "550",
+    "-shared", "-Xcompiler", "-fPIC", "-diag-suppress", "550", "-ldl",
 ]
 
 

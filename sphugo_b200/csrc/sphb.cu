@@ -9,6 +9,10 @@
 #include "sphb_kernels.cuh"
 #include "../../include/sphb.h"
 
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstdarg>
@@ -32,6 +36,36 @@ struct Soa {  // one copy of the per-particle state (two copies: the reorder gat
 };
 
 }  // namespace
+
+// the slab ring inside the library (sphb_ring.inc)
+#define RING_SLACK 0.5  // an owned particle may sit this many h_max outside its slab before it must migrate
+struct RingState {
+  bool on = false;
+  int rank = 0, nranks = 1;
+  bool periodic = false;
+  int left = -1, right = -1;             // neighbour ranks (-1: none)
+  double x_lo = 0.0, x_hi = 0.0, safety = 1.15;
+  int64_t halo_cap = 0;                  // records per side
+  double h_max = 0.0, v_max = 0.0;       // all-reduced maxima of the last cycle
+  double excursion = 0.0;                // bound of the drift out of the slab since the last migration
+  int64_t n_global = 0;
+  int migrate_every = 0, migrations = 0;
+  int cycle_len = 0;                     // evaluations since the last rebuild (inclusive)
+  bool reuse_pending = false;            // the last evaluation was a reuse evaluation (its refusal count is on its way)
+  bool want_idx = false;                 // the halo pack in progress records the source indices
+  double* sbuf[2] = {nullptr, nullptr};  // send: low side, high side
+  double* rbuf[2] = {nullptr, nullptr};  // receive: from the left, from the right
+  int* sidx[2] = {nullptr, nullptr};     // pre-sort index of every packed particle
+  uint32_t* hsrc[2] = {nullptr, nullptr};// sorted index of every packed particle
+  uint32_t* inv = nullptr;               // inverse permutation of the last reorder
+  int64_t inv_cap = 0;
+  int64_t nsend[2] = {0, 0}, nrecv[2] = {0, 0}, ghost0 = 0;
+  double* red_dev = nullptr;             // small device scratch of the host all-reduces
+  int* refused_host = nullptr;           // pinned
+  void* comm = nullptr;                  // ncclComm_t
+  int comm_rank = 0, comm_size = 1;
+  struct sphb_sim* peer[2] = {nullptr, nullptr};  // slabs in one process
+};
 
 struct sphb_sim {
   sphb_params prm{};
@@ -102,6 +136,8 @@ struct sphb_sim {
   bool lists_ext = false;     // nn / nx / dexcl / rs describe the current particles (order and displacement chain)
   int reuse_age = 0;          // reuse evaluations since the rebuild
   sphb_params list_prm{};     // parameters of the rebuild (a change invalidates the displacement bookkeeping)
+  RingState ring;
+  bool interleaved = false;   // ring, inside a cycle: ghosts sit between the owned particles (sorted order)
   uint32_t stat_enq = 0, stat_seen = 0;  // records enqueued / read back
   int reuse_cooldown = 0;
   std::string err;
@@ -233,7 +269,8 @@ enum { MODE_ASIS = 0, MODE_INIT = 1, MODE_DRIFT = 2 };
 int refresh_stats(sphb_sim* s) {
   const int ntot = (int)(s->n + s->nghost);
   const int nb = ntot > 0 ? std::min(STAT_BLOCKS, cdiv(ntot, 256)) : 1;
-  k_stats_partial<<<nb, 256, 0, s->st>>>(s->a.pos, s->a.vel, s->a.pc, s->a.e, (int)s->n, s->statPart);
+  k_stats_partial<<<nb, 256, 0, s->st>>>(s->a.pos, s->a.vel, s->a.pc, s->a.e, s->interleaved ? ntot : (int)s->n, s->statPart,
+                                         s->interleaved ? s->a.ghost : nullptr);
   k_stats_final<<<1, 32 * STAT_N, 0, s->st>>>(s->statPart, nb, s->stats);
   s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 2;
   CKL(s);
@@ -335,7 +372,7 @@ void launch_force(sphb_sim* s, int ntot, const PhysP& ph, bool integrate) {
   io.next_grid = s->fuse_keys ? s->grid_next : nullptr;
   io.next_keys = s->keys; io.next_rank = s->rank; io.next_count = s->cellCount;
   io.rs = s->force_rs; io.stale = s->force_stale ? s->rs : nullptr;
-  if (integrate) cudaMemsetAsync(s->qmax + 1, 0, sizeof(uint32_t), s->st);  // max |v|^2 after this kick
+  if (integrate && !(s->slab_on && s->force_stale)) cudaMemsetAsync(s->qmax + 1, 0, sizeof(uint32_t), s->st);  // max |v|^2 after this kick (ring: of the cycle)
   io.pos = s->a.pos; io.vel = s->a.vel; io.e = s->a.e; io.vdot = s->a.vdot; io.edot = s->a.edot;
   if (!s->slab_on) {
     if (integrate) launch_force_p<KERNEL, true, false>(s, io, ntot, ph);
@@ -363,7 +400,7 @@ void compact_in_place(sphb_sim* s, int nslots, int nkeep) {
 // ext: start a reuse cycle (extended lists); want_hacc: the smoothing-length accumulator will be consumed by the next
 // evaluation's grid (not when a reuse evaluation follows: it needs no grid)
 int build_neighbours(sphb_sim* s, int mode, const double hor[2], const double ver[2], int kernel, bool timed, bool ext = false,
-                     bool want_hacc = true) {
+                     bool want_hacc = true, uint32_t* inv = nullptr) {
   const int ntot = (int)(s->n + s->nghost);
   if (ntot <= 0) return fail(s, SPHB_E_STATE, "Simulation not initialized: no particles (sph.go:92-94)");
   // Fully periodic runs (single handle, or a slab of a periodic ring) need no statistics pass per evaluation: the box
@@ -406,7 +443,7 @@ int build_neighbours(sphb_sim* s, int mode, const double hor[2], const double ve
   StateIn in{s->a.pos, s->a.vel, s->a.vdot, s->a.vpred, s->a.e, s->a.edot, s->a.epred, s->a.id, s->a.pc, s->a.ghost};
   StateOut out{s->b.pos, s->b.vel, s->b.vdot, s->b.vpred, s->b.e, s->b.edot, s->b.epred, s->b.id, s->b.pc, s->b.ghost, s->spos, s->hguess};
   const int rb = cdiv(ntot, 256);
-#define REORDER(MODE, LEAN) k_reorder<MODE, LEAN><<<rb, 256, 0, s->st>>>(in, out, s->keys, s->perm, ntot, s->grid, dtH, s->cellStart, s->keysSorted)
+#define REORDER(MODE, LEAN) k_reorder<MODE, LEAN><<<rb, 256, 0, s->st>>>(in, out, s->keys, s->perm, ntot, s->grid, dtH, s->cellStart, s->keysSorted, inv)
   // `timed` = called from forces(): a force evaluation follows and overwrites VDot, EDot; kNN rewrites {rho, c, h, P}
   if (timed) {
     if (mode == MODE_DRIFT) REORDER(2, true); else if (mode == MODE_INIT) REORDER(1, true); else REORDER(0, true);
@@ -467,49 +504,71 @@ void launch_reuse_update(sphb_sim* s, int ntot, bool rebuild) {
   s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 1;
 }
 
+// what an evaluation does about the list reuse
+struct EvalPlan {
+  bool reuse = false;         // exact kNN from the stored candidates instead of sort + tile search
+  bool next_reuse = false;    // the next evaluation may be a reuse evaluation: keep the displacement books (ring: and the ghosts)
+  bool predicted = false;     // reuse: drift-1 + predict already ran (ring: before the halo is gathered)
+  bool defer_update = false;  // the caller launches k_reuse_update itself (ring: after the all-reduce of the statistics)
+};
+
+// drop the ghosts (ring / slab mode): the few owned particles sorted behind index n move into the ghosts' slots
+void drop_ghosts(sphb_sim* s) {
+  if (s->nghost) compact_in_place(s, (int)(s->n + s->nghost), (int)s->n);
+  s->nghost = 0;
+  s->have_list = false;
+  s->interleaved = false;
+  invalidate_reuse(s);
+}
+
 // CalculateForces (sph.go:403-435) [+ kick, drift-2, wrap, reflections when integrate (sph.go:122-193)]
-int forces(sphb_sim* s, int mode, bool integrate) {
+int forces_plan(sphb_sim* s, int mode, bool integrate, const EvalPlan& plan) {
   if (s->prm.kernel == SPHB_KERNEL_TOPHAT)
     return fail(s, SPHB_E_KERNEL, "TopHat2D.DF: not defined. derivative is delta distribution! (sph.go:251-253)");
   const int ntot = (int)(s->n + s->nghost);
   const PhysP ph = make_phys(s->prm, s->prm.kernel);
-  // ---- plan: rebuild (sort + tile search) or reuse (exact kNN from the stored candidates)
-  const bool cyc = s->reuse_on && !s->slab_on && mode == MODE_DRIFT && integrate;  // an ordinary step
-  if (cyc) {
-    reuse_poll(s);
-    if (s->reuse_cooldown > 0 && --s->reuse_cooldown == 0 && s->reuse_period == 1) s->reuse_period = 2;
-  }
-  const int period = s->reuse_period_fixed ? s->reuse_period_fixed : s->reuse_period;
-  const bool reuse = cyc && s->lists_ext && same_params(s->prm, s->list_prm) && s->reuse_age + 1 < period;
-  // may the NEXT evaluation be a reuse evaluation?  (then this one keeps the displacement books, and prepares no grid / keys)
-  const bool next_reuse = cyc && (reuse ? s->reuse_age + 2 < period : (period > 1 && s->have_h));
+  const bool reuse = plan.reuse, next_reuse = plan.next_reuse;
+  // the smoothing-length accumulator feeds the next rebuild's grid; a ring also takes its running max h / max speed from it
+  const bool want_hacc = !next_reuse || s->slab_on;
   int rc;
   if (!reuse) {
-    rc = build_neighbours(s, mode, s->prm.hor, s->prm.ver, s->prm.kernel, true, next_reuse, !next_reuse);
+    uint32_t* inv = nullptr;
+    if (s->slab_on && s->ring.on && next_reuse) {
+      if (s->ring.inv_cap < s->cap) {
+        CK(s, cudaStreamSynchronize(s->st));
+        cudaFree(s->ring.inv); s->ring.inv = nullptr; s->ring.inv_cap = 0;
+        CK(s, dalloc(s->ring.inv, (size_t)s->cap));
+        s->ring.inv_cap = s->cap;
+      }
+      inv = s->ring.inv;
+    }
+    rc = build_neighbours(s, mode, s->prm.hor, s->prm.ver, s->prm.kernel, true, next_reuse, want_hacc, inv);
     if (rc) return rc;
     s->lists_ext = s->lists_ext && next_reuse;
     s->reuse_age = 0;
     if (s->lists_ext) s->list_prm = s->prm;
   } else {
     if (ntot <= 0) return fail(s, SPHB_E_STATE, "Simulation not initialized: no particles (sph.go:92-94)");
-    const bool periodic = !axis_open(s->prm.ver) && !axis_open(s->prm.hor);
+    const bool periodic = !axis_open(s->prm.ver) && !axis_open(s->prm.hor) && (!s->slab_on || (s->slab.has_left && s->slab.has_right));
     s->grid_next_ready = false;
-    s->hscale = periodic && !next_reuse ? 16777216.0 / std::max(s->prm.hor[1] - s->prm.hor[0], s->prm.ver[1] - s->prm.ver[0]) : 0.0;
-    s->hacc_valid = periodic && !next_reuse;
+    s->hscale = periodic && want_hacc ? 16777216.0 / std::max(s->prm.hor[1] - s->prm.hor[0], s->prm.ver[1] - s->prm.ver[0]) : 0.0;
+    s->hacc_valid = periodic && want_hacc;
     drop_ready_keys(s);
-    cudaEventRecord(s->ev[SPHB_PH_KEYS], s->st);
+    if (!plan.predicted) cudaEventRecord(s->ev[SPHB_PH_KEYS], s->st);
     cudaEventRecord(s->ev[SPHB_PH_SORT], s->st);
     cudaEventRecord(s->ev[SPHB_PH_REORDER], s->st);
     Soa& a = s->a;
-    k_predict<<<cdiv(ntot, 256), 256, 0, s->st>>>(a.pos, a.vel, a.vdot, a.e, a.edot, a.vpred, a.epred, s->spos, ntot, s->grid,
-                                                  s->prm.dt_half, nullptr);
+    if (!plan.predicted)
+      k_predict<<<cdiv(ntot, 256), 256, 0, s->st>>>(a.pos, a.vel, a.vdot, a.e, a.edot, a.vpred, a.epred, s->spos, ntot, s->grid,
+                                                    s->prm.dt_half, s->slab_on ? a.ghost : nullptr);
     cudaMemsetAsync(s->failCount, 0, sizeof(int), s->st);
-    cudaMemsetAsync(s->qmax, 0, sizeof(uint32_t), s->st);
+    if (!s->slab_on) cudaMemsetAsync(s->qmax, 0, sizeof(uint32_t), s->st);  // (a ring keeps the max h of the whole cycle)
     cudaEventRecord(s->ev[SPHB_PH_KNN], s->st);
     if (s->prm.kernel == 1) launch_knn_reuse<1>(s, ntot, ph); else launch_knn_reuse<2>(s, ntot, ph);
     s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 3;
     s->counters[SPHB_CNT_REUSE_STEPS] += 1;
     s->reuse_age += 1;
+    s->have_list = true;
     CKL(s);
   }
   cudaEventRecord(s->ev[SPHB_PH_FORCE], s->st);
@@ -526,17 +585,23 @@ int forces(sphb_sim* s, int mode, bool integrate) {
   if (s->prm.kernel == 1) launch_force<1>(s, ntot, ph, integrate);
   else launch_force<2>(s, ntot, ph, integrate);
   s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 1;
-  if (s->force_rs || reuse) launch_reuse_update(s, ntot, !reuse);  // (the last evaluation of a cycle: for the record only)
-  if (!next_reuse) invalidate_reuse(s);  // the cycle ends here
+  if (!plan.defer_update && (s->force_rs || reuse)) launch_reuse_update(s, ntot, !reuse);  // (last evaluation of a cycle: for the record only)
+  const bool keep = next_reuse && s->lists_ext;
+  if (!keep) invalidate_reuse(s);  // the cycle ends here
   if (s->fuse_keys) {
     s->grid_next_ready = s->keys_ready = true;
     s->keys_dtH = s->prm.dt_half; s->keys_n = ntot;
     s->next_hor[0] = s->prm.hor[0]; s->next_hor[1] = s->prm.hor[1]; s->next_ver[0] = s->prm.ver[0]; s->next_ver[1] = s->prm.ver[1];
   }
-  if (s->slab_on) {  // drop the ghosts: the few owned particles sorted behind index n move into the ghosts' slots
-    compact_in_place(s, ntot, (int)s->n);
-    s->nghost = 0;
-    s->have_list = false;
+  if (s->slab_on) {
+    if (!keep) {  // drop the ghosts: the few owned particles sorted behind index n move into the ghosts' slots
+      compact_in_place(s, ntot, (int)s->n);
+      s->nghost = 0;
+      s->have_list = false;
+      s->interleaved = false;
+    } else {
+      s->interleaved = s->nghost > 0;  // reuse evaluations follow: the ghosts stay where the sort put them
+    }
   }
   cudaEventRecord(s->ev[SPHB_PH_TOTAL], s->st);
   s->ev_valid = true;
@@ -545,6 +610,22 @@ int forces(sphb_sim* s, int mode, bool integrate) {
   else { rc = refresh_stats(s); if (rc) return rc; }
   CKL(s);
   return SPHB_OK;
+}
+
+// the schedule of a single handle (sphb_step); the slab protocol of include/sphb.h (sphb_slab_step_*) never reuses, the
+// ring driver (sphb_ring.inc) plans for all ranks at once
+int forces(sphb_sim* s, int mode, bool integrate) {
+  EvalPlan plan;
+  const bool cyc = s->reuse_on && !s->slab_on && mode == MODE_DRIFT && integrate;  // an ordinary step
+  if (cyc) {
+    reuse_poll(s);
+    if (s->reuse_cooldown > 0 && --s->reuse_cooldown == 0 && s->reuse_period == 1) s->reuse_period = 2;
+  }
+  const int period = s->reuse_period_fixed ? s->reuse_period_fixed : s->reuse_period;
+  plan.reuse = cyc && s->lists_ext && same_params(s->prm, s->list_prm) && s->reuse_age + 1 < period;
+  // may the NEXT evaluation be a reuse evaluation?  (then this one keeps the displacement books, and prepares no grid / keys)
+  plan.next_reuse = cyc && (plan.reuse ? s->reuse_age + 2 < period : (period > 1 && s->have_h));
+  return forces_plan(s, mode, integrate, plan);
 }
 
 int check_async(sphb_sim* s) {
@@ -780,6 +861,7 @@ int grow_capacity(sphb_sim* s, int64_t need) {
   s->nn = t.nn; s->failList = t.failList; s->nx = t.nx; s->dexcl = t.dexcl;
   old.release();
   invalidate_reuse(s);
+  cudaFree(s->ring.inv); s->ring.inv = nullptr; s->ring.inv_cap = 0;
   s->cap = ncap;
   s->ncell_max = (int)ncm;
   s->ntiles_cap = ntiles;
@@ -811,6 +893,50 @@ int require_dense_ids(sphb_sim* s) {
   return SPHB_OK;
 }
 
+// ring, inside a cycle: the owned particles are gathered through an index list (their order is arbitrary; join on id)
+template <typename T>
+int download_gathered(sphb_sim* s, const T* src, const uint32_t* list, int64_t n, void* host) {
+  int rc = ensure_scratch(s, (size_t)n * sizeof(T)); if (rc) return rc;
+  k_gather_list<T><<<cdiv(n, 256), 256, 0, s->st>>>(src, list, (int)n, (T*)s->scratch);
+  CKL(s);
+  CK(s, cudaMemcpyAsync(host, s->scratch, (size_t)n * sizeof(T), cudaMemcpyDeviceToHost, s->st));
+  CK(s, cudaStreamSynchronize(s->st));
+  return SPHB_OK;
+}
+
+int download_interleaved(sphb_sim* s, uint32_t mask, void* const* hp) {
+  const int64_t n = s->n;
+  const int ntot = (int)(s->n + s->nghost);
+  if (mask & (SPHB_MASK(SPHB_F_NN_IDX) | SPHB_MASK(SPHB_F_NN_DIST) | SPHB_MASK(SPHB_F_NN_POS)))
+    return fail(s, SPHB_E_STATE, "ring: neighbour lists cannot be downloaded in the middle of a reuse cycle (their indices include ghosts)");
+  uint32_t* list = s->perm;  // free outside a rebuild evaluation
+  CK(s, cudaMemsetAsync(s->packCount, 0, sizeof(int), s->st));
+  k_ring_owned_list<<<cdiv(ntot, 256), 256, 0, s->st>>>(s->a.ghost, ntot, list, s->packCount);
+  CKL(s);
+  int rc;
+#define DG(field, src, T) \
+  if (mask & SPHB_MASK(field)) { if ((rc = download_gathered<T>(s, (src), list, n, hp[field]))) return rc; }
+  DG(SPHB_F_POS, s->a.pos, double2); DG(SPHB_F_VEL, s->a.vel, double2); DG(SPHB_F_E, s->a.e, double);
+  DG(SPHB_F_EDOT, s->a.edot, double); DG(SPHB_F_VDOT, s->a.vdot, double2); DG(SPHB_F_EPRED, s->a.epred, double);
+  DG(SPHB_F_VPRED, s->a.vpred, double2); DG(SPHB_F_ID, s->a.id, int64_t);
+#undef DG
+  if (mask & (SPHB_MASK(SPHB_F_RHO) | SPHB_MASK(SPHB_F_C) | SPHB_MASK(SPHB_F_H))) {
+    rc = ensure_scratch(s, (size_t)n * 7 * sizeof(double)); if (rc) return rc;
+    double4* pcg = (double4*)s->scratch;
+    double* sc = (double*)(pcg + n);
+    k_gather_list<double4><<<cdiv(n, 256), 256, 0, s->st>>>(s->a.pc, list, (int)n, pcg);
+    k_split_pc<<<cdiv(n, 256), 256, 0, s->st>>>(pcg, (int)n, sc, sc + n, sc + 2 * n);
+    CKL(s);
+    if (mask & SPHB_MASK(SPHB_F_RHO)) CK(s, cudaMemcpyAsync(hp[SPHB_F_RHO], sc, n * 8, cudaMemcpyDeviceToHost, s->st));
+    if (mask & SPHB_MASK(SPHB_F_C)) CK(s, cudaMemcpyAsync(hp[SPHB_F_C], sc + n, n * 8, cudaMemcpyDeviceToHost, s->st));
+    if (mask & SPHB_MASK(SPHB_F_H)) CK(s, cudaMemcpyAsync(hp[SPHB_F_H], sc + 2 * n, n * 8, cudaMemcpyDeviceToHost, s->st));
+    CK(s, cudaStreamSynchronize(s->st));
+  }
+  return SPHB_OK;
+}
+
+void ring_comm_destroy(sphb_sim* s);
+
 }  // namespace
 
 // =================================================================================================
@@ -837,6 +963,10 @@ void sphb_destroy(sphb_sim* s) {
   cudaFree(s->packCount); cudaFree(s->hacc); cudaFree(s->qmax);
   cudaFree(s->nx); cudaFree(s->dexcl); cudaFree(s->rs); cudaFree(s->stat_dev);
   if (s->stat_host) cudaFreeHost(s->stat_host);
+  for (int side = 0; side < 2; ++side) { cudaFree(s->ring.sbuf[side]); cudaFree(s->ring.rbuf[side]); cudaFree(s->ring.sidx[side]); cudaFree(s->ring.hsrc[side]); }
+  cudaFree(s->ring.inv); cudaFree(s->ring.red_dev);
+  if (s->ring.refused_host) cudaFreeHost(s->ring.refused_host);
+  if (s->ring.comm) ring_comm_destroy(s);
   cudaFree(s->dflags); cudaFree(s->statPart); cudaFree(s->stats); cudaFree(s->grid); cudaFree(s->grid_next); cudaFree(s->scratch);
   for (auto& ev : s->ev) if (ev) cudaEventDestroy(ev);
   if (s->st) cudaStreamDestroy(s->st);
@@ -866,6 +996,7 @@ int sphb_append(sphb_sim* s, int64_t n, const double* pos_xy, const double* vel_
                 const int64_t* id) {
   int rc = enter(s); if (rc) return rc;
   if (n < 0 || (n > 0 && !pos_xy)) return fail(s, SPHB_E_INVALID, "bad particle arrays");
+  if (s->interleaved) drop_ghosts(s);  // ring, inside a cycle (state-changing calls are collective: every rank ends it)
   if (s->nghost) return fail(s, SPHB_E_STATE, "append while ghosts are attached");
   if (n == 0) return SPHB_OK;
   if (s->n + n > s->cap) {  // Go's append reallocates (sph.go:79)
@@ -895,6 +1026,7 @@ int sphb_step(sphb_sim* s, int32_t nsteps) {
 
 int sphb_calc_forces(sphb_sim* s) {
   int rc = enter(s); if (rc) return rc;
+  if (s->interleaved) drop_ghosts(s);
   if (s->slab_on) return fail(s, SPHB_E_STATE, "slab mode: use sphb_slab_step_begin / _end");
   return forces(s, MODE_ASIS, false);
 }
@@ -950,6 +1082,7 @@ int sphb_download(sphb_sim* s, uint32_t mask, void* const* hp, int64_t capacity,
   for (int f = 0; f < SPHB_F_COUNT; ++f)
     if ((mask & SPHB_MASK(f)) && !hp[f]) return fail(s, SPHB_E_INVALID, "host_ptrs[%d] is NULL", f);
   if (n == 0) return SPHB_OK;
+  if (s->interleaved) return download_interleaved(s, mask, hp);
 #define D2H(field, src, bytes) \
   if (mask & SPHB_MASK(field)) CK(s, cudaMemcpyAsync(hp[field], (src), (size_t)(bytes), cudaMemcpyDeviceToHost, s->st))
   D2H(SPHB_F_POS, s->a.pos, n * 16);
@@ -1003,6 +1136,7 @@ int sphb_download(sphb_sim* s, uint32_t mask, void* const* hp, int64_t capacity,
 
 int sphb_upload(sphb_sim* s, uint32_t mask, const void* const* hp, int64_t n) {
   int rc = enter(s); if (rc) return rc;
+  if (s->interleaved) drop_ghosts(s);
   if (n != s->n) return fail(s, SPHB_E_INVALID, "upload: n = %lld but the simulation holds %lld particles", (long long)n, (long long)s->n);
   const uint32_t allowed = SPHB_MASK(SPHB_F_POS) | SPHB_MASK(SPHB_F_VEL) | SPHB_MASK(SPHB_F_E) | SPHB_MASK(SPHB_F_RHO) |
                            SPHB_MASK(SPHB_F_VDOT) | SPHB_MASK(SPHB_F_EDOT) | SPHB_MASK(SPHB_F_EPRED) | SPHB_MASK(SPHB_F_VPRED);
@@ -1037,6 +1171,7 @@ int sphb_upload(sphb_sim* s, uint32_t mask, const void* const* hp, int64_t n) {
 
 int sphb_upload_by_id(sphb_sim* s, uint32_t mask, const void* const* hp, int64_t n) {
   int rc = enter(s); if (rc) return rc;
+  if (s->interleaved) drop_ghosts(s);
   if (n != s->n) return fail(s, SPHB_E_INVALID, "upload: n = %lld but the simulation holds %lld particles", (long long)n, (long long)s->n);
   const uint32_t allowed = SPHB_MASK(SPHB_F_POS) | SPHB_MASK(SPHB_F_VEL) | SPHB_MASK(SPHB_F_E);
   if (mask & ~allowed) return fail(s, SPHB_E_INVALID, "upload_by_id: POS, VEL, E only (mask 0x%x)", mask);
@@ -1092,6 +1227,7 @@ int sphb_frame(sphb_sim* s, int32_t width, int32_t height, float* xy_out, uint8_
                int64_t capacity, int64_t* n_out) {
   int rc = enter(s); if (rc) return rc;
   rc = check_async(s); if (rc) return rc;
+  if (s->interleaved) return fail(s, SPHB_E_STATE, "ring: sphb_frame in the middle of a reuse cycle is not supported (download the fields instead)");
   const int64_t n = s->n;
   if (n_out) *n_out = n;
   if (!xy_out || !colour_out) return fail(s, SPHB_E_INVALID, "xy_out / colour_out is NULL");
@@ -1177,5 +1313,7 @@ int sphb_counters(const sphb_sim* s, int64_t* out, int32_t n) {
 
 // ---- slab decomposition: implemented in sphb_slab.inc (same translation unit) ----
 #include "sphb_slab.inc"
+// ---- the slab ring inside the library (NCCL or slabs in one process) ----
+#include "sphb_ring.inc"
 
 }  // extern "C"

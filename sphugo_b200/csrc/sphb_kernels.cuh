@@ -345,7 +345,8 @@ struct StateOut {
 template <int MODE, bool LEAN>
 __global__ void __launch_bounds__(256) k_reorder(StateIn in, StateOut out, const uint32_t* __restrict__ keys,
                                                 const uint32_t* __restrict__ perm, int n, const GridP* __restrict__ gp, double dtH,
-                                                const uint32_t* __restrict__ cellStart, uint32_t* __restrict__ keysSorted) {
+                                                const uint32_t* __restrict__ cellStart, uint32_t* __restrict__ keysSorted,
+                                                uint32_t* __restrict__ inv) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   const GridP g = *gp;
@@ -392,6 +393,7 @@ __global__ void __launch_bounds__(256) k_reorder(StateIn in, StateOut out, const
   sp.y = g.wrapy ? wrap_coord(p.y, g.loy, g.Ly) : p.y;
   out.spos[j] = sp;
   keysSorted[j] = c;
+  if (inv) inv[i] = j;  // where the particle went (ring: halo sources / ghost destinations of the reuse evaluations)
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -1654,7 +1656,8 @@ __global__ void __launch_bounds__(256) k_pack_halo(const double2* __restrict__ p
                                                   const double* __restrict__ epred, const int64_t* __restrict__ id,
                                                   const double4* __restrict__ pc, int n, SlabP sl, int mode, double dtH,
                                                   double* __restrict__ buf_lo, double* __restrict__ buf_hi, int cap,
-                                                  int* __restrict__ counters, uint32_t* __restrict__ dflags) {
+                                                  int* __restrict__ counters, uint32_t* __restrict__ dflags,
+                                                  int* __restrict__ idx_lo, int* __restrict__ idx_hi) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   bool want_lo = false, want_hi = false;
   double2 p = make_double2(0, 0), v = make_double2(0, 0);
@@ -1672,6 +1675,7 @@ __global__ void __launch_bounds__(256) k_pack_halo(const double2* __restrict__ p
     if (slot < 0) continue;
     if (slot >= cap) { atomicOr(dflags, DFLAG_BUF_FULL); continue; }
     double* r = (side == 0 ? buf_lo : buf_hi) + (size_t)slot * HALO_REC;
+    if (idx_lo) (side == 0 ? idx_lo : idx_hi)[slot] = i;  // ring: the same particles are sent again by every reuse evaluation
     r[0] = p.x; r[1] = p.y;
     if (mode == 0) {
       const double2 vp = vpred[i];
@@ -1808,12 +1812,13 @@ __device__ __forceinline__ double stat_init(int k) {
 
 __global__ void __launch_bounds__(256) k_stats_partial(const double2* __restrict__ pos, const double2* __restrict__ vel,
                                                       const double4* __restrict__ pc, const double* __restrict__ e, int n,
-                                                      double* __restrict__ part) {
+                                                      double* __restrict__ part, const uint8_t* __restrict__ gflag) {
   __shared__ double sh[8][STAT_N];
   double v[STAT_N];
 #pragma unroll
   for (int k = 0; k < STAT_N; ++k) v[k] = stat_init(k);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (gflag && gflag[i] != GF_OWNED) continue;  // ghosts interleaved with the owned particles (ring, inside a cycle)
     double2 p = pos[i];
     double4 q = pc[i];
     const double2 u = vel[i];
@@ -2027,3 +2032,4 @@ __global__ void __launch_bounds__(256) k_iota64(int64_t* __restrict__ id, int n,
 }
 
 #include "sphb_reuse.cuh"
+#include "sphb_ring.cuh"

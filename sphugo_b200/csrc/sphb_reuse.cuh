@@ -69,6 +69,12 @@ __global__ void __launch_bounds__(REUSE_THREADS) k_knn_reuse(const double2* __re
   uint32_t* cx = nx + (size_t)(ii >> 5) * (SPHB_KX * 32) + (ii & 31);
   const bool wrap = g.wrapx | g.wrapy;  // (slab frames do not wrap: ghosts stand in for the images)
   const double hLx = 0.5 * g.Lx, hLy = 0.5 * g.Ly;
+  // Only warps with a query next to the periodic seam look for images.  (Were a candidate beyond the seam after all,
+  // its unshifted distance is about a period: the half-period test on the largest key below refuses the particle.)
+  const double reach = 2.0 * dex + D;
+  const bool near_seam = valid && ((g.wrapx && (pa.x - reach < g.lox || pa.x + reach >= g.lox + g.Lx)) ||
+                                   (g.wrapy && (pa.y - reach < g.loy || pa.y + reach >= g.loy + g.Ly)));
+  const bool img = wrap && __any_sync(0xffffffffu, near_seam);
   const double qxm = __dadd_rn(pa.x, g.Lx), qxp = __dadd_rn(pa.x, -g.Lx);  // candidate image -1 / +1: query + (-img L)
   const double qym = __dadd_rn(pa.y, g.Ly), qyp = __dadd_rn(pa.y, -g.Ly);
   const TD INF = F32 ? (TD)3.0e38f : (TD)1.7976931348623157e308;
@@ -86,11 +92,21 @@ __global__ void __launch_bounds__(REUSE_THREADS) k_knn_reuse(const double2* __re
     for (int u = 0; u < 8; ++u) en[u] = valid ? cs[u * 32] : 0xffffffffu;
 #pragma unroll
     for (int u = 0; u < 8; ++u) pb[u] = spos[en[u] == 0xffffffffu ? ii : (int)(en[u] & IDX_MASK)];
+    if (!img) {  // away from the seam every candidate is a centre image: entries that still say otherwise (the pair has
+      uint32_t stale = 0;  // crossed the seam together since the build) are reset, the force kernel reads the code
+#pragma unroll
+      for (int u = 0; u < 8; ++u) stale |= (en[u] >> IMG_SHIFT) ^ 5u;
+      if (stale) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (en[u] != 0xffffffffu && (en[u] >> IMG_SHIFT) != 5u) cs[u * 32] = (en[u] & IDX_MASK) | (5u << IMG_SHIFT);
+      }
+    }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const bool have = en[u] != 0xffffffffu;
       double qx = pa.x, qy = pa.y;
-      if (wrap) {  // nearest image from the current positions (a candidate may have crossed the seam since the build)
+      if (img) {  // nearest image from the current positions (a candidate may have crossed the seam since the build)
         int sx = 0, sy = 0;
         if (g.wrapx) { const double d0 = pa.x - pb[u].x; sx = d0 > hLx ? 1 : (d0 < -hLx ? -1 : 0); }
         if (g.wrapy) { const double d0 = pa.y - pb[u].y; sy = d0 > hLy ? 1 : (d0 < -hLy ? -1 : 0); }

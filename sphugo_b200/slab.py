@@ -482,6 +482,94 @@ class LocalSlabSim:
 
 
 # ------------------------------------------------------------------------------------------------
+# the ring inside the library (include/sphb.h "slab ring"): the protocol above, in C++, behind sphb_ring_step
+# ------------------------------------------------------------------------------------------------
+class LocalRingSim:
+    """all slabs of a ring in this process, stepped by sphb_ring_step_local (the exchange is a device copy): the whole
+    in-library protocol - halo, ghosts kept across reuse evaluations, migration, schedule - on one GPU"""
+
+    def __init__(self, params, topo: Topology, pos, vel=None, e=None, ids=None, h_max_hint=None, migrate_every=0,
+                 safety=0.0, halo_cap=None):
+        from . import _lib as L
+        self.L = L
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 2)
+        n = len(pos)
+        ids = np.arange(n, dtype=np.int64) if ids is None else np.asarray(ids, dtype=np.int64)
+        vel = np.zeros((n, 2)) if vel is None else np.asarray(vel, dtype=np.float64).reshape(n, 2)
+        e = np.zeros(n) if e is None else np.asarray(e, dtype=np.float64)
+        owner = topo.owner_of(pos[:, 0])
+        self.topo, self.handles = topo, []
+        for r in range(topo.world):
+            m = owner == r
+            h = L.Handle(params, pos[m], vel[m], e[m], None, ids[m], capacity=n)
+            lo, hi = topo.interval(r)
+            h.ring_set(r, topo.world, topo.periodic, lo, hi, float(h_max_hint or default_h_hint(n, 1.0)), halo_cap or n,
+                       safety, migrate_every)
+            self.handles.append(h)
+
+    def step(self, nsteps=1):
+        self.L.ring_step_local(self.handles, nsteps)
+
+    def append(self, pos, vel=None, e=None, rho=None, ids=None):
+        for r, h in enumerate(self.handles):
+            part = _route_to_owner(self.topo, r, pos, vel, e, rho, ids)
+            if len(part[0]):
+                h.append(*part)
+
+    def state(self, fields):
+        parts = [h.download(list(dict.fromkeys(list(fields) + ["id"]))) for h in self.handles]
+        d = {k: np.concatenate([p[k] for p in parts], axis=0) for k in parts[0]}
+        o = np.argsort(d["id"], kind="stable")
+        return {k: v[o] for k, v in d.items()}
+
+    def counts(self):
+        return [h.n for h in self.handles]
+
+    def info(self):
+        return [h.ring_info() for h in self.handles]
+
+    def close(self):
+        for h in self.handles:
+            h.close()
+
+
+class RingSim:
+    """one rank of a multi-GPU ring: everything happens inside libsphb (NCCL); torch.distributed is used once, to hand
+    the NCCL unique id from rank 0 to the others"""
+
+    def __init__(self, params, topo: Topology, rank: int, pos, vel=None, e=None, ids=None, h_max_hint=None,
+                 capacity=None, halo_cap=None, migrate_every=0, safety=0.0):
+        import torch
+        import torch.distributed as dist
+        from . import _lib as L
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 2)
+        n = len(pos)
+        self.h = L.Handle(params, pos, vel, e, None, ids, capacity=int(capacity or (n + max(4096, n // 4))))
+        lo, hi = topo.interval(rank)
+        self.h.ring_set(rank, topo.world, topo.periodic, lo, hi, float(h_max_hint or 0.0), int(halo_cap or max(4096, n // 8)),
+                        safety, migrate_every)
+        dev = torch.device("cuda", params.device) if dist.get_backend() == "nccl" else torch.device("cpu")
+        idt = torch.zeros(L.NCCL_ID_BYTES, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(L.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        self.h.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, topo.world)
+        self.topo, self.rank = topo, rank
+
+    def step(self, nsteps=1):
+        self.h.ring_step(nsteps)
+
+    def append(self, pos, vel=None, e=None, rho=None, ids=None):
+        part = _route_to_owner(self.topo, self.rank, pos, vel, e, rho, ids)
+        if len(part[0]):
+            self.h.append(*part)
+
+    @property
+    def handle(self):
+        return self.h
+
+
+# ------------------------------------------------------------------------------------------------
 # bench.py --gpus N (N > 1): weak scaling, one rank per GPU
 # ------------------------------------------------------------------------------------------------
 def bench(args, nx, ny, box, phys, desc, rank, world, local):

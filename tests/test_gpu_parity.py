@@ -310,8 +310,10 @@ def test_by_id_transfers_follow_the_callers_order():
     b.upload_by_id(pos=st["pos"], vel=st["vel"], e=st["e"])
     a.step(2); b.step(2)
     sa, sb = a.state(["pos", "vel", "e", "rho", "id"]), b.state(["pos", "vel", "e", "rho", "id"])
+    # (a is in the middle of a list-reuse cycle, b rebuilt its lists after the upload: same neighbours, but the 32-term
+    # sums run in a different order)
     for f in ("pos", "vel", "e", "rho"):
-        assert np.array_equal(sa[f], sb[f]), f
+        assert U.rel_err(sa[f], sb[f], np.abs(sb[f]).max() * 1e-3) <= 1e-12, f
     f_dev, f_id = a.frame(640, 480, ids=True), a.frame(640, 480, ids=False)
     o = np.argsort(f_dev["id"], kind="stable")
     assert np.array_equal(f_dev["xy"][o], f_id["xy"]) and np.array_equal(f_dev["colour"][o], f_id["colour"])
