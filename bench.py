@@ -225,6 +225,102 @@ def make_ic(nx, ny, box, rank, world):
     return pos, (x0, x0 + cols * sx)
 
 
+# ---- additional legs of the default run: the other BASELINE.json configurations on this GPU -----------------------
+def leg_ic(name):
+    """(pos, params kwargs, description, e0) of a single-GPU leg"""
+    from sphugo_b200 import gen, gorand
+    mon = dict(gamma=1.66666, particle_mass=1.0, kernel=1)
+    if name == "c3p":
+        return (gen.jittered_lattice(1024, 1024), dict(mon, hor=(0.0, 1.0), ver=(0.0, 1.0), accel=(0.0, 0.2), dt_half=0.001),
+                "C3-P (BASELINE configs[2]): 2^20 jittered-lattice particles, periodic [0,1]^2, Monaghan, g=(0,0.2)")
+    if name == "c3u":
+        return (gen.uniform_rect(1 << 20), dict(mon, hor=(0.0, 1.0), ver=(0.0, 1.0), accel=(0.0, 0.2), dt_half=0.001),
+                "C3-U (BASELINE configs[2]): 2^20 i.i.d. uniform particles, periodic [0,1]^2, Monaghan, g=(0,0.2)")
+    if name == "c4":
+        return (gen.shock_tube(1 << 24), dict(mon, hor=(0.0, 1.0), ver=(0.0, 1.0), accel=(0.0, 0.0), dt_half=2.5e-4),
+                "C4 shock tube (BASELINE configs[3]): 2^24 particles, number-density ratio 4:1 across x = 0.5, periodic [0,1]^2, Monaghan")
+    if name == "c4dam":
+        from sphugo_b200 import _lib as L
+        return (gen.dam_break(1 << 24), dict(gamma=1.66666, particle_mass=1.0, kernel=2, accel=(0.0, 0.55), dt_half=1.25e-4,
+                                             refl=(0.0, 1.0, L.OPEN_LO, 1.0)),
+                "C4 dam break (BASELINE configs[3]): 2^24 particles filling [0,0.25]x[0.5,1], open box, reflections L 0 / R 1 / D 1, "
+                "g=(0,0.55), Wendland (the physics of the reference's tube config, config-parser.go:926-973)")
+    if name == "speed":
+        return (gorand.uniform_rect_spawn(100000)["pos"], dict(mon, accel=(0.0, 0.2), dt_half=0.02),
+                "examples/speed-test (speed-test.go:22-45): 100000 particles of the Go math/rand stream, open box, dt_half 0.02, g=(0,0.2)")
+    raise SystemExit(f"unknown leg {name}")
+
+
+def run_leg(name, precision, K, W, device, fresh=False):
+    """device-resident throughput of one leg; fresh = time the first K steps of a new simulation (speed-test's protocol)"""
+    import torch
+    from sphugo_b200 import _lib as L
+    pos, kw, desc = leg_ic(name)
+    n = len(pos)
+    g = L.Handle(L.make_params(precision=precision, device=device, **kw), pos, None, np.full(n, 0.01))
+    del pos
+    ext = torch.cuda.ExternalStream(g.stream, device=torch.device("cuda", device))
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if not fresh:
+        g.step(1 + W)
+    g.sync()
+    c0 = g.counters()
+    t0 = time.perf_counter()
+    ev0.record(ext)
+    g.step(K)
+    ev1.record(ext)
+    g.sync()
+    wall = time.perf_counter() - t0
+    ms = ev0.elapsed_time(ev1) / K
+    c1 = g.counters()
+    sum_e = g.reduce(L.SUM_E)
+    g.close()
+    peak, _ = measured_peak()
+    b = sum(B_ALG_BY_PREC[precision].values())
+    return {"leg": name, "workload": desc, "particles": n, "dtype": "f64" if precision == 64 else "f32", "steps": K,
+            "ms_per_step": ms, "value": n / (ms * 1e-3), "unit": UNIT, "wall_ms_per_step": wall / K * 1e3,
+            "step_roofline_frac": n * b / (ms * 1e-3) / 1e9 / peak, "alg_bytes_per_particle": b,
+            "fallback_fraction": (c1["knn_fallback"] - c0["knn_fallback"]) / (n * K),
+            "reuse_steps": c1["reuse_steps"] - c0["reuse_steps"], "sum_E": sum_e,
+            "protocol": "first K steps of a fresh simulation (step 0 evaluates the forces twice)" if fresh else f"K steps after step 0 + {W} warm-up steps"}
+
+
+def speed_test_cpu(steps):
+    """the reference arm of the speed-test leg: the oracle on the IDENTICAL input, full size, from a fresh simulation"""
+    from oracle import oracle as orc
+    from sphugo_b200 import gorand
+    ic = gorand.uniform_rect_spawn(100000)
+    o = orc.Oracle(orc.make_params(dt_half=0.02, accel=(0.0, 0.2)), ic["pos"], ic["vel"], ic["e"])
+    t0 = time.perf_counter()
+    o.step(steps)
+    el = time.perf_counter() - t0
+    e = o.total_energy()
+    o.close()
+    return {"value": 100000 * steps / el, "unit": UNIT, "ms_per_step": el / steps * 1e3, "steps": steps, "cores": 1, "kind": "port", "sum_E": e}
+
+
+def run_legs(args, device):
+    legs = []
+    for name, precs in (("c3p", (64, 32)), ("c3u", (64, 32)), ("c4", (64, 32)), ("c4dam", (64,))):
+        for prec in precs:
+            try:
+                legs.append(run_leg(name, prec, 20 if name.startswith("c3") else 10, 3, device))
+            except Exception as ex:  # a leg must not take the headline line down with it
+                legs.append({"leg": name, "dtype": f"f{prec}", "error": str(ex)[:300]})
+    try:
+        run_leg("speed", 64, 20, 0, device, fresh=True)  # (the first run warms the device up)
+        sp = run_leg("speed", 64, 20, 0, device, fresh=True)
+        if not args.no_cpu:
+            cpu = speed_test_cpu(20)
+            sp["cpu_same_input"] = cpu
+            sp["same_config"] = True
+            sp["ratio_vs_cpu_same_input"] = sp["value"] / cpu["value"]
+        legs.append(sp)
+    except Exception as ex:
+        legs.append({"leg": "speed", "error": str(ex)[:300]})
+    return legs
+
+
 def run_ours(args):
     import torch
     from sphugo_b200 import _lib as L
@@ -396,6 +492,8 @@ def run_ours(args):
                   "refused_fraction": (c1["knn_fallback"] - c0["knn_fallback"]) / (n * K)},
         "clocks": clocks,
         "other_build": other,
+        # the other BASELINE.json configurations that fit one GPU, device-resident, for the record (not the headline)
+        "legs": None if args.no_legs else run_legs(args, local),
     }
     emit(line)
 
@@ -418,6 +516,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (tuning sweeps only)")
     ap.add_argument("--no-other-build", action="store_true", help="skip the extra leg that times the other precision build")
+    ap.add_argument("--no-legs", action="store_true", help="skip the legs on the other BASELINE configurations (C3-U/P, C4, speed-test)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -130,9 +130,10 @@ struct sphb_sim {
   int reuse_period = 4;       // evaluations per cycle: one rebuild + (period - 1) reuse evaluations; 1 = never reuse
   int reuse_period_max = 8, reuse_period_fixed = 0;
   double reuse_skin = 0.25;   // extended candidates are collected up to h (1 + skin)
-  int reuse_capb = 32, reuse_ncw = 320;
+  int reuse_capb = 32, reuse_ncw = 256;
   ReuseState* force_rs = nullptr;  // arguments of the force launch in progress
   bool force_stale = false;
+  bool cell_per_h_fixed = false;   // SPHB_CELL_PER_H given: no adjustment for extended searches
   bool lists_ext = false;     // nn / nx / dexcl / rs describe the current particles (order and displacement chain)
   int reuse_age = 0;          // reuse evaluations since the rebuild
   sphb_params list_prm{};     // parameters of the rebuild (a change invalidates the displacement bookkeeping)
@@ -256,6 +257,14 @@ int enter(sphb_sim* s) {
 
 // the state changed under the lists (upload, append, parameters): the next evaluation is a rebuild
 void invalidate_reuse(sphb_sim* s) { s->lists_ext = false; s->reuse_age = 0; }
+
+// grid parameters of an evaluation; ext: its tile search collects candidates up to h (1 + skin), and three rows of
+// cells must cover that reach
+GridTune grid_tune(const sphb_sim* s, bool ext) {
+  GridTune t = s->gtune;
+  if (ext && !s->cell_per_h_fixed) t.cell_per_h = std::max(t.cell_per_h, (1.0 + s->reuse_skin) * 1.016);
+  return t;
+}
 
 // the force epilogue left the next step's cell counts in cellCount: forget them (the state changed under them)
 void drop_ready_keys(sphb_sim* s) {
@@ -422,7 +431,7 @@ int build_neighbours(sphb_sim* s, int mode, const double hor[2], const double ve
   if (timed) cudaEventRecord(s->ev[SPHB_PH_KEYS], s->st);
   if (same_box) std::swap(s->grid, s->grid_next);
   else k_make_grid<<<1, 32, 0, s->st>>>(s->stats, ntot, hor[0], hor[1], ver[0], ver[1], make_slabp(s), s->slab_on ? 1 : 0,
-                                        s->gtune, s->grid, s->hacc, hscale_prev > 0.0 ? hscale_prev : 1.0, use_hacc ? 1 : 0);
+                                        grid_tune(s, ext && s->have_h), s->grid, s->hacc, hscale_prev > 0.0 ? hscale_prev : 1.0, use_hacc ? 1 : 0);
   s->hacc_valid = periodic && want_hacc;  // the kNN below refills the accumulator
   cudaMemsetAsync(s->qmax, 0, sizeof(uint32_t), s->st);  // max h of this evaluation
   const bool keys_ok = same_box && s->keys_ready && mode == MODE_DRIFT && dtH == s->keys_dtH && ntot == s->keys_n;
@@ -576,8 +585,10 @@ int forces_plan(sphb_sim* s, int mode, bool integrate, const EvalPlan& plan) {
   // and the force epilogue emits the next step's cell keys (no k_keys pass in the next step).
   s->fuse_keys = integrate && !s->slab_on && s->hacc_valid && !next_reuse && !axis_open(s->prm.hor) && !axis_open(s->prm.ver);
   if (s->fuse_keys) {
+    // (the next evaluation is a rebuild; in an ordinary run of steps it starts a reuse cycle, i.e. searches with the skin)
+    const bool next_ext = s->reuse_on && (s->reuse_period_fixed ? s->reuse_period_fixed : s->reuse_period) > 1;
     k_make_grid<<<1, 32, 0, s->st>>>(s->stats, ntot, s->prm.hor[0], s->prm.hor[1], s->prm.ver[0], s->prm.ver[1], make_slabp(s), 0,
-                                     s->gtune, s->grid_next, s->hacc, s->hscale, 1);
+                                     grid_tune(s, next_ext), s->grid_next, s->hacc, s->hscale, 1);
     s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 1;
   }
   s->force_rs = (next_reuse && s->lists_ext) ? s->rs : nullptr;
@@ -766,7 +777,7 @@ int create_common(const sphb_params* p, int64_t n, int64_t capacity, const doubl
   if (const char* ev = getenv("SPHB_REUSE_SKIN")) s->reuse_skin = std::max(0.03, std::min(1.0, atof(ev)));
   if (const char* ev = getenv("SPHB_REUSE_CAPB")) s->reuse_capb = std::max(24, std::min(96, atoi(ev)));
   if (const char* ev = getenv("SPHB_REUSE_NCW")) s->reuse_ncw = std::max(128, std::min(1024, atoi(ev) / 8 * 8));
-  if (const char* ev = getenv("SPHB_CELL_PER_H")) s->gtune.cell_per_h = atof(ev);
+  if (const char* ev = getenv("SPHB_CELL_PER_H")) { s->gtune.cell_per_h = atof(ev); s->cell_per_h_fixed = true; }
   if (const char* ev = getenv("SPHB_PPC0")) s->gtune.ppc0 = atof(ev);
   if (const char* ev = getenv("SPHB_FORCE_NC")) s->gtune.force_nc = atoi(ev);
   if (const char* ev = getenv("SPHB_GUESS_MARGIN")) s->ktune.guess_margin = atof(ev);

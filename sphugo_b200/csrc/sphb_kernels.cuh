@@ -539,12 +539,12 @@ __device__ __forceinline__ void knn_accumulate_h(const KnnOut& out, bool ok, boo
 // extended list of an accepted lane (rebuild evaluations): the up to SPHB_KX nearest entries of column B and the exclusion
 // radius.  Every candidate the lane saw and did not keep has a key >= T, everything it did not see lies beyond rgx, and
 // fp32 keys are within delta of the true d^2: dexcl^2 = min(T (1 - 2 delta), rgx^2 (1 - 1e-5)).  Warp-collective.
-__device__ __forceinline__ void knn_write_ext(const KnnExt& ex, const uint2* colB, const uint32_t* candE, int nb, bool ok,
-                                              bool bovf, int tile, int lane, int i, double rgx, double delta, double h) {
+__device__ __forceinline__ double knn_write_ext(const KnnExt& ex, const uint2* colB, const uint32_t* candE, int nb, bool ok,
+                                                bool bovf, int tile, int lane, int i, double rgx, double delta, double h) {
   const bool sel = ok && !bovf && nb > SPHB_KX;
   uint32_t T, akey;
   knn_select_drop(colB, nb, sel ? nb - SPHB_KX : 0, sel, T, akey);
-  if (!ok) return;  // refused lanes: the fallback kernel writes their (empty) extended list
+  if (!ok) return 0.0;  // refused lanes: the fallback kernel writes their (empty) extended list
   uint32_t* xp = ex.nx + (size_t)tile * (SPHB_KX * 32) + lane;
   int w = 0;
   double dx = h;    // second column overflowed: unknown candidates were lost, nothing beyond h is certain
@@ -559,6 +559,7 @@ __device__ __forceinline__ void knn_write_ext(const KnnExt& ex, const uint2* col
   }
   for (; w < SPHB_KX; ++w) xp[w * 32] = 0xffffffffu;
   ex.dexcl[i] = dx;
+  return dx;
 }
 
 template <int KERNEL, bool F32, bool EXT>
@@ -890,7 +891,12 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
         out.pc[i] = make_double4((double)rho, (double)c, h, (double)(c * c / ((float)ph.gamma * rho)));
       }
       const double hacc_h = (double)(ok ? h2f * rsqrtf(fmaxf(h2f, 1e-37f)) : 0.0f);
-      if (EXT) knn_write_ext(ex, colB, candE, (int)((kq - qbase) >> 8), ok, bovf, tile, lane, i, rgx, delta, hacc_h * 1.000001);
+      if (EXT) {
+        const double dxl = knn_write_ext(ex, colB, candE, (int)((kq - qbase) >> 8), ok, bovf, tile, lane, i, rgx, delta, hacc_h * 1.000001);
+        // slab mode: the exclusion radius is only valid if everything within it was local (ghost layer wide enough)
+        if (ok && g.sides && (((g.sides & 1) && xa - g.ox < dxl) || ((g.sides & 2) && g.ox + (double)g.ncx * g.dx - xa < dxl)))
+          atomicOr(dflags, DFLAG_GHOST_THIN);
+      }
       knn_accumulate_h(out, ok, owned, hacc_h);
       continue;
     }
@@ -967,7 +973,11 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
       const double c = c2 > 0.0 ? fast_sqrt(c2, fast_rsqrt(c2)) : sqrt(c2);
       out.pc[i] = make_double4(rho, c, h, c * c * fast_rcp(ph.gamma * rho));
     }
-    if (EXT) knn_write_ext(ex, colB, candE, (int)((kq - qbase) >> 8), ok, bovf, tile, lane, i, rgx, delta, ok ? sqrt(h2) : 0.0);
+    if (EXT) {
+      const double dxl = knn_write_ext(ex, colB, candE, (int)((kq - qbase) >> 8), ok, bovf, tile, lane, i, rgx, delta, ok ? sqrt(h2) : 0.0);
+      if (ok && g.sides && (((g.sides & 1) && xa - g.ox < dxl) || ((g.sides & 2) && g.ox + (double)g.ncx * g.dx - xa < dxl)))
+        atomicOr(dflags, DFLAG_GHOST_THIN);
+    }
     knn_accumulate_h(out, ok, owned, ok ? sqrt(h2) : 0.0);
   }
 }
@@ -1128,7 +1138,7 @@ __global__ void __launch_bounds__(128) k_knn_fallback(const double2* __restrict_
     const double h = sqrt(h2);
     const double inv_h = 1.0 / h;
     if (lane == 0 && fx.dexcl) fx.dexcl[i] = h;  // everything outside the list is at least h away, nothing more is known
-    if (lane == 0 && g.sides && (((g.sides & 1) && pa.x - g.ox < h) || ((g.sides & 2) && g.ox + (double)g.ncx * g.dx - pa.x < h)))
+    if (!STALE && lane == 0 && g.sides && (((g.sides & 1) && pa.x - g.ox < h) || ((g.sides & 2) && g.ox + (double)g.ncx * g.dx - pa.x < h)))
       atomicOr(dflags, DFLAG_GHOST_THIN);
     double acc = kern_F<KERNEL>(fmin(sqrt(td) * inv_h, 1.0));
 #pragma unroll

@@ -195,8 +195,9 @@ __global__ void __launch_bounds__(REUSE_THREADS) k_knn_reuse(const double2* __re
     out.failList[slot] = i;
   }
   if (ok) {
-    if (g.sides && (((g.sides & 1) && pa.x - g.ox < h) || ((g.sides & 2) && g.ox + (double)g.ncx * g.dx - pa.x < h)))
-      atomicOr(dflags, DFLAG_GHOST_THIN);
+    // (slab mode: no geometric ghost-layer test here - the grid is the rebuild's, the particles have moved on.  The
+    // rebuild verified that everything within dexcl was local; the certificate above does the rest, and the force kernel
+    // still refuses a neighbour whose rho was never evaluated.)
     const double ep = epred[i];
     if (F32) {
       const float h2f = (float)h2;
