@@ -335,7 +335,7 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    nx, ny, box, phys, desc = workload(args.workload, world)
+    nx, ny, box, phys, desc = workload("c4" if args.workload == "c4dam" else args.workload, world)
     global B_ALG, B_ALG_TOTAL
     B_ALG = B_ALG_BY_PREC[args.precision]
     B_ALG_TOTAL = sum(B_ALG.values())
@@ -346,8 +346,8 @@ def run_ours(args):
         from sphugo_b200 import slab
         return slab.bench(args, nx, ny, box, phys, desc, rank, world, local)
 
-    if args.workload == "c4":
-        pos, _, _ = make_ic_c4(0, 1)
+    if args.workload in ("c4", "c4dam"):
+        raise SystemExit("single-GPU C4 numbers are legs of the default run (bench.py without --workload); --workload c4 / c4dam is for --gpus N")
     else:
         pos, _ = make_ic(nx, ny, box, 0, 1)
     n = len(pos)
@@ -445,7 +445,7 @@ def run_ours(args):
         # the other build of the library on the same workload (device-resident steps only), for the record
         op = 32 if args.precision == 64 else 64
         prm2 = L.make_params(hor=(0.0, box[0]), ver=(0.0, box[1]), device=local, **dict(phys, precision=op))
-        pos2 = make_ic_c4(0, 1)[0] if args.workload == "c4" else make_ic(nx, ny, box, 0, 1)[0]
+        pos2 = make_ic(nx, ny, box, 0, 1)[0]
         g2 = L.Handle(prm2, pos2, None, e0)
         del pos2
         g2.step(1 + W)
@@ -511,7 +511,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c5", choices=["c3", "c4", "c5"])
+    ap.add_argument("--workload", default="c5", choices=["c3", "c4", "c4dam", "c5"])
     ap.add_argument("--precision", type=int, default=64, choices=[64, 32], help="64: reference arithmetic; 32: the fp32 build")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (tuning sweeps only)")

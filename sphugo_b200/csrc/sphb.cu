@@ -127,7 +127,7 @@ struct sphb_sim {
   ReuseStat* stat_dev = nullptr;
   ReuseStat* stat_host = nullptr;  // pinned ring of REUSE_RING records (non-blocking feedback for the schedule)
   bool reuse_on = true;       // SPHB_REUSE=0 switches it off
-  int reuse_period = 4;       // evaluations per cycle: one rebuild + (period - 1) reuse evaluations; 1 = never reuse
+  int reuse_period = 2;       // evaluations per cycle: one rebuild + (period - 1) reuse evaluations; 1 = never reuse
   int reuse_period_max = 8, reuse_period_fixed = 0;
   double reuse_skin = 0.25;   // extended candidates are collected up to h (1 + skin)
   int reuse_capb = 32, reuse_ncw = 256;
@@ -140,6 +140,9 @@ struct sphb_sim {
   RingState ring;
   bool interleaved = false;   // ring, inside a cycle: ghosts sit between the owned particles (sorted order)
   uint32_t stat_enq = 0, stat_seen = 0;  // records enqueued / read back
+  cudaEvent_t stat_event = nullptr;      // recorded behind the last record's copy
+  bool stat_event_valid = false;
+  bool reuse_abort = false;              // the policy ended the current cycle: the next evaluation rebuilds
   int reuse_cooldown = 0;
   std::string err;
 };
@@ -476,27 +479,38 @@ int build_neighbours(sphb_sim* s, int mode, const double hor[2], const double ve
 }
 
 // ---- schedule of the list reuse ------------------------------------------------------------------
-// Every evaluation that can be followed by a reuse evaluation ends with k_reuse_update, which also leaves a record
-// {age, refused particles, D} in a pinned host ring.  The host never waits for it: it reads whatever has arrived when it
-// plans the next step.  Policy: a reuse evaluation that refused more than 0.2 % of the particles ends the cycle one
-// evaluation earlier from now on; a cycle whose last evaluation refused fewer than 0.02 % is lengthened by one.
+// Every evaluation of a cycle ends with k_reuse_update, which leaves a record {age, refused particles, D} in a pinned
+// host ring.  Before it plans an evaluation the host waits for the record of the previous one (the wait costs one
+// kernel-launch latency per step: the device has nothing else queued) and applies the policy below.  A cycle is one
+// rebuild + (period - 1) reuse evaluations:
+//   - a reuse evaluation that refused more than 0.5 % of the particles ends its cycle at once, and cycles are from now
+//     on that much shorter (refused particles take the ring-expansion search, ~50 times the cost of an accepted one);
+//   - a cycle that completed with less than 0.1 % refused in its last evaluation lengthens the next one by one;
+//   - period 1 (no reuse) is tried again after a cool-down.
+// Handles below 2^14 particles do not reuse unless SPHB_REUSE_PERIOD fixes a period (their steps are launch bound).
+void reuse_policy(sphb_sim* s, unsigned age, double frac, bool rebuild) {
+  if (s->reuse_period_fixed || rebuild) return;
+  if (frac > 5e-3) {
+    s->reuse_period = std::max(1, std::min(s->reuse_period, (int)age));
+    s->reuse_abort = true;
+    if (s->reuse_period == 1) s->reuse_cooldown = 48;
+  } else if (frac < 1e-3 && (int)age == s->reuse_period - 1 && s->reuse_period < s->reuse_period_max) {
+    s->reuse_period += 1;
+  }
+}
+
 void reuse_poll(sphb_sim* s) {
-  if (!s->stat_host || s->reuse_period_fixed) return;
+  if (!s->stat_host) return;
+  if (s->stat_seen < s->stat_enq && s->stat_event_valid) cudaEventSynchronize(s->stat_event);
   while (s->stat_seen < s->stat_enq) {
     const volatile ReuseStat* r = &s->stat_host[(s->stat_seen + 1) % REUSE_RING];
     if (r->seq != s->stat_seen + 1 || r->seq2 != r->seq) {
       if (s->stat_enq - s->stat_seen >= REUSE_RING) { s->stat_seen = s->stat_enq - REUSE_RING / 2; continue; }  // overwritten
-      break;  // not there yet
+      break;  // (cannot happen after the wait above)
     }
     s->stat_seen += 1;
-    if (r->rebuild || r->n == 0) continue;
-    const double frac = (double)r->refused / (double)r->n;
-    if (frac > 2e-3) {
-      s->reuse_period = std::max(1, std::min(s->reuse_period, (int)r->age));
-      if (s->reuse_period == 1) s->reuse_cooldown = 64;  // not even one reuse evaluation pays: try again later
-    } else if (frac < 2e-4 && (int)r->age == s->reuse_period - 1 && s->reuse_period < s->reuse_period_max) {
-      s->reuse_period += 1;
-    }
+    if (r->n == 0) continue;
+    reuse_policy(s, r->age, (double)r->refused / (double)r->n, r->rebuild != 0);
   }
 }
 
@@ -510,6 +524,8 @@ void launch_reuse_update(sphb_sim* s, int ntot, bool rebuild) {
   k_reuse_update<<<1, 32, 0, s->st>>>(s->rs, s->grid, ntot, rebuild ? 1 : 0, s->failCount, s->hacc, s->hscale, cs, s->stat_dev);
   s->stat_enq += 1;
   cudaMemcpyAsync(&s->stat_host[s->stat_enq % REUSE_RING], s->stat_dev, sizeof(ReuseStat), cudaMemcpyDeviceToHost, s->st);
+  if (!s->stat_event_valid) s->stat_event_valid = cudaEventCreateWithFlags(&s->stat_event, cudaEventDisableTiming) == cudaSuccess;
+  if (s->stat_event_valid) cudaEventRecord(s->stat_event, s->st);
   s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 1;
 }
 
@@ -627,13 +643,15 @@ int forces_plan(sphb_sim* s, int mode, bool integrate, const EvalPlan& plan) {
 // ring driver (sphb_ring.inc) plans for all ranks at once
 int forces(sphb_sim* s, int mode, bool integrate) {
   EvalPlan plan;
-  const bool cyc = s->reuse_on && !s->slab_on && mode == MODE_DRIFT && integrate;  // an ordinary step
+  const bool cyc = s->reuse_on && !s->slab_on && mode == MODE_DRIFT && integrate &&
+                   (s->reuse_period_fixed || s->n >= 16384);  // an ordinary step of a handle worth the bookkeeping
   if (cyc) {
     reuse_poll(s);
     if (s->reuse_cooldown > 0 && --s->reuse_cooldown == 0 && s->reuse_period == 1) s->reuse_period = 2;
   }
   const int period = s->reuse_period_fixed ? s->reuse_period_fixed : s->reuse_period;
-  plan.reuse = cyc && s->lists_ext && same_params(s->prm, s->list_prm) && s->reuse_age + 1 < period;
+  plan.reuse = cyc && s->lists_ext && !s->reuse_abort && same_params(s->prm, s->list_prm) && s->reuse_age + 1 < period;
+  s->reuse_abort = false;
   // may the NEXT evaluation be a reuse evaluation?  (then this one keeps the displacement books, and prepares no grid / keys)
   plan.next_reuse = cyc && (plan.reuse ? s->reuse_age + 2 < period : (period > 1 && s->have_h));
   return forces_plan(s, mode, integrate, plan);
@@ -974,6 +992,7 @@ void sphb_destroy(sphb_sim* s) {
   cudaFree(s->packCount); cudaFree(s->hacc); cudaFree(s->qmax);
   cudaFree(s->nx); cudaFree(s->dexcl); cudaFree(s->rs); cudaFree(s->stat_dev);
   if (s->stat_host) cudaFreeHost(s->stat_host);
+  if (s->stat_event_valid) cudaEventDestroy(s->stat_event);
   for (int side = 0; side < 2; ++side) { cudaFree(s->ring.sbuf[side]); cudaFree(s->ring.rbuf[side]); cudaFree(s->ring.sidx[side]); cudaFree(s->ring.hsrc[side]); }
   cudaFree(s->ring.inv); cudaFree(s->ring.red_dev);
   if (s->ring.refused_host) cudaFreeHost(s->ring.refused_host);

@@ -573,17 +573,25 @@ class RingSim:
 # bench.py --gpus N (N > 1): weak scaling, one rank per GPU
 # ------------------------------------------------------------------------------------------------
 def bench(args, nx, ny, box, phys, desc, rank, world, local):
-    import json
+    """one rank of `bench.py --gpus N`: the ring inside the library (sphb_ring_step over NCCL)"""
     import time
     import torch
     import torch.distributed as dist
     from . import _lib as L
     import bench as B  # repo-root bench.py (helpers: make_ic, ClockSampler, measured_peak)
 
-    if args.workload == "c4":  # strong scaling, non-uniform density: equal-count slabs
-        pos, ids, bounds = B.make_ic_c4(rank, world)
-        n_local, n_total = len(pos), 1 << 24
-        h_hint = 2.0 * default_h_hint(n_total, 1.0)  # the dilute half has twice the mean spacing
+    if args.workload in ("c4", "c4dam"):  # strong scaling, non-uniform density: equal-count slabs
+        pos_all, kw, desc4 = B.leg_ic(args.workload)
+        periodic = args.workload == "c4"
+        lo, hi = (0.0, 1.0) if periodic else (float(pos_all[:, 0].min()), float(pos_all[:, 0].max()) + 1e-9)
+        bounds = equal_count_bounds(pos_all[:, 0], world, lo, hi)
+        m = (pos_all[:, 0] >= bounds[rank]) & (pos_all[:, 0] < bounds[rank + 1])
+        pos, ids = np.ascontiguousarray(pos_all[m]), np.nonzero(m)[0].astype(np.int64)
+        n_local, n_total = len(pos), len(pos_all)
+        del pos_all
+        h_hint = 2.0 * default_h_hint(n_total, 1.0 if periodic else 0.125)  # (the dilute half has twice the mean spacing)
+        prm = L.make_params(precision=args.precision, device=local, **kw)
+        desc = desc4 + f"; {world} GPU(s), equal-count x-slabs, strong scaling"
     else:
         pos, (x0, x1) = B.make_ic(nx, ny, box, rank, world)
         n_local = len(pos)
@@ -591,16 +599,15 @@ def bench(args, nx, ny, box, phys, desc, rank, world, local):
         bounds = [box[0] * k / world for k in range(world + 1)]
         ids = np.arange(n_local, dtype=np.int64) + rank * n_local
         h_hint = default_h_hint(n_total, box[0] * box[1])
-    topo = Topology(world, bounds, periodic=True)
-    prm = L.make_params(hor=(0.0, box[0]), ver=(0.0, box[1]), device=local, **phys)
-    sim = DistSlabSim(prm, topo, rank, pos, None, np.full(n_local, 0.01), ids, h_max_hint=h_hint,
-                      capacity=n_local + max(1 << 20, n_local // 8), halo_cap=max(1 << 18, n_local // 16),
-                      migrate_every=0)
+        periodic = True
+        prm = L.make_params(hor=(0.0, box[0]), ver=(0.0, box[1]), device=local, **phys)
+    topo = Topology(world, bounds, periodic=periodic)
+    sim = RingSim(prm, topo, rank, pos, None, np.full(n_local, 0.01), ids, h_max_hint=h_hint,
+                  capacity=n_local + max(1 << 20, n_local // 8), halo_cap=max(1 << 18, n_local // 16))
     del pos
     K, W = args.steps, max(args.warmup, 3)
     sim.step(1 + W)
     sim.handle.sync()
-    sim.prof = {}
     c0 = sim.handle.counters()
     sampler = B.ClockSampler(local)
     sampler.start()
@@ -619,42 +626,36 @@ def bench(args, nx, ny, box, phys, desc, rank, world, local):
     dev_ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop()
     c1 = sim.handle.counters()
+    info = sim.handle.ring_info()
     t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device=torch.device("cuda", local))
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    cnt = torch.tensor([sim.handle.n], dtype=torch.int64, device=torch.device("cuda", local))
+    cnt = torch.tensor([sim.handle.n, c1["knn_fallback"] - c0["knn_fallback"]], dtype=torch.int64, device=torch.device("cuda", local))
     dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     dev_ms, wall_ms = float(t[0]), float(t[1])
-    # per-phase split, from separate untimed steps on every rank: wall time of each protocol phase with a
-    # device sync after it (halo pack, exchange, ghost insertion, the evaluation itself, all-reduce, migration) and the
-    # library's CUDA-event timers of the last evaluation (keys, sort, reorder, knn, force)
-    KP = min(K, 5)
-    was_profiling, prof_timed = sim.profile, dict(sim.prof)
-    migrations_before = sim.schedule.migrations
-    sim.profile, sim.prof = True, {}
-    sim.step(KP)
-    sim.handle.sync()
-    slab_phases = {k: v * 1e3 / KP for k, v in sim.prof.items()}
-    slab_phases["migrations_in_these_steps"] = sim.schedule.migrations - migrations_before
-    device_phases = dict(sim.handle.phase_times())
-    sim.profile, sim.prof = was_profiling, prof_timed
-    if rank == 0 and sim.profile:
-        import sys
-        print("slab phases, ms per step (wall, synchronised):",
-              {k: round(v * 1e3 / K, 3) for k, v in sim.prof.items()}, "device phases of the last evaluation:",
-              {k: round(v, 3) for k, v in sim.handle.phase_times().items()}, file=sys.stderr)
+    # device phases of separate untimed steps on rank 0 (library CUDA-event timers), by kind of evaluation
+    KP = max(2, min(K, int(info["period"]) + 1))
+    ph = {"rebuild": [], "reuse": []}
+    for _ in range(KP):
+        r0 = sim.handle.counters()["reuse_steps"]
+        sim.step(1)
+        kind = "reuse" if sim.handle.counters()["reuse_steps"] > r0 else "rebuild"
+        ph[kind].append(sim.handle.phase_times())
+    device_phases = {k: {f: float(np.mean([p[f] for p in v])) for f in v[0]} for k, v in ph.items() if v}
     if rank == 0:
         peak, peak_src = B.measured_peak()
         ms_per_step = dev_ms / K
         value = n_total * K / (dev_ms * 1e-3)
         achieved = n_total * B.B_ALG_TOTAL / (ms_per_step * 1e-3) / 1e9 / world  # per GPU
+        reuse_steps = c1["reuse_steps"] - c0["reuse_steps"]
         line = {
             "metric": B.METRIC, "value": value, "unit": B.UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "strong" if args.workload == "c4" else "weak", "vs_baseline": None,
+            "scaling": "strong" if args.workload.startswith("c4") else "weak", "vs_baseline": None,
             "dtype": "f64" if args.precision == 64 else "f32", "data": "synthetic",
-            "config": {"workload": desc, "particles": n_total, "particles_after": int(cnt.item()),
-                       "decomposition": f"{world} x-slabs, periodic ring, one ghost exchange per evaluation (NCCL send/recv), "
-                                        f"migration when the excursion bound nears the ghost slack ({sim.schedule.migrations} in {sim.schedule.steps} steps)",
+            "config": {"workload": desc, "particles": n_total, "particles_after": int(cnt[0]),
+                       "decomposition": f"{world} x-slabs, {'periodic ring' if periodic else 'open chain'}, inside libsphb (sphb_ring_step): NCCL send/recv of the halo "
+                                        f"on the library stream, ghosts kept across reuse evaluations, migration at rebuilds when the excursion bound nears "
+                                        f"the ghost slack ({int(info['migrations'])} so far)",
                        "timing": "CUDA events on each rank's library stream around K steps, max over ranks",
                        "wall_ms_per_step": wall_ms / K},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -664,10 +665,13 @@ def bench(args, nx, ny, box, phys, desc, rank, world, local):
             "e2e": {"value": n_total * K / (wall_ms * 1e-3), "unit": B.UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                     "what": "wall clock of the same K steps including host orchestration and NCCL exchange; state stays device resident"},
             "gpu_launches": c1["kernel_launches"] - c0["kernel_launches"],
-            "knn_fallback_particles": c1["knn_fallback"] - c0["knn_fallback"],
+            "knn_fallback_particles": int(cnt[1]),
+            "reuse": {"reuse_steps": reuse_steps, "rebuild_steps": K - reuse_steps, "period": int(info["period"]),
+                      "refused_fraction": int(cnt[1]) / (n_total * K), "ghosts_rank0": int(info["ghosts"])},
             "clocks": clocks,
-            "phases": {"slab_wall_ms_per_step": slab_phases, "device_ms_last_evaluation": device_phases,
-                       "what": f"rank 0, {KP} separate untimed steps with a device sync after every protocol phase"},
+            "phases": {"device_ms": device_phases,
+                       "what": f"rank 0, {KP} separate untimed steps: library CUDA-event timers per kind of evaluation; for reuse evaluations "
+                               "'keys' = predict + halo gather / exchange / scatter, for rebuilds the exchange precedes the timers"},
         }
         B.emit(line)
     dist.barrier()

@@ -149,15 +149,15 @@ def test_reuse_fp32_build():
 def test_reuse_adaptive_schedule_and_invalidation():
     """default (adaptive) schedule: reuse evaluations happen, an upload or an append in between forces a rebuild, and the
     trajectory equals the one without reuse"""
-    n = 64
+    n = 160  # (handles below 2^14 particles do not reuse on their own)
     pos = gen.jittered_lattice(n, n)
     kw = dict(hor=(0.0, 1.0), ver=(0.0, 1.0), accel=(0.0, 0.2), dt_half=0.98 / n)
     g = L.Handle(L.make_params(**kw), pos, None, np.full(len(pos), 0.01), capacity=len(pos) + 64)
     with env(SPHB_REUSE=0):
         g0 = L.Handle(L.make_params(**kw), pos, None, np.full(len(pos), 0.01), capacity=len(pos) + 64)
     for h in (g, g0):
-        h.step(6)
-    assert g.counters()["reuse_steps"] >= 3
+        h.step(8)
+    assert g.counters()["reuse_steps"] >= 3  # periods 2, 3, 4: rebuild, reuse, rebuild, reuse, reuse, rebuild, reuse, reuse
     extra = np.array([[0.503, 0.501], [0.25, 0.75]])
     for h in (g, g0):
         h.append(extra, None, np.full(2, 0.01), None, np.arange(len(pos), len(pos) + 2, dtype=np.int64))

@@ -73,7 +73,7 @@ def test_ring_fp32_build_with_reuse():
 
 
 def test_ring_adaptive_schedule_matches_single_handle():
-    pos = gen.jittered_lattice(64, 64)
+    pos = gen.jittered_lattice(128, 128)
     n = len(pos)
     kw = dict(hor=(0.0, 1.0), ver=(0.0, 1.0), accel=(0.0, 0.2), dt_half=0.002)
     pg = L.make_params(**kw)
