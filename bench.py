@@ -39,9 +39,15 @@ _JSON_OUT = None
 
 
 def emit(line: dict):
-    out = _JSON_OUT or sys.stdout
-    out.write(json.dumps(line) + "\n")
-    out.flush()
+    """the one JSON line, on the process's ORIGINAL stdout (main() points fd 1 at stderr for everything else; the saved
+    descriptor travels through the environment because slab.py imports this file as a second module object)"""
+    fd = os.environ.get("SPHB_BENCH_JSON_FD")
+    data = (json.dumps(line) + "\n").encode()
+    if fd:
+        os.write(int(fd), data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
 
 
 METRIC = "particle-updates/s per SPH step (k=32)"
@@ -502,9 +508,8 @@ def main():
     # rank 0 prints exactly one JSON line on stdout.  Libraries may write to fd 1 on their own (NCCL_DEBUG=VERSION / INFO
     # print with a bare printf): the process's fd 1 is pointed at stderr for the whole run and the JSON line goes to
     # the saved original stdout.  The caller's NCCL_* environment is left as it is.
-    global _JSON_OUT
     sys.stdout.flush()
-    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.environ["SPHB_BENCH_JSON_FD"] = str(os.dup(1))
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)

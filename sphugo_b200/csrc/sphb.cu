@@ -51,7 +51,7 @@ struct RingState {
   int64_t n_global = 0;
   int migrate_every = 0, migrations = 0;
   int cycle_len = 0;                     // evaluations since the last rebuild (inclusive)
-  bool reuse_pending = false;            // the last evaluation was a reuse evaluation (its refusal count is on its way)
+  int pending_kind = 0, pending_age = 0; // feedback on its way: 1 = of a rebuild, 2 = of a reuse evaluation (and its age)
   bool want_idx = false;                 // the halo pack in progress records the source indices
   double* sbuf[2] = {nullptr, nullptr};  // send: low side, high side
   double* rbuf[2] = {nullptr, nullptr};  // receive: from the left, from the right
@@ -143,6 +143,7 @@ struct sphb_sim {
   cudaEvent_t stat_event = nullptr;      // recorded behind the last record's copy
   bool stat_event_valid = false;
   bool reuse_abort = false;              // the policy ended the current cycle: the next evaluation rebuilds
+  int calm_steps = 0;                    // consecutive rebuilds whose tile search refused < 0.1 % of the particles
   int reuse_cooldown = 0;
   std::string err;
 };
@@ -486,10 +487,16 @@ int build_neighbours(sphb_sim* s, int mode, const double hor[2], const double ve
 //   - a reuse evaluation that refused more than 0.5 % of the particles ends its cycle at once, and cycles are from now
 //     on that much shorter (refused particles take the ring-expansion search, ~50 times the cost of an accepted one);
 //   - a cycle that completed with less than 0.1 % refused in its last evaluation lengthens the next one by one;
-//   - period 1 (no reuse) is tried again after a cool-down.
+//   - period 1 (no reuse) is tried again after a cool-down;
+//   - no cycle starts unless the tile search itself refused less than 0.1 % of the particles in the last two rebuilds
+//     (i.i.d. clouds, shock fronts, free surfaces: their smoothing lengths change by more than the skin per step).
 // Handles below 2^14 particles do not reuse unless SPHB_REUSE_PERIOD fixes a period (their steps are launch bound).
 void reuse_policy(sphb_sim* s, unsigned age, double frac, bool rebuild) {
-  if (s->reuse_period_fixed || rebuild) return;
+  if (rebuild) {  // what the tile search itself refused: a flow that upsets even the full search is no candidate for reuse
+    s->calm_steps = frac < 1e-3 ? s->calm_steps + 1 : 0;
+    return;
+  }
+  if (s->reuse_period_fixed) return;
   if (frac > 5e-3) {
     s->reuse_period = std::max(1, std::min(s->reuse_period, (int)age));
     s->reuse_abort = true;
@@ -535,6 +542,7 @@ struct EvalPlan {
   bool next_reuse = false;    // the next evaluation may be a reuse evaluation: keep the displacement books (ring: and the ghosts)
   bool predicted = false;     // reuse: drift-1 + predict already ran (ring: before the halo is gathered)
   bool defer_update = false;  // the caller launches k_reuse_update itself (ring: after the all-reduce of the statistics)
+  bool record = false;        // leave a feedback record even if no cycle is running (what the tile search refused)
 };
 
 // drop the ghosts (ring / slab mode): the few owned particles sorted behind index n move into the ghosts' slots
@@ -612,7 +620,7 @@ int forces_plan(sphb_sim* s, int mode, bool integrate, const EvalPlan& plan) {
   if (s->prm.kernel == 1) launch_force<1>(s, ntot, ph, integrate);
   else launch_force<2>(s, ntot, ph, integrate);
   s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 1;
-  if (!plan.defer_update && (s->force_rs || reuse)) launch_reuse_update(s, ntot, !reuse);  // (last evaluation of a cycle: for the record only)
+  if (!plan.defer_update && (s->force_rs || reuse || plan.record)) launch_reuse_update(s, ntot, !reuse);  // (outside a cycle: for the record only)
   const bool keep = next_reuse && s->lists_ext;
   if (!keep) invalidate_reuse(s);  // the cycle ends here
   if (s->fuse_keys) {
@@ -653,7 +661,9 @@ int forces(sphb_sim* s, int mode, bool integrate) {
   plan.reuse = cyc && s->lists_ext && !s->reuse_abort && same_params(s->prm, s->list_prm) && s->reuse_age + 1 < period;
   s->reuse_abort = false;
   // may the NEXT evaluation be a reuse evaluation?  (then this one keeps the displacement books, and prepares no grid / keys)
-  plan.next_reuse = cyc && (plan.reuse ? s->reuse_age + 2 < period : (period > 1 && s->have_h));
+  const bool calm = s->reuse_period_fixed || s->calm_steps >= 2;
+  plan.next_reuse = cyc && (plan.reuse ? s->reuse_age + 2 < period : (period > 1 && s->have_h && calm));
+  plan.record = cyc;
   return forces_plan(s, mode, integrate, plan);
 }
 
