@@ -121,8 +121,10 @@ struct sphb_sim {
   KnnTune ktune{};
   int force_nrec = 672;       // staged neighbour records per force block (shared memory)
   // certified reuse of the neighbour lists (sphb_kernels.cuh, ReuseState)
-  uint32_t* nx = nullptr;     // extended list [tile][SPHB_KX][lane]
-  double* dexcl = nullptr;    // exclusion radius per particle
+  uint16_t* ns = nullptr;     // candidate slots [tile][SPHB_K + SPHB_KX][lane] in the tile's staged block
+  TileInfo* tinfo = nullptr;  // [tile]: extent of the staged block (npc = 0: none)
+  uint2* ptab = nullptr;      // [tile][32]: its pieces
+  double* dexcl = nullptr;    // exclusion radius per particle (0: no slots)
   ReuseState* rs = nullptr;   // device bookkeeping
   ReuseStat* stat_dev = nullptr;
   ReuseStat* stat_host = nullptr;  // pinned ring of REUSE_RING records (non-blocking feedback for the schedule)
@@ -130,7 +132,7 @@ struct sphb_sim {
   int reuse_period = 2;       // evaluations per cycle: one rebuild + (period - 1) reuse evaluations; 1 = never reuse
   int reuse_period_max = 8, reuse_period_fixed = 0;
   double reuse_skin = 0.25;   // extended candidates are collected up to h (1 + skin)
-  int reuse_capb = 32, reuse_ncw = 256;
+  int reuse_ncw = 384;       // staged slots per tile of a rebuild that starts a cycle (<= 512: slots are 9-bit in the annulus pass)
   ReuseState* force_rs = nullptr;  // arguments of the force launch in progress
   bool force_stale = false;
   bool cell_per_h_fixed = false;   // SPHB_CELL_PER_H given: no adjustment for extended searches
@@ -291,6 +293,10 @@ int refresh_stats(sphb_sim* s) {
   return SPHB_OK;
 }
 
+KnnExt make_ext(sphb_sim* s, bool on) {
+  return KnnExt{on ? s->ns : nullptr, on ? s->tinfo : nullptr, on ? s->ptab : nullptr, on ? s->dexcl : nullptr, s->reuse_skin};
+}
+
 template <int KERNEL, bool F32, bool EXT>
 void launch_knn_p(sphb_sim* s, int ntot, const PhysP& ph) {
   KnnOut out{s->hacc, s->hscale, s->qmax, s->a.pc, s->nn, s->failList, s->failCount};
@@ -298,8 +304,7 @@ void launch_knn_p(sphb_sim* s, int ntot, const PhysP& ph) {
   KnnTune kt = s->ktune;
   kt.cap = s->have_h ? s->ktune.cap : s->ktune.cap0;  // first evaluation: radius from a density estimate, wider spread
   kt.ncw = s->have_h ? (EXT ? s->reuse_ncw : s->ktune.ncw) : s->ktune.ncw0;
-  KnnExt ex{EXT ? s->nx : nullptr, EXT ? s->dexcl : nullptr, s->reuse_skin, EXT ? s->reuse_capb : 0};
-  const size_t smem = (size_t)KNN_WARPS * knn_smem_bytes_per_warp(kt.cap, kt.ncw, F32, ex.capb);
+  const size_t smem = (size_t)KNN_WARPS * knn_smem_bytes_per_warp(kt.cap, kt.ncw, F32);
   static bool attr_done[64] = {};  // function attributes are per device (one handle per GPU, maybe several per process)
   if (!attr_done[s->device & 63]) {
     cudaFuncSetAttribute(k_knn_tile<KERNEL, F32, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -307,21 +312,35 @@ void launch_knn_p(sphb_sim* s, int ntot, const PhysP& ph) {
   }
   k_knn_tile<KERNEL, F32, EXT><<<cdiv(tiles, KNN_WARPS), KNN_THREADS, smem, s->st>>>(s->spos, s->keysSorted, s->cellStart,
                                                                                    s->hguess, s->a.epred, ntot, s->grid, ph, kt, out,
-                                                                                   s->slab_on ? s->a.ghost : nullptr, s->dflags, ex);
+                                                                                   s->slab_on ? s->a.ghost : nullptr, s->dflags, make_ext(s, EXT));
 }
 
-// ext: the evaluation starts a reuse cycle (extended lists + exclusion radii are written)
+// ext: the evaluation starts a reuse cycle: the tile search keeps its staged blocks and the candidates' slots, the
+// annulus pass adds the further candidates and the exclusion radii
 template <int KERNEL>
 void launch_knn(sphb_sim* s, int ntot, const PhysP& ph, bool ext) {
   ext = ext && s->have_h;  // (the first evaluation has no previous h to take the skin from)
   if (s->prm.precision == 32) { if (ext) launch_knn_p<KERNEL, true, true>(s, ntot, ph); else launch_knn_p<KERNEL, true, false>(s, ntot, ph); }
   else { if (ext) launch_knn_p<KERNEL, false, true>(s, ntot, ph); else launch_knn_p<KERNEL, false, false>(s, ntot, ph); }
   KnnOut out{s->hacc, s->hscale, s->qmax, s->a.pc, s->nn, s->failList, s->failCount};
-  FbExt fx{ext ? s->nx : nullptr, ext ? s->dexcl : nullptr, nullptr};
+  FbExt fx{ext ? s->dexcl : nullptr, nullptr};
+  const uint8_t* gf = s->slab_on ? s->a.ghost : nullptr;
   k_knn_fallback<KERNEL, false><<<148 * 4, 128, 0, s->st>>>(s->spos, s->keysSorted, s->cellStart, s->hguess,
-                                                          s->a.epred, ntot, s->grid, ph, out, s->slab_on ? s->a.ghost : nullptr, s->dflags, fx);
+                                                          s->a.epred, ntot, s->grid, ph, out, gf, s->dflags, fx);
+  if (ext) {
+    KnnTune kt = s->ktune;
+    kt.ncw = s->reuse_ncw;
+    static bool attr_done[64] = {};
+    if (!attr_done[s->device & 63]) {
+      cudaFuncSetAttribute(k_knn_annulus, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      attr_done[s->device & 63] = true;
+    }
+    k_knn_annulus<<<cdiv(cdiv(ntot, 32), KNN_WARPS), KNN_THREADS, (size_t)KNN_WARPS * annulus_smem_bytes_per_warp(kt.ncw), s->st>>>(
+        s->spos, s->keysSorted, s->cellStart, s->hguess, s->a.pc, ntot, s->grid, kt, make_ext(s, true), gf, s->dflags);
+    s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 1;
+  }
   s->have_h = true;
-  s->lists_ext = ext;  // (forces() completes the bookkeeping; any other caller leaves plain lists)
+  s->lists_ext = ext;  // (forces_plan completes the bookkeeping; any other caller leaves plain lists)
 }
 
 // REUSE evaluation: exact kNN from the stored candidates, refused particles to the ring-expansion search on the stale cells
@@ -329,17 +348,18 @@ template <int KERNEL>
 void launch_knn_reuse(sphb_sim* s, int ntot, const PhysP& ph) {
   KnnOut out{s->hacc, s->hscale, s->qmax, s->a.pc, s->nn, s->failList, s->failCount};
   const bool f32 = s->prm.precision == 32;
-  const size_t smem = (size_t)REUSE_NC * REUSE_THREADS * (f32 ? 4 : 8);
+  const size_t smem = (size_t)REUSE_WARPS * reuse_smem_bytes_per_warp(s->reuse_ncw, f32);
   static bool attr_done[64] = {};
   if (!attr_done[s->device & 63]) {
-    cudaFuncSetAttribute(k_knn_reuse<KERNEL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    cudaFuncSetAttribute(k_knn_reuse<KERNEL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(k_knn_reuse<KERNEL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(k_knn_reuse<KERNEL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     attr_done[s->device & 63] = true;
   }
   const uint8_t* gf = s->slab_on ? s->a.ghost : nullptr;
-  if (f32) k_knn_reuse<KERNEL, true><<<cdiv(ntot, REUSE_THREADS), REUSE_THREADS, smem, s->st>>>(s->spos, s->a.epred, ntot, s->grid, ph, out, s->nx, s->dexcl, s->rs, gf, s->dflags);
-  else k_knn_reuse<KERNEL, false><<<cdiv(ntot, REUSE_THREADS), REUSE_THREADS, smem, s->st>>>(s->spos, s->a.epred, ntot, s->grid, ph, out, s->nx, s->dexcl, s->rs, gf, s->dflags);
-  FbExt fx{s->nx, s->dexcl, s->rs};
+  const int nb = cdiv(cdiv(ntot, 32), REUSE_WARPS);
+  if (f32) k_knn_reuse<KERNEL, true><<<nb, REUSE_WARPS * 32, smem, s->st>>>(s->spos, s->a.epred, ntot, s->grid, ph, out, make_ext(s, true), s->reuse_ncw, s->rs, gf, s->dflags);
+  else k_knn_reuse<KERNEL, false><<<nb, REUSE_WARPS * 32, smem, s->st>>>(s->spos, s->a.epred, ntot, s->grid, ph, out, make_ext(s, true), s->reuse_ncw, s->rs, gf, s->dflags);
+  FbExt fx{s->dexcl, s->rs};
   k_knn_fallback<KERNEL, true><<<148 * 4, 128, 0, s->st>>>(s->spos, s->keysSorted, s->cellStart, s->hguess,
                                                          s->a.epred, ntot, s->grid, ph, out, gf, s->dflags, fx);
 }
@@ -760,7 +780,9 @@ int create_common(const sphb_params* p, int64_t n, int64_t capacity, const doubl
   CKC(dalloc(s->tileSum, (size_t)s->ntiles_cap));
   CKC(cudaMemsetAsync(s->cellCount, 0, ((size_t)s->ntiles_cap * SC_TILE + 8) * sizeof(uint32_t), s->st));
   CKC(dalloc(s->nn, cap32 * SPHB_K));
-  CKC(dalloc(s->nx, cap32 * SPHB_KX));
+  CKC(dalloc(s->ns, cap32 * (SPHB_K + SPHB_KX)));
+  CKC(dalloc(s->tinfo, cap32 / 32 + 1));
+  CKC(dalloc(s->ptab, cap32 + 32));
   CKC(dalloc(s->dexcl, cap));
   CKC(dalloc(s->rs, 1));
   CKC(cudaMemsetAsync(s->rs, 0, sizeof(ReuseState), s->st));
@@ -803,8 +825,7 @@ int create_common(const sphb_params* p, int64_t n, int64_t capacity, const doubl
   if (const char* ev = getenv("SPHB_REUSE_PERIOD")) s->reuse_period_fixed = std::max(1, std::min(64, atoi(ev)));
   if (const char* ev = getenv("SPHB_REUSE_MAX")) s->reuse_period_max = std::max(1, std::min(64, atoi(ev)));
   if (const char* ev = getenv("SPHB_REUSE_SKIN")) s->reuse_skin = std::max(0.03, std::min(1.0, atof(ev)));
-  if (const char* ev = getenv("SPHB_REUSE_CAPB")) s->reuse_capb = std::max(24, std::min(96, atoi(ev)));
-  if (const char* ev = getenv("SPHB_REUSE_NCW")) s->reuse_ncw = std::max(128, std::min(1024, atoi(ev) / 8 * 8));
+  if (const char* ev = getenv("SPHB_REUSE_NCW")) s->reuse_ncw = std::max(128, std::min(512, atoi(ev) / 32 * 32));
   if (const char* ev = getenv("SPHB_CELL_PER_H")) { s->gtune.cell_per_h = atof(ev); s->cell_per_h_fixed = true; }
   if (const char* ev = getenv("SPHB_PPC0")) s->gtune.ppc0 = atof(ev);
   if (const char* ev = getenv("SPHB_FORCE_NC")) s->gtune.force_nc = atoi(ev);
@@ -830,12 +851,15 @@ struct CapArrays {
   double2* spos = nullptr;
   double* hguess = nullptr;
   uint32_t *keys = nullptr, *keysSorted = nullptr, *rank = nullptr, *perm = nullptr;
-  uint32_t *cellStart = nullptr, *cellCount = nullptr, *tileSum = nullptr, *nn = nullptr, *nx = nullptr;
+  uint32_t *cellStart = nullptr, *cellCount = nullptr, *tileSum = nullptr, *nn = nullptr;
+  uint16_t* ns = nullptr;
+  TileInfo* tinfo = nullptr;
+  uint2* ptab = nullptr;
   double* dexcl = nullptr;
   int* failList = nullptr;
   void release() {
     free_soa(a); free_soa(b);
-    cudaFree(nx); cudaFree(dexcl);
+    cudaFree(ns); cudaFree(tinfo); cudaFree(ptab); cudaFree(dexcl);
     cudaFree(spos); cudaFree(hguess); cudaFree(keys); cudaFree(keysSorted); cudaFree(rank); cudaFree(perm);
     cudaFree(cellStart); cudaFree(cellCount); cudaFree(tileSum); cudaFree(nn); cudaFree(failList);
     *this = CapArrays{};
@@ -872,7 +896,9 @@ int grow_capacity(sphb_sim* s, int64_t need) {
   CKG(dalloc(t.cellCount, ncount));
   CKG(dalloc(t.tileSum, (size_t)ntiles));
   CKG(dalloc(t.nn, cap32 * SPHB_K));
-  CKG(dalloc(t.nx, cap32 * SPHB_KX));
+  CKG(dalloc(t.ns, cap32 * (SPHB_K + SPHB_KX)));
+  CKG(dalloc(t.tinfo, cap32 / 32 + 1));
+  CKG(dalloc(t.ptab, cap32 + 32));
   CKG(dalloc(t.dexcl, cap));
   CKG(dalloc(t.failList, cap));
   const size_t n = (size_t)s->n;
@@ -894,10 +920,10 @@ int grow_capacity(sphb_sim* s, int64_t need) {
   CapArrays old;
   old.a = s->a; old.b = s->b; old.spos = s->spos; old.hguess = s->hguess; old.keys = s->keys; old.keysSorted = s->keysSorted;
   old.rank = s->rank; old.perm = s->perm; old.cellStart = s->cellStart; old.cellCount = s->cellCount; old.tileSum = s->tileSum;
-  old.nn = s->nn; old.failList = s->failList; old.nx = s->nx; old.dexcl = s->dexcl;
+  old.nn = s->nn; old.failList = s->failList; old.ns = s->ns; old.tinfo = s->tinfo; old.ptab = s->ptab; old.dexcl = s->dexcl;
   s->a = t.a; s->b = t.b; s->spos = t.spos; s->hguess = t.hguess; s->keys = t.keys; s->keysSorted = t.keysSorted;
   s->rank = t.rank; s->perm = t.perm; s->cellStart = t.cellStart; s->cellCount = t.cellCount; s->tileSum = t.tileSum;
-  s->nn = t.nn; s->failList = t.failList; s->nx = t.nx; s->dexcl = t.dexcl;
+  s->nn = t.nn; s->failList = t.failList; s->ns = t.ns; s->tinfo = t.tinfo; s->ptab = t.ptab; s->dexcl = t.dexcl;
   old.release();
   invalidate_reuse(s);
   cudaFree(s->ring.inv); s->ring.inv = nullptr; s->ring.inv_cap = 0;
@@ -1000,7 +1026,7 @@ void sphb_destroy(sphb_sim* s) {
   cudaFree(s->keys); cudaFree(s->keysSorted); cudaFree(s->rank); cudaFree(s->perm);
   cudaFree(s->cellCount); cudaFree(s->tileSum); cudaFree(s->cellStart); cudaFree(s->nn); cudaFree(s->failList); cudaFree(s->failCount);
   cudaFree(s->packCount); cudaFree(s->hacc); cudaFree(s->qmax);
-  cudaFree(s->nx); cudaFree(s->dexcl); cudaFree(s->rs); cudaFree(s->stat_dev);
+  cudaFree(s->ns); cudaFree(s->tinfo); cudaFree(s->ptab); cudaFree(s->dexcl); cudaFree(s->rs); cudaFree(s->stat_dev);
   if (s->stat_host) cudaFreeHost(s->stat_host);
   if (s->stat_event_valid) cudaEventDestroy(s->stat_event);
   for (int side = 0; side < 2; ++side) { cudaFree(s->ring.sbuf[side]); cudaFree(s->ring.rbuf[side]); cudaFree(s->ring.sidx[side]); cudaFree(s->ring.hsrc[side]); }

@@ -40,12 +40,19 @@ struct PhysP {
   int kernel;
 };
 
-struct KnnExt {           // extended list of a rebuild evaluation (nx == nullptr: off)
-  uint32_t* nx;          // [tile][SPHB_KX][lane]
+// What a rebuild evaluation leaves for the reuse evaluations of its cycle, per tile (32 consecutive particles of the
+// sorted order): the staged union block of the tile search - its pieces (contiguous index ranges, one per grid row and
+// periodic image) and extent - taken wide enough for the skin.  The candidates of a particle are then 16-bit slots of
+// that block: a reuse evaluation stages the same ranges again (current positions, coalesced) and never gathers.
+struct TileInfo { int npc, nst, c0, c1, r0, r1; };  // npc = 0: the tile has no shared block (no reuse for its particles)
+struct KnnExt {           // (ns == nullptr: off)
+  uint16_t* ns;          // candidate slots [tile][SPHB_K + SPHB_KX][lane]; 0xffff = none
+  TileInfo* tinfo;       // [tile]
+  uint2* ptab;           // [tile][32] = {first index | image code << 28, length} of piece p
   double* dexcl;
   double skin;           // candidates are collected up to h_prev * (1 + skin)
-  int capb;              // slots of the second column
 };
+#define NS_NONE 0xffffu
 
 struct KnnTune {
   double guess_margin;   // search radius = h_prev * (1 + margin)
@@ -434,9 +441,8 @@ struct KnnOut {
 
 // shared memory per warp: the staged candidates of the tile {fp64 position (exact phase), fp32 tile-relative
 // position (filter), list entry} = 28 B each, and a column of CAP slots x 32 lanes x {fp32 key, staged slot}
-__host__ __device__ inline size_t knn_smem_bytes_per_warp(int cap, int ncw, bool f32, int capb = 0) {
-  // the fp32 build stages no fp64 positions; capb = slots of the second column (extended list, rebuild evaluations)
-  return (size_t)(cap + capb) * 256 + (size_t)ncw * (f32 ? 12 : 28);
+__host__ __device__ inline size_t knn_smem_bytes_per_warp(int cap, int ncw, bool f32) {
+  return (size_t)cap * 256 + (size_t)ncw * (f32 ? 12 : 28);  // the fp32 build stages no fp64 positions
 }
 
 __device__ __forceinline__ int warp_min_i(int v, uint32_t mask) {
@@ -468,24 +474,6 @@ __device__ __forceinline__ void knn_append(uint32_t& kp, float d2f, uint32_t en,
       "}\n"
       : "+r"(kp)
       : "f"(d2f), "r"(en), "f"(thr));
-}
-
-// the same with a second column for the extended list: d2f < thr goes to column A (kp), thr <= d2f < thrx to column B (kq)
-__device__ __forceinline__ void knn_append2(uint32_t& kp, uint32_t& kq, float d2f, uint32_t en, float thr, float thrx) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p, q;\n\t"
-      ".reg .b32 kb;\n\t"
-      "setp.lt.f32 p, %2, %4;\n\t"
-      "setp.lt.and.f32 q, %2, %5, !p;\n\t"
-      "mov.b32 kb, %2;\n\t"
-      "@p st.shared.v2.b32 [%0], {kb, %3};\n\t"
-      "@p add.u32 %0, %0, 256;\n\t"
-      "@q st.shared.v2.b32 [%1], {kb, %3};\n\t"
-      "@q add.u32 %1, %1, 256;\n\t"
-      "}\n"
-      : "+r"(kp), "+r"(kq)
-      : "f"(d2f), "r"(en), "f"(thr), "f"(thrx));
 }
 
 // Selection on a lane's column of fp32 keys (bit patterns): the mrem largest keys are to be dropped.  Five keys per pass
@@ -536,30 +524,16 @@ __device__ __forceinline__ void knn_accumulate_h(const KnnOut& out, bool ok, boo
   }
 }
 
-// extended list of an accepted lane (rebuild evaluations): the up to SPHB_KX nearest entries of column B and the exclusion
-// radius.  Every candidate the lane saw and did not keep has a key >= T, everything it did not see lies beyond rgx, and
-// fp32 keys are within delta of the true d^2: dexcl^2 = min(T (1 - 2 delta), rgx^2 (1 - 1e-5)).  Warp-collective.
-__device__ __forceinline__ double knn_write_ext(const KnnExt& ex, const uint2* colB, const uint32_t* candE, int nb, bool ok,
-                                                bool bovf, int tile, int lane, int i, double rgx, double delta, double h) {
-  const bool sel = ok && !bovf && nb > SPHB_KX;
-  uint32_t T, akey;
-  knn_select_drop(colB, nb, sel ? nb - SPHB_KX : 0, sel, T, akey);
-  if (!ok) return 0.0;  // refused lanes: the fallback kernel writes their (empty) extended list
-  uint32_t* xp = ex.nx + (size_t)tile * (SPHB_KX * 32) + lane;
-  int w = 0;
-  double dx = h;    // second column overflowed: unknown candidates were lost, nothing beyond h is certain
-  if (!bovf) {
-    double d2x = rgx * rgx * (1.0 - 1e-5);
-    if (T != 0xffffffffu) d2x = fmin(d2x, (double)__uint_as_float(T) * (1.0 - 2.0 * delta));
-    for (int s = 0; s < nb; ++s) {
-      const uint2 ke = colB[s * 32];
-      if (ke.x < T && w < SPHB_KX) { xp[w * 32] = candE[ke.y]; ++w; }
-    }
-    dx = sqrt(d2x);
-  }
-  for (; w < SPHB_KX; ++w) xp[w * 32] = 0xffffffffu;
-  ex.dexcl[i] = dx;
-  return dx;
+// radius up to which a rebuild collects candidates: h_prev (1 + skin), from the search radius rg = h_prev (1 + margin)
+__device__ __forceinline__ double knn_ext_radius(double rg, double margin, double skin) { return rg * ((1.0 + skin) / (1.0 + margin)); }
+
+// unwrapped cell range containing every point within r of (xa, ya) (clamped to one period either side)
+__device__ __forceinline__ void knn_cell_range(const GridP& g, double xa, double ya, double r, int cxa, int cya, int& clo, int& chi,
+                                               int& rlo, int& rhi) {
+  clo = (int)floor((xa - r - g.ox) * g.inv_dx); chi = (int)floor((xa + r - g.ox) * g.inv_dx);
+  rlo = (int)floor((ya - r - g.oy) * g.inv_dy); rhi = (int)floor((ya + r - g.oy) * g.inv_dy);
+  clo = max(min(clo, cxa), -g.ncx); chi = min(max(chi, cxa), 2 * g.ncx - 1);
+  rlo = max(min(rlo, cya), -g.ncy); rhi = min(max(rhi, cya), 2 * g.ncy - 1);
 }
 
 template <int KERNEL, bool F32, bool EXT>
@@ -574,19 +548,16 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
   const GridP g = *gp;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int CAP = tune.cap, NCW = tune.ncw, CAPB = EXT ? ex.capb : 0;
-  unsigned char* wb = smem_raw + (size_t)warp * knn_smem_bytes_per_warp(CAP, NCW, F32, CAPB);
+  const int CAP = tune.cap, NCW = tune.ncw;
+  unsigned char* wb = smem_raw + (size_t)warp * knn_smem_bytes_per_warp(CAP, NCW, F32);
   uint2* col = reinterpret_cast<uint2*>(wb) + lane;                                  // [slot * 32] = {key, staged slot}
-  uint2* colB = reinterpret_cast<uint2*>(wb + (size_t)CAP * 256) + lane;             // second column (EXT): rg <= d < rgx
-  const size_t cbase = (size_t)(CAP + CAPB) * 256;
+  const size_t cbase = (size_t)CAP * 256;
   float2* candF = reinterpret_cast<float2*>(wb + cbase);                             // fp32 tile-relative positions
   const float4* candF4 = reinterpret_cast<const float4*>(candF);                     // two staged candidates each
   uint32_t* candE = reinterpret_cast<uint32_t*>(wb + cbase + (size_t)NCW * 8);       // index | image code << 28
   double2* candD = reinterpret_cast<double2*>(wb + cbase + (size_t)NCW * 12);        // exact positions (fp64 build)
   const uint32_t kbase = (uint32_t)__cvta_generic_to_shared(col);
   const uint32_t klim = kbase + (uint32_t)(CAP - 8) * 256u;  // beyond this fewer than 8 free slots remain
-  const uint32_t qbase = (uint32_t)__cvta_generic_to_shared(colB);
-  const uint32_t qlim = qbase + (uint32_t)(CAPB - 8) * 256u;
 
   const int tile = blockIdx.x * KNN_WARPS + warp;
   if (tile * 32 >= n) return;  // whole warp out of range (warp-uniform)
@@ -618,18 +589,21 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
     }
   }
   const double rg2 = rg * rg;
-  // EXT: the lane collects candidates up to rgx = rg-equivalent with the skin instead of the margin; those between rg
-  // and rgx feed the extended list
-  const double rgx = EXT ? rg * ((1.0 + ex.skin) / (1.0 + tune.guess_margin)) : rg;
-  // unwrapped cell range that contains every point within rw = rgx (1 + 1e-4): the lane scans only these cells.
+  // unwrapped cell range that contains every point within rw = rg (1 + 1e-4): the lane scans only these cells.
   // The widening matters in the fp32 build: a candidate outside them has a true d^2 > rg^2 (1 + 2e-4), so even
   // with its fp32 key error (< 1.5e-5 relative, enforced below) it cannot undercut an accepted h^2 < thr.
-  const double rw = rgx * (1.0 + 1e-4);
+  const double rw = rg * (1.0 + 1e-4);
   int clo = (int)floor((xa - rw - g.ox) * g.inv_dx), chi = (int)floor((xa + rw - g.ox) * g.inv_dx);
   int rlo = (int)floor((ya - rw - g.oy) * g.inv_dy), rhi = (int)floor((ya + rw - g.oy) * g.inv_dy);
   // (clamped to one period either side: non-finite or absurd positions must not overflow the range arithmetic)
   clo = max(min(clo, cxa), -g.ncx); chi = min(max(chi, cxa), 2 * g.ncx - 1);
   rlo = max(min(rlo, cya), -g.ncy); rhi = min(max(rhi, cya), 2 * g.ncy - 1);
+  // EXT: the staged block of the whole tile is taken wide enough for the skin (rgx = h_prev (1 + skin)) and kept for the
+  // cycle's reuse evaluations; the lanes' own windows stay those of rg
+  const double rgx = EXT ? knn_ext_radius(rg, tune.guess_margin, ex.skin) : rg;
+  int xlo = clo, xhi = chi, ylo = rlo, yhi = rhi;
+  if (EXT) knn_cell_range(g, xa, ya, rgx * (1.0 + 1e-4), cxa, cya, xlo, xhi, ylo, yhi);
+  bool ext_try = EXT;   // first pass: all lanes of the tile as one group on the wide block
 
   // One pass of the whole pipeline per group of lanes that sit in the same grid row (a tile is a strip of one
   // row, so there is one group unless the tile straddles the end of a row).
@@ -637,16 +611,18 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
   // the staging area: the group is then halved (lanes are ordered along the strip) and retried.
   uint32_t todo = __ballot_sync(0xffffffffu, valid);
   int maxlanes = 32;
+  if (EXT && lane == 0) ex.tinfo[tile].npc = 0;  // (set again below if the tile gets a shared block)
+  uint16_t* nsp = EXT ? ex.ns + (size_t)tile * ((SPHB_K + SPHB_KX) * 32) + lane : nullptr;
   while (todo) {
     const int lead = __ffs(todo) - 1;
     const int grow = __shfl_sync(0xffffffffu, cya, lead);
-    const uint32_t cand = __ballot_sync(0xffffffffu, valid && cya == grow) & todo;
+    const uint32_t cand = ext_try ? todo : (__ballot_sync(0xffffffffu, valid && cya == grow) & todo);
     const uint32_t grp = __ballot_sync(0xffffffffu, ((cand >> lane) & 1u) && __popc(cand & ((1u << lane) - 1u)) < maxlanes);
     todo &= ~grp;
     const bool mine = (grp >> lane) & 1u;
     bool bad = false;  // stencil wider than the period / fp32 bound not applicable / staging area full: fallback
-    int c0 = warp_min_i(clo, grp), c1 = warp_max_i(chi, grp);
-    int r0 = warp_min_i(rlo, grp), r1 = warp_max_i(rhi, grp);
+    int c0 = warp_min_i(ext_try ? xlo : clo, grp), c1 = warp_max_i(ext_try ? xhi : chi, grp);
+    int r0 = warp_min_i(ext_try ? ylo : rlo, grp), r1 = warp_max_i(ext_try ? yhi : rhi, grp);
     bool gbad = false;
     if (g.wrapx) { if (c1 - c0 + 1 > g.ncx) gbad = true; }
     else { c0 = max(c0, 0); c1 = min(c1, g.ncx - 1); c0 = min(c0, g.ncx - 1); c1 = max(c1, 0); }
@@ -679,6 +655,10 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
       nst = __shfl_sync(0xffffffffu, incl, 31);
       if (nst > NCW) big = true;
     }
+    if (ext_try && (big || gbad)) {  // no shared wide block for this tile: the ordinary search, no reuse for its particles
+      ext_try = false; todo |= grp;
+      continue;
+    }
     if (big) {
       const int nl = __popc(grp);
       if (nl > 1) { todo |= grp; maxlanes = nl >> 1; continue; }  // retry with half the lanes
@@ -694,7 +674,7 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
     const double yref = g.oy + 0.5 * (double)(r0 + r1 + 1) * g.dy;
     double V = fmax(0.5 * (double)(c1 - c0 + 1) * g.dx, 0.5 * (double)(r1 - r0 + 1) * g.dy);
     // clamped border cells of an open axis may hold particles beyond the block: bound by the queries' reach
-    V = fmax(V, warp_max_d(mine ? fmax(fabs(xa - xref), fabs(ya - yref)) + rgx : 0.0));
+    V = fmax(V, warp_max_d(mine ? fmax(fabs(xa - xref), fabs(ya - yref)) + (ext_try ? rgx : rg) : 0.0));
     const float qfx = (float)(xa - xref), qfy = (float)(ya - yref);
     const float2 nqx2 = make_float2(-qfx, -qfx), nqy2 = make_float2(-qfy, -qfy);
     const double delta = 3.0 * (2.384185791015625e-07 * V / fmax(rg, 1e-300) + 4.76837158203125e-07);
@@ -703,8 +683,7 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
     if (mine && !(delta < (F32 ? 1.5e-5 : 1e-3))) bad = true;
     const float thr0 = (float)(rg2 * (1.0 + delta)) * 1.0000002f;
     float thrf = (mine && !bad) ? thr0 : -1.0f;
-    const float thrx0 = (float)(rgx * rgx * (1.0 + delta)) * 1.0000002f;
-    float thrxf = (EXT && mine && !bad) ? thrx0 : -1.0f;
+
     const float Vf = (float)V * 1.000001f;
 
     // window of piece 0 (see the filter below): issued here so that its two lookups overlap the staging loads
@@ -750,9 +729,8 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
     }
     __syncwarp();
 
-    uint32_t kp = kbase, kq = qbase;
+    uint32_t kp = kbase;
     bool ovf = false;  // column (nearly) full: stop appending, the lane goes to the fallback
-    bool bovf = false; // second column full: the lane keeps an empty extended list
     // phase 1: fp32 filter, branch-free.  A lane only scans its own window of every piece: the candidates in the
     // cells its search disc touches (a contiguous slot range, from two cellStart lookups per piece, fetched one
     // piece ahead).  The trip count is the longest window of the warp; a window that would run past the end of
@@ -787,15 +765,9 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
           d2f[2 * u] = d2.x;
           d2f[2 * u + 1] = d2.y;
         }
-        if (kp > klim) { ovf = true; thrf = -1.0f; thrxf = -1.0f; }
-        if (EXT) {
-          if (kq > qlim) { bovf = true; thrxf = -1.0f; }
+        if (kp > klim) { ovf = true; thrf = -1.0f; }
 #pragma unroll
-          for (int u = 0; u < 8; ++u) knn_append2(kp, kq, d2f[u], (uint32_t)(c + u), thrf, thrxf);
-        } else {
-#pragma unroll
-          for (int u = 0; u < 8; ++u) knn_append(kp, d2f[u], (uint32_t)(c + u), thrf);
-        }
+        for (int u = 0; u < 8; ++u) knn_append(kp, d2f[u], (uint32_t)(c + u), thrf);
       }
     }
     __syncwarp();
@@ -837,9 +809,6 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
           if (ke[u].x < T && !self) {  // at most cnt - 1 - m = 32 entries qualify; kept <= s0 + u: only slots already read
             col[kept * 32] = ke[u];
             ++kept;
-          } else if (EXT && !self && ke[u].x != 0xffffffffu) {  // dropped by the selection: nearer than all of column B
-            if (kq < qbase + (uint32_t)CAPB * 256u) { colB[((kq - qbase) >> 8) * 32] = ke[u]; kq += 256u; }
-            else bovf = true;
           }
         }
       }
@@ -868,6 +837,7 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
         for (int s = 0; s < SPHB_K; ++s) {
           const uint2 ke = col[s * 32];
           np[s * 32] = candE[ke.y];
+          if (EXT && ext_try) nsp[s * 32] = (uint16_t)ke.y;
           const float q2 = __uint_as_float(ke.x) * (inv_h * inv_h);
           float rq;
           asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rq) : "f"(fmaxf(q2, 1e-30f)));
@@ -891,11 +861,10 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
         out.pc[i] = make_double4((double)rho, (double)c, h, (double)(c * c / ((float)ph.gamma * rho)));
       }
       const double hacc_h = (double)(ok ? h2f * rsqrtf(fmaxf(h2f, 1e-37f)) : 0.0f);
-      if (EXT) {
-        const double dxl = knn_write_ext(ex, colB, candE, (int)((kq - qbase) >> 8), ok, bovf, tile, lane, i, rgx, delta, hacc_h * 1.000001);
-        // slab mode: the exclusion radius is only valid if everything within it was local (ghost layer wide enough)
-        if (ok && g.sides && (((g.sides & 1) && xa - g.ox < dxl) || ((g.sides & 2) && g.ox + (double)g.ncx * g.dx - xa < dxl)))
-          atomicOr(dflags, DFLAG_GHOST_THIN);
+      if (EXT && ext_try) {  // the shared block of the tile, for the annulus pass and the cycle's reuse evaluations
+        if (ok) ex.dexcl[i] = 1.0;  // "has slots" (the annulus pass writes the radius; refused lanes get 0 from the fallback)
+        if (lane < npc) ex.ptab[(size_t)tile * 32 + lane] = make_uint2((uint32_t)p_s | (p_code << IMG_SHIFT), (uint32_t)p_len);
+        if (lane == 0) ex.tinfo[tile] = TileInfo{npc, nst, c0, c1, r0, r1};
       }
       knn_accumulate_h(out, ok, owned, hacc_h);
       continue;
@@ -907,11 +876,12 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
       if (!anyimg) {  // warp-uniform: no periodic image in this tile's block, the query is never shifted
 #pragma unroll
         for (int s0 = 0; s0 < SPHB_K; s0 += 8) {
-          uint32_t en[8];
+          uint32_t en[8], sls[8];
           double2 pb[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const uint32_t sl = col[(s0 + u) * 32].y;
+            sls[u] = sl;
             pb[u] = candD[sl];
             en[u] = candE[sl];
           }
@@ -920,6 +890,7 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
             const double d2 = dist_sq(xa - pb[u].x, ya - pb[u].y);
             h2 = fmax(h2, d2);
             np[(s0 + u) * 32] = en[u];
+            if (EXT && ext_try) nsp[(s0 + u) * 32] = (uint16_t)sls[u];
             *reinterpret_cast<double*>(&col[(s0 + u) * 32]) = d2;
           }
         }
@@ -928,11 +899,12 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
         const double qym = __dadd_rn(ya, g.Ly), qyp = __dadd_rn(ya, -g.Ly);
 #pragma unroll
         for (int s0 = 0; s0 < SPHB_K; s0 += 8) {
-          uint32_t en[8];
+          uint32_t en[8], sls[8];
           double2 pb[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const uint32_t sl = col[(s0 + u) * 32].y;
+            sls[u] = sl;
             pb[u] = candD[sl];
             en[u] = candE[sl];
           }
@@ -944,6 +916,7 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
             const double d2 = dist_sq(qx - pb[u].x, qy - pb[u].y);
             h2 = fmax(h2, d2);
             np[(s0 + u) * 32] = en[u];
+            if (EXT && ext_try) nsp[(s0 + u) * 32] = (uint16_t)sls[u];
             *reinterpret_cast<double*>(&col[(s0 + u) * 32]) = d2;
           }
         }
@@ -973,10 +946,10 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
       const double c = c2 > 0.0 ? fast_sqrt(c2, fast_rsqrt(c2)) : sqrt(c2);
       out.pc[i] = make_double4(rho, c, h, c * c * fast_rcp(ph.gamma * rho));
     }
-    if (EXT) {
-      const double dxl = knn_write_ext(ex, colB, candE, (int)((kq - qbase) >> 8), ok, bovf, tile, lane, i, rgx, delta, ok ? sqrt(h2) : 0.0);
-      if (ok && g.sides && (((g.sides & 1) && xa - g.ox < dxl) || ((g.sides & 2) && g.ox + (double)g.ncx * g.dx - xa < dxl)))
-        atomicOr(dflags, DFLAG_GHOST_THIN);
+    if (EXT && ext_try) {
+      if (ok) ex.dexcl[i] = 1.0;
+      if (lane < npc) ex.ptab[(size_t)tile * 32 + lane] = make_uint2((uint32_t)p_s | (p_code << IMG_SHIFT), (uint32_t)p_len);
+      if (lane == 0) ex.tinfo[tile] = TileInfo{npc, nst, c0, c1, r0, r1};
     }
     knn_accumulate_h(out, ok, owned, ok ? sqrt(h2) : 0.0);
   }
@@ -996,8 +969,7 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
 // candidate is therefore corrected to the nearest one - unless the block spans more than half a period, in which case
 // all three images of every cell are scanned (exact whatever the cells say: positions are the current ones).
 struct FbExt {
-  uint32_t* nx;            // extended list to clear (nullptr: none)
-  double* dexcl;
+  double* dexcl;           // set to 0 = "no candidate slots" for the particles searched here (nullptr: no reuse bookkeeping)
   const ReuseState* rs;    // STALE: D
 };
 
@@ -1127,7 +1099,6 @@ __global__ void __launch_bounds__(128) k_knn_fallback(const double2* __restrict_
     }
     const int tile = i >> 5, ql = i & 31;
     uint32_t* nncol = out.nn + (size_t)tile * 32 * 32 + ql;
-    if (fx.nx && lane < SPHB_KX) fx.nx[(size_t)tile * (SPHB_KX * 32) + lane * 32 + ql] = 0xffffffffu;  // no extended list
     if (found < SPHB_K) {
       if (lane == 0) atomicOr(dflags, DFLAG_UNDERFULL);
       nncol[lane * 32] = 0xffffffffu;
@@ -1137,7 +1108,7 @@ __global__ void __launch_bounds__(128) k_knn_fallback(const double2* __restrict_
     const double h2 = __shfl_sync(0xffffffffu, td, 0);
     const double h = sqrt(h2);
     const double inv_h = 1.0 / h;
-    if (lane == 0 && fx.dexcl) fx.dexcl[i] = h;  // everything outside the list is at least h away, nothing more is known
+    if (lane == 0 && fx.dexcl) fx.dexcl[i] = 0.0;  // its list has no slots in the tile's block: full search until the next rebuild
     if (!STALE && lane == 0 && g.sides && (((g.sides & 1) && pa.x - g.ox < h) || ((g.sides & 2) && g.ox + (double)g.ncx * g.dx - pa.x < h)))
       atomicOr(dflags, DFLAG_GHOST_THIN);
     double acc = kern_F<KERNEL>(fmin(sqrt(td) * inv_h, 1.0));
