@@ -121,7 +121,7 @@ struct sphb_sim {
   KnnTune ktune{};
   int force_nrec = 672;       // staged neighbour records per force block (shared memory)
   // certified reuse of the neighbour lists (sphb_kernels.cuh, ReuseState)
-  uint16_t* ns = nullptr;     // candidate slots [tile][SPHB_K + SPHB_KX][lane] in the tile's staged block
+  uint32_t* nx = nullptr;     // further candidates [tile][SPHB_KX][lane]
   TileInfo* tinfo = nullptr;  // [tile]: extent of the staged block (npc = 0: none)
   uint2* ptab = nullptr;      // [tile][32]: its pieces
   double* dexcl = nullptr;    // exclusion radius per particle (0: no slots)
@@ -294,7 +294,7 @@ int refresh_stats(sphb_sim* s) {
 }
 
 KnnExt make_ext(sphb_sim* s, bool on) {
-  return KnnExt{on ? s->ns : nullptr, on ? s->tinfo : nullptr, on ? s->ptab : nullptr, on ? s->dexcl : nullptr, s->reuse_skin};
+  return KnnExt{on ? s->nx : nullptr, on ? s->tinfo : nullptr, on ? s->ptab : nullptr, on ? s->dexcl : nullptr, s->reuse_skin};
 }
 
 template <int KERNEL, bool F32, bool EXT>
@@ -348,17 +348,16 @@ template <int KERNEL>
 void launch_knn_reuse(sphb_sim* s, int ntot, const PhysP& ph) {
   KnnOut out{s->hacc, s->hscale, s->qmax, s->a.pc, s->nn, s->failList, s->failCount};
   const bool f32 = s->prm.precision == 32;
-  const size_t smem = (size_t)REUSE_WARPS * reuse_smem_bytes_per_warp(s->reuse_ncw, f32);
+  const size_t smem = (size_t)REUSE_NC * REUSE_THREADS * (f32 ? 4 : 8);
   static bool attr_done[64] = {};
   if (!attr_done[s->device & 63]) {
-    cudaFuncSetAttribute(k_knn_reuse<KERNEL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    cudaFuncSetAttribute(k_knn_reuse<KERNEL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(k_knn_reuse<KERNEL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(k_knn_reuse<KERNEL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     attr_done[s->device & 63] = true;
   }
   const uint8_t* gf = s->slab_on ? s->a.ghost : nullptr;
-  const int nb = cdiv(cdiv(ntot, 32), REUSE_WARPS);
-  if (f32) k_knn_reuse<KERNEL, true><<<nb, REUSE_WARPS * 32, smem, s->st>>>(s->spos, s->a.epred, ntot, s->grid, ph, out, make_ext(s, true), s->reuse_ncw, s->rs, gf, s->dflags);
-  else k_knn_reuse<KERNEL, false><<<nb, REUSE_WARPS * 32, smem, s->st>>>(s->spos, s->a.epred, ntot, s->grid, ph, out, make_ext(s, true), s->reuse_ncw, s->rs, gf, s->dflags);
+  if (f32) k_knn_reuse<KERNEL, true><<<cdiv(ntot, REUSE_THREADS), REUSE_THREADS, smem, s->st>>>(s->spos, s->a.epred, ntot, s->grid, ph, out, s->nx, s->dexcl, s->rs, gf, s->dflags);
+  else k_knn_reuse<KERNEL, false><<<cdiv(ntot, REUSE_THREADS), REUSE_THREADS, smem, s->st>>>(s->spos, s->a.epred, ntot, s->grid, ph, out, s->nx, s->dexcl, s->rs, gf, s->dflags);
   FbExt fx{s->dexcl, s->rs};
   k_knn_fallback<KERNEL, true><<<148 * 4, 128, 0, s->st>>>(s->spos, s->keysSorted, s->cellStart, s->hguess,
                                                          s->a.epred, ntot, s->grid, ph, out, gf, s->dflags, fx);
@@ -780,7 +779,7 @@ int create_common(const sphb_params* p, int64_t n, int64_t capacity, const doubl
   CKC(dalloc(s->tileSum, (size_t)s->ntiles_cap));
   CKC(cudaMemsetAsync(s->cellCount, 0, ((size_t)s->ntiles_cap * SC_TILE + 8) * sizeof(uint32_t), s->st));
   CKC(dalloc(s->nn, cap32 * SPHB_K));
-  CKC(dalloc(s->ns, cap32 * (SPHB_K + SPHB_KX)));
+  CKC(dalloc(s->nx, cap32 * SPHB_KX));
   CKC(dalloc(s->tinfo, cap32 / 32 + 1));
   CKC(dalloc(s->ptab, cap32 + 32));
   CKC(dalloc(s->dexcl, cap));
@@ -852,14 +851,14 @@ struct CapArrays {
   double* hguess = nullptr;
   uint32_t *keys = nullptr, *keysSorted = nullptr, *rank = nullptr, *perm = nullptr;
   uint32_t *cellStart = nullptr, *cellCount = nullptr, *tileSum = nullptr, *nn = nullptr;
-  uint16_t* ns = nullptr;
+  uint32_t* nx = nullptr;
   TileInfo* tinfo = nullptr;
   uint2* ptab = nullptr;
   double* dexcl = nullptr;
   int* failList = nullptr;
   void release() {
     free_soa(a); free_soa(b);
-    cudaFree(ns); cudaFree(tinfo); cudaFree(ptab); cudaFree(dexcl);
+    cudaFree(nx); cudaFree(tinfo); cudaFree(ptab); cudaFree(dexcl);
     cudaFree(spos); cudaFree(hguess); cudaFree(keys); cudaFree(keysSorted); cudaFree(rank); cudaFree(perm);
     cudaFree(cellStart); cudaFree(cellCount); cudaFree(tileSum); cudaFree(nn); cudaFree(failList);
     *this = CapArrays{};
@@ -896,7 +895,7 @@ int grow_capacity(sphb_sim* s, int64_t need) {
   CKG(dalloc(t.cellCount, ncount));
   CKG(dalloc(t.tileSum, (size_t)ntiles));
   CKG(dalloc(t.nn, cap32 * SPHB_K));
-  CKG(dalloc(t.ns, cap32 * (SPHB_K + SPHB_KX)));
+  CKG(dalloc(t.nx, cap32 * SPHB_KX));
   CKG(dalloc(t.tinfo, cap32 / 32 + 1));
   CKG(dalloc(t.ptab, cap32 + 32));
   CKG(dalloc(t.dexcl, cap));
@@ -920,10 +919,10 @@ int grow_capacity(sphb_sim* s, int64_t need) {
   CapArrays old;
   old.a = s->a; old.b = s->b; old.spos = s->spos; old.hguess = s->hguess; old.keys = s->keys; old.keysSorted = s->keysSorted;
   old.rank = s->rank; old.perm = s->perm; old.cellStart = s->cellStart; old.cellCount = s->cellCount; old.tileSum = s->tileSum;
-  old.nn = s->nn; old.failList = s->failList; old.ns = s->ns; old.tinfo = s->tinfo; old.ptab = s->ptab; old.dexcl = s->dexcl;
+  old.nn = s->nn; old.failList = s->failList; old.nx = s->nx; old.tinfo = s->tinfo; old.ptab = s->ptab; old.dexcl = s->dexcl;
   s->a = t.a; s->b = t.b; s->spos = t.spos; s->hguess = t.hguess; s->keys = t.keys; s->keysSorted = t.keysSorted;
   s->rank = t.rank; s->perm = t.perm; s->cellStart = t.cellStart; s->cellCount = t.cellCount; s->tileSum = t.tileSum;
-  s->nn = t.nn; s->failList = t.failList; s->ns = t.ns; s->tinfo = t.tinfo; s->ptab = t.ptab; s->dexcl = t.dexcl;
+  s->nn = t.nn; s->failList = t.failList; s->nx = t.nx; s->tinfo = t.tinfo; s->ptab = t.ptab; s->dexcl = t.dexcl;
   old.release();
   invalidate_reuse(s);
   cudaFree(s->ring.inv); s->ring.inv = nullptr; s->ring.inv_cap = 0;
@@ -1026,7 +1025,7 @@ void sphb_destroy(sphb_sim* s) {
   cudaFree(s->keys); cudaFree(s->keysSorted); cudaFree(s->rank); cudaFree(s->perm);
   cudaFree(s->cellCount); cudaFree(s->tileSum); cudaFree(s->cellStart); cudaFree(s->nn); cudaFree(s->failList); cudaFree(s->failCount);
   cudaFree(s->packCount); cudaFree(s->hacc); cudaFree(s->qmax);
-  cudaFree(s->ns); cudaFree(s->tinfo); cudaFree(s->ptab); cudaFree(s->dexcl); cudaFree(s->rs); cudaFree(s->stat_dev);
+  cudaFree(s->nx); cudaFree(s->tinfo); cudaFree(s->ptab); cudaFree(s->dexcl); cudaFree(s->rs); cudaFree(s->stat_dev);
   if (s->stat_host) cudaFreeHost(s->stat_host);
   if (s->stat_event_valid) cudaEventDestroy(s->stat_event);
   for (int side = 0; side < 2; ++side) { cudaFree(s->ring.sbuf[side]); cudaFree(s->ring.rbuf[side]); cudaFree(s->ring.sidx[side]); cudaFree(s->ring.hsrc[side]); }

@@ -43,16 +43,15 @@ struct PhysP {
 // What a rebuild evaluation leaves for the reuse evaluations of its cycle, per tile (32 consecutive particles of the
 // sorted order): the staged union block of the tile search - its pieces (contiguous index ranges, one per grid row and
 // periodic image) and extent - taken wide enough for the skin.  The candidates of a particle are then 16-bit slots of
-// that block: a reuse evaluation stages the same ranges again (current positions, coalesced) and never gathers.
+// that block for the annulus pass that follows the tile search (sphb_reuse.cuh).
 struct TileInfo { int npc, nst, c0, c1, r0, r1; };  // npc = 0: the tile has no shared block (no reuse for its particles)
-struct KnnExt {           // (ns == nullptr: off)
-  uint16_t* ns;          // candidate slots [tile][SPHB_K + SPHB_KX][lane]; 0xffff = none
+struct KnnExt {           // (nx == nullptr: off)
+  uint32_t* nx;          // further candidates [tile][SPHB_KX][lane], list entries like nn; 0xffffffff = none
   TileInfo* tinfo;       // [tile]
   uint2* ptab;           // [tile][32] = {first index | image code << 28, length} of piece p
   double* dexcl;
   double skin;           // candidates are collected up to h_prev * (1 + skin)
 };
-#define NS_NONE 0xffffu
 
 struct KnnTune {
   double guess_margin;   // search radius = h_prev * (1 + margin)
@@ -612,7 +611,6 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
   uint32_t todo = __ballot_sync(0xffffffffu, valid);
   int maxlanes = 32;
   if (EXT && lane == 0) ex.tinfo[tile].npc = 0;  // (set again below if the tile gets a shared block)
-  uint16_t* nsp = EXT ? ex.ns + (size_t)tile * ((SPHB_K + SPHB_KX) * 32) + lane : nullptr;
   while (todo) {
     const int lead = __ffs(todo) - 1;
     const int grow = __shfl_sync(0xffffffffu, cya, lead);
@@ -837,7 +835,6 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
         for (int s = 0; s < SPHB_K; ++s) {
           const uint2 ke = col[s * 32];
           np[s * 32] = candE[ke.y];
-          if (EXT && ext_try) nsp[s * 32] = (uint16_t)ke.y;
           const float q2 = __uint_as_float(ke.x) * (inv_h * inv_h);
           float rq;
           asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rq) : "f"(fmaxf(q2, 1e-30f)));
@@ -862,7 +859,8 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
       }
       const double hacc_h = (double)(ok ? h2f * rsqrtf(fmaxf(h2f, 1e-37f)) : 0.0f);
       if (EXT && ext_try) {  // the shared block of the tile, for the annulus pass and the cycle's reuse evaluations
-        if (ok) ex.dexcl[i] = 1.0;  // "has slots" (the annulus pass writes the radius; refused lanes get 0 from the fallback)
+        // for the annulus pass: the smallest key the selection did not take (nothing dropped: the acceptance threshold)
+        if (ok) ex.dexcl[i] = (double)(T != 0xffffffffu ? __uint_as_float(T) : thr0);
         if (lane < npc) ex.ptab[(size_t)tile * 32 + lane] = make_uint2((uint32_t)p_s | (p_code << IMG_SHIFT), (uint32_t)p_len);
         if (lane == 0) ex.tinfo[tile] = TileInfo{npc, nst, c0, c1, r0, r1};
       }
@@ -890,7 +888,6 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
             const double d2 = dist_sq(xa - pb[u].x, ya - pb[u].y);
             h2 = fmax(h2, d2);
             np[(s0 + u) * 32] = en[u];
-            if (EXT && ext_try) nsp[(s0 + u) * 32] = (uint16_t)sls[u];
             *reinterpret_cast<double*>(&col[(s0 + u) * 32]) = d2;
           }
         }
@@ -916,7 +913,6 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
             const double d2 = dist_sq(qx - pb[u].x, qy - pb[u].y);
             h2 = fmax(h2, d2);
             np[(s0 + u) * 32] = en[u];
-            if (EXT && ext_try) nsp[(s0 + u) * 32] = (uint16_t)sls[u];
             *reinterpret_cast<double*>(&col[(s0 + u) * 32]) = d2;
           }
         }
@@ -947,7 +943,7 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
       out.pc[i] = make_double4(rho, c, h, c * c * fast_rcp(ph.gamma * rho));
     }
     if (EXT && ext_try) {
-      if (ok) ex.dexcl[i] = 1.0;
+      if (ok) ex.dexcl[i] = (double)(T != 0xffffffffu ? __uint_as_float(T) : thr0);
       if (lane < npc) ex.ptab[(size_t)tile * 32 + lane] = make_uint2((uint32_t)p_s | (p_code << IMG_SHIFT), (uint32_t)p_len);
       if (lane == 0) ex.tinfo[tile] = TileInfo{npc, nst, c0, c1, r0, r1};
     }
@@ -969,7 +965,7 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
 // candidate is therefore corrected to the nearest one - unless the block spans more than half a period, in which case
 // all three images of every cell are scanned (exact whatever the cells say: positions are the current ones).
 struct FbExt {
-  double* dexcl;           // set to 0 = "no candidate slots" for the particles searched here (nullptr: no reuse bookkeeping)
+  double* dexcl;           // set to 0 = "no further candidates known" for the particles searched here (nullptr: no reuse bookkeeping)
   const ReuseState* rs;    // STALE: D
 };
 

@@ -59,13 +59,15 @@ __device__ __forceinline__ TilePieces tile_pieces(const KnnExt& ex, int tile, in
 // Rebuild evaluations, after the tile search: the further candidates of every particle - those between its new h and
 // rgx = h_prev (1 + skin) - from the tile's shared block, as slots; the up to SPHB_KX nearest are kept, and the exclusion
 // radius dexcl: every particle that is neither a neighbour nor kept is at least that far away.
-//   fp32 keys on the tile frame (error bound delta as in the tile search).  The 32 neighbours are excluded by IDENTITY
-//   (their slots are known), not by key; candidates the lane saw and did not keep have a key >= T, what it did not see
-//   lies beyond rgx:  dexcl^2 = min(T (1 - 2 delta), rgx^2 (1 - 1e-5)).
+//   fp32 keys in the tile search's own frame, computed by the same instructions from the same staged values, so they
+//   are bit-identical to the keys that search ranked: it leaves, per particle, the smallest key it did NOT take (or its
+//   acceptance threshold) in dexcl, and the candidates here are exactly the staged particles with a key in
+//   [that key, rgx^2 (1 + delta)).  Candidates the lane saw and did not keep have a key >= T, what it did not see lies
+//   beyond rgx:  dexcl^2 = min(T (1 - 2 delta), rgx^2 (1 - 1e-5)).
 // Column entries are 32-bit: key bits 31..9 (truncated: only ever lowers a bound) | slot (9 bits).
 // -------------------------------------------------------------------------------------------------
 #define ANN_CAP 48
-__host__ __device__ inline size_t annulus_smem_bytes_per_warp(int ncw) { return (size_t)ANN_CAP * 128 + (size_t)ncw * 8 + (size_t)(ncw / 32) * 128; }
+__host__ __device__ inline size_t annulus_smem_bytes_per_warp(int ncw) { return (size_t)ANN_CAP * 128 + (size_t)ncw * 12; }
 
 __global__ void __launch_bounds__(KNN_THREADS) k_knn_annulus(const double2* __restrict__ spos, const uint32_t* __restrict__ keys,
                                                             const uint32_t* __restrict__ cellStart, const double* __restrict__ hguess,
@@ -80,14 +82,14 @@ __global__ void __launch_bounds__(KNN_THREADS) k_knn_annulus(const double2* __re
   uint32_t* col = reinterpret_cast<uint32_t*>(wb) + lane;                              // [slot * 32]
   float2* candF = reinterpret_cast<float2*>(wb + (size_t)ANN_CAP * 128);                // fp32 tile-relative positions, pairs
   const float4* candF4 = reinterpret_cast<const float4*>(candF);
-  uint32_t* mb = reinterpret_cast<uint32_t*>(wb + (size_t)ANN_CAP * 128 + (size_t)NCW * 8) + lane;  // member bits [word * 32]
+  uint32_t* candE = reinterpret_cast<uint32_t*>(wb + (size_t)ANN_CAP * 128 + (size_t)NCW * 8);     // index | image code << 28
   const int tile = blockIdx.x * KNN_WARPS + warp;
   if (tile * 32 >= n) return;
   const int i = tile * 32 + lane;
   const bool valid = i < n && (gflag == nullptr || gflag[i] != GF_OUTER);
   const TileInfo ti = ex.tinfo[tile];
   if (ti.npc == 0) { if (valid) ex.dexcl[i] = 0.0; return; }  // no shared block: its particles take the full search
-  double xa = 0, ya = 0, h = 0, rgx = 0;
+  double xa = 0, ya = 0, h = 0, rgx = 0, tkey = 0;
   int cxa = 0, cya = 0;
   if (valid) {
     const double2 p = spos[i];
@@ -97,9 +99,9 @@ __global__ void __launch_bounds__(KNN_THREADS) k_knn_annulus(const double2* __re
     cxa = (int)(k - (uint32_t)cya * (uint32_t)g.ncx);
     h = pc[i].z;
     rgx = knn_ext_radius(hguess[i] * (1.0 + tune.guess_margin), tune.guess_margin, ex.skin);  // the radius the block was sized for
+    tkey = ex.dexcl[i];  // the tile search's first key beyond the 32 neighbours (0: it refused the lane - no extended list)
   }
-  // a lane the tile search refused (its list came from the fallback kernel: no slots) or without a previous h
-  bool ok = valid && h > 0.0 && rgx > h && ex.dexcl[i] != 0.0;
+  bool ok = valid && h > 0.0 && rgx > h && tkey > 0.0;
   int clo, chi, rlo, rhi;
   knn_cell_range(g, xa, ya, rgx * (1.0 + 1e-4), cxa, cya, clo, chi, rlo, rhi);
   const TilePieces P = tile_pieces(ex, tile, ti.npc, lane);
@@ -112,11 +114,10 @@ __global__ void __launch_bounds__(KNN_THREADS) k_knn_annulus(const double2* __re
   const float qfx = (float)(xa - xref), qfy = (float)(ya - yref);
   const float2 nqx2 = make_float2(-qfx, -qfx), nqy2 = make_float2(-qfy, -qfy);
   const double delta = 3.0 * (2.384185791015625e-07 * V / fmax(h, 1e-300) + 4.76837158203125e-07);
-  if (ok && !(delta < 1e-3)) ok = false;
+  // (below this bound a particle outside the tile search's own windows cannot have a key under its threshold)
+  if (ok && !(delta < 5e-5)) ok = false;
   const float Vf = (float)V * 1.000001f;
-  // stage (fp32 positions only) and clear the member bits
-  for (int w = 0; w < NCW / 32; ++w) mb[w * 32] = 0u;
-  int self_slot = -1;
+  // stage: fp32 positions and list entries
   __syncwarp();
   for (int pc_ = 0; pc_ < npc; ++pc_) {
     const int s = __shfl_sync(0xffffffffu, P.s, pc_), len = __shfl_sync(0xffffffffu, P.len, pc_);
@@ -131,24 +132,15 @@ __global__ void __launch_bounds__(KNN_THREADS) k_knn_annulus(const double2* __re
         const double2 pb = spos[s + t];
         fx = (float)(pb.x + sx); fy = (float)(pb.y + sy);
         if (!(fabsf(fx) <= Vf && fabsf(fy) <= Vf)) { fx = 3.0e18f; fy = 3.0e18f; }
+        candE[off + t] = (uint32_t)(s + t) | (code << IMG_SHIFT);
       }
       float* cf = reinterpret_cast<float*>(candF) + (size_t)((off + t) >> 1) * 4 + ((off + t) & 1);
       cf[0] = fx; cf[2] = fy;
     }
-    if (valid && code == 5u && i >= s && i < s + len) self_slot = off + (i - s);
-  }
-  const uint16_t* nsr = ex.ns + (size_t)tile * ((SPHB_K + SPHB_KX) * 32) + lane;
-  if (ok) {
-#pragma unroll 8
-    for (int s = 0; s < SPHB_K; ++s) {
-      const uint32_t sl = nsr[s * 32];
-      mb[(sl >> 5) * 32] |= 1u << (sl & 31u);
-    }
-    if (self_slot >= 0) mb[(self_slot >> 5) * 32] |= 1u << (self_slot & 31);
   }
   __syncwarp();
-  // filter: keys in [h^2 (1 - 4 delta), rgx^2 (1 + delta)) over the lane's own windows
-  const float lo = ok ? (float)(h * h * (1.0 - 4.0 * delta)) : 1.0f;
+  // filter: keys in [first key beyond the neighbours, rgx^2 (1 + delta)) over the lane's own windows
+  const float lo = ok ? (float)tkey : 1.0f;
   const float hi = ok ? (float)(rgx * rgx * (1.0 + delta)) * 1.0000002f : -1.0f;
   int cnt = 0;
   bool ovf = false;
@@ -183,12 +175,8 @@ __global__ void __launch_bounds__(KNN_THREADS) k_knn_annulus(const double2* __re
   }
   __syncwarp();
   if (ovf) ok = false;
-  // drop the neighbours themselves (by slot) and, beyond SPHB_KX candidates, the farthest: largest packed entries
-  int nb = 0;
-  for (int s = 0; s < (ok ? cnt : 0); ++s) {
-    const uint32_t e = col[s * 32], sl = e & 511u;
-    if (!((mb[(sl >> 5) * 32] >> (sl & 31u)) & 1u)) { col[nb * 32] = e; ++nb; }
-  }
+  // beyond SPHB_KX candidates the farthest are dropped: largest packed entries
+  const int nb = ok ? cnt : 0;
   uint32_t T = 0xffffffffu;
   {
     int mrem = ok && nb > SPHB_KX ? nb - SPHB_KX : 0;
@@ -213,7 +201,7 @@ __global__ void __launch_bounds__(KNN_THREADS) k_knn_annulus(const double2* __re
       }
     }
   }
-  uint16_t* nsw = ex.ns + (size_t)tile * ((SPHB_K + SPHB_KX) * 32) + lane + SPHB_K * 32;
+  uint32_t* nsw = ex.nx + (size_t)tile * (SPHB_KX * 32) + lane;
   int w = 0;
   double dx = 0.0;
   if (ok) {
@@ -221,7 +209,7 @@ __global__ void __launch_bounds__(KNN_THREADS) k_knn_annulus(const double2* __re
     if (T != 0xffffffffu) d2x = fmin(d2x, (double)__uint_as_float(T & ~511u) * (1.0 - 2.0 * delta));
     for (int s = 0; s < nb; ++s) {
       const uint32_t e = col[s * 32];
-      if (e < T && w < SPHB_KX) { nsw[w * 32] = (uint16_t)(e & 511u); ++w; }
+      if (e < T && w < SPHB_KX) { nsw[w * 32] = candE[e & 511u]; ++w; }
     }
     dx = sqrt(d2x);
     // slab mode: the exclusion radius is only valid if everything within it was local (ghost layer wide enough)
@@ -229,87 +217,56 @@ __global__ void __launch_bounds__(KNN_THREADS) k_knn_annulus(const double2* __re
       atomicOr(dflags, DFLAG_GHOST_THIN);
   }
   if (valid) {
-    for (; w < SPHB_KX; ++w) nsw[w * 32] = (uint16_t)NS_NONE;
+    for (; w < SPHB_KX; ++w) nsw[w * 32] = 0xffffffffu;
     ex.dexcl[i] = dx;
   }
 }
 
 // -------------------------------------------------------------------------------------------------
-// Reuse evaluations: exact kNN(32) from the stored candidates.  One warp per tile, one query per lane.  The warp stages
-// the tile's shared block (current positions, coalesced, fp64) and every lane evaluates its <= 48 candidate slots:
-// slots 0..31 are the neighbours of the previous evaluation, 32..47 the further candidates.  Pass 1 computes d^2 of
-// every candidate exactly as the reference does ((p + offset) - b, nearest periodic image; linear-algebra.go:61-64) into
-// a shared-memory column and keeps, on integer keys, the 4 largest of the first group and the 4 smallest of the second.
-// The 32 smallest of the 48 are the first group with its m largest exchanged for the m smallest of the second, m =
-// number of crossing pairs (m = 4: refused).  Keys are the high words of the fp64 d^2 (fp32 build: the fp32 d^2): key
-// order implies exact order when the keys differ, so the partition is certified by  max key kept < min key not kept
-// (ties / near ties: refused).  The exchanged candidates swap slots (and the neighbour list entry is rewritten), h^2 =
-// max, density and sound speed as in the tile kernel, and the certificate  h + D < dexcl.
+// exact kNN(32) from the stored candidates.  One thread per particle; slots 0..31 (nn) hold the neighbours of the
+// previous evaluation, slots 32..47 (nx) the further candidates.  Pass 1 evaluates d^2 of every candidate exactly as the
+// reference does ((p + offset) - b, nearest periodic image; linear-algebra.go:61-64) into a shared-memory column and
+// keeps, on integer keys, the 4 largest of the first group and the 4 smallest of the second.  The 32 smallest of the 48
+// are the first group with its m largest exchanged for the m smallest of the second, m = number of crossing pairs
+// (m = 4: refused).  Keys are the high words of the fp64 d^2 (fp32 build: the fp32 d^2): key order implies exact order
+// when the keys differ, so the partition is certified by  max key kept < min key not kept  (ties / near ties: refused).
+// Then: the exchanged entries swap places in the lists (nn stays "the 32 neighbours", any order), h^2 = max, density
+// and sound speed as in the tile kernel, and the certificate  h + D < dexcl.
 // -------------------------------------------------------------------------------------------------
+#define REUSE_THREADS 128
 #define REUSE_NC (SPHB_K + SPHB_KX)
-#define REUSE_WARPS 2
-__host__ __device__ inline size_t reuse_smem_bytes_per_warp(int ncw, bool f32) { return (size_t)REUSE_NC * 32 * (f32 ? 4 : 8) + (size_t)ncw * 20; }
 
 template <typename T> __device__ __forceinline__ uint32_t reuse_key(T d2);
 template <> __device__ __forceinline__ uint32_t reuse_key<double>(double d2) { return (uint32_t)__double2hiint(d2); }
 template <> __device__ __forceinline__ uint32_t reuse_key<float>(float d2) { return __float_as_uint(d2); }
 
 template <int KERNEL, bool F32>
-__global__ void __launch_bounds__(REUSE_WARPS * 32) k_knn_reuse(const double2* __restrict__ spos, const double* __restrict__ epred,
-                                                               int n, const GridP* __restrict__ gp, PhysP ph, KnnOut out, KnnExt ex,
-                                                               int ncw, const ReuseState* __restrict__ rs,
-                                                               const uint8_t* __restrict__ gflag, uint32_t* __restrict__ dflags) {
+__global__ void __launch_bounds__(REUSE_THREADS) k_knn_reuse(const double2* __restrict__ spos, const double* __restrict__ epred,
+                                                            int n, const GridP* __restrict__ gp, PhysP ph, KnnOut out,
+                                                            uint32_t* __restrict__ nx, const double* __restrict__ dexcl,
+                                                            const ReuseState* __restrict__ rs,
+                                                            const uint8_t* __restrict__ gflag, uint32_t* __restrict__ dflags) {
   typedef typename std::conditional<F32, float, double>::type TD;
   extern __shared__ __align__(16) unsigned char rsm[];
+  TD* dcol = reinterpret_cast<TD*>(rsm) + threadIdx.x;  // [slot * REUSE_THREADS]
   const GridP g = *gp;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned char* wb = rsm + (size_t)warp * reuse_smem_bytes_per_warp(ncw, F32);
-  double2* candD = reinterpret_cast<double2*>(wb);                                         // current positions of the block
-  uint32_t* candE = reinterpret_cast<uint32_t*>(wb + (size_t)ncw * 16);                    // index | image code << 28
-  TD* dcol = reinterpret_cast<TD*>(wb + (size_t)ncw * 20) + lane;                          // [slot * 32]
-  const int tile = blockIdx.x * REUSE_WARPS + warp;
-  if (tile * 32 >= n) return;
-  const int i = tile * 32 + lane;
+  const int i = blockIdx.x * REUSE_THREADS + threadIdx.x;
   const bool valid = i < n && (gflag == nullptr || gflag[i] != GF_OUTER);
   const bool owned = i < n && (gflag == nullptr || gflag[i] == GF_OWNED);
-  const TileInfo ti = ex.tinfo[tile];
   const double D = rs->D;
-  const int ii = i < n ? i : 0;
+  const int ii = valid ? i : 0;
   const double2 pa = spos[ii];
-  const double dex = valid ? ex.dexcl[ii] : 0.0;
-  bool ok = valid && ti.npc > 0 && dex > 0.0;  // (dexcl = 0: the particle has no slots - refused by the tile search, no shared block)
-  if (!__any_sync(0xffffffffu, ok)) {  // nothing to reuse in this tile
-    if (valid) { const int slot = atomicAdd(out.failCount, 1); out.failList[slot] = i; }
-    knn_accumulate_h(out, false, owned, 0.0);
-    return;
-  }
-  // stage the block
-  const TilePieces P = tile_pieces(ex, tile, ti.npc, lane);
-  bool anyimg = false;
-  for (int pc_ = 0; pc_ < ti.npc; ++pc_) {
-    const int s = __shfl_sync(0xffffffffu, P.s, pc_), len = __shfl_sync(0xffffffffu, P.len, pc_);
-    const int off = __shfl_sync(0xffffffffu, P.off, pc_);
-    const uint32_t code = __shfl_sync(0xffffffffu, P.code, pc_);
-    anyimg |= code != 5u;
-    for (int t = lane; t < len; t += 32) {
-      candD[off + t] = spos[s + t];
-      candE[off + t] = (uint32_t)(s + t) | (5u << IMG_SHIFT);  // (the image is decided below, from the current positions)
-    }
-  }
-  __syncwarp();
-  uint32_t* cn = out.nn + (size_t)tile * 1024 + lane;
-  uint16_t* cs = ex.ns + (size_t)tile * (REUSE_NC * 32) + lane;
+  const double dex = dexcl[ii];
+  uint32_t* cn = out.nn + (size_t)(ii >> 5) * 1024 + (ii & 31);
+  uint32_t* cx = nx + (size_t)(ii >> 5) * (SPHB_KX * 32) + (ii & 31);
   const bool wrap = g.wrapx | g.wrapy;  // (slab frames do not wrap: ghosts stand in for the images)
   const double hLx = 0.5 * g.Lx, hLy = 0.5 * g.Ly;
   // Only warps with a query next to the periodic seam look for images.  (Were a candidate beyond the seam after all,
   // its unshifted distance is about a period: the half-period test on the largest key below refuses the particle.)
   const double reach = 2.0 * dex + D;
-  const bool near_seam = ok && ((g.wrapx && (pa.x - reach < g.lox || pa.x + reach >= g.lox + g.Lx)) ||
-                                (g.wrapy && (pa.y - reach < g.loy || pa.y + reach >= g.loy + g.Ly)));
+  const bool near_seam = valid && ((g.wrapx && (pa.x - reach < g.lox || pa.x + reach >= g.lox + g.Lx)) ||
+                                   (g.wrapy && (pa.y - reach < g.loy || pa.y + reach >= g.loy + g.Ly)));
   const bool img = wrap && __any_sync(0xffffffffu, near_seam);
-  // neighbour-list entries carry the image code (the force kernel reads it): with images in play every entry is
-  // rewritten from the current positions; away from the seam only if the block still has image pieces from the build
-  const bool recode = img || anyimg;
   const double qxm = __dadd_rn(pa.x, g.Lx), qxp = __dadd_rn(pa.x, -g.Lx);  // candidate image -1 / +1: query + (-img L)
   const double qym = __dadd_rn(pa.y, g.Ly), qyp = __dadd_rn(pa.y, -g.Ly);
   const TD INF = F32 ? (TD)3.0e38f : (TD)1.7976931348623157e308;
@@ -320,33 +277,45 @@ __global__ void __launch_bounds__(REUSE_WARPS * 32) k_knn_reuse(const double2* _
   bool empty_in = false;
 #pragma unroll 1
   for (int s0 = 0; s0 < REUSE_NC; s0 += 8) {
-    uint32_t sl[8];
+    uint32_t* cs = s0 < SPHB_K ? cn + s0 * 32 : cx + (s0 - SPHB_K) * 32;
+    uint32_t en[8];
+    double2 pb[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) sl[u] = ok ? (uint32_t)cs[(s0 + u) * 32] : NS_NONE;
+    for (int u = 0; u < 8; ++u) en[u] = (valid && dex > 0.0) ? cs[u * 32] : 0xffffffffu;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) pb[u] = spos[en[u] == 0xffffffffu ? ii : (int)(en[u] & IDX_MASK)];
+    if (!img) {  // away from the seam every candidate is a centre image: entries that still say otherwise (the pair has
+      uint32_t stale = 0;  // crossed the seam together since the build) are reset, the force kernel reads the code
+#pragma unroll
+      for (int u = 0; u < 8; ++u) stale |= (en[u] >> IMG_SHIFT) ^ 5u;
+      if (stale) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (en[u] != 0xffffffffu && (en[u] >> IMG_SHIFT) != 5u) cs[u * 32] = (en[u] & IDX_MASK) | (5u << IMG_SHIFT);
+      }
+    }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const bool have = sl[u] != NS_NONE;
-      const double2 pb = candD[have ? sl[u] : 0u];
+      const bool have = en[u] != 0xffffffffu;
       double qx = pa.x, qy = pa.y;
       if (img) {  // nearest image from the current positions (a candidate may have crossed the seam since the build)
         int sx = 0, sy = 0;
-        if (g.wrapx) { const double d0 = pa.x - pb.x; sx = d0 > hLx ? 1 : (d0 < -hLx ? -1 : 0); }
-        if (g.wrapy) { const double d0 = pa.y - pb.y; sy = d0 > hLy ? 1 : (d0 < -hLy ? -1 : 0); }
+        if (g.wrapx) { const double d0 = pa.x - pb[u].x; sx = d0 > hLx ? 1 : (d0 < -hLx ? -1 : 0); }
+        if (g.wrapy) { const double d0 = pa.y - pb[u].y; sy = d0 > hLy ? 1 : (d0 < -hLy ? -1 : 0); }
         qx = sx == 0 ? pa.x : (sx < 0 ? qxm : qxp);
         qy = sy == 0 ? pa.y : (sy < 0 ? qym : qyp);
-        if (have && s0 < SPHB_K) cn[(s0 + u) * 32] = (candE[sl[u]] & IDX_MASK) | (img_code(sx, sy) << IMG_SHIFT);
-      } else if (recode && have && s0 < SPHB_K) {
-        cn[(s0 + u) * 32] = candE[sl[u]];
+        const uint32_t ne = (en[u] & IDX_MASK) | (img_code(sx, sy) << IMG_SHIFT);
+        if (have && ne != en[u]) cs[u * 32] = ne;
       }
       TD d2;
       if (F32) {
-        const float fx = (float)(qx - pb.x), fy = (float)(qy - pb.y);
+        const float fx = (float)(qx - pb[u].x), fy = (float)(qy - pb[u].y);
         d2 = (TD)fmaf(fy, fy, fx * fx);
       } else {
-        d2 = (TD)dist_sq(qx - pb.x, qy - pb.y);
+        d2 = (TD)dist_sq(qx - pb[u].x, qy - pb[u].y);
       }
       d2 = have ? d2 : INF;
-      dcol[(s0 + u) * 32] = d2;
+      dcol[(s0 + u) * REUSE_THREADS] = d2;
       uint32_t k = reuse_key<TD>(d2), a;
       if (have) kmax = max(kmax, k);
       if (s0 < SPHB_K) {
@@ -370,7 +339,7 @@ __global__ void __launch_bounds__(REUSE_WARPS * 32) k_knn_reuse(const double2* _
   const uint32_t tOUT = m == 0 ? 0u : (m == 1 ? b0 : (m == 2 ? b1 : b2));           // keys <= tOUT enter it
   const uint32_t in_max = max(m == 0 ? t0 : (m == 1 ? t1 : (m == 2 ? t2 : t3)), m == 0 ? 0u : tOUT);
   const uint32_t out_min = min(m == 0 ? b0 : (m == 1 ? b1 : (m == 2 ? b2 : b3)), tIN);
-  if (empty_in || c3) ok = false;
+  bool ok = valid && !empty_in && !c3 && dex > 0.0;
   // strict key order <=> exact order (fp32 build: fp32 order; ties may fall either way there but must be consistent)
   if (!(in_max < out_min)) ok = false;
   // the nearest image is the only one in reach while every candidate is nearer than half a period
@@ -384,14 +353,14 @@ __global__ void __launch_bounds__(REUSE_WARPS * 32) k_knn_reuse(const double2* _
   TD h2 = (TD)0;
 #pragma unroll 8
   for (int s = 0; s < SPHB_K; ++s) {
-    const TD d = dcol[s * 32];
+    const TD d = dcol[s * REUSE_THREADS];
     const bool leave = m > 0 && reuse_key<TD>(d) >= tIN;
     lmask |= leave ? (1u << s) : 0u;
     h2 = leave ? h2 : (d > h2 ? d : h2);
   }
 #pragma unroll 8
   for (int s = 0; s < SPHB_KX; ++s) {
-    const TD d = dcol[(SPHB_K + s) * 32];
+    const TD d = dcol[(SPHB_K + s) * REUSE_THREADS];
     const bool enter = m > 0 && reuse_key<TD>(d) <= tOUT;
     emask |= enter ? (1u << s) : 0u;
     h2 = enter ? (d > h2 ? d : h2) : h2;
@@ -399,21 +368,12 @@ __global__ void __launch_bounds__(REUSE_WARPS * 32) k_knn_reuse(const double2* _
   if (__popc(lmask) != m || __popc(emask) != m) ok = false;  // equal keys inside a group
   if (ok) {
     while (lmask) {  // exchange (at most 3 pairs)
-      const int sa = __ffs(lmask) - 1, sb = SPHB_K + __ffs(emask) - 1;
+      const int sl = __ffs(lmask) - 1, so = __ffs(emask) - 1;
       lmask &= lmask - 1; emask &= emask - 1;
-      const uint16_t la = cs[sa * 32], lb = cs[sb * 32];
-      cs[sa * 32] = lb; cs[sb * 32] = la;
-      uint32_t en = candE[lb];
-      if (img) {  // the entering candidate's image, as pass 1 found it
-        const double2 pb = candD[lb];
-        int sx = 0, sy = 0;
-        if (g.wrapx) { const double d0 = pa.x - pb.x; sx = d0 > hLx ? 1 : (d0 < -hLx ? -1 : 0); }
-        if (g.wrapy) { const double d0 = pa.y - pb.y; sy = d0 > hLy ? 1 : (d0 < -hLy ? -1 : 0); }
-        en = (en & IDX_MASK) | (img_code(sx, sy) << IMG_SHIFT);
-      }
-      cn[sa * 32] = en;
-      const TD da = dcol[sa * 32], db = dcol[sb * 32];
-      dcol[sa * 32] = db; dcol[sb * 32] = da;
+      const uint32_t ea = cn[sl * 32], eb = cx[so * 32];
+      cn[sl * 32] = eb; cx[so * 32] = ea;
+      const TD da = dcol[sl * REUSE_THREADS], db = dcol[(SPHB_K + so) * REUSE_THREADS];
+      dcol[sl * REUSE_THREADS] = db; dcol[(SPHB_K + so) * REUSE_THREADS] = da;
     }
   }
   // certificate: nothing outside the candidate set can be within h
@@ -438,7 +398,7 @@ __global__ void __launch_bounds__(REUSE_WARPS * 32) k_knn_reuse(const double2* _
       float acc = 0.0f;
 #pragma unroll 8
       for (int s = 0; s < SPHB_K; ++s) {
-        const float q2 = (float)dcol[s * 32] * (inv_h * inv_h);
+        const float q2 = (float)dcol[s * REUSE_THREADS] * (inv_h * inv_h);
         float rq;
         asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rq) : "f"(fmaxf(q2, 1e-30f)));
         const float q = fminf(q2 * rq, 1.0f);
@@ -464,7 +424,7 @@ __global__ void __launch_bounds__(REUSE_WARPS * 32) k_knn_reuse(const double2* _
       double acc = 0.0;
 #pragma unroll 4
       for (int s = 0; s < SPHB_K; ++s) {
-        const double d2 = (double)dcol[s * 32];
+        const double d2 = (double)dcol[s * REUSE_THREADS];
         const double d = d2 * fast_rsqrt(d2 + 1e-300);  // coincident particles: d = 0
         acc += kern_F<KERNEL>(d * inv_h);
       }
