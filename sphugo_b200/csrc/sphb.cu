@@ -130,9 +130,9 @@ struct sphb_sim {
   ReuseStat* stat_host = nullptr;  // pinned ring of REUSE_RING records (non-blocking feedback for the schedule)
   bool reuse_on = true;       // SPHB_REUSE=0 switches it off
   int reuse_period = 2;       // evaluations per cycle: one rebuild + (period - 1) reuse evaluations; 1 = never reuse
-  int reuse_period_max = 8, reuse_period_fixed = 0;
+  int reuse_period_max = 7, reuse_period_fixed = 0;
   double reuse_skin = 0.25;   // extended candidates are collected up to h (1 + skin)
-  int reuse_ncw = 384;       // staged slots per tile of a rebuild that starts a cycle (<= 512: slots are 9-bit in the annulus pass)
+  int reuse_ncw = 416;       // staged slots per tile of a rebuild that starts a cycle (<= 512: slots are 9-bit in the annulus pass)
   ReuseState* force_rs = nullptr;  // arguments of the force launch in progress
   bool force_stale = false;
   bool cell_per_h_fixed = false;   // SPHB_CELL_PER_H given: no adjustment for extended searches
@@ -503,9 +503,9 @@ int build_neighbours(sphb_sim* s, int mode, const double hor[2], const double ve
 // host ring.  Before it plans an evaluation the host waits for the record of the previous one (the wait costs one
 // kernel-launch latency per step: the device has nothing else queued) and applies the policy below.  A cycle is one
 // rebuild + (period - 1) reuse evaluations:
-//   - a reuse evaluation that refused more than 0.5 % of the particles ends its cycle at once, and cycles are from now
+//   - a reuse evaluation that refused more than 0.8 % of the particles ends its cycle at once, and cycles are from now
 //     on that much shorter (refused particles take the ring-expansion search, ~50 times the cost of an accepted one);
-//   - a cycle that completed with less than 0.1 % refused in its last evaluation lengthens the next one by one;
+//   - a cycle that completed with less than 0.3 % refused in its last evaluation lengthens the next one by one;
 //   - period 1 (no reuse) is tried again after a cool-down;
 //   - no cycle starts unless the tile search itself refused less than 0.1 % of the particles in the last two rebuilds
 //     (i.i.d. clouds, shock fronts, free surfaces: their smoothing lengths change by more than the skin per step).
@@ -516,11 +516,11 @@ void reuse_policy(sphb_sim* s, unsigned age, double frac, bool rebuild) {
     return;
   }
   if (s->reuse_period_fixed) return;
-  if (frac > 5e-3) {
+  if (frac > 8e-3) {
     s->reuse_period = std::max(1, std::min(s->reuse_period, (int)age));
     s->reuse_abort = true;
     if (s->reuse_period == 1) s->reuse_cooldown = 48;
-  } else if (frac < 1e-3 && (int)age == s->reuse_period - 1 && s->reuse_period < s->reuse_period_max) {
+  } else if (frac < 3e-3 && (int)age == s->reuse_period - 1 && s->reuse_period < s->reuse_period_max) {
     s->reuse_period += 1;
   }
 }

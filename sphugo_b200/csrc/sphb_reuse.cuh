@@ -275,15 +275,22 @@ __global__ void __launch_bounds__(REUSE_THREADS) k_knn_reuse(const double2* __re
   uint32_t b0 = 0xffffffffu, b1 = 0xffffffffu, b2 = 0xffffffffu, b3 = 0xffffffffu;  // smallest keys of slots 32..47
   uint32_t kmax = 0;  // largest key of any candidate
   bool empty_in = false;
+  // the list entries are requested one batch ahead of their use, so that only the position gathers are waited for
+  const bool live = valid && dex > 0.0;
+  uint32_t en[8], en_next[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) en[u] = live ? cn[u * 32] : 0xffffffffu;
 #pragma unroll 1
   for (int s0 = 0; s0 < REUSE_NC; s0 += 8) {
     uint32_t* cs = s0 < SPHB_K ? cn + s0 * 32 : cx + (s0 - SPHB_K) * 32;
-    uint32_t en[8];
     double2 pb[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) en[u] = (valid && dex > 0.0) ? cs[u * 32] : 0xffffffffu;
-#pragma unroll
     for (int u = 0; u < 8; ++u) pb[u] = spos[en[u] == 0xffffffffu ? ii : (int)(en[u] & IDX_MASK)];
+    if (s0 + 8 < REUSE_NC) {
+      const uint32_t* cs1 = s0 + 8 < SPHB_K ? cn + (s0 + 8) * 32 : cx + (s0 + 8 - SPHB_K) * 32;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) en_next[u] = live ? cs1[u * 32] : 0xffffffffu;
+    }
     if (!img) {  // away from the seam every candidate is a centre image: entries that still say otherwise (the pair has
       uint32_t stale = 0;  // crossed the seam together since the build) are reset, the force kernel reads the code
 #pragma unroll
@@ -331,6 +338,8 @@ __global__ void __launch_bounds__(REUSE_THREADS) k_knn_reuse(const double2* __re
         b3 = min(b3, k);
       }
     }
+  #pragma unroll
+    for (int u = 0; u < 8; ++u) en[u] = en_next[u];
   }
   // crossing pairs: the k-th largest of the first group against the k-th smallest of the second
   const bool c0 = t0 > b0, c1 = c0 && t1 > b1, c2 = c1 && t2 > b2, c3 = c2 && t3 > b3;
