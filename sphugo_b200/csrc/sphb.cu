@@ -129,8 +129,8 @@ struct sphb_sim {
   ReuseStat* stat_dev = nullptr;
   ReuseStat* stat_host = nullptr;  // pinned ring of REUSE_RING records (non-blocking feedback for the schedule)
   bool reuse_on = true;       // SPHB_REUSE=0 switches it off
-  int reuse_period = 2;       // evaluations per cycle: one rebuild + (period - 1) reuse evaluations; 1 = never reuse
-  int reuse_period_max = 7, reuse_period_fixed = 0;
+  int reuse_period = 2;       // (unused by the budget schedule; reported): one rebuild + (period - 1) reuse evaluations; 1 = never reuse
+  int reuse_period_max = 12, reuse_period_fixed = 0;
   double reuse_skin = 0.25;   // extended candidates are collected up to h (1 + skin)
   int reuse_ncw = 416;       // staged slots per tile of a rebuild that starts a cycle (<= 512: slots are 9-bit in the annulus pass)
   ReuseState* force_rs = nullptr;  // arguments of the force launch in progress
@@ -146,6 +146,9 @@ struct sphb_sim {
   bool stat_event_valid = false;
   bool reuse_abort = false;              // the policy ended the current cycle: the next evaluation rebuilds
   int calm_steps = 0;                    // consecutive rebuilds whose tile search refused < 0.1 % of the particles
+  double reuse_kappa = 0.6;              // share of the skin the displacement bound may use up (adapts)
+  double fb_D = 0.0, fb_D_prev = 0.0, fb_dy = 0.0, fb_last_frac = 0.0;  // last feedback record
+  bool fb_valid = false;
   int reuse_cooldown = 0;
   std::string err;
 };
@@ -499,30 +502,40 @@ int build_neighbours(sphb_sim* s, int mode, const double hor[2], const double ve
 }
 
 // ---- schedule of the list reuse ------------------------------------------------------------------
-// Every evaluation of a cycle ends with k_reuse_update, which leaves a record {age, refused particles, D} in a pinned
-// host ring.  Before it plans an evaluation the host waits for the record of the previous one (the wait costs one
-// kernel-launch latency per step: the device has nothing else queued) and applies the policy below.  A cycle is one
-// rebuild + (period - 1) reuse evaluations:
-//   - a reuse evaluation that refused more than 0.8 % of the particles ends its cycle at once, and cycles are from now
-//     on that much shorter (refused particles take the ring-expansion search, ~50 times the cost of an accepted one);
-//   - a cycle that completed with less than 0.3 % refused in its last evaluation lengthens the next one by one;
-//   - period 1 (no reuse) is tried again after a cool-down;
+// Every step ends with k_reuse_update, which leaves a record {age, refused particles, D, grid row height} in a pinned
+// host ring.  Before it plans an evaluation the host waits for the record of the previous one (one kernel-launch
+// latency per step: the device has nothing else queued) and decides:
+//   - a reuse evaluation is planned only while D, the displacement bound the certificate will see (it is in the
+//     record: exact, not predicted), stays below  kappa x skin x mean h  - all certificates fail together once D eats
+//     the skin, and a refused particle costs ~50 accepted ones, so the cycle must end before that cliff;
+//   - kappa adapts: a cycle that ended on this budget with < 0.15 % refused in its last evaluation raises it by 0.05
+//     (to 0.9 at most), an evaluation that refused > 0.5 % lowers it by 0.1 (0.2 at least) and ends the cycle at once;
 //   - no cycle starts unless the tile search itself refused less than 0.1 % of the particles in the last two rebuilds
-//     (i.i.d. clouds, shock fronts, free surfaces: their smoothing lengths change by more than the skin per step).
-// Handles below 2^14 particles do not reuse unless SPHB_REUSE_PERIOD fixes a period (their steps are launch bound).
-void reuse_policy(sphb_sim* s, unsigned age, double frac, bool rebuild) {
-  if (rebuild) {  // what the tile search itself refused: a flow that upsets even the full search is no candidate for reuse
-    s->calm_steps = frac < 1e-3 ? s->calm_steps + 1 : 0;
+//     (i.i.d. clouds, free surfaces: their smoothing lengths change by more than the search margin per step);
+//   - handles below 2^14 particles do not reuse (their steps are launch bound).
+// SPHB_REUSE_PERIOD = p fixes cycles of p evaluations instead (tests, sweeps).
+struct ReuseFeedback { unsigned age; double frac, D, dy; bool rebuild; };
+
+void reuse_policy(sphb_sim* s, const ReuseFeedback& f) {
+  s->fb_D_prev = (!f.rebuild && f.age > 0) ? s->fb_D : 0.0;
+  s->fb_D = f.D; s->fb_dy = f.dy; s->fb_valid = true;
+  if (f.rebuild) {  // what the tile search itself refused: a flow that upsets even the full search is no candidate for reuse
+    s->calm_steps = f.frac < 1e-3 ? s->calm_steps + 1 : 0;
     return;
   }
   if (s->reuse_period_fixed) return;
-  if (frac > 8e-3) {
-    s->reuse_period = std::max(1, std::min(s->reuse_period, (int)age));
+  if (f.frac > 5e-3) {
+    s->reuse_kappa = std::max(0.2, s->reuse_kappa - 0.1);
     s->reuse_abort = true;
-    if (s->reuse_period == 1) s->reuse_cooldown = 48;
-  } else if (frac < 3e-3 && (int)age == s->reuse_period - 1 && s->reuse_period < s->reuse_period_max) {
-    s->reuse_period += 1;
   }
+  s->fb_last_frac = f.frac;
+}
+
+// may an evaluation that sees the displacement bound D reuse the lists?
+bool reuse_budget_ok(const sphb_sim* s, double D) {
+  if (!s->fb_valid || !(s->fb_dy > 0.0)) return false;
+  const double hmean = s->fb_dy / grid_tune(s, true).cell_per_h;  // the grid rows follow the mean h
+  return D <= s->reuse_kappa * s->reuse_skin * hmean;
 }
 
 void reuse_poll(sphb_sim* s) {
@@ -536,8 +549,28 @@ void reuse_poll(sphb_sim* s) {
     }
     s->stat_seen += 1;
     if (r->n == 0) continue;
-    reuse_policy(s, r->age, (double)r->refused / (double)r->n, r->rebuild != 0);
+    reuse_policy(s, ReuseFeedback{r->age, (double)r->refused / (double)r->n, (double)r->D, (double)r->dy, r->rebuild != 0});
   }
+}
+
+// the plan of an ordinary step from the feedback: {reuse now, may the next evaluation reuse}
+void reuse_plan(sphb_sim* s, bool lists_ok, bool& reuse, bool& next_reuse) {
+  const bool calm = s->reuse_period_fixed || s->calm_steps >= 2;
+  if (s->reuse_period_fixed) {
+    const int period = s->reuse_period_fixed;
+    reuse = lists_ok && s->reuse_age + 1 < period;
+    next_reuse = reuse ? s->reuse_age + 2 < period : (period > 1 && s->have_h);
+    return;
+  }
+  const int amax = s->reuse_period_max;
+  reuse = lists_ok && !s->reuse_abort && s->reuse_age + 1 < amax && reuse_budget_ok(s, s->fb_D);
+  if (lists_ok && !reuse && !s->reuse_abort && s->reuse_age > 0 && s->fb_last_frac < 1.5e-3)  // the budget ended a clean cycle
+    s->reuse_kappa = std::min(0.9, s->reuse_kappa + 0.05);
+  s->reuse_abort = false;
+  // next evaluation: the bound grows by about what it grew last time
+  const double growth = s->fb_D - s->fb_D_prev;
+  if (reuse) next_reuse = s->reuse_age + 2 < amax && reuse_budget_ok(s, s->fb_D + 1.1 * growth);
+  else next_reuse = s->have_h && calm && amax > 1 && s->reuse_kappa > 0.0;
 }
 
 bool same_params(const sphb_params& a, const sphb_params& b) { return std::memcmp(&a, &b, sizeof(sphb_params)) == 0; }
@@ -629,7 +662,7 @@ int forces_plan(sphb_sim* s, int mode, bool integrate, const EvalPlan& plan) {
   s->fuse_keys = integrate && !s->slab_on && s->hacc_valid && !next_reuse && !axis_open(s->prm.hor) && !axis_open(s->prm.ver);
   if (s->fuse_keys) {
     // (the next evaluation is a rebuild; in an ordinary run of steps it starts a reuse cycle, i.e. searches with the skin)
-    const bool next_ext = s->reuse_on && (s->reuse_period_fixed ? s->reuse_period_fixed : s->reuse_period) > 1;
+    const bool next_ext = s->reuse_on && (s->reuse_period_fixed ? s->reuse_period_fixed > 1 : s->calm_steps >= 2);
     k_make_grid<<<1, 32, 0, s->st>>>(s->stats, ntot, s->prm.hor[0], s->prm.hor[1], s->prm.ver[0], s->prm.ver[1], make_slabp(s), 0,
                                      grid_tune(s, next_ext), s->grid_next, s->hacc, s->hscale, 1);
     s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 1;
@@ -674,14 +707,8 @@ int forces(sphb_sim* s, int mode, bool integrate) {
                    (s->reuse_period_fixed || s->n >= 16384);  // an ordinary step of a handle worth the bookkeeping
   if (cyc) {
     reuse_poll(s);
-    if (s->reuse_cooldown > 0 && --s->reuse_cooldown == 0 && s->reuse_period == 1) s->reuse_period = 2;
+    reuse_plan(s, s->lists_ext && same_params(s->prm, s->list_prm), plan.reuse, plan.next_reuse);
   }
-  const int period = s->reuse_period_fixed ? s->reuse_period_fixed : s->reuse_period;
-  plan.reuse = cyc && s->lists_ext && !s->reuse_abort && same_params(s->prm, s->list_prm) && s->reuse_age + 1 < period;
-  s->reuse_abort = false;
-  // may the NEXT evaluation be a reuse evaluation?  (then this one keeps the displacement books, and prepares no grid / keys)
-  const bool calm = s->reuse_period_fixed || s->calm_steps >= 2;
-  plan.next_reuse = cyc && (plan.reuse ? s->reuse_age + 2 < period : (period > 1 && s->have_h && calm));
   plan.record = cyc;
   return forces_plan(s, mode, integrate, plan);
 }

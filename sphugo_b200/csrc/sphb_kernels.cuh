@@ -86,7 +86,7 @@ struct ReuseState {
 };
 struct ReuseStat {                // one record per evaluation, copied to pinned host memory (non-blocking feedback)
   unsigned int seq, age, refused, n;
-  float D, hmean;
+  float D, dy;                    // D after this evaluation's displacement; row height of the grid in use (~ mean h)
   unsigned int rebuild, seq2;     // seq2 == seq marks a complete record
 };
 

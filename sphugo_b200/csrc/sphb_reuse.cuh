@@ -470,9 +470,7 @@ __global__ void k_reuse_update(ReuseState* __restrict__ rs, const GridP* __restr
     ReuseStat r;
     r.seq = rs->seq; r.age = rs->age; r.refused = (unsigned)failCount[0]; r.n = (unsigned)n;  // (rebuild: refused by the tile search)
     r.D = (float)rs->D;
-    unsigned long long hs = 0, hc = 0;
-    if (hacc && hscale > 0.0) for (int k = 0; k < HACC_N; ++k) { hs += hacc[2 * k]; hc += hacc[2 * k + 1]; }
-    r.hmean = hc ? (float)((double)hs / hscale / (double)hc) : 0.0f;
+    r.dy = (float)gp->dy;
     r.rebuild = (unsigned)rebuild; r.seq2 = r.seq;
     *stat = r;
   }

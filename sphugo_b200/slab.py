@@ -633,7 +633,7 @@ def bench(args, nx, ny, box, phys, desc, rank, world, local):
     dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     dev_ms, wall_ms = float(t[0]), float(t[1])
     # device phases of separate untimed steps on rank 0 (library CUDA-event timers), by kind of evaluation
-    KP = max(2, min(K, int(info["period"]) + 1))
+    KP = max(2, min(K, 8))
     ph = {"rebuild": [], "reuse": []}
     for _ in range(KP):
         r0 = sim.handle.counters()["reuse_steps"]
@@ -666,7 +666,7 @@ def bench(args, nx, ny, box, phys, desc, rank, world, local):
                     "what": "wall clock of the same K steps including host orchestration and NCCL exchange; state stays device resident"},
             "gpu_launches": c1["kernel_launches"] - c0["kernel_launches"],
             "knn_fallback_particles": int(cnt[1]),
-            "reuse": {"reuse_steps": reuse_steps, "rebuild_steps": K - reuse_steps, "period": int(info["period"]),
+            "reuse": {"reuse_steps": reuse_steps, "rebuild_steps": K - reuse_steps, "fixed_period": int(info["period"]),
                       "refused_fraction": int(cnt[1]) / (n_total * K), "ghosts_rank0": int(info["ghosts"])},
             "clocks": clocks,
             "phases": {"device_ms": device_phases,

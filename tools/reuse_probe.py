@@ -21,7 +21,7 @@ def main():
     ap.add_argument("--steps", type=int, default=24)
     ap.add_argument("--precision", type=int, default=64)
     a = ap.parse_args()
-    os.environ.setdefault("SPHB_REUSE_PERIOD", "12")
+    pass  # (SPHB_REUSE_PERIOD fixes the cycle length; default: the library's own schedule)
     nx, ny, box, phys, desc = B.workload(a.workload, 1)
     pos = B.make_ic_c4(0, 1)[0] if a.workload == "c4" else B.make_ic(nx, ny, box, 0, 1)[0]
     n = len(pos)
