@@ -154,6 +154,7 @@ struct sphb_sim {
 };
 
 #define REUSE_RING 64
+#define REUSE_MIN_N (1 << 21)  // below this a step is short enough for the schedule's host wait to show
 
 namespace {
 
@@ -512,7 +513,7 @@ int build_neighbours(sphb_sim* s, int mode, const double hor[2], const double ve
 //     (to 0.9 at most), an evaluation that refused > 0.5 % lowers it by 0.1 (0.2 at least) and ends the cycle at once;
 //   - no cycle starts unless the tile search itself refused less than 0.1 % of the particles in the last two rebuilds
 //     (i.i.d. clouds, free surfaces: their smoothing lengths change by more than the search margin per step);
-//   - handles below 2^14 particles do not reuse (their steps are launch bound).
+//   - handles below 2^21 particles do not reuse (the host wait of the schedule shows in steps that short).
 // SPHB_REUSE_PERIOD = p fixes cycles of p evaluations instead (tests, sweeps).
 struct ReuseFeedback { unsigned age; double frac, D, dy; bool rebuild; };
 
@@ -538,14 +539,16 @@ bool reuse_budget_ok(const sphb_sim* s, double D) {
   return D <= s->reuse_kappa * s->reuse_skin * hmean;
 }
 
-void reuse_poll(sphb_sim* s) {
+// block: wait for the record of the previous evaluation (inside a cycle the plan needs its D); otherwise take what has
+// arrived - outside a cycle the records only count calm rebuilds, and steps keep being enqueued without a host wait
+void reuse_poll(sphb_sim* s, bool block) {
   if (!s->stat_host) return;
-  if (s->stat_seen < s->stat_enq && s->stat_event_valid) cudaEventSynchronize(s->stat_event);
+  if (block && s->stat_seen < s->stat_enq && s->stat_event_valid) cudaEventSynchronize(s->stat_event);
   while (s->stat_seen < s->stat_enq) {
     const volatile ReuseStat* r = &s->stat_host[(s->stat_seen + 1) % REUSE_RING];
     if (r->seq != s->stat_seen + 1 || r->seq2 != r->seq) {
       if (s->stat_enq - s->stat_seen >= REUSE_RING) { s->stat_seen = s->stat_enq - REUSE_RING / 2; continue; }  // overwritten
-      break;  // (cannot happen after the wait above)
+      break;  // not there yet
     }
     s->stat_seen += 1;
     if (r->n == 0) continue;
@@ -704,9 +707,9 @@ int forces_plan(sphb_sim* s, int mode, bool integrate, const EvalPlan& plan) {
 int forces(sphb_sim* s, int mode, bool integrate) {
   EvalPlan plan;
   const bool cyc = s->reuse_on && !s->slab_on && mode == MODE_DRIFT && integrate &&
-                   (s->reuse_period_fixed || s->n >= 16384);  // an ordinary step of a handle worth the bookkeeping
+                   (s->reuse_period_fixed || s->n >= REUSE_MIN_N);  // an ordinary step of a handle worth the bookkeeping
   if (cyc) {
-    reuse_poll(s);
+    reuse_poll(s, s->lists_ext);
     reuse_plan(s, s->lists_ext && same_params(s->prm, s->list_prm), plan.reuse, plan.next_reuse);
   }
   plan.record = cyc;

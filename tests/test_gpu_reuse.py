@@ -149,7 +149,7 @@ def test_reuse_fp32_build():
 def test_reuse_adaptive_schedule_and_invalidation():
     """default (adaptive) schedule: reuse evaluations happen, an upload or an append in between forces a rebuild, and the
     trajectory equals the one without reuse"""
-    n = 160  # (handles below 2^14 particles do not reuse on their own)
+    n = 1456  # (handles below 2^21 particles do not reuse on their own)
     pos = gen.jittered_lattice(n, n)
     kw = dict(hor=(0.0, 1.0), ver=(0.0, 1.0), accel=(0.0, 0.2), dt_half=0.98 / n)
     g = L.Handle(L.make_params(**kw), pos, None, np.full(len(pos), 0.01), capacity=len(pos) + 64)
@@ -159,7 +159,7 @@ def test_reuse_adaptive_schedule_and_invalidation():
         h.step(12)
     # two calm rebuilds first, then cycles of 2, 3, 4 evaluations: at least four reuse evaluations in twelve steps
     assert g.counters()["reuse_steps"] >= 4
-    extra = np.array([[0.503, 0.501], [0.25, 0.75]])
+    extra = np.array([[0.50003, 0.50001], [0.25, 0.75]])
     for h in (g, g0):
         h.append(extra, None, np.full(2, 0.01), None, np.arange(len(pos), len(pos) + 2, dtype=np.int64))
         h.step(5)
