@@ -183,16 +183,20 @@ def run_reference(args):
         return
     nx, ny, box, phys, desc = workload(args.workload, args.gpus)
     t_all = time.perf_counter()
-    sample_nx = 512 if args.steps * 4 <= 80 else 256
-    # K steps of the bounded sample after W warm-up steps (W capped: each costs seconds of CPU)
+    # The reference arm runs BASELINE configs[2] in full - the 2^20-particle C3-P box, the largest BASELINE configuration
+    # a serial CPU path steps in seconds - with its own dt: the repo arm's `legs` hold the same configuration (leg c3p,
+    # f64), so that one published pair is like for like.  Against the headline workload (2^25 particles per GPU) the
+    # figure is an extrapolation that flatters the CPU (its cost per particle grows ~ log N).
+    sample_nx = 1024
     from oracle import oracle as orc
     from sphugo_b200 import gen
     pos = gen.jittered_lattice(sample_nx, sample_nx)
     n_s = len(pos)
-    po = orc.make_params(hor=(0.0, 1.0), ver=(0.0, 1.0), accel=phys["accel"], dt_half=0.001 * 1024.0 / sample_nx)
+    po = orc.make_params(hor=(0.0, 1.0), ver=(0.0, 1.0), accel=(0.0, 0.2), dt_half=0.001)
     o = orc.Oracle(po, pos, None, np.full(n_s, 0.01))
-    o.step(1 + min(args.warmup, 1))
-    K = max(1, min(args.steps, 8))
+    Wr = min(args.warmup, 1)
+    o.step(1 + Wr)  # step 0 evaluates the forces twice (sph.go:89-103): excluded, like in the repo arm
+    K = max(1, min(args.steps, 3))
     t0 = time.perf_counter()
     o.step(K)
     el = time.perf_counter() - t0
@@ -200,12 +204,16 @@ def run_reference(args):
     v = n_s * K / el
     line = {
         "metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": K,
-        "warmup": 1 + min(args.warmup, 1), "ms_per_step": el / K * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": 1 + Wr, "ms_per_step": el / K * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "sample": f"{sample_nx}x{sample_nx} periodic jittered lattice ({n_s} particles) of the same kind"},
+        "config": {"workload": desc,
+                   "sample": f"BASELINE configs[2] in full: {sample_nx}x{sample_nx} periodic jittered lattice ({n_s} particles), dt_half 0.001, "
+                             "g=(0,0.2), Monaghan - identical to leg c3p / f64 of the repo arm (same_config there); an extrapolation "
+                             "against the headline workload"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                          "sample": f"{K} Step() calls on {n_s} particles; C restatement of the serial Go path "
-                                   "(Go toolchain absent; package sim starts no goroutines so GOMAXPROCS is irrelevant)"},
+                                   "(Go toolchain absent here and on the GPU box, profiles/r02_go_probe.txt; package sim starts no "
+                                   "goroutines so GOMAXPROCS is irrelevant)"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t_all,
     }
@@ -381,30 +389,40 @@ def run_ours(args):
     clocks = sampler.stop()
     c1 = g.counters()
     ms_per_step = dev_ms / K
-    # per-phase split from the library's CUDA-event phase timers (separate, untimed steps)
-    phase_acc = {k: 0.0 for k in L.PHASES}
-    KP = min(K, 5)
+    # per-phase split from the library's CUDA-event phase timers (separate, untimed steps), by kind of evaluation:
+    # a rebuild (sort, reorder, tile search [+ annulus pass when it starts a reuse cycle]) or a reuse evaluation
+    # (predict in the "reorder" slot, exact kNN from the stored candidates in the "knn" slot)
+    KP = max(min(K, 14), 2)
+    kinds = {"rebuild": [], "reuse": []}
     for _ in range(KP):
+        r0 = g.counters()["reuse_steps"]
         g.step(1)
         pt = g.phase_times()
-        for k in L.PHASES:
-            phase_acc[k] += pt[k]
+        kinds["reuse" if g.counters()["reuse_steps"] > r0 else "rebuild"].append(pt)
     value = n * K / (dev_ms * 1e-3)
     peak, peak_src = measured_peak()
     step_achieved = n * B_ALG_TOTAL / (ms_per_step * 1e-3) / 1e9
+    n_reuse_timed = c1["reuse_steps"] - c0["reuse_steps"]
+    share = {"reuse": n_reuse_timed / K, "rebuild": 1.0 - n_reuse_timed / K}  # of the timed region
+    if not kinds["reuse"]:
+        share = {"reuse": 0.0, "rebuild": 1.0}
+    mean_ms = {kind: {k: float(np.mean([p[k] for p in v])) for k in L.PHASES} for kind, v in kinds.items() if v}
     phases = {}
     for k in ("keys", "sort", "reorder", "knn", "force"):
-        ms = phase_acc[k] / KP
+        # average launch time of the phase over the timed region's mix of evaluations
+        ms = sum(share[kind] * mean_ms[kind][k] for kind in mean_ms)
         # a phase fused into another kernel (keys: emitted by the force epilogue on periodic steps) has no launch of
         # its own: the timer brackets nothing and a bandwidth figure would be meaningless
-        fused = ms < 0.02 and k == "keys"
+        fused = ms < 0.02 and k in ("keys", "sort")
         gbs = n * B_ALG[k] / (ms * 1e-3) / 1e9 if ms > 0 and not fused else None
         phases[k] = {"ms": ms, "alg_GBps": gbs, "frac": gbs / peak if gbs else None}
         if fused:
-            phases[k]["fused_into"] = "force epilogue of the previous step"
-    dom = max(("keys", "sort", "reorder", "knn", "force"), key=lambda k: phase_acc[k])
-    dom_kernel = {"knn": "k_knn_tile (+ k_knn_fallback for refused particles)", "force": "k_force_st",
-                  "reorder": "k_reorder", "keys": "k_keys", "sort": "counting-sort kernels"}[dom]
+            phases[k]["fused_into"] = "force epilogue of the previous step (keys) / not run by reuse evaluations"
+    phases["by_kind_ms"] = mean_ms
+    phases["mix_of_timed_region"] = share
+    dom = max(("keys", "sort", "reorder", "knn", "force"), key=lambda k: phases[k]["ms"])
+    dom_kernel = {"knn": "k_knn_tile + k_knn_annulus (rebuilds) / k_knn_reuse (reuse evaluations), + k_knn_fallback for refused particles",
+                  "force": "k_force_st", "reorder": "k_reorder / k_predict", "keys": "k_keys", "sort": "counting-sort kernels"}[dom]
     traffic = ncu_traffic(f"{dom}_{args.workload}_f{args.precision}")
 
     h2d = d2h = 0

@@ -47,6 +47,7 @@ struct RingState {
   double x_lo = 0.0, x_hi = 0.0, safety = 1.15;
   int64_t halo_cap = 0;                  // records per side
   double h_max = 0.0, v_max = 0.0;       // all-reduced maxima of the last cycle
+  double h_max_run = 0.0, v_max_run = 0.0; // the same, running (read every evaluation)
   double excursion = 0.0;                // bound of the drift out of the slab since the last migration
   int64_t n_global = 0;
   int migrate_every = 0, migrations = 0;

@@ -156,7 +156,8 @@ def test_reuse_adaptive_schedule_and_invalidation():
     with env(SPHB_REUSE=0):
         g0 = L.Handle(L.make_params(**kw), pos, None, np.full(len(pos), 0.01), capacity=len(pos) + 64)
     for h in (g, g0):
-        h.step(12)
+        for _ in range(12):  # (a caller that looks at every step, like simviewer: the schedule learns from finished steps)
+            h.step(1); h.sync()
     # two calm rebuilds first, then cycles of 2, 3, 4 evaluations: at least four reuse evaluations in twelve steps
     assert g.counters()["reuse_steps"] >= 4
     extra = np.array([[0.50003, 0.50001], [0.25, 0.75]])
