@@ -147,7 +147,7 @@ struct sphb_sim {
   bool stat_event_valid = false;
   bool reuse_abort = false;              // the policy ended the current cycle: the next evaluation rebuilds
   int calm_steps = 0;                    // consecutive rebuilds whose tile search refused < 0.1 % of the particles
-  double reuse_kappa = 0.6;              // share of the skin the displacement bound may use up (adapts)
+  double reuse_kappa = 0.75;             // share of the skin the displacement bound may use up (adapts)
   double fb_D = 0.0, fb_D_prev = 0.0, fb_dy = 0.0, fb_last_frac = 0.0;  // last feedback record
   bool fb_valid = false;
   int reuse_cooldown = 0;

@@ -49,4 +49,24 @@ for prec in (64, 32):
     g.step(2); g.sync()
     assert g.n == len(pos) + len(extra)
     g.close()
+# list reuse (rebuild on the wide block + annulus pass, reuse evaluations, stale-cell fallback), single handle and ring
+os.environ["SPHB_REUSE_PERIOD"] = "4"
+for prec in (64, 32):
+    for pos, kw in ((gen.jittered_lattice(64, 64), dict(hor=(0.0, 1.0), ver=(0.0, 1.0), accel=(0.0, 0.2), dt_half=0.01)),
+                    (gen.shock_tube(6000), dict(hor=(0.0, 1.0), ver=(0.0, 1.0), dt_half=2e-3)),
+                    (gen.spawn([(3000, (0, 0), (1, 1))])["pos"], dict(accel=(0.0, 0.2), dt_half=0.002))):
+        g = L.Handle(L.make_params(precision=prec, **kw), pos, None, np.full(len(pos), 0.01))
+        g.step(7); g.sync()
+        assert g.counters()["reuse_steps"] >= 4
+        g.state(["pos", "rho", "nn_idx"]); g.close()
+    pos = gen.jittered_lattice(96, 96)
+    n = len(pos)
+    pg = L.make_params(hor=(0.0, 1.0), ver=(0.0, 1.0), dt_half=0.002, precision=prec)
+    sim = slab.LocalRingSim(pg, slab.Topology(2, [0.0, 0.5, 1.0], True), pos, np.tile([[3.0, 1.0]], (n, 1)), np.full(n, 0.01),
+                            h_max_hint=slab.default_h_hint(n, 1.0))
+    sim.step(6)
+    sim.state(["pos", "rho"])
+    assert sum(sim.counts()) == n
+    sim.close()
+del os.environ["SPHB_REUSE_PERIOD"]
 print("sanitizer workload done")
