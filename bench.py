@@ -244,6 +244,10 @@ def leg_ic(name):
     """(pos, params kwargs, description, e0) of a single-GPU leg"""
     from sphugo_b200 import gen, gorand
     mon = dict(gamma=1.66666, particle_mass=1.0, kernel=1)
+    if name == "c5":
+        return (gen.jittered_lattice(8192, 4096, (0.0, 0.0), (0.5, 0.25)),
+                dict(mon, hor=(0.0, 0.5), ver=(0.0, 0.25), accel=(0.0, 0.2), dt_half=6e-5),
+                "C5 share (the headline workload): 2^25 jittered-lattice particles, periodic box 0.5x0.25, Monaghan, g=(0,0.2)")
     if name == "c3p":
         return (gen.jittered_lattice(1024, 1024), dict(mon, hor=(0.0, 1.0), ver=(0.0, 1.0), accel=(0.0, 0.2), dt_half=0.001),
                 "C3-P (BASELINE configs[2]): 2^20 jittered-lattice particles, periodic [0,1]^2, Monaghan, g=(0,0.2)")
@@ -265,13 +269,13 @@ def leg_ic(name):
     raise SystemExit(f"unknown leg {name}")
 
 
-def run_leg(name, precision, K, W, device, fresh=False):
+def run_leg(name, precision, K, W, device, fresh=False, flags=0):
     """device-resident throughput of one leg; fresh = time the first K steps of a new simulation (speed-test's protocol)"""
     import torch
     from sphugo_b200 import _lib as L
     pos, kw, desc = leg_ic(name)
     n = len(pos)
-    g = L.Handle(L.make_params(precision=precision, device=device, **kw), pos, None, np.full(n, 0.01))
+    g = L.Handle(L.make_params(precision=precision, device=device, flags=flags, **kw), pos, None, np.full(n, 0.01))
     del pos
     ext = torch.cuda.ExternalStream(g.stream, device=torch.device("cuda", device))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -291,7 +295,7 @@ def run_leg(name, precision, K, W, device, fresh=False):
     g.close()
     peak, _ = measured_peak()
     b = sum(B_ALG_BY_PREC[precision].values())
-    return {"leg": name, "workload": desc, "particles": n, "dtype": "f64" if precision == 64 else "f32", "steps": K,
+    return {"leg": name + ("+reuse" if flags & 2 else ""), "workload": desc, "particles": n, "dtype": "f64" if precision == 64 else "f32", "steps": K,
             "ms_per_step": ms, "value": n / (ms * 1e-3), "unit": UNIT, "wall_ms_per_step": wall / K * 1e3,
             "step_roofline_frac": n * b / (ms * 1e-3) / 1e9 / peak, "alg_bytes_per_particle": b,
             "fallback_fraction": (c1["knn_fallback"] - c0["knn_fallback"]) / (n * K),
@@ -321,6 +325,13 @@ def run_legs(args, device):
                 legs.append(run_leg(name, prec, 20 if name.startswith("c3") else 10, 3, device))
             except Exception as ex:  # a leg must not take the headline line down with it
                 legs.append({"leg": name, "dtype": f"f{prec}", "error": str(ex)[:300]})
+    # the headline workload with the certified list reuse switched on (SPHB_FLAG_REUSE_LISTS; off by default): long
+    # enough for the schedule to settle (rebuild + reuse cycles), same device-resident protocol
+    for prec in (64, 32):
+        try:
+            legs.append(run_leg("c5", prec, 42, 6, device, flags=2))
+        except Exception as ex:
+            legs.append({"leg": "c5+reuse", "dtype": f"f{prec}", "error": str(ex)[:300]})
     try:
         run_leg("speed", 64, 20, 0, device, fresh=True)  # (the first run warms the device up)
         sp = run_leg("speed", 64, 20, 0, device, fresh=True)
@@ -354,6 +365,8 @@ def run_ours(args):
     B_ALG = B_ALG_BY_PREC[args.precision]
     B_ALG_TOTAL = sum(B_ALG.values())
     phys["precision"] = args.precision
+    if args.reuse:
+        phys["flags"] = 2
     if args.precision == 32:
         desc = desc.replace("fp64", "fp32 build (fp32 pair arithmetic, fp64 state)")
     if world > 1:
@@ -540,6 +553,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (tuning sweeps only)")
     ap.add_argument("--no-other-build", action="store_true", help="skip the extra leg that times the other precision build")
     ap.add_argument("--no-legs", action="store_true", help="skip the legs on the other BASELINE configurations (C3-U/P, C4, speed-test)")
+    ap.add_argument("--reuse", action="store_true", help="switch the certified neighbour-list reuse on (SPHB_FLAG_REUSE_LISTS)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -70,6 +70,9 @@ typedef struct {
 } sphb_params;
 
 #define SPHB_FLAG_KEEP_NN_LIST 1u /* always materialise the neighbour list (needed by download of NN_*) */
+#define SPHB_FLAG_REUSE_LISTS 2u  /* certified reuse of the neighbour lists between rebuilds (exact kNN from stored
+                                     candidates under a displacement certificate; DESIGN.md "list reuse").  Results are
+                                     the same exact kNN either way; off by default - see DESIGN.md for what it buys */
 
 typedef struct sphb_sim sphb_sim; /* opaque, owned by the library */
 

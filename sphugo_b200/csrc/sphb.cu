@@ -129,7 +129,7 @@ struct sphb_sim {
   ReuseState* rs = nullptr;   // device bookkeeping
   ReuseStat* stat_dev = nullptr;
   ReuseStat* stat_host = nullptr;  // pinned ring of REUSE_RING records (non-blocking feedback for the schedule)
-  bool reuse_on = true;       // SPHB_REUSE=0 switches it off
+  bool reuse_on = false;      // SPHB_FLAG_REUSE_LISTS in sphb_params.flags, or SPHB_REUSE=1 / SPHB_REUSE_PERIOD in the environment
   int reuse_period = 2;       // (unused by the budget schedule; reported): one rebuild + (period - 1) reuse evaluations; 1 = never reuse
   int reuse_period_max = 12, reuse_period_fixed = 0;
   double reuse_skin = 0.25;   // extended candidates are collected up to h (1 + skin)
@@ -146,6 +146,8 @@ struct sphb_sim {
   cudaEvent_t stat_event = nullptr;      // recorded behind the last record's copy
   bool stat_event_valid = false;
   bool reuse_abort = false;              // the policy ended the current cycle: the next evaluation rebuilds
+  bool touched = false;                  // the caller changed the state (upload, append, parameters) since the last step
+  int touched_streak = 0;                // consecutive steps that were preceded by such a change
   int calm_steps = 0;                    // consecutive rebuilds whose tile search refused < 0.1 % of the particles
   double reuse_kappa = 0.75;             // share of the skin the displacement bound may use up (adapts)
   double fb_D = 0.0, fb_D_prev = 0.0, fb_dy = 0.0, fb_last_frac = 0.0;  // last feedback record
@@ -709,9 +711,15 @@ int forces(sphb_sim* s, int mode, bool integrate) {
   EvalPlan plan;
   const bool cyc = s->reuse_on && !s->slab_on && mode == MODE_DRIFT && integrate &&
                    (s->reuse_period_fixed || s->n >= REUSE_MIN_N);  // an ordinary step of a handle worth the bookkeeping
+  if (mode == MODE_DRIFT && integrate) {
+    s->touched_streak = s->touched ? s->touched_streak + 1 : 0;
+    s->touched = false;
+  }
   if (cyc) {
     reuse_poll(s, s->lists_ext);
     reuse_plan(s, s->lists_ext && same_params(s->prm, s->list_prm), plan.reuse, plan.next_reuse);
+    // a caller that rewrites the state before every step (bench.py's e2e loop) would pay for extended lists it never uses
+    if (!plan.reuse && s->touched_streak > 0) plan.next_reuse = false;
   }
   plan.record = cyc;
   return forces_plan(s, mode, integrate, plan);
@@ -762,6 +770,7 @@ int upload_common(sphb_sim* s, int64_t off, int64_t n, const double* pos_xy, con
   s->grid_next_ready = false;
   s->have_list = false;
   invalidate_reuse(s);
+  s->touched = true;
   return SPHB_OK;
 }
 
@@ -851,8 +860,9 @@ int create_common(const sphb_params* p, int64_t n, int64_t capacity, const doubl
   s->ktune.cap0 = 80;
   s->ktune.ncw = p->precision == 32 ? 256 : 224;
   s->ktune.ncw0 = 512;
+  s->reuse_on = (p->flags & SPHB_FLAG_REUSE_LISTS) != 0;
+  if (const char* ev = getenv("SPHB_REUSE_PERIOD")) { s->reuse_period_fixed = std::max(1, std::min(64, atoi(ev))); s->reuse_on = true; }
   if (const char* ev = getenv("SPHB_REUSE")) s->reuse_on = atoi(ev) != 0;
-  if (const char* ev = getenv("SPHB_REUSE_PERIOD")) s->reuse_period_fixed = std::max(1, std::min(64, atoi(ev)));
   if (const char* ev = getenv("SPHB_REUSE_MAX")) s->reuse_period_max = std::max(1, std::min(64, atoi(ev)));
   if (const char* ev = getenv("SPHB_REUSE_SKIN")) s->reuse_skin = std::max(0.03, std::min(1.0, atof(ev)));
   if (const char* ev = getenv("SPHB_REUSE_NCW")) s->reuse_ncw = std::max(128, std::min(512, atoi(ev) / 32 * 32));
@@ -1076,7 +1086,7 @@ int sphb_set_params(sphb_sim* s, const sphb_params* p) {
   rc = check_params(s, p); if (rc) return rc;
   if (p->device != s->device) return fail(s, SPHB_E_INVALID, "device cannot change after create");
   if (p->precision != s->prm.precision) return fail(s, SPHB_E_INVALID, "precision cannot change after create");
-  if (!same_params(s->prm, *p)) invalidate_reuse(s);
+  if (!same_params(s->prm, *p)) { invalidate_reuse(s); s->touched = true; }
   s->prm = *p;
   return SPHB_OK;
 }
@@ -1259,7 +1269,7 @@ int sphb_upload(sphb_sim* s, uint32_t mask, const void* const* hp, int64_t n) {
   }
   if (mask & SPHB_MASK(SPHB_F_POS)) s->have_list = false;  // the list describes the old positions; h stays a valid first guess
   if (mask & (SPHB_MASK(SPHB_F_POS) | SPHB_MASK(SPHB_F_VEL))) drop_ready_keys(s);  // they were keys of the old state
-  if (mask) invalidate_reuse(s);
+  if (mask) { invalidate_reuse(s); s->touched = true; }
   s->stats_dirty = true;
   CK(s, cudaStreamSynchronize(s->st));
   return SPHB_OK;
@@ -1292,6 +1302,7 @@ int sphb_upload_by_id(sphb_sim* s, uint32_t mask, const void* const* hp, int64_t
   if (mask & SPHB_MASK(SPHB_F_POS)) s->have_list = false;
   if (mask & (SPHB_MASK(SPHB_F_POS) | SPHB_MASK(SPHB_F_VEL))) drop_ready_keys(s);
   invalidate_reuse(s);
+  s->touched = true;
   s->stats_dirty = true;
   CK(s, cudaStreamSynchronize(s->st));  // host buffers are borrowed for the duration of the call only
   return SPHB_OK;

@@ -152,7 +152,8 @@ def test_reuse_adaptive_schedule_and_invalidation():
     n = 1456  # (handles below 2^21 particles do not reuse on their own)
     pos = gen.jittered_lattice(n, n)
     kw = dict(hor=(0.0, 1.0), ver=(0.0, 1.0), accel=(0.0, 0.2), dt_half=0.98 / n)
-    g = L.Handle(L.make_params(**kw), pos, None, np.full(len(pos), 0.01), capacity=len(pos) + 64)
+    with env(SPHB_REUSE=1):
+        g = L.Handle(L.make_params(**kw), pos, None, np.full(len(pos), 0.01), capacity=len(pos) + 64)
     with env(SPHB_REUSE=0):
         g0 = L.Handle(L.make_params(**kw), pos, None, np.full(len(pos), 0.01), capacity=len(pos) + 64)
     for h in (g, g0):

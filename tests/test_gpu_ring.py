@@ -78,8 +78,9 @@ def test_ring_default_schedule_matches_single_handle():
     kw = dict(hor=(0.0, 1.0), ver=(0.0, 1.0), accel=(0.0, 0.2), dt_half=0.002)
     pg = L.make_params(**kw)
     g = L.Handle(pg, pos, None, np.full(n, 0.01))
-    sim = slab.LocalRingSim(pg, slab.Topology(2, [0.0, 0.5, 1.0], True), pos, None, np.full(n, 0.01),
-                            h_max_hint=slab.default_h_hint(n, 1.0))
+    with env(SPHB_REUSE=1):
+        sim = slab.LocalRingSim(pg, slab.Topology(2, [0.0, 0.5, 1.0], True), pos, None, np.full(n, 0.01),
+                                h_max_hint=slab.default_h_hint(n, 1.0))
     g.step(9); sim.step(9)
     a, b = g.state(FIELDS), sim.state(FIELDS)
     assert (a["id"] == b["id"]).all()
