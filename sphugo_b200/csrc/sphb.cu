@@ -741,7 +741,9 @@ int forces(sphb_sim* s, int mode, bool integrate) {
     // a caller that rewrites the state before every step (bench.py's e2e loop) would pay for extended lists it never uses
     if (!plan.reuse && s->touched_streak > 0) plan.next_reuse = false;
   }
-  plan.record = ordinary;  // every ordinary step leaves a feedback record (search width, reuse schedule)
+  // ordinary steps leave a feedback record (search width, reuse schedule); small handles, whose steps are launch bound,
+  // only every fourth step
+  plan.record = ordinary && (cyc || s->n >= (1 << 20) || (s->cur_step & 3) == 0);
   return forces_plan(s, mode, integrate, plan);
 }
 
