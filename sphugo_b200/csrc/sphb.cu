@@ -148,6 +148,7 @@ struct sphb_sim {
   bool reuse_abort = false;              // the policy ended the current cycle: the next evaluation rebuilds
   int search_level = 0, search_calm = 0; // width of the tile search (margin / column capacity), adapted from its refusals
   bool search_level_fixed = false;       // SPHB_GUESS_MARGIN / SPHB_KNN_CAP given
+  bool no_record = false;                // SPHB_NO_RECORD=1: no feedback records (diagnostic)
   bool touched = false;                  // the caller changed the state (upload, append, parameters) since the last step
   int touched_streak = 0;                // consecutive steps that were preceded by such a change
   int calm_steps = 0;                    // consecutive rebuilds whose tile search refused < 0.1 % of the particles
@@ -743,7 +744,7 @@ int forces(sphb_sim* s, int mode, bool integrate) {
   }
   // ordinary steps leave a feedback record (search width, reuse schedule); small handles, whose steps are launch bound,
   // only every fourth step
-  plan.record = ordinary && (cyc || s->n >= (1 << 20) || (s->cur_step & 3) == 0);
+  plan.record = ordinary && !s->no_record && (cyc || s->n >= (1 << 22) || (s->cur_step & 3) == 0);
   return forces_plan(s, mode, integrate, plan);
 }
 
@@ -883,6 +884,7 @@ int create_common(const sphb_params* p, int64_t n, int64_t capacity, const doubl
   s->ktune.ncw = p->precision == 32 ? 256 : 224;
   s->ktune.ncw0 = 512;
   s->reuse_on = (p->flags & SPHB_FLAG_REUSE_LISTS) != 0;
+  if (const char* ev = getenv("SPHB_NO_RECORD")) s->no_record = atoi(ev) != 0;
   if (const char* ev = getenv("SPHB_REUSE_PERIOD")) { s->reuse_period_fixed = std::max(1, std::min(64, atoi(ev))); s->reuse_on = true; }
   if (const char* ev = getenv("SPHB_REUSE")) s->reuse_on = atoi(ev) != 0;
   if (const char* ev = getenv("SPHB_REUSE_MAX")) s->reuse_period_max = std::max(1, std::min(64, atoi(ev)));
