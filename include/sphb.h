@@ -173,6 +173,14 @@ int sphb_upload(sphb_sim* s, uint32_t field_mask, const void* const* host_ptrs, 
  * this - not sphb_upload - is the call for "Go mutated Root.Particles between two steps". */
 int sphb_upload_by_id(sphb_sim* s, uint32_t field_mask, const void* const* host_ptrs, int64_t n);
 
+/* sphb_upload_by_id in two halves, for a caller that has the next step's particle fields ready while the current step is
+ * still running (a replay, a coupled solver on the host): _begin starts the host-to-device copies on a copy stream of the
+ * handle, into a staging area of their own, and returns; steps enqueued before or after it keep running.  _end waits for
+ * the copies (the host buffers are borrowed from _begin to _end), then scatters the staged fields into the device order
+ * behind the steps enqueued so far.  One upload in flight per handle. */
+int sphb_upload_by_id_begin(sphb_sim* s, uint32_t field_mask, const void* const* host_ptrs, int64_t n);
+int sphb_upload_by_id_end(sphb_sim* s);
+
 int sphb_reduce(sphb_sim* s, int32_t which, double* out); /* TotalEnergy / TotalDensity / TotalMomentum */
 
 /* Per-particle frame data as (*Animator).CurrentFrame derives it (sim/animator.go:75-101), computed on the device so

@@ -39,6 +39,7 @@ EXPORTS = [
     "sphb_download", "sphb_upload", "sphb_upload_by_id", "sphb_reduce", "sphb_frame", "sphb_phase_times", "sphb_counters", "sphb_create_device",
     "sphb_slab_set", "sphb_max_h", "sphb_max_speed", "sphb_slab_step_begin", "sphb_slab_pack_halo", "sphb_slab_add_ghosts",
     "sphb_slab_step_end", "sphb_slab_pack_migrants", "sphb_slab_add_migrants", "sphb_slab_finish_migration",
+    "sphb_upload_by_id_begin", "sphb_upload_by_id_end",
     "sphb_comm_unique_id", "sphb_comm_init", "sphb_ring_set", "sphb_ring_step", "sphb_ring_step_local", "sphb_ring_info",
 ]
 NCCL_ID_BYTES = 128
@@ -129,6 +130,10 @@ def lib():
     L.sphb_reduce.argtypes = [vp, C.c_int32, dp]
     L.sphb_upload_by_id.restype = C.c_int
     L.sphb_upload_by_id.argtypes = L.sphb_upload.argtypes
+    L.sphb_upload_by_id_begin.restype = C.c_int
+    L.sphb_upload_by_id_begin.argtypes = L.sphb_upload.argtypes
+    L.sphb_upload_by_id_end.restype = C.c_int
+    L.sphb_upload_by_id_end.argtypes = [vp]
     L.sphb_frame.restype = C.c_int
     L.sphb_frame.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp, C.c_int64, ip]
     L.sphb_phase_times.restype = C.c_int
@@ -317,6 +322,24 @@ class Handle:
             ptrs[FIELD_BIT[name]] = a.ctypes.data
             mask |= 1 << FIELD_BIT[name]
         self._chk(lib().sphb_upload_by_id(self._h, mask, ptrs, n))
+
+    def upload_by_id_begin(self, **fields):
+        """first half of upload_by_id: starts the copies and returns; the arrays must stay alive (and unchanged) until
+        upload_by_id_end"""
+        n = self.n
+        ptrs, mask, keep = (C.c_void_p * len(FIELDS))(), 0, []
+        for name, a in fields.items():
+            shp, dt = FIELD_SHAPE[name]
+            a = np.ascontiguousarray(a, dtype=dt).reshape((n,) + shp)
+            keep.append(a)
+            ptrs[FIELD_BIT[name]] = a.ctypes.data
+            mask |= 1 << FIELD_BIT[name]
+        self._up_keep = keep
+        self._chk(lib().sphb_upload_by_id_begin(self._h, mask, ptrs, n))
+
+    def upload_by_id_end(self):
+        self._chk(lib().sphb_upload_by_id_end(self._h))
+        self._up_keep = None
 
     def reduce(self, which):
         out = C.c_double()

@@ -98,6 +98,14 @@ struct sphb_sim {
   int keys_n = 0;
   void* scratch = nullptr;    // download / upload staging
   size_t scratchBytes = 0;
+  // split upload (sphb_upload_by_id_begin / _end): the host-to-device copies run on a copy stream into a staging area of
+  // their own, next to whatever steps are enqueued on the compute stream
+  cudaStream_t st_copy = nullptr;
+  cudaEvent_t up_done = nullptr, up_free = nullptr;
+  void* up_stage = nullptr;
+  size_t up_stage_bytes = 0;
+  uint32_t up_mask = 0;       // fields of the upload in flight (0: none)
+  int64_t up_n = 0;
   int ncell_max = 0;
   bool stats_dirty = true;
   bool have_list = false;     // nn/spos/grid describe the current particle order
@@ -1093,6 +1101,10 @@ void sphb_destroy(sphb_sim* s) {
   cudaFree(s->nx); cudaFree(s->tinfo); cudaFree(s->ptab); cudaFree(s->dexcl); cudaFree(s->rs); cudaFree(s->stat_dev);
   if (s->stat_host) cudaFreeHost(s->stat_host);
   if (s->stat_event_valid) cudaEventDestroy(s->stat_event);
+  if (s->st_copy) { cudaStreamSynchronize(s->st_copy); cudaStreamDestroy(s->st_copy); }
+  if (s->up_done) cudaEventDestroy(s->up_done);
+  if (s->up_free) cudaEventDestroy(s->up_free);
+  cudaFree(s->up_stage);
   for (int side = 0; side < 2; ++side) { cudaFree(s->ring.sbuf[side]); cudaFree(s->ring.rbuf[side]); cudaFree(s->ring.sidx[side]); cudaFree(s->ring.hsrc[side]); }
   cudaFree(s->ring.inv); cudaFree(s->ring.red_dev);
   if (s->ring.refused_host) cudaFreeHost(s->ring.refused_host);
@@ -1329,6 +1341,69 @@ int sphb_upload_by_id(sphb_sim* s, uint32_t mask, const void* const* hp, int64_t
   s->touched = true;
   s->stats_dirty = true;
   CK(s, cudaStreamSynchronize(s->st));  // host buffers are borrowed for the duration of the call only
+  return SPHB_OK;
+}
+
+int sphb_upload_by_id_begin(sphb_sim* s, uint32_t mask, const void* const* hp, int64_t n) {
+  int rc = enter(s); if (rc) return rc;
+  if (s->up_mask) return fail(s, SPHB_E_STATE, "upload_by_id_begin: an upload is already in flight (call sphb_upload_by_id_end)");
+  if (n != s->n) return fail(s, SPHB_E_INVALID, "upload: n = %lld but the simulation holds %lld particles", (long long)n, (long long)s->n);
+  const uint32_t allowed = SPHB_MASK(SPHB_F_POS) | SPHB_MASK(SPHB_F_VEL) | SPHB_MASK(SPHB_F_E);
+  if (mask & ~allowed) return fail(s, SPHB_E_INVALID, "upload_by_id: POS, VEL, E only (mask 0x%x)", mask);
+  if (mask && !hp) return fail(s, SPHB_E_INVALID, "host_ptrs is NULL");
+  for (int f = 0; f < SPHB_F_COUNT; ++f)
+    if ((mask & SPHB_MASK(f)) && !hp[f]) return fail(s, SPHB_E_INVALID, "host_ptrs[%d] is NULL", f);
+  if (n == 0 || mask == 0) return SPHB_OK;
+  if (s->slab_on) return fail(s, SPHB_E_STATE, "upload_by_id: not available in slab mode (a handle owns a subset of the ids)");
+  if (!s->st_copy) {
+    CK(s, cudaStreamCreateWithFlags(&s->st_copy, cudaStreamNonBlocking));
+    CK(s, cudaEventCreateWithFlags(&s->up_done, cudaEventDisableTiming));
+    CK(s, cudaEventCreateWithFlags(&s->up_free, cudaEventDisableTiming));
+  }
+  if ((size_t)n * 40 > s->up_stage_bytes) {
+    CK(s, cudaStreamSynchronize(s->st));
+    CK(s, cudaStreamSynchronize(s->st_copy));
+    cudaFree(s->up_stage); s->up_stage = nullptr; s->up_stage_bytes = 0;
+    CK(s, cudaMalloc(&s->up_stage, (size_t)n * 40));
+    s->up_stage_bytes = (size_t)n * 40;
+  } else {
+    CK(s, cudaStreamWaitEvent(s->st_copy, s->up_free, 0));  // the previous upload's scatter has read the staging area
+  }
+  double2* sp = (double2*)s->up_stage;
+  double2* sv = sp + n;
+  double* se = (double*)(sv + n);
+  if (mask & SPHB_MASK(SPHB_F_POS)) CK(s, cudaMemcpyAsync(sp, hp[SPHB_F_POS], (size_t)n * 16, cudaMemcpyHostToDevice, s->st_copy));
+  if (mask & SPHB_MASK(SPHB_F_VEL)) CK(s, cudaMemcpyAsync(sv, hp[SPHB_F_VEL], (size_t)n * 16, cudaMemcpyHostToDevice, s->st_copy));
+  if (mask & SPHB_MASK(SPHB_F_E)) CK(s, cudaMemcpyAsync(se, hp[SPHB_F_E], (size_t)n * 8, cudaMemcpyHostToDevice, s->st_copy));
+  CK(s, cudaEventRecord(s->up_done, s->st_copy));
+  s->up_mask = mask; s->up_n = n;
+  return SPHB_OK;
+}
+
+int sphb_upload_by_id_end(sphb_sim* s) {
+  int rc = enter(s); if (rc) return rc;
+  if (!s->up_mask) return SPHB_OK;
+  const uint32_t mask = s->up_mask;
+  const int64_t n = s->up_n;
+  s->up_mask = 0;
+  CK(s, cudaEventSynchronize(s->up_done));  // the host buffers are the caller's again
+  if (n != s->n) return fail(s, SPHB_E_STATE, "upload_by_id_end: the particle count changed while the upload was in flight");
+  if (s->interleaved) drop_ghosts(s);
+  rc = require_dense_ids(s); if (rc) return rc;
+  double2* sp = (double2*)s->up_stage;
+  double2* sv = sp + n;
+  double* se = (double*)(sv + n);
+  k_gather_by_id<<<cdiv(n, 256), 256, 0, s->st>>>(s->a.id, (int)n, (mask & SPHB_MASK(SPHB_F_POS)) ? sp : nullptr,
+                                                 (mask & SPHB_MASK(SPHB_F_VEL)) ? sv : nullptr,
+                                                 (mask & SPHB_MASK(SPHB_F_E)) ? se : nullptr, s->a.pos, s->a.vel, s->a.e);
+  s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 1;
+  CKL(s);
+  CK(s, cudaEventRecord(s->up_free, s->st));
+  if (mask & SPHB_MASK(SPHB_F_POS)) s->have_list = false;
+  if (mask & (SPHB_MASK(SPHB_F_POS) | SPHB_MASK(SPHB_F_VEL))) drop_ready_keys(s);
+  invalidate_reuse(s);
+  s->touched = true;
+  s->stats_dirty = true;
   return SPHB_OK;
 }
 

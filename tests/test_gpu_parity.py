@@ -399,3 +399,28 @@ def test_golden_c3_c4_small(precision, tol):
     # velocities started at zero: measured against the largest one
     assert np.abs(st["vel"] - g["vel"]).max() <= tol * np.abs(g["vel"]).max()
     h.close()
+
+
+def test_split_upload_matches_the_serial_one():
+    """sphb_upload_by_id_begin / _end: the copies run next to the step enqueued before them; same state as the serial call"""
+    pos = gen.jittered_lattice(64, 64)
+    n = len(pos)
+    kw = dict(hor=(0.0, 1.0), ver=(0.0, 1.0), accel=(0.0, 0.2), dt_half=0.002)
+    a = L.Handle(L.make_params(**kw), pos, None, np.full(n, 0.01))
+    b = L.Handle(L.make_params(**kw), pos, None, np.full(n, 0.01))
+    rng = np.random.default_rng(5)
+    a.step(1); b.step(1)
+    for k in range(3):
+        st = a.state(["pos", "vel", "e", "id"])
+        new = dict(pos=st["pos"] + 1e-4 * rng.standard_normal((n, 2)), vel=st["vel"] + 1e-3 * rng.standard_normal((n, 2)), e=st["e"] * 1.01)
+        a.step(1); a.upload_by_id(**new); a.step(1)
+        b.step(1)                      # asynchronous: still running when the copies start
+        b.upload_by_id_begin(**new)
+        with pytest.raises(L.SphbError):
+            b.upload_by_id_begin(**new)  # one upload in flight per handle
+        b.upload_by_id_end()
+        b.step(1)
+        sa, sb = a.state(["pos", "vel", "e", "rho", "h"]), b.state(["pos", "vel", "e", "rho", "h"])
+        for f in ("pos", "vel", "e", "rho", "h"):
+            assert np.array_equal(sa[f], sb[f]), (f, k)
+    a.close(); b.close()
