@@ -146,6 +146,23 @@ func (sim *Simulation) backend() *gpuBackend {
 		capacity := len(ps) + 100000 // sph.go:45 reserves 100000 as well
 		check(nil, C.sphb_create(&prm, C.int64_t(len(ps)), C.int64_t(capacity), dptr(pos), dptr(vel), dptr(e), dptr(rho), iptr(id), &b.h))
 		b.uploaded = len(ps)
+		if sim.CurrentStep > 0 && len(ps) > 0 {
+			// a device copy made in the middle of a run (simviewer replaced the Simulation value, or the first GPU call
+			// comes after CPU steps): carry the derivatives the predictor reads (sph.go:108-117) and the step counter
+			// over, so that the next Step() does not repeat the step-0 initialisation (sph.go:89-103)
+			vdot := make([]float64, 2*len(ps))
+			edot := make([]float64, len(ps))
+			for i := range ps {
+				vdot[2*i], vdot[2*i+1] = ps[i].VDot.X, ps[i].VDot.Y
+				edot[i] = ps[i].EDot
+			}
+			var ptrs [C.SPHB_F_COUNT]unsafe.Pointer
+			ptrs[C.SPHB_F_VDOT] = unsafe.Pointer(&vdot[0])
+			ptrs[C.SPHB_F_EDOT] = unsafe.Pointer(&edot[0])
+			mask := C.uint32_t(1<<C.SPHB_F_VDOT | 1<<C.SPHB_F_EDOT)
+			check(b, C.sphb_upload(b.h, mask, (*unsafe.Pointer)(unsafe.Pointer(&ptrs[0])), C.int64_t(len(ps))))
+			check(b, C.sphb_set_current_step(b.h, C.int64_t(sim.CurrentStep)))
+		}
 		backendsMu.Lock()
 		backends[sim] = b
 		backendsMu.Unlock()

@@ -93,7 +93,11 @@ enum {
                                      the reference's order: descending distance, slot 0 = farthest = h
                                      (nearest-neighbour.go:139-153) */
   SPHB_F_NN_DIST = 12,/* double[32n] Particle.NNDists[k] for the same slots */
-  SPHB_F_NN_POS = 13, /* double[64n] Particle.NNPos[k] (neighbour image position in the query frame) */
+  SPHB_F_NN_POS = 13, /* double[64n] Particle.NNPos[k] (neighbour image position in the query frame).  Like the reference's
+                         field it describes the EVALUATION (nearest-neighbour.go:80): after sphb_knn / sphb_calc_forces it
+                         is exact; after sphb_step the particle has since been kicked and drifted, and the value returned
+                         is its current Pos plus the evaluation-time offset to the neighbour (a particle that wrapped or
+                         was reflected in that step carries the jump) */
   SPHB_F_COUNT = 14
 };
 #define SPHB_MASK(f) (1u << (f))
@@ -137,6 +141,10 @@ int sphb_set_params(sphb_sim* s, const sphb_params* p);
 int sphb_get_params(const sphb_sim* s, sphb_params* p);
 int64_t sphb_count(const sphb_sim* s);        /* len(sim.Root.Particles) */
 int64_t sphb_current_step(const sphb_sim* s); /* sim.CurrentStep */
+/* for a handle created from a simulation that has already stepped (sim.CurrentStep > 0: the Go shim re-creates its device
+ * copy when simviewer replaces the Simulation value): sets the counter, so that the next sphb_step does not run the
+ * step-0 initialisation (VPred = Vel, EPred = E, forces once; sph.go:89-103) again.  Upload VDOT / EDOT as well. */
+int sphb_set_current_step(sphb_sim* s, int64_t step);
 
 /* == append(sim.Root.Particles, spawned...) + MakeCells (sph.go:75-86).  Beyond the capacity the device arrays are
  * reallocated at twice the size (SPHB_E_NOMEM if that fails or 2^28-1 particles per device would be exceeded; the

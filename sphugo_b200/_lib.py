@@ -35,7 +35,7 @@ HALO_RECORD_DOUBLES, MIGRANT_RECORD_DOUBLES = 10, 12
 
 EXPORTS = [
     "sphb_create", "sphb_destroy", "sphb_last_error", "sphb_set_params", "sphb_get_params", "sphb_count",
-    "sphb_current_step", "sphb_append", "sphb_step", "sphb_calc_forces", "sphb_knn", "sphb_density", "sphb_stream", "sphb_sync",
+    "sphb_current_step", "sphb_set_current_step", "sphb_append", "sphb_step", "sphb_calc_forces", "sphb_knn", "sphb_density", "sphb_stream", "sphb_sync",
     "sphb_download", "sphb_upload", "sphb_upload_by_id", "sphb_reduce", "sphb_frame", "sphb_phase_times", "sphb_counters", "sphb_create_device",
     "sphb_slab_set", "sphb_max_h", "sphb_max_speed", "sphb_slab_step_begin", "sphb_slab_pack_halo", "sphb_slab_add_ghosts",
     "sphb_slab_step_end", "sphb_slab_pack_migrants", "sphb_slab_add_migrants", "sphb_slab_finish_migration",
@@ -108,6 +108,8 @@ def lib():
     L.sphb_count.argtypes = [vp]
     L.sphb_current_step.restype = C.c_int64
     L.sphb_current_step.argtypes = [vp]
+    L.sphb_set_current_step.restype = C.c_int
+    L.sphb_set_current_step.argtypes = [vp, C.c_int64]
     L.sphb_append.restype = C.c_int
     L.sphb_append.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp]
     L.sphb_step.restype = C.c_int

@@ -1133,6 +1133,12 @@ int sphb_get_params(const sphb_sim* s, sphb_params* p) {
 }
 int64_t sphb_count(const sphb_sim* s) { return s ? s->n : -1; }
 int64_t sphb_current_step(const sphb_sim* s) { return s ? s->cur_step : -1; }
+int sphb_set_current_step(sphb_sim* s, int64_t step) {
+  if (!s) return SPHB_E_INVALID;
+  if (step < 0) return fail(s, SPHB_E_INVALID, "negative step");
+  s->cur_step = step;
+  return SPHB_OK;
+}
 
 int sphb_append(sphb_sim* s, int64_t n, const double* pos_xy, const double* vel_xy, const double* e, const double* rho,
                 const int64_t* id) {

@@ -424,3 +424,27 @@ def test_split_upload_matches_the_serial_one():
         for f in ("pos", "vel", "e", "rho", "h"):
             assert np.array_equal(sa[f], sb[f]), (f, k)
     a.close(); b.close()
+
+
+def test_device_copy_made_in_the_middle_of_a_run():
+    """sphb_set_current_step: a handle created from the state of a simulation that has already stepped (what the Go shim
+    does when simviewer replaces the Simulation value) continues it without repeating the step-0 initialisation"""
+    pos = gen.jittered_lattice(48, 48)
+    n = len(pos)
+    kw = dict(hor=(0.0, 1.0), ver=(0.0, 1.0), accel=(0.0, 0.2), dt_half=0.002)
+    a = L.Handle(L.make_params(**kw), pos, None, np.full(n, 0.01))
+    a.step(2)
+    st = a.state(["pos", "vel", "e", "rho", "vdot", "edot", "id"])
+    b = L.Handle(L.make_params(**kw), st["pos"], st["vel"], st["e"], st["rho"], st["id"])
+    b.upload(vdot=st["vdot"], edot=st["edot"])  # (device order = creation order = id order here)
+    assert L.lib().sphb_set_current_step(b._h, 2) == 0 and b.current_step == 2
+    a.step(1); b.step(1)
+    sa, sb = a.state(["pos", "vel", "e", "rho", "h"]), b.state(["pos", "vel", "e", "rho", "h"])
+    for f in ("pos", "vel", "e", "rho", "h"):
+        assert U.rel_err(sb[f], sa[f], np.abs(sa[f]).max() * 1e-3) <= 1e-12, f
+    # without the counter the copy would start over: VPred = Vel and a force evaluation before the step
+    c = L.Handle(L.make_params(**kw), st["pos"], st["vel"], st["e"], st["rho"], st["id"])
+    c.upload(vdot=st["vdot"], edot=st["edot"])
+    c.step(1)
+    assert U.rel_err(c.state(["vel"])["vel"], sa["vel"], np.abs(sa["vel"]).max() * 1e-3) > 1e-9
+    a.close(); b.close(); c.close()
