@@ -322,7 +322,7 @@ def run_legs(args, device):
     for name, precs in (("c3p", (64, 32)), ("c3u", (64, 32)), ("c4", (64, 32)), ("c4dam", (64,))):
         for prec in precs:
             try:
-                legs.append(run_leg(name, prec, 20 if name.startswith("c3") else 10, 3, device))
+                legs.append(run_leg(name, prec, 20 if name.startswith("c3") else 10, 6, device))
             except Exception as ex:  # a leg must not take the headline line down with it
                 legs.append({"leg": name, "dtype": f"f{prec}", "error": str(ex)[:300]})
     # the headline workload with the certified list reuse switched on (SPHB_FLAG_REUSE_LISTS; off by default): long

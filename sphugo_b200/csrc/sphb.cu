@@ -549,7 +549,7 @@ void reuse_policy(sphb_sim* s, const ReuseFeedback& f) {
     // warp-wide ring search.  Measured on 2^20 i.i.d. particles: 12.9 % refused at 2 % / 47 (1.55 ms per step), 1.6 % at
     // 4 % / 56 (0.89 ms), 0.14 % at 6 % / 56 (0.85 ms); the jittered lattice of the same size pays 8 % for the wide search.
     if (!s->search_level_fixed) {
-      if (f.frac > 1e-2 && s->search_level < 2) { s->search_level += 1; s->search_calm = 0; }
+      if (f.frac > 1e-2 && s->search_level < 2) { s->search_level = f.frac > 5e-2 ? 2 : s->search_level + 1; s->search_calm = 0; }
       else if (f.frac < 2e-4) { if (++s->search_calm >= 16 && s->search_level > 0) { s->search_level -= 1; s->search_calm = 0; } }
       else s->search_calm = 0;
     }
