@@ -133,7 +133,11 @@ struct sphb_sim {
   uint32_t* nx = nullptr;     // further candidates [tile][SPHB_KX][lane]
   TileInfo* tinfo = nullptr;  // [tile]: extent of the staged block (npc = 0: none)
   uint2* ptab = nullptr;      // [tile][32]: its pieces
-  double* dexcl = nullptr;    // exclusion radius per particle (0: no slots)
+  double* dexcl = nullptr;    // exclusion radius per particle (0: no further candidates known)
+  float2* ucum = nullptr;     // cumulative displacement since the rebuild (local displacement bound)
+  float4* ubox = nullptr;     // its bounding box per coarse cell
+  int ubox_cap = 0;
+  uint32_t* ubox_ok = nullptr;
   ReuseState* rs = nullptr;   // device bookkeeping
   ReuseStat* stat_dev = nullptr;
   ReuseStat* stat_host = nullptr;  // pinned ring of REUSE_RING records (non-blocking feedback for the schedule)
@@ -153,6 +157,7 @@ struct sphb_sim {
   uint32_t stat_enq = 0, stat_seen = 0;  // records enqueued / read back
   cudaEvent_t stat_event = nullptr;      // recorded behind the last record's copy
   bool stat_event_valid = false;
+  bool reuse_local = true;               // SPHB_REUSE_LOCAL=0: certificates use the global displacement bound only
   bool reuse_abort = false;              // the policy ended the current cycle: the next evaluation rebuilds
   int search_level = 0, search_calm = 0; // width of the tile search (margin / column capacity), adapted from its refusals
   bool search_level_fixed = false;       // SPHB_GUESS_MARGIN / SPHB_KNN_CAP given
@@ -381,8 +386,9 @@ void launch_knn_reuse(sphb_sim* s, int ntot, const PhysP& ph) {
     attr_done[s->device & 63] = true;
   }
   const uint8_t* gf = s->slab_on ? s->a.ghost : nullptr;
-  if (f32) k_knn_reuse<KERNEL, true><<<cdiv(ntot, REUSE_THREADS), REUSE_THREADS, smem, s->st>>>(s->spos, s->a.epred, ntot, s->grid, ph, out, s->nx, s->dexcl, s->rs, gf, s->dflags);
-  else k_knn_reuse<KERNEL, false><<<cdiv(ntot, REUSE_THREADS), REUSE_THREADS, smem, s->st>>>(s->spos, s->a.epred, ntot, s->grid, ph, out, s->nx, s->dexcl, s->rs, gf, s->dflags);
+  const float2* uc = (s->slab_on || !s->reuse_local) ? nullptr : s->ucum;  // (a ring has no displacement sums for its ghosts)
+  if (f32) k_knn_reuse<KERNEL, true><<<cdiv(ntot, REUSE_THREADS), REUSE_THREADS, smem, s->st>>>(s->spos, s->a.epred, ntot, s->grid, ph, out, s->nx, s->dexcl, s->rs, gf, s->dflags, s->keysSorted, uc, s->ubox, s->ubox_ok);
+  else k_knn_reuse<KERNEL, false><<<cdiv(ntot, REUSE_THREADS), REUSE_THREADS, smem, s->st>>>(s->spos, s->a.epred, ntot, s->grid, ph, out, s->nx, s->dexcl, s->rs, gf, s->dflags, s->keysSorted, uc, s->ubox, s->ubox_ok);
   FbExt fx{s->dexcl, s->rs};
   k_knn_fallback<KERNEL, true><<<148 * 4, 128, 0, s->st>>>(s->spos, s->keysSorted, s->cellStart, s->hguess,
                                                          s->a.epred, ntot, s->grid, ph, out, gf, s->dflags, fx);
@@ -429,6 +435,7 @@ void launch_force(sphb_sim* s, int ntot, const PhysP& ph, bool integrate) {
   io.next_grid = s->fuse_keys ? s->grid_next : nullptr;
   io.next_keys = s->keys; io.next_rank = s->rank; io.next_count = s->cellCount;
   io.rs = s->force_rs; io.stale = s->force_stale ? s->rs : nullptr;
+  io.ucum = (s->force_rs && !s->slab_on && s->reuse_local) ? s->ucum : nullptr; io.ucum_reset = s->force_stale ? 0 : 1;
   if (integrate && !(s->slab_on && s->force_stale)) cudaMemsetAsync(s->qmax + 1, 0, sizeof(uint32_t), s->st);  // max |v|^2 after this kick (ring: of the cycle)
   io.pos = s->a.pos; io.vel = s->a.vel; io.e = s->a.e; io.vdot = s->a.vdot; io.edot = s->a.edot;
   if (!s->slab_on) {
@@ -599,7 +606,7 @@ void reuse_plan(sphb_sim* s, bool lists_ok, bool& reuse, bool& next_reuse) {
   const int amax = s->reuse_period_max;
   reuse = lists_ok && !s->reuse_abort && s->reuse_age + 1 < amax && reuse_budget_ok(s, s->fb_D);
   if (lists_ok && !reuse && !s->reuse_abort && s->reuse_age > 0 && s->fb_last_frac < 1.5e-3)  // the budget ended a clean cycle
-    s->reuse_kappa = std::min(0.9, s->reuse_kappa + 0.05);
+    s->reuse_kappa = std::min(s->reuse_local && !s->slab_on ? 2.5 : 0.9, s->reuse_kappa + (s->reuse_local && !s->slab_on ? 0.15 : 0.05));
   s->reuse_abort = false;
   // next evaluation: the bound grows by about what it grew last time
   const double growth = s->fb_D - s->fb_D_prev;
@@ -706,6 +713,10 @@ int forces_plan(sphb_sim* s, int mode, bool integrate, const EvalPlan& plan) {
   if (s->prm.kernel == 1) launch_force<1>(s, ntot, ph, integrate);
   else launch_force<2>(s, ntot, ph, integrate);
   s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 1;
+  if (s->force_rs && !s->slab_on && s->reuse_local) {  // bounding boxes of the cumulative displacements (local bound)
+    k_ucum_bbox<<<148 * 4, 256, 0, s->st>>>(s->ucum, s->cellStart, s->grid, s->ubox, s->ubox_cap, s->ubox_ok);
+    s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 1;
+  }
   if (!plan.defer_update && (s->force_rs || reuse || plan.record)) launch_reuse_update(s, ntot, !reuse);  // (outside a cycle: for the record only)
   const bool keep = next_reuse && s->lists_ext;
   if (!keep) invalidate_reuse(s);  // the cycle ends here
@@ -854,6 +865,11 @@ int create_common(const sphb_params* p, int64_t n, int64_t capacity, const doubl
   CKC(dalloc(s->tinfo, cap32 / 32 + 1));
   CKC(dalloc(s->ptab, cap32 + 32));
   CKC(dalloc(s->dexcl, cap));
+  CKC(dalloc(s->ucum, cap));
+  s->ubox_cap = (int)(ncm / 8 + 1024);
+  CKC(dalloc(s->ubox, (size_t)s->ubox_cap));
+  CKC(dalloc(s->ubox_ok, 1));
+  CKC(cudaMemsetAsync(s->ubox_ok, 0, sizeof(uint32_t), s->st));
   CKC(dalloc(s->rs, 1));
   CKC(cudaMemsetAsync(s->rs, 0, sizeof(ReuseState), s->st));
   CKC(dalloc(s->stat_dev, 1));
@@ -893,6 +909,8 @@ int create_common(const sphb_params* p, int64_t n, int64_t capacity, const doubl
   s->ktune.ncw0 = 512;
   s->reuse_on = (p->flags & SPHB_FLAG_REUSE_LISTS) != 0;
   if (const char* ev = getenv("SPHB_NO_RECORD")) s->no_record = atoi(ev) != 0;
+  if (const char* ev = getenv("SPHB_REUSE_LOCAL")) s->reuse_local = atoi(ev) != 0;
+  if (const char* ev = getenv("SPHB_REUSE_KAPPA")) s->reuse_kappa = atof(ev);
   if (const char* ev = getenv("SPHB_REUSE_PERIOD")) { s->reuse_period_fixed = std::max(1, std::min(64, atoi(ev))); s->reuse_on = true; }
   if (const char* ev = getenv("SPHB_REUSE")) s->reuse_on = atoi(ev) != 0;
   if (const char* ev = getenv("SPHB_REUSE_MAX")) s->reuse_period_max = std::max(1, std::min(64, atoi(ev)));
@@ -928,10 +946,12 @@ struct CapArrays {
   TileInfo* tinfo = nullptr;
   uint2* ptab = nullptr;
   double* dexcl = nullptr;
+  float2* ucum = nullptr;
+  float4* ubox = nullptr;
   int* failList = nullptr;
   void release() {
     free_soa(a); free_soa(b);
-    cudaFree(nx); cudaFree(tinfo); cudaFree(ptab); cudaFree(dexcl);
+    cudaFree(nx); cudaFree(tinfo); cudaFree(ptab); cudaFree(dexcl); cudaFree(ucum); cudaFree(ubox);
     cudaFree(spos); cudaFree(hguess); cudaFree(keys); cudaFree(keysSorted); cudaFree(rank); cudaFree(perm);
     cudaFree(cellStart); cudaFree(cellCount); cudaFree(tileSum); cudaFree(nn); cudaFree(failList);
     *this = CapArrays{};
@@ -972,6 +992,8 @@ int grow_capacity(sphb_sim* s, int64_t need) {
   CKG(dalloc(t.tinfo, cap32 / 32 + 1));
   CKG(dalloc(t.ptab, cap32 + 32));
   CKG(dalloc(t.dexcl, cap));
+  CKG(dalloc(t.ucum, cap));
+  CKG(dalloc(t.ubox, (size_t)(ncm / 8 + 1024)));
   CKG(dalloc(t.failList, cap));
   const size_t n = (size_t)s->n;
   const cudaMemcpyKind dd = cudaMemcpyDeviceToDevice;
@@ -992,10 +1014,10 @@ int grow_capacity(sphb_sim* s, int64_t need) {
   CapArrays old;
   old.a = s->a; old.b = s->b; old.spos = s->spos; old.hguess = s->hguess; old.keys = s->keys; old.keysSorted = s->keysSorted;
   old.rank = s->rank; old.perm = s->perm; old.cellStart = s->cellStart; old.cellCount = s->cellCount; old.tileSum = s->tileSum;
-  old.nn = s->nn; old.failList = s->failList; old.nx = s->nx; old.tinfo = s->tinfo; old.ptab = s->ptab; old.dexcl = s->dexcl;
+  old.nn = s->nn; old.failList = s->failList; old.nx = s->nx; old.tinfo = s->tinfo; old.ptab = s->ptab; old.dexcl = s->dexcl; old.ucum = s->ucum; old.ubox = s->ubox;
   s->a = t.a; s->b = t.b; s->spos = t.spos; s->hguess = t.hguess; s->keys = t.keys; s->keysSorted = t.keysSorted;
   s->rank = t.rank; s->perm = t.perm; s->cellStart = t.cellStart; s->cellCount = t.cellCount; s->tileSum = t.tileSum;
-  s->nn = t.nn; s->failList = t.failList; s->nx = t.nx; s->tinfo = t.tinfo; s->ptab = t.ptab; s->dexcl = t.dexcl;
+  s->nn = t.nn; s->failList = t.failList; s->nx = t.nx; s->tinfo = t.tinfo; s->ptab = t.ptab; s->dexcl = t.dexcl; s->ucum = t.ucum; s->ubox = t.ubox; s->ubox_cap = (int)(ncm / 8 + 1024);
   old.release();
   invalidate_reuse(s);
   cudaFree(s->ring.inv); s->ring.inv = nullptr; s->ring.inv_cap = 0;
@@ -1099,6 +1121,7 @@ void sphb_destroy(sphb_sim* s) {
   cudaFree(s->cellCount); cudaFree(s->tileSum); cudaFree(s->cellStart); cudaFree(s->nn); cudaFree(s->failList); cudaFree(s->failCount);
   cudaFree(s->packCount); cudaFree(s->hacc); cudaFree(s->qmax);
   cudaFree(s->nx); cudaFree(s->tinfo); cudaFree(s->ptab); cudaFree(s->dexcl); cudaFree(s->rs); cudaFree(s->stat_dev);
+  cudaFree(s->ucum); cudaFree(s->ubox); cudaFree(s->ubox_ok);
   if (s->stat_host) cudaFreeHost(s->stat_host);
   if (s->stat_event_valid) cudaEventDestroy(s->stat_event);
   if (s->st_copy) { cudaStreamSynchronize(s->st_copy); cudaStreamDestroy(s->st_copy); }

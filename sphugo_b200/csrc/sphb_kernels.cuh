@@ -1189,6 +1189,8 @@ struct ForceIO {
   // table is the last rebuild's, so the staging lookups are shifted back by the mean displacement and widened by D
   ReuseState* rs;
   const ReuseState* stale;
+  float2* ucum;     // with rs: cumulative displacement of every particle since the rebuild (local displacement bound)
+  int ucum_reset;   // this evaluation is the rebuild: the sum starts here
 };
 
 // -------------------------------------------------------------------------------------------------
@@ -1574,6 +1576,11 @@ __device__ __forceinline__ void force_block(const ForceIO& io, int n, const Grid
       const double sc = 1048576.0 * g.inv_dy;  // fixed point: 2^-20 of a cell row (k_reuse_update divides by the same)
       const int qx = (int)fmin(fmax(rint(ddx * sc), -1048576.0), 1048576.0), qy = (int)fmin(fmax(rint(ddy * sc), -1048576.0), 1048576.0);
       const int sx_ = __reduce_add_sync(m, qx), sy_ = __reduce_add_sync(m, qy);
+      if (io.ucum) {
+        float2 u = io.ucum_reset ? make_float2(0.0f, 0.0f) : io.ucum[i];
+        u.x += (float)ddx; u.y += (float)ddy;
+        io.ucum[i] = u;
+      }
       if ((threadIdx.x & 31) == (__ffs(m) - 1)) {
         atomicMax(&io.rs->Mbits, dm);
         long long* a = io.rs->sum[blockIdx.x & (RS_SLOTS - 1)];

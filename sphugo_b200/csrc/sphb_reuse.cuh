@@ -223,6 +223,88 @@ __global__ void __launch_bounds__(KNN_THREADS) k_knn_annulus(const double2* __re
 }
 
 // -------------------------------------------------------------------------------------------------
+// Local displacement bound.  The global D is set by the fastest of all particles; what the certificate of particle i
+// needs is a bound on |u_i - u_j| for the particles j that can reach it.  The cells of the rebuild's grid are grouped
+// into coarse cells of 3 rows x (>= 3 rows' worth of) columns; after every step of a cycle k_ucum_bbox takes the bounding
+// box of the cumulative displacements u of the particles of each coarse cell (by their cell at the rebuild: the sorted
+// order does not change).  For particle i, L_i = largest distance from u_i to a corner of the union of the 3 x 3 boxes
+// around its coarse cell bounds |u_i - u_j| for every j of that block; a particle outside the block was at least one
+// coarse cell edge E away at the rebuild and has come closer by at most the global D.  So the certificate may use
+// L_i instead of D whenever  E - D > h'.  (u is accumulated in fp32: the rounding, < 64 x 2^-24 of |u| over a cycle, is
+// added to L_i.)
+// -------------------------------------------------------------------------------------------------
+// the fine cells of an axis are dealt out evenly: coarse index = (fine index x ng) / nc, so that EVERY coarse cell is
+// at least floor(nc / ng) fine cells wide (a wrapping block must not have a narrow last cell on one side)
+struct CoarseGeom { int ngx, ngy; double edge; };
+__device__ __forceinline__ CoarseGeom coarse_geom(const GridP& g) {
+  CoarseGeom c;
+  const int fy = 3, fx = max(1, (int)ceil(3.0 * g.dy * g.inv_dx));
+  c.ngx = max(1, g.ncx / fx); c.ngy = max(1, g.ncy / fy);
+  c.edge = fmin((double)(g.ncx / c.ngx) * g.dx, (double)(g.ncy / c.ngy) * g.dy);
+  return c;
+}
+__device__ __forceinline__ int coarse_of(int fine, int nc, int ng) { return (int)(((long long)fine * ng) / nc); }
+__device__ __forceinline__ int coarse_first(int coarse, int nc, int ng) { return (int)(((long long)coarse * nc + ng - 1) / ng); }
+
+// one warp per coarse cell (grid-stride): box[cell] = {min ux, max ux, min uy, max uy}; an empty cell gets an empty box
+__global__ void __launch_bounds__(256) k_ucum_bbox(const float2* __restrict__ ucum, const uint32_t* __restrict__ cellStart,
+                                                  const GridP* __restrict__ gp, float4* __restrict__ box, int box_cap,
+                                                  uint32_t* __restrict__ ok_flag) {
+  const GridP g = *gp;
+  const CoarseGeom c = coarse_geom(g);
+  const int ncoarse = c.ngx * c.ngy;
+  const int lane = threadIdx.x & 31;
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  if (gwarp == 0 && lane == 0) *ok_flag = (ncoarse <= box_cap && c.ngx >= 3 && c.ngy >= 3) ? 1u : 0u;
+  if (ncoarse > box_cap) return;
+  for (int cc = gwarp; cc < ncoarse; cc += nwarps) {
+    const int gy = cc / c.ngx, gx = cc - gy * c.ngx;
+    const int x0 = coarse_first(gx, g.ncx, c.ngx), x1 = coarse_first(gx + 1, g.ncx, c.ngx) - 1;
+    float mnx = 3e38f, mxx = -3e38f, mny = 3e38f, mxy = -3e38f;
+    for (int r = coarse_first(gy, g.ncy, c.ngy); r < coarse_first(gy + 1, g.ncy, c.ngy); ++r) {
+      const int s = (int)cellStart[r * g.ncx + x0], e = (int)cellStart[r * g.ncx + x1 + 1];
+      for (int t = s + lane; t < e; t += 32) {
+        const float2 u = ucum[t];
+        mnx = fminf(mnx, u.x); mxx = fmaxf(mxx, u.x); mny = fminf(mny, u.y); mxy = fmaxf(mxy, u.y);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+      mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o)); mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+    }
+    if (lane == 0) box[cc] = make_float4(mnx, mxx, mny, mxy);
+  }
+}
+
+// L_i (see above) for the particle with cell key `key` and cumulative displacement u; 1.8e308 if not applicable
+__device__ __forceinline__ double reuse_local_bound(const GridP& g, uint32_t key, float2 u, const float4* __restrict__ box,
+                                                    double& edge) {
+  const CoarseGeom c = coarse_geom(g);
+  edge = c.edge;
+  const int cy = (int)(key / (uint32_t)g.ncx), cx = (int)(key - (uint32_t)cy * (uint32_t)g.ncx);
+  const int gx = coarse_of(cx, g.ncx, c.ngx), gy = coarse_of(cy, g.ncy, c.ngy);
+  float mnx = u.x, mxx = u.x, mny = u.y, mxy = u.y;
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy) {
+    int y = gy + dy;
+    if (g.wrapy) y = y < 0 ? y + c.ngy : (y >= c.ngy ? y - c.ngy : y);
+    else if (y < 0 || y >= c.ngy) continue;
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      int x = gx + dx;
+      if (g.wrapx) x = x < 0 ? x + c.ngx : (x >= c.ngx ? x - c.ngx : x);
+      else if (x < 0 || x >= c.ngx) continue;
+      const float4 b = __ldg(&box[y * c.ngx + x]);
+      mnx = fminf(mnx, b.x); mxx = fmaxf(mxx, b.y); mny = fminf(mny, b.z); mxy = fmaxf(mxy, b.w);
+    }
+  }
+  const double ex = fmax((double)u.x - (double)mnx, (double)mxx - (double)u.x), ey = fmax((double)u.y - (double)mny, (double)mxy - (double)u.y);
+  const double umax = fmax(fmax(fabs((double)mnx), fabs((double)mxx)), fmax(fabs((double)mny), fabs((double)mxy)));
+  return sqrt(ex * ex + ey * ey) * (1.0 + 1e-6) + 1.6e-5 * umax;
+}
+
+// -------------------------------------------------------------------------------------------------
 // exact kNN(32) from the stored candidates.  One thread per particle; slots 0..31 (nn) hold the neighbours of the
 // previous evaluation, slots 32..47 (nx) the further candidates.  Pass 1 evaluates d^2 of every candidate exactly as the
 // reference does ((p + offset) - b, nearest periodic image; linear-algebra.go:61-64) into a shared-memory column and
@@ -245,7 +327,9 @@ __global__ void __launch_bounds__(REUSE_THREADS) k_knn_reuse(const double2* __re
                                                             int n, const GridP* __restrict__ gp, PhysP ph, KnnOut out,
                                                             uint32_t* __restrict__ nx, const double* __restrict__ dexcl,
                                                             const ReuseState* __restrict__ rs,
-                                                            const uint8_t* __restrict__ gflag, uint32_t* __restrict__ dflags) {
+                                                            const uint8_t* __restrict__ gflag, uint32_t* __restrict__ dflags,
+                                                            const uint32_t* __restrict__ keys, const float2* __restrict__ ucum,
+                                                            const float4* __restrict__ ubox, const uint32_t* __restrict__ ubox_ok) {
   typedef typename std::conditional<F32, float, double>::type TD;
   extern __shared__ __align__(16) unsigned char rsm[];
   TD* dcol = reinterpret_cast<TD*>(rsm) + threadIdx.x;  // [slot * REUSE_THREADS]
@@ -389,7 +473,13 @@ __global__ void __launch_bounds__(REUSE_THREADS) k_knn_reuse(const double2* __re
   double h = 0.0;
   if (ok) {
     h = F32 ? (double)sqrtf((float)h2) * 1.0000002 : sqrt((double)h2);
-    if (!((h + D) * (1.0 + 1e-12) < dex)) ok = false;
+    double Di = D;
+    if (ucum && *ubox_ok) {  // local displacement bound, where a particle from beyond the 3 x 3 block cannot reach h
+      double edge;
+      const double Li = reuse_local_bound(g, keys[i], ucum[i], ubox, edge);
+      if (edge - D > h * (1.0 + 1e-9)) Di = fmin(D, Li);
+    }
+    if (!((h + Di) * (1.0 + 1e-12) < dex)) ok = false;
   }
   if (valid && !ok) {
     const int slot = atomicAdd(out.failCount, 1);
