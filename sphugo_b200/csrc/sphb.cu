@@ -157,7 +157,8 @@ struct sphb_sim {
   uint32_t stat_enq = 0, stat_seen = 0;  // records enqueued / read back
   cudaEvent_t stat_event = nullptr;      // recorded behind the last record's copy
   bool stat_event_valid = false;
-  bool reuse_local = true;               // SPHB_REUSE_LOCAL=0: certificates use the global displacement bound only
+  bool reuse_local = false;              // SPHB_REUSE_LOCAL=1: certificates may use the local displacement bound (measured: the
+                                         // cycles get 40 % longer, the bookkeeping costs as much - sphb_reuse.cuh)
   bool reuse_abort = false;              // the policy ended the current cycle: the next evaluation rebuilds
   int search_level = 0, search_calm = 0; // width of the tile search (margin / column capacity), adapted from its refusals
   bool search_level_fixed = false;       // SPHB_GUESS_MARGIN / SPHB_KNN_CAP given

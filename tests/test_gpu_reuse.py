@@ -140,6 +140,15 @@ def test_reuse_tiny_periodic_box_multi_image():
     _cycle_case(pos, steps=6, period=3, hor=(0.0, 1.0), ver=(0.0, 1.0), dt_half=0.002, check_oracle=False)
 
 
+def test_reuse_with_the_local_displacement_bound():
+    """SPHB_REUSE_LOCAL=1: certificates use the bound from the 3 x 3 block of coarse cells; long cycle, every step exact"""
+    n = 96
+    with env(SPHB_REUSE_LOCAL=1):
+        _cycle_case(gen.jittered_lattice(n, n), steps=14, period=12, hor=(0.0, 1.0), ver=(0.0, 1.0), accel=(0.0, 0.2),
+                    dt_half=0.98 / n, check_oracle=False)
+        _cycle_case(gen.spawn([(3000, (0, 0), (1, 1))])["pos"], steps=7, period=5, accel=(0.0, 0.2), dt_half=0.002, check_oracle=False)
+
+
 def test_reuse_fp32_build():
     n = 96
     _cycle_case(gen.jittered_lattice(n, n), steps=9, period=5, precision=32, hor=(0.0, 1.0), ver=(0.0, 1.0),
