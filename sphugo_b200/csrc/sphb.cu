@@ -62,6 +62,7 @@ struct RingState {
   int64_t inv_cap = 0;
   int64_t nsend[2] = {0, 0}, nrecv[2] = {0, 0}, ghost0 = 0;
   double* red_dev = nullptr;             // small device scratch of the host all-reduces
+  struct RingMsg* msg = nullptr;         // device block of the single-wait rebuild (sphb_ring.cuh)
   int* refused_host = nullptr;           // pinned
   void* comm = nullptr;                  // ncclComm_t
   int comm_rank = 0, comm_size = 1;
@@ -1130,7 +1131,7 @@ void sphb_destroy(sphb_sim* s) {
   if (s->up_free) cudaEventDestroy(s->up_free);
   cudaFree(s->up_stage);
   for (int side = 0; side < 2; ++side) { cudaFree(s->ring.sbuf[side]); cudaFree(s->ring.rbuf[side]); cudaFree(s->ring.sidx[side]); cudaFree(s->ring.hsrc[side]); }
-  cudaFree(s->ring.inv); cudaFree(s->ring.red_dev);
+  cudaFree(s->ring.inv); cudaFree(s->ring.red_dev); cudaFree(s->ring.msg);
   if (s->ring.refused_host) cudaFreeHost(s->ring.refused_host);
   if (s->ring.comm) ring_comm_destroy(s);
   cudaFree(s->dflags); cudaFree(s->statPart); cudaFree(s->stats); cudaFree(s->grid); cudaFree(s->grid_next); cudaFree(s->scratch);

@@ -62,3 +62,28 @@ __global__ void __launch_bounds__(256) k_gather_list(const T* __restrict__ in, c
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k < count) out[k] = in[list[k]];
 }
+
+// the device-side half of a rebuild's single host round trip: {max h, max |v|} for the max all-reduce, {refused, n,
+// row height x n} for the sum all-reduce, the two pack counts for the neighbours, the status word - gathered into one
+// block so that ONE copy and ONE wait bring everything to the host after the NCCL group
+struct RingMsg {
+  double vmax[2];      // in / out of the max all-reduce
+  double vsum[3];      // in / out of the sum all-reduce
+  int cnt_out[2];      // records packed for the low / high neighbour
+  int cnt_in[2];       // records the left / right neighbour packed for this rank (ncclRecv)
+  unsigned dflags;
+  int pad;
+};
+__global__ void k_ring_msg(RingMsg* __restrict__ m, const uint32_t* __restrict__ qmax, int qmax_valid, const int* __restrict__ failCount,
+                           int pending, int n, const GridP* __restrict__ gp, const int* __restrict__ packCount,
+                           const uint32_t* __restrict__ dflags) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  m->vmax[0] = qmax_valid ? (double)__uint_as_float(qmax[0]) : 0.0;
+  m->vmax[1] = qmax_valid ? sqrt((double)__uint_as_float(qmax[1])) * (1.0 + 1e-7) : 0.0;
+  m->vsum[0] = pending ? (double)failCount[0] : 0.0;
+  m->vsum[1] = (double)n;
+  m->vsum[2] = pending ? gp->dy * (double)n : 0.0;
+  m->cnt_out[0] = packCount[0]; m->cnt_out[1] = packCount[1];
+  m->cnt_in[0] = 0; m->cnt_in[1] = 0;
+  m->dflags = *dflags;
+}
