@@ -1287,7 +1287,8 @@ __device__ __forceinline__ NbrRec<R> make_rec(const ForceIO& io, const GridP& g,
 template <typename R> struct OwnRec { R x, y, xl, yl, vx, vy, rhoh, cs, hh, P, inv_h; };  // (xl, yl): fp32 residual of (x, y)
 
 // one pair of AccelerationAndEDot2D (sph.go:357-397): adds to (ax, ay, aed); sel = 0 discards the pair
-template <int KERNEL, typename R>
+// RAW: the neighbour's {rhoh, cs, hh} hold rho, c, h as stored (bulk-staged records): the scaling rides on the additions
+template <int KERNEL, typename R, bool RAW = false>
 __device__ __forceinline__ void pair_term(const OwnRec<R>& o, const NbrRec<R>& b, bool sel, R& ax, R& ay, R& aed) {
   R rx = b.x - o.x, ry = b.y - o.y;
   if (sizeof(R) == 4) { rx -= o.xl; ry -= o.yl; }  // own position to full precision: only the neighbour's rounding is left
@@ -1300,7 +1301,9 @@ __device__ __forceinline__ void pair_term(const OwnRec<R>& o, const NbrRec<R>& b
   R dk = kern_DF_r<KERNEL, R>(q);
   // artificial viscosity, sph.go:375-388: mu = vr hAB / (r^2 + eta^2), Pi = (-alpha cAB mu + beta mu^2) / rhoAB for
   // approaching pairs (vr < 0): min(vr, 0) makes mu, hence Pi, vanish otherwise
-  const R cs = o.cs + b.cs, rs = o.rhoh + b.rhoh, hs = o.hh + b.hh;  // -0.75 cAB, rhoAB, hAB
+  R cs, rs, hs;  // -0.75 cAB, rhoAB, hAB
+  if (RAW) { cs = fma(R(-0.375), b.cs, o.cs); rs = fma(R(0.5), b.rhoh, o.rhoh); hs = fma(R(0.5), b.hh, o.hh); }
+  else { cs = o.cs + b.cs; rs = o.rhoh + b.rhoh; hs = o.hh + b.hh; }
   const R den = r2 + R(0.01);
   const R dneg = fmin(dot, R(0.0));
   R mu, pi;
@@ -1320,16 +1323,52 @@ __device__ __forceinline__ void pair_term(const OwnRec<R>& o, const NbrRec<R>& b
   aed = fma(dot, dk, aed);
 }
 
+// ---- bulk-copy staging of the fp64 build (cp.async.bulk, the 1-D TMA path: SASS UBLKCP) -------------------------------
+// One elected thread per piece copies the piece's rows of spos / vpred / pc straight from global into shared memory; the
+// copy engine signals an mbarrier with the byte count.  The records land RAW ({x, y}, {vx, vy}, {rho, c, h, P}); the pair
+// loop folds rho/2, -0.375 c, h/2 into its additions (pair_term<RAW>), so a block away from the periodic seam never
+// touches the staged bytes: no staging loop, no second barrier.  Seam blocks (and slab mode, for the thin-ghost marker)
+// patch the positions of image pieces in place.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// record layout of the bulk-staged area: nrec x {x, y}, nrec x {vx, vy}, nrec x {rho, c, h, P} (32 bytes each, as stored)
+__device__ __forceinline__ NbrRec<double> load_rec_bulk(const double2* __restrict__ sm, int nrec, int sl) {
+  const double2 a = sm[sl], b = sm[nrec + sl], c = sm[2 * nrec + 2 * sl], d = sm[2 * nrec + 2 * sl + 1];
+  return NbrRec<double>{a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+}
+
 struct ForceSt {           // block tables of the staged kernel
   int cls_s[FORCE_NCLS], cls_e[FORCE_NCLS], cls_cmin[FORCE_NCLS], cls_cmax[FORCE_NCLS];
   uint32_t stc[FORCE_NPIECE];           // piece keys (code << 28 | start), ascending; unused = 0xffffffff
   uint2 tab[FORCE_NPIECE + 1];          // [t] = {key - staged offset, key + length} of piece t - 1; [0] = {0, 0}: "not staged"
   int p_s[FORCE_NPIECE], p_len[FORCE_NPIECE], p_off[FORCE_NPIECE], p_code[FORCE_NPIECE];
   int np;
+  int fix;  // bulk staging: some piece is a periodic image (its positions need the shift)
 };
 
 // the 32 pair interactions of one particle; NP = number of staged pieces the lookup distinguishes
-template <int KERNEL, bool SLAB, typename R, int NP>
+template <int KERNEL, bool SLAB, typename R, int NP, bool BULK>
 __device__ __forceinline__ void force_pairs(const ForceIO& io, int n, const GridP& g, const ForceSt& T,
                                             const typename RealV<R>::T* __restrict__ sm, int nrec, int i,
                                             const OwnRec<R>& own, const double4& ref, const uint32_t (&ent0)[8],
@@ -1362,9 +1401,11 @@ __device__ __forceinline__ void force_pairs(const ForceIO& io, int n, const Grid
       const bool hit = ent < de.y;
       const int sl = hit ? (int)(ent - de.x) : 0;
       allhit = allhit && hit;
-      const NbrRec<R> b = load_rec(sm, nrec, sl);
+      NbrRec<R> b;
+      if constexpr (BULK) b = load_rec_bulk(sm, nrec, sl);
+      else b = load_rec(sm, nrec, sl);
       if (SLAB) thin |= hit && b.rhoh < R(0.0);
-      pair_term<KERNEL, R>(own, b, hit, ax, ay, aed);
+      pair_term<KERNEL, R, BULK>(own, b, hit, ax, ay, aed);
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) cur[u] = nxt[u];
@@ -1391,8 +1432,10 @@ __device__ __forceinline__ void force_block(const ForceIO& io, int n, const Grid
                                             int nrec, uint32_t* __restrict__ dflags) {
   typedef typename RealV<R>::T RV;
   constexpr bool F32 = sizeof(R) == 4;
+  constexpr bool BULK = !F32;  // the fp32 build converts while it stages, so its records cannot be byte copies
   const GridP g = *gp;
   __shared__ ForceSt T;
+  __shared__ __align__(8) unsigned long long stage_bar;
   extern __shared__ __align__(16) unsigned char fsm[];
   RV* sm = reinterpret_cast<RV*>(fsm);  // RealV<R>::N arrays of nrec vectors
   const int tid = threadIdx.x, lane = tid & 31;
@@ -1400,6 +1443,7 @@ __device__ __forceinline__ void force_block(const ForceIO& io, int n, const Grid
   const int i = i0 + tid;
   const bool active = i < n && (!SLAB || io.gflag[i] == GF_OWNED);
   if (tid < FORCE_NCLS) { T.cls_s[tid] = 0x7fffffff; T.cls_e[tid] = 0; T.cls_cmin[tid] = FORCE_CODE_MIXED; T.cls_cmax[tid] = 0; }
+  if (BULK && tid == 0) mbar_init(&stage_bar, 1);
   __syncthreads();
 
   double2 pa = make_double2(0.0, 0.0), va = make_double2(0.0, 0.0);
@@ -1491,7 +1535,19 @@ __device__ __forceinline__ void force_block(const ForceIO& io, int n, const Grid
       T.p_s[rk] = s; T.p_len[rk] = len; T.p_off[rk] = off; T.p_code[rk] = code;
     }
     if (lane >= np && lane < FORCE_NPIECE) { T.stc[lane] = 0xffffffffu; T.tab[lane + 1] = make_uint2(0u, 0u); }
-    if (lane == 0) { T.tab[0] = make_uint2(0u, 0u); T.np = np; }
+    const uint32_t shm = __ballot_sync(0xffffffffu, v && code != 5);
+    if (lane == 0) { T.tab[0] = make_uint2(0u, 0u); T.np = np; T.fix = shm != 0u; }
+    if constexpr (BULK) {  // the copies are in flight while the block meets at the barrier below
+      const uint32_t tot = __reduce_add_sync(0xffffffffu, v ? (uint32_t)len : 0u);
+      if (lane == 0) mbar_expect_tx(&stage_bar, tot * 64u);
+      __syncwarp();
+      if (v) {
+        double2* smb = reinterpret_cast<double2*>(fsm);
+        bulk_g2s(smb + off, io.spos + s, (uint32_t)len * 16u, &stage_bar);
+        bulk_g2s(smb + nrec + off, io.vpred + s, (uint32_t)len * 16u, &stage_bar);
+        bulk_g2s(smb + 2 * nrec + 2 * off, io.pc + s, (uint32_t)len * 32u, &stage_bar);
+      }
+    }
   }
   __syncthreads();
   // block-local origin of the fp32 frame: position and predicted velocity of the middle particle of the block
@@ -1502,12 +1558,29 @@ __device__ __forceinline__ void force_block(const ForceIO& io, int n, const Grid
     ref = make_double4(pr.x, pr.y, vr.x, vr.y);
   }
   const int np = T.np;
-  for (int m = 0; m < np; ++m) {  // stage (coalesced)
-    const int s = T.p_s[m], len = T.p_len[m], off = T.p_off[m], code = T.p_code[m];
-    for (int t = tid; t < len; t += FORCE_THREADS)
-      store_rec(sm, nrec, off + t, make_rec<R, SLAB>(io, g, s + t, code, ref));
+  if constexpr (BULK) {
+    mbar_wait(&stage_bar, 0u);  // every thread waits for the bytes itself: no block barrier unless something is patched
+    if (SLAB || T.fix) {
+      double2* smb = reinterpret_cast<double2*>(fsm);
+      for (int m = 0; m < np; ++m) {
+        const int s = T.p_s[m], len = T.p_len[m], off = T.p_off[m], code = T.p_code[m];
+        const bool shifted = code != 5;
+        const double sx = (double)((code >> 2) - 1) * g.Lx, sy = (double)((code & 3) - 1) * g.Ly;
+        for (int t = tid; t < len; t += FORCE_THREADS) {
+          if (SLAB && io.gflag[s + t] == GF_OUTER) smb[2 * nrec + 2 * (off + t)].x = -1.0;  // its rho, c, h were not evaluated
+          if (shifted) { double2 pp = smb[off + t]; pp.x += sx; pp.y += sy; smb[off + t] = pp; }
+        }
+      }
+      __syncthreads();
+    }
+  } else {
+    for (int m = 0; m < np; ++m) {  // stage (coalesced)
+      const int s = T.p_s[m], len = T.p_len[m], off = T.p_off[m], code = T.p_code[m];
+      for (int t = tid; t < len; t += FORCE_THREADS)
+        store_rec(sm, nrec, off + t, make_rec<R, SLAB>(io, g, s + t, code, ref));
+    }
+    __syncthreads();
   }
-  __syncthreads();
   if (!active) return;
 
   OwnRec<R> own;
@@ -1518,8 +1591,8 @@ __device__ __forceinline__ void force_block(const ForceIO& io, int n, const Grid
   own.inv_h = pair_rcp((R)qa.z);
   R ax = R(0.0), ay = R(0.0), aed = R(0.0);
   bool thin = false;
-  if (np <= 3) force_pairs<KERNEL, SLAB, R, 3>(io, n, g, T, sm, nrec, i, own, ref, ent0, ax, ay, aed, thin);
-  else force_pairs<KERNEL, SLAB, R, FORCE_NPIECE>(io, n, g, T, sm, nrec, i, own, ref, ent0, ax, ay, aed, thin);
+  if (np <= 3) force_pairs<KERNEL, SLAB, R, 3, BULK>(io, n, g, T, sm, nrec, i, own, ref, ent0, ax, ay, aed, thin);
+  else force_pairs<KERNEL, SLAB, R, FORCE_NPIECE, BULK>(io, n, g, T, sm, nrec, i, own, ref, ent0, ax, ay, aed, thin);
   if (SLAB && thin) atomicOr(dflags, DFLAG_GHOST_THIN);
   const double h = qa.z;
   const double f = ph.mass * ph.DFpref / (h * h * h);
