@@ -1444,6 +1444,11 @@ __device__ __forceinline__ void force_block(const ForceIO& io, int n, const Grid
   const bool active = i < n && (!SLAB || io.gflag[i] == GF_OWNED);
   if (tid < FORCE_NCLS) { T.cls_s[tid] = 0x7fffffff; T.cls_e[tid] = 0; T.cls_cmin[tid] = FORCE_CODE_MIXED; T.cls_cmax[tid] = 0; }
   if (BULK && tid == 0) mbar_init(&stage_bar, 1);
+  if (INTEGRATE && active && (tid & 7) == 0) {  // the epilogue's rows: in L2 by the time the pairs are done
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(io.pos + i));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(io.vel + i));
+    if ((tid & 15) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(io.e + i));
+  }
   __syncthreads();
 
   double2 pa = make_double2(0.0, 0.0), va = make_double2(0.0, 0.0);
@@ -1456,6 +1461,9 @@ __device__ __forceinline__ void force_block(const ForceIO& io, int n, const Grid
     const uint32_t* col = io.nn + (size_t)(i >> 5) * 1024 + (i & 31);
 #pragma unroll
     for (int u = 0; u < 8; ++u) ent0[u] = col[u * 32];  // in flight during the staging phase
+    // rows 8..31 of the warp's list tile (one 128-byte line each) into L2: under the register cap ptxas sinks the pair
+    // loop's look-ahead loads to the end of a batch, so their latency is what a warp waits for
+    if (lane >= 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(io.nn + (size_t)(i >> 5) * 1024 + lane * 32));
     cya = (int)(k / (uint32_t)g.ncx);
     cxa = (int)(k - (uint32_t)cya * (uint32_t)g.ncx);
     double rw = qa.z * (1.0 + 1e-6), lx = pa.x, ly = pa.y;
