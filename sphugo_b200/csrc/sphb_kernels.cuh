@@ -1215,6 +1215,9 @@ struct ForceIO {
 // The viscosity means are staged pre-scaled: rho/2, -0.375 c, h/2 (sph.go:379-386 with alpha = 0.75).
 // -------------------------------------------------------------------------------------------------
 #define FORCE_THREADS 128
+#ifndef FORCE_MINB
+#define FORCE_MINB 5
+#endif
 #define FORCE_NPIECE 6
 #define FORCE_RMAX 2
 #define FORCE_NCLS ((2 * FORCE_RMAX + 1) * 3)
@@ -1675,7 +1678,7 @@ __device__ __forceinline__ void force_block(const ForceIO& io, int n, const Grid
 // the two builds as separate kernels: the fp64 one is capped at 96 registers (5 blocks of 128 threads per SM, the
 // number the staging area allows), the fp32 one is left to ptxas (64 registers, 8 blocks)
 template <int KERNEL, bool INTEGRATE, bool SLAB>
-__global__ void __launch_bounds__(FORCE_THREADS, 5) k_force_st(ForceIO io, int n, const GridP* __restrict__ gp, PhysP ph, int nrec,
+__global__ void __launch_bounds__(FORCE_THREADS, FORCE_MINB) k_force_st(ForceIO io, int n, const GridP* __restrict__ gp, PhysP ph, int nrec,
                                                               uint32_t* __restrict__ dflags) {
   force_block<KERNEL, INTEGRATE, SLAB, double>(io, n, gp, ph, nrec, dflags);
 }
