@@ -564,6 +564,9 @@ __global__ void __launch_bounds__(KNN_THREADS, 5) k_knn_tile(const double2* __re
   // queries: owned particles and (slab mode) inner ghosts; outer ghosts are candidates only
   const bool valid = i < n && (gflag == nullptr || gflag[i] != GF_OUTER);
   const bool owned = i < n && (gflag == nullptr || gflag[i] == GF_OWNED);
+  // an outer ghost is a candidate only: its {rho, c, h, P} are never evaluated.  rho = -1 marks it where the force kernel
+  // will find it (its bulk-staged records are raw copies of these rows): a pair with such a neighbour is refused
+  if (i < n && !valid) out.pc[i] = make_double4(-1.0, 0.0, 0.0, 0.0);
 
   double xa = 0, ya = 0, rg = 0, ep = 0;
   int cxa = 0, cya = 0;
@@ -1330,8 +1333,7 @@ __device__ __forceinline__ void pair_term(const OwnRec<R>& o, const NbrRec<R>& b
 // One elected thread per piece copies the piece's rows of spos / vpred / pc straight from global into shared memory; the
 // copy engine signals an mbarrier with the byte count.  The records land RAW ({x, y}, {vx, vy}, {rho, c, h, P}); the pair
 // loop folds rho/2, -0.375 c, h/2 into its additions (pair_term<RAW>), so a block away from the periodic seam never
-// touches the staged bytes: no staging loop, no second barrier.  Seam blocks (and slab mode, for the thin-ghost marker)
-// patch the positions of image pieces in place.
+// touches the staged bytes: no staging loop, no second barrier.  Seam blocks patch the positions of image pieces in place.
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -1571,16 +1573,13 @@ __device__ __forceinline__ void force_block(const ForceIO& io, int n, const Grid
   const int np = T.np;
   if constexpr (BULK) {
     mbar_wait(&stage_bar, 0u);  // every thread waits for the bytes itself: no block barrier unless something is patched
-    if (SLAB || T.fix) {
+    if (T.fix) {  // (slab mode: an outer ghost's row already carries rho = -1, written by the tile search)
       double2* smb = reinterpret_cast<double2*>(fsm);
       for (int m = 0; m < np; ++m) {
-        const int s = T.p_s[m], len = T.p_len[m], off = T.p_off[m], code = T.p_code[m];
-        const bool shifted = code != 5;
+        const int len = T.p_len[m], off = T.p_off[m], code = T.p_code[m];
+        if (code == 5) continue;
         const double sx = (double)((code >> 2) - 1) * g.Lx, sy = (double)((code & 3) - 1) * g.Ly;
-        for (int t = tid; t < len; t += FORCE_THREADS) {
-          if (SLAB && io.gflag[s + t] == GF_OUTER) smb[2 * nrec + 2 * (off + t)].x = -1.0;  // its rho, c, h were not evaluated
-          if (shifted) { double2 pp = smb[off + t]; pp.x += sx; pp.y += sy; smb[off + t] = pp; }
-        }
+        for (int t = tid; t < len; t += FORCE_THREADS) { double2 pp = smb[off + t]; pp.x += sx; pp.y += sy; smb[off + t] = pp; }
       }
       __syncthreads();
     }
