@@ -95,6 +95,11 @@ struct sphb_sim {
   bool grid_next_ready = false;
   bool fuse_keys = false;      // the force launch in progress emits the next step's keys
   bool keys_ready = false;     // keys / rank / cellCount already hold the next step's cell keys (force epilogue)
+  // slab mode (ring fast path): the slab the NEXT evaluation will set is known before this evaluation's force kernel (its
+  // ghost widths come from maxima that lag one evaluation), so the fusion applies there too: owned particles get their
+  // keys in the epilogue, the ghosts theirs when they arrive
+  bool next_slab_valid = false;
+  sphb_slab next_slab{}, keys_slab{};
   double keys_dtH = 0.0, next_hor[2] = {0, 0}, next_ver[2] = {0, 0};
   int keys_n = 0;
   void* scratch = nullptr;    // download / upload staging
@@ -396,15 +401,20 @@ void launch_knn_reuse(sphb_sim* s, int ntot, const PhysP& ph) {
                                                          s->a.epred, ntot, s->grid, ph, out, gf, s->dflags, fx);
 }
 
-SlabP make_slabp(const sphb_sim* s) {
+SlabP make_slabp_of(const sphb_sim* s, const sphb_slab& b) {
   SlabP sl{};
-  sl.x_lo = s->slab.x_lo; sl.x_hi = s->slab.x_hi; sl.ghost_w = s->slab.ghost_w; sl.inner_w = s->slab.inner_w;
-  sl.has_left = s->slab.has_left; sl.has_right = s->slab.has_right;
+  sl.x_lo = b.x_lo; sl.x_hi = b.x_hi; sl.ghost_w = b.ghost_w; sl.inner_w = b.inner_w;
+  sl.has_left = b.has_left; sl.has_right = b.has_right;
   if (s->slab_on && !axis_open(s->prm.hor)) {  // image frame centred on the slab
     sl.Lx = s->prm.hor[1] - s->prm.hor[0];
-    sl.frame_lo = 0.5 * (s->slab.x_lo + s->slab.x_hi) - 0.5 * sl.Lx;
+    sl.frame_lo = 0.5 * (b.x_lo + b.x_hi) - 0.5 * sl.Lx;
   }
   return sl;
+}
+SlabP make_slabp(const sphb_sim* s) { return make_slabp_of(s, s->slab); }
+bool same_slab(const sphb_slab& a, const sphb_slab& b) {
+  return a.x_lo == b.x_lo && a.x_hi == b.x_hi && a.ghost_w == b.ghost_w && a.inner_w == b.inner_w && a.has_left == b.has_left &&
+         a.has_right == b.has_right;
 }
 
 template <int KERNEL, bool INTEGRATE, bool SLAB, typename R>
@@ -450,15 +460,17 @@ void launch_force(sphb_sim* s, int ntot, const PhysP& ph, bool integrate) {
   else launch_force_p<KERNEL, false, true>(s, io, ntot, ph);
 }
 
-// keep the entries of [0, nslots) flagged GF_OWNED, in place, in [0, nkeep) (nkeep = their number); failList / rank
-// are free outside the kNN / sort phases and serve as the hole / filler lists
+// keep the entries of [0, nslots) flagged GF_OWNED, in place, in [0, nkeep) (nkeep = their number); failList / perm
+// are free outside the kNN / sort phases and serve as the hole / filler lists.  Cell keys the force epilogue has already
+// produced for the next step (keys_ready) move with their particles.
 void compact_in_place(sphb_sim* s, int nslots, int nkeep) {
   if (nslots <= 0) return;
   cudaMemsetAsync(s->packCount, 0, 2 * sizeof(int), s->st);
-  k_find_holes<<<cdiv(nslots, 256), 256, 0, s->st>>>(s->a.ghost, nslots, nkeep, s->failList, s->rank, s->packCount);
+  k_find_holes<<<cdiv(nslots, 256), 256, 0, s->st>>>(s->a.ghost, nslots, nkeep, s->failList, s->perm, s->packCount);
   SoaPtr a{s->a.pos, s->a.vel, s->a.vdot, s->a.vpred, s->a.e, s->a.edot, s->a.epred, s->a.id, s->a.pc, s->a.ghost};
   const int moved_max = std::max(1, nslots - nkeep);  // fillers sit in [nkeep, nslots)
-  k_fill_holes<<<std::min(cdiv(moved_max, 256), 148 * 8), 256, 0, s->st>>>(a, s->failList, s->rank, s->packCount, s->dflags);
+  k_fill_holes<<<std::min(cdiv(moved_max, 256), 148 * 8), 256, 0, s->st>>>(a, s->failList, s->perm, s->packCount, s->dflags,
+                                                                          s->keys_ready ? s->keys : nullptr, s->rank);
   s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 2;
 }
 
@@ -475,8 +487,9 @@ int build_neighbours(sphb_sim* s, int mode, const double hor[2], const double ve
   const bool periodic = !axis_open(ver) && !axis_open(hor) && (!s->slab_on || (s->slab.has_left && s->slab.has_right));
   invalidate_reuse(s);
   // a fused step already built this evaluation's grid (and consumed the accumulator for it)
-  const bool same_box = s->grid_next_ready && periodic && !s->slab_on && hor[0] == s->next_hor[0] && hor[1] == s->next_hor[1] &&
-                        ver[0] == s->next_ver[0] && ver[1] == s->next_ver[1];
+  const bool same_box = s->grid_next_ready && periodic && hor[0] == s->next_hor[0] && hor[1] == s->next_hor[1] &&
+                        ver[0] == s->next_ver[0] && ver[1] == s->next_ver[1] &&
+                        (s->slab_on ? (s->keys_slab.has_left && same_slab(s->slab, s->keys_slab)) : !s->keys_slab.has_left);
   if (s->grid_next_ready && !same_box) s->hacc_valid = false;  // the accumulator went into a grid that does not apply
   s->grid_next_ready = false;
   const bool use_hacc = periodic && s->hacc_valid;
@@ -491,9 +504,15 @@ int build_neighbours(sphb_sim* s, int mode, const double hor[2], const double ve
                                         grid_tune(s, ext && s->have_h), s->grid, s->hacc, hscale_prev > 0.0 ? hscale_prev : 1.0, use_hacc ? 1 : 0);
   s->hacc_valid = periodic && want_hacc;  // the kNN below refills the accumulator
   cudaMemsetAsync(s->qmax, 0, sizeof(uint32_t), s->st);  // max h of this evaluation
-  const bool keys_ok = same_box && s->keys_ready && mode == MODE_DRIFT && dtH == s->keys_dtH && ntot == s->keys_n;
-  if (keys_ok) s->keys_ready = false;  // consumed: the scan below zeroes cellCount again
-  else {
+  const bool keys_ok = same_box && s->keys_ready && mode == MODE_DRIFT && dtH == s->keys_dtH && (int)s->n == s->keys_n;
+  if (keys_ok) {
+    s->keys_ready = false;  // consumed: the scan below zeroes cellCount again
+    if (s->nghost) {        // slab mode: the owned particles have their keys, the ghosts have just arrived
+      const size_t o = (size_t)s->n;
+      k_keys<true><<<cdiv((int)s->nghost, 256), 256, 0, s->st>>>(s->a.pos + o, s->a.vel + o, (int)s->nghost, s->grid, dtH, s->keys + o, s->rank + o, s->cellCount);
+      s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 1;
+    }
+  } else {
     drop_ready_keys(s);
     if (mode == MODE_DRIFT) k_keys<true><<<cdiv(ntot, 256), 256, 0, s->st>>>(s->a.pos, s->a.vel, ntot, s->grid, dtH, s->keys, s->rank, s->cellCount);
     else k_keys<false><<<cdiv(ntot, 256), 256, 0, s->st>>>(s->a.pos, s->a.vel, ntot, s->grid, dtH, s->keys, s->rank, s->cellCount);
@@ -702,11 +721,14 @@ int forces_plan(sphb_sim* s, int mode, bool integrate, const EvalPlan& plan) {
   cudaEventRecord(s->ev[SPHB_PH_FORCE], s->st);
   // Periodic single-handle steps: the next grid only depends on the mean h the kNN above produced, so it is built now
   // and the force epilogue emits the next step's cell keys (no k_keys pass in the next step).
-  s->fuse_keys = integrate && !s->slab_on && s->hacc_valid && !next_reuse && !axis_open(s->prm.hor) && !axis_open(s->prm.ver);
+  const bool slab_fuse = s->slab_on && s->next_slab_valid && s->next_slab.has_left && s->next_slab.has_right && !reuse;
+  s->next_slab_valid = false;
+  s->fuse_keys = integrate && (!s->slab_on || slab_fuse) && s->hacc_valid && !next_reuse && !axis_open(s->prm.hor) && !axis_open(s->prm.ver);
   if (s->fuse_keys) {
     // (the next evaluation is a rebuild; in an ordinary run of steps it starts a reuse cycle, i.e. searches with the skin)
     const bool next_ext = s->reuse_on && (s->reuse_period_fixed ? s->reuse_period_fixed > 1 : s->calm_steps >= 2);
-    k_make_grid<<<1, 32, 0, s->st>>>(s->stats, ntot, s->prm.hor[0], s->prm.hor[1], s->prm.ver[0], s->prm.ver[1], make_slabp(s), 0,
+    k_make_grid<<<1, 32, 0, s->st>>>(s->stats, ntot, s->prm.hor[0], s->prm.hor[1], s->prm.ver[0], s->prm.ver[1],
+                                     s->slab_on ? make_slabp_of(s, s->next_slab) : make_slabp(s), s->slab_on ? 1 : 0,
                                      grid_tune(s, next_ext), s->grid_next, s->hacc, s->hscale, 1);
     s->counters[SPHB_CNT_KERNEL_LAUNCHES] += 1;
   }
@@ -724,7 +746,8 @@ int forces_plan(sphb_sim* s, int mode, bool integrate, const EvalPlan& plan) {
   if (!keep) invalidate_reuse(s);  // the cycle ends here
   if (s->fuse_keys) {
     s->grid_next_ready = s->keys_ready = true;
-    s->keys_dtH = s->prm.dt_half; s->keys_n = ntot;
+    s->keys_dtH = s->prm.dt_half; s->keys_n = (int)s->n;  // (slab mode: the owned particles; ntot otherwise)
+    s->keys_slab = s->slab_on ? s->next_slab : sphb_slab{};
     s->next_hor[0] = s->prm.hor[0]; s->next_hor[1] = s->prm.hor[1]; s->next_ver[0] = s->prm.ver[0]; s->next_ver[1] = s->prm.ver[1];
   }
   if (s->slab_on) {

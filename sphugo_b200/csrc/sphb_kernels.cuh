@@ -1635,10 +1635,10 @@ __device__ __forceinline__ void force_block(const ForceIO& io, int n, const Grid
     io.pos[i] = p;
     io.vel[i] = v;
     io.e[i] = e;
-    if (!SLAB && io.next_grid) {  // == k_keys<true> of the next step
+    if (io.next_grid) {  // == k_keys<true> of the next step (slab mode: of the owned particles)
       const GridP gn = *io.next_grid;
       const double xd = __dadd_rn(p.x, __dmul_rn(v.x, ph.dtH)), yd = __dadd_rn(p.y, __dmul_rn(v.y, ph.dtH));
-      const double xs = gn.wrapx ? wrap_coord(xd, gn.lox, gn.Lx) : xd, ys = gn.wrapy ? wrap_coord(yd, gn.loy, gn.Ly) : yd;
+      const double xs = (gn.wrapx | gn.framex) ? wrap_coord(xd, gn.lox, gn.Lx) : xd, ys = gn.wrapy ? wrap_coord(yd, gn.loy, gn.Ly) : yd;
       const uint32_t k = (uint32_t)cell_of(ys, gn.oy, gn.inv_dy, gn.ncy) * (uint32_t)gn.ncx + (uint32_t)cell_of(xs, gn.ox, gn.inv_dx, gn.ncx);
       io.next_keys[i] = k;
       io.next_rank[i] = atomicAdd(&io.next_count[k], 1u);
@@ -1852,7 +1852,8 @@ struct SoaPtr {
 };
 
 __global__ void __launch_bounds__(256) k_fill_holes(SoaPtr a, const int* __restrict__ holes, const uint32_t* __restrict__ fillers,
-                                                   const int* __restrict__ counters, uint32_t* __restrict__ dflags) {
+                                                   const int* __restrict__ counters, uint32_t* __restrict__ dflags,
+                                                   uint32_t* __restrict__ keys, uint32_t* __restrict__ rank) {
   const int nh = counters[0];
   if (blockIdx.x == 0 && threadIdx.x == 0 && counters[1] != nh) atomicOr(dflags, DFLAG_BUF_FULL);  // cannot happen
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nh; k += gridDim.x * blockDim.x) {
@@ -1861,6 +1862,7 @@ __global__ void __launch_bounds__(256) k_fill_holes(SoaPtr a, const int* __restr
     a.pos[d] = a.pos[f]; a.vel[d] = a.vel[f]; a.vdot[d] = a.vdot[f]; a.vpred[d] = a.vpred[f];
     a.e[d] = a.e[f]; a.edot[d] = a.edot[f]; a.epred[d] = a.epred[f];
     a.id[d] = a.id[f]; a.pc[d] = a.pc[f]; a.ghost[d] = GF_OWNED;
+    if (keys) { keys[d] = keys[f]; rank[d] = rank[f]; }  // the next step's cell key and arrival rank (force epilogue)
   }
 }
 

@@ -25,7 +25,8 @@ def main():
     steps = int(os.environ.get("RING_CHECK_STEPS", "11"))
     pos = gen.jittered_lattice(nx, nx)
     n = len(pos)
-    vel = np.tile([[1.5, -0.7]], (n, 1))
+    vx = float(os.environ.get("RING_CHECK_VX", "1.5"))  # 1.5: a migration nearly every step; 0.1: one in ten (fused keys)
+    vel = np.tile([[vx, -0.7 * vx / 1.5]], (n, 1))
     e = np.full(n, 0.01)
     kw = dict(hor=(0.0, 1.0), ver=(0.0, 1.0), accel=(0.0, 0.2), dt_half=0.4 / nx)
     topo = slab.Topology(world, [k / world for k in range(world + 1)], True)
