@@ -69,6 +69,24 @@ def test_sm100a_sass_only():
     assert "sm_100a" in out and "sm_90" not in out
 
 
+def test_fp64_force_kernel_stages_with_the_bulk_copy_engine():
+    """every fp64 instantiation of k_force_st stages its neighbour records with cp.async.bulk (SASS UBLKCP) behind
+    an mbarrier (SYNCS), keeps its 96-register budget and does not spill; the fp32 twin converts on the way in and has none."""
+    from sphugo_b200 import build
+    lib = build.build()
+    res = subprocess.run(["cuobjdump", "-res-usage", lib], capture_output=True, text=True).stdout
+    usage = dict(re.findall(r"Function (\S+?):\s*\n?\s*(REG:\d+ STACK:\d+)", res))
+    f64 = [k for k in usage if "k_force_stIL" in k]
+    assert len(f64) == 8, sorted(usage)[:5]
+    for k in f64:
+        assert usage[k] == "REG:96 STACK:0", (k, usage[k])
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", f64[0], lib], capture_output=True, text=True).stdout
+    assert sass.count("UBLKCP") == 3 and "SYNCS.ARRIVE.TRANS64" in sass and "SYNCS.PHASECHK.TRANS64.TRYWAIT" in sass
+    f32 = [k for k in usage if "k_force_st32IL" in k]
+    sass32 = subprocess.run(["cuobjdump", "-sass", "-fun", f32[0], lib], capture_output=True, text=True).stdout
+    assert len(sass32) > 1000 and "UBLKCP" not in sass32
+
+
 def test_every_entry_point_is_mapped_in_integration_md():
     """INTEGRATION.md names, for every declared entry point, the reference interface it replaces"""
     text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
